@@ -1,0 +1,257 @@
+/*
+ * repas_vision.h -- C ABI of the B200-native RGB-D -> point-cloud hot path.
+ *
+ * The reference (blanklavender/repas-vision) is a folder of Python scripts with
+ * no FFI of its own; the boundary it offers is a set of Python call shapes.  Each
+ * entry point below names the reference call site(s) it replaces (paths are
+ * relative to the reference checkout).  The Python host in
+ * repas_vision_b200/ binds this header with ctypes; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every pointer named d_* is DEVICE memory owned by the caller (PyTorch's
+ *    caching allocator in this repo); the library allocates nothing on the hot
+ *    path and keeps no pointer after the call returns;
+ *  - every call is asynchronous and ordered on `stream` (a cudaStream_t passed
+ *    as void*); results are ready when the stream reaches that point;
+ *  - every call returns an int status (RV_OK == 0).  rv_last_error(ctx) holds
+ *    the text of the last failure on that context.  No exception crosses the ABI;
+ *  - clouds are SoA: six planes x,y,z,r,g,b of `plane_stride` elements each,
+ *    element type float32 or float64 (RvDType);
+ *  - images are row-major, pixel (u = column, v = row), pixel centres at
+ *    integer coordinates (create_masked_ply.py:77,94-95).
+ */
+#ifndef REPAS_VISION_H
+#define REPAS_VISION_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RV_ABI_VERSION 1
+
+typedef struct rv_ctx rv_ctx;
+typedef void *rv_stream; /* cudaStream_t */
+
+/* ---- status codes ------------------------------------------------------- */
+enum RvStatus {
+  RV_OK = 0,
+  RV_EINVAL = 1,    /* bad shape / dtype / enum / null pointer               */
+  RV_ECAPACITY = 2, /* an output capacity was too small (counts still valid) */
+  RV_ECUDA = 3,     /* a CUDA runtime call failed; see rv_last_error          */
+  RV_EALIGN = 4,    /* pointer or stride violates the stated alignment        */
+  RV_EWORKSPACE = 5 /* workspace smaller than rv_*_workspace_bytes said       */
+};
+
+/* ---- element types ------------------------------------------------------ */
+enum RvDType { RV_F32 = 0, RV_F64 = 1 };
+
+/* ---- camera model --------------------------------------------------------
+ * Intrinsics JSON on disk: {fx,fy,cx,cy,width,height[,dist_coeffs]}
+ * (create_masked_ply.py:27-43, april_tag_detector_solvepnp.py:51-66) or the
+ * RealSense form {fx,fy,ppx,ppy,coeffs,distortion_model}
+ * (vis_tool_april_tag_pose_validaiton.py:38-47).  dist = (k1,k2,p1,p2,k3).   */
+enum RvDistortion {
+  RV_DIST_NONE = 0,
+  RV_DIST_BROWN_CONRADY = 1,         /* forward model; deprojection inverts it iteratively */
+  RV_DIST_INVERSE_BROWN_CONRADY = 2, /* closed form on deprojection                        */
+  RV_DIST_MODIFIED_BROWN_CONRADY = 3 /* forward model on projection only                   */
+};
+
+typedef struct RvCam {
+  double fx, fy, cx, cy;
+  double dist[5];
+  int32_t model; /* RvDistortion */
+  int32_t width;
+  int32_t height;
+  int32_t reserved;
+} RvCam;
+
+/* ---- depth unit rules --------------------------------
+ * MUL_F32 : f32(u16) * f32(scale)    better_three_capture.py:118-125, april_tag_bg_removal_pl.py:286-288
+ * DIV_F32 : f32(u16) / f32(scale)    custom_reader.py:39-40, Open3D RGBDImage (depth_scale = 1000)
+ * DIV_F64 : f64(u16) / scale         canopy_return.py:312-315
+ * `scale` is 0.001 for MUL_F32 and 1000.0 for the DIV rules in the reference. */
+enum RvUnitRule { RV_UNIT_MUL_F32 = 0, RV_UNIT_DIV_F32 = 1, RV_UNIT_DIV_F64 = 2 };
+
+enum RvDepthKind { RV_DEPTH_U16 = 0, RV_DEPTH_F32_METERS = 1 };
+
+/* ---- output modes of the deprojection kernel ------------------------------ */
+enum RvDeprojectMode {
+  RV_MODE_COMPACT_ORDERED = 0,   /* row-major order of valid pixels, == numpy `[valid]` (create_masked_ply.py:89-100) */
+  RV_MODE_COMPACT_UNORDERED = 1, /* tiles land in arrival order; order inside a 2048-pixel tile is kept              */
+  RV_MODE_DENSE_ZERO = 2,        /* one record per pixel, zeros where invalid (rs.pointcloud / Orbbec RGB_POINT)     */
+  RV_MODE_DENSE_NAN = 3          /* one record per pixel, NaN xyz where invalid (Open3D project_valid_depth_only=False) */
+};
+
+enum RvColorScale {
+  RV_COLOR_UNIT = 0, /* u8 / 255.0 in [0,1]   (create_masked_ply.py:100)             */
+  RV_COLOR_255 = 1   /* raw 0..255 as floats (Orbbec RGB_POINT, better_three_capture.py:235-237) */
+};
+
+typedef struct RvDeprojectParams {
+  RvCam cam;            /* intrinsics of the grid the depth lives on (the colour camera after alignment) */
+  int32_t depth_kind;   /* RvDepthKind */
+  int32_t unit_rule;    /* RvUnitRule, used when depth_kind == RV_DEPTH_U16 */
+  double unit_scale;    /* 0.001 or 1000.0, see RvUnitRule */
+  int32_t use_seg_mask; /* 1: d_mask is read; keep mask>0 (or mask==0 when invert_mask) create_masked_ply.py:79-83 */
+  int32_t invert_mask;
+  int32_t use_depth_trunc; /* 1: z32 >= (float)depth_trunc -> invalid (Open3D create_from_color_and_depth) */
+  int32_t use_zclip;       /* 1: keep z_min <= Z <= z_max, inclusive (view_point_cloud.py:109-116) */
+  double depth_trunc;
+  double z_min, z_max;
+  int32_t use_radius; /* 1: keep ||p||_2 < r_max, strict (distance_masking_on_ply.py:12-16) */
+  int32_t use_aabb;   /* 1: keep aabb_min <= p <= aabb_max per axis, inclusive (april_tag_bg_removal_pl.py:450-455) */
+  double r_max;
+  double aabb_min[3];
+  double aabb_max[3];
+  int32_t mode;        /* RvDeprojectMode */
+  int32_t out_dtype;   /* RvDType of the six output planes */
+  int32_t color_scale; /* RvColorScale */
+  int32_t reserved;
+} RvDeprojectParams;
+
+/* ---- context -------------------------------------------------------------- */
+int rv_abi_version(void);
+const char *rv_build_info(void); /* "sm_100a nvcc 12.9 ..." */
+int rv_create(int device, rv_ctx **out_ctx);
+int rv_destroy(rv_ctx *ctx);
+const char *rv_last_error(const rv_ctx *ctx);
+const char *rv_status_string(int status);
+int rv_sm_count(const rv_ctx *ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+int64_t rv_launch_count(const rv_ctx *ctx);
+
+/* ---- a1/a2: depth units -----------------------------------------------------
+ * replaces depth_to_meters (better_three_capture.py:118-125) and the inline
+ * `astype(float32)/1000.0` conversions (custom_reader.py:39-40).
+ * d_depth: n uint16 ; d_out: n float32 (DIV_F64 results are rounded to f32). */
+int rv_depth_to_meters(rv_ctx *ctx, const uint16_t *d_depth, int64_t n, int unit_rule, double unit_scale,
+                       float *d_out, rv_stream stream);
+
+/* ---- a6: depth -> colour registration ---------------------------------------
+ * replaces AlignFilter(align_to_stream=COLOR_STREAM).process
+ * (better_three_capture.py:169,188; april_tag_detector_ToF.py:169,183) and
+ * rs.align(rs.stream.color).process (capture_aligned_all.py:75,197;
+ * canopy_return.py:442,453).  Semantics: SURVEY Appendix B.3 (librealsense
+ * align z16 -> other): each depth pixel's two half-pixel corners are
+ * deprojected, moved by (R,t), projected into the colour camera and rounded;
+ * the covered rectangle takes the minimum raw depth (z-buffer).  float32
+ * geometry, no fused multiply-add.
+ *  d_depth      [B,Hd,Wd] uint16
+ *  R (9, COLUMN-major as librealsense stores it) and t (3): host pointers
+ *  d_out        [B,Hc,Wc] uint16, 0 where no depth pixel lands
+ *  d_winner     [B,Hc,Wc] int32 source index (y*Wd+x) of the winning depth pixel,
+ *               lowest index on ties, -1 where empty; may be NULL
+ *  d_ws         workspace of rv_register_workspace_bytes(B,Hc,Wc) bytes, 16-B aligned */
+size_t rv_register_workspace_bytes(int B, int Hc, int Wc);
+int rv_register_depth_to_color(rv_ctx *ctx, const uint16_t *d_depth, int B, const RvCam *depth_cam,
+                               const RvCam *color_cam, const float *R_colmajor, const float *t, float depth_units,
+                               uint16_t *d_out, int32_t *d_winner, void *d_ws, size_t ws_bytes, rv_stream stream);
+
+/* ---- distortion ray table -----------------------------------------------------
+ * Per-pixel normalised ray (xn, yn) of a distorted camera, so the deprojection
+ * kernel multiplies instead of iterating (rs2_deproject_pixel_to_point semantics,
+ * SURVEY Appendix B.3, in float64).  d_table: [H,W,2] float64. */
+int rv_build_ray_table(rv_ctx *ctx, const RvCam *cam, double *d_table, rv_stream stream);
+
+/* ---- a3/a5/a7/a8/a9: deprojection + masks + stream compaction -------------------
+ * replaces create_masked_pointcloud (create_masked_ply.py:56-107), the SDK
+ * clouds PointCloudFilter.process (better_three_capture.py:235-237) and
+ * rs.pointcloud.calculate (capture_aligned_all.py:209-216) in the dense modes,
+ * and fuses the cloud predicates of distance_masking_on_ply.py:12-19,
+ * view_point_cloud.py:109-116 and april_tag_bg_removal_pl.py:450-455.
+ *  d_depth   [B,H,W] uint16 or float32 (params->depth_kind)
+ *  d_bgr     [B,H,W,3] uint8, BGR order (cv2 / SDK bgr8); may be NULL (no colour planes written)
+ *  d_mask    [B,H,W] uint8 segmentation mask, or NULL
+ *  d_ray_table  [H,W,2] float64 from rv_build_ray_table, required iff cam.model != RV_DIST_NONE
+ *  d_out     six planes (x,y,z,r,g,b), plane p of frame b starts at element
+ *            p*plane_stride + b*frame_stride; compact modes write counts[b] elements per
+ *            plane, dense modes H*W.  frame_stride is the per-frame capacity.
+ *  d_valid   [B,H,W] uint8 (1 = kept) or NULL
+ *  d_src_index  same addressing as one plane, int32 source pixel index of each output point, or NULL
+ *  d_counts  [B] int64 kept points per frame (written in every mode)
+ *  d_ws      rv_deproject_workspace_bytes(B,H,W) bytes
+ * Points beyond frame_stride are not written; counts[b] still reports the true
+ * number so the caller can detect RV_ECAPACITY after synchronising. */
+size_t rv_deproject_workspace_bytes(int B, int H, int W);
+int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, const uint8_t *d_mask,
+                      const double *d_ray_table, int B, int H, int W, const RvDeprojectParams *params, void *d_out,
+                      int64_t plane_stride, int64_t frame_stride, uint8_t *d_valid, int32_t *d_src_index,
+                      int64_t *d_counts, void *d_ws, size_t ws_bytes, rv_stream stream);
+
+/* ---- a8/a9 on an existing cloud -------------------------------------------------
+ * the stand-alone form of the predicates above (distance_masking_on_ply.py,
+ * view_point_cloud.py --z-min/--z-max, AABB crop): ordered compaction of an
+ * n-point SoA cloud.  Only use_zclip/use_radius/use_aabb and their values are read
+ * from params.  d_count: one int64. */
+size_t rv_filter_workspace_bytes(int64_t n);
+int rv_filter_cloud(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int dtype, int has_color,
+                    const RvDeprojectParams *params, void *d_out, int64_t out_plane_stride, int64_t *d_count,
+                    void *d_ws, size_t ws_bytes, rv_stream stream);
+
+/* ---- a11: 4x4 pose transform + merge ------------------------------------------
+ * replaces geometry.transform(T) (final_view_with_cad.py:333,
+ * vis_tool_april_tag_pose_validaiton.py:239-245) and PointCloud `+`
+ * (concatenation) for the four_pose_captures fusion.
+ * For view v: p' = (T_v [p,1])[:3] / (T_v [p,1])[3] in float64, colours copied.
+ *  T            host, n_views x 16 doubles, row-major 4x4 (np.loadtxt layout, 6dof_icp_export.py:55-70)
+ *  d_in[v]      host array of device pointers to each view's six-plane cloud
+ *  n[v], in_plane_stride[v]  host arrays
+ *  d_out        merged cloud, view v starts at sum(n[0..v-1])
+ *  d_bounds     6 doubles (min xyz, max xyz) of the merged cloud, or NULL.  Must be
+ *               pre-initialised by rv_bounds_init when several calls accumulate. */
+int rv_bounds_init(rv_ctx *ctx, double *d_bounds, rv_stream stream);
+int rv_transform_merge(rv_ctx *ctx, int n_views, const void *const *d_in, const int64_t *in_plane_stride,
+                       const int64_t *n, const double *T, int in_dtype, int has_color, void *d_out,
+                       int64_t out_plane_stride, int out_dtype, double *d_bounds, rv_stream stream);
+
+/* ---- a12: voxel grid downsampling -----------------------------------------------
+ * replaces PointCloud.voxel_down_sample(voxel_size) (17 call sites, e.g.
+ * mpa_icp_export.py:44,174; create_masked_ply.py:164; view_point_cloud.py:120).
+ * Semantics: SURVEY Appendix B.1 -- origin = min_bound - voxel/2, key =
+ * floor((p - origin)/voxel) per axis in float64, output = per-voxel mean of
+ * points and colours, order unspecified.
+ *  d_in         six-plane cloud (three planes when has_color == 0)
+ *  d_bounds     6 doubles min/max of the cloud, or NULL (computed internally)
+ *  d_out        up to out_capacity voxels, six planes
+ *  d_keys       [3, out_capacity] int32 voxel indices, or NULL
+ *  d_counts_out [out_capacity] int32 points per voxel, or NULL
+ *  d_m          one int64: number of voxels (true number even if > out_capacity)
+ * Each voxel index must fit 21 bits (extent/voxel < 2^21); otherwise d_m is set to -1. */
+size_t rv_voxel_workspace_bytes(int64_t n);
+int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int in_dtype,
+                        int has_color, double voxel_size, const double *d_bounds, void *d_out,
+                        int64_t out_plane_stride, int out_dtype, int64_t out_capacity, int32_t *d_keys,
+                        int32_t *d_counts_out, int64_t *d_m, void *d_ws, size_t ws_bytes, rv_stream stream);
+
+/* ---- a13 (next): PLY vertex records on device -----------------------
+ * packs an SoA cloud into the binary little-endian vertex records that
+ * o3d.io.write_point_cloud emits (create_masked_ply.py:177): xyz as float32 or
+ * float64 followed by uchar red,green,blue = round(clamp(c,0,1)*255).
+ * d_records: n * (3*sizeof(coord) + 3) bytes. */
+int rv_pack_ply_records(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int in_dtype,
+                        int has_color, int color_scale, int coord_dtype, uint8_t *d_records, rv_stream stream);
+
+/* ---- a2 (next): windowed median depth ------------------------------
+ * replaces get_depth_at_pixel (canopy_return.py:279-317) and median_depth
+ * (final_view.py:132-141): median of the non-zero raw depths in a win x win
+ * window clipped to the image; numpy median (mean of the two middle values for
+ * even counts); result in raw units as float64, NaN when the window holds no
+ * valid depth.
+ *  d_depth [H,W] uint16 ; d_uv [n,2] int32 (x,y) ; d_out [n] float64 */
+int rv_median_depth_window(rv_ctx *ctx, const uint16_t *d_depth, int H, int W, const int32_t *d_uv, int64_t n,
+                           int window, double *d_out, rv_stream stream);
+
+/* ---- (next): NV12 -> BGR ---------------------------------------------
+ * replaces cv2.cvtColor(nv12, COLOR_YUV2BGR_NV12) in frame_to_bgr_image
+ * (better_three_capture.py:101-106).  d_nv12: [B, H*3/2, W] uint8; d_bgr: [B,H,W,3]. */
+int rv_nv12_to_bgr(rv_ctx *ctx, const uint8_t *d_nv12, int B, int H, int W, uint8_t *d_bgr, rv_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REPAS_VISION_H */

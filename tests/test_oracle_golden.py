@@ -1,0 +1,122 @@
+"""Pins the CPU oracle to the reference: every golden in tests/golden/reference_golden.json was
+produced by the reference's own functions (tests/golden/make_golden.py); the four canopy_y
+values are fixtures the reference itself ships.  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CAL, CANOPY_TS, FRAMES, blob_mask, load_frame, sha
+from oracle import oracle_c, oracle_np as O
+
+
+def test_canopy_known_answers(golden, rs720):
+    """realsense_d415i/canopy_detection/new-captures/canopy_y_*.txt: median depth window +
+    /1000.0 + pinhole deprojection, formatted "{Y:.4f}" (canopy_return.py:404-407)."""
+    assert len(golden["canopy"]) == 4
+    for rec in golden["canopy"]:
+        _, depth = load_frame(rec["ts"])
+        x, y = rec["pixel"]
+        d = O.median_depth_window(depth, x, y, 5)
+        if d is None or d <= 0:
+            d = O.median_depth_window(depth, x, y, 11)
+        dm = d / 1000.0
+        assert dm == rec["depth_m"]
+        X, Y, Z = O.deproject_pixel_to_point(rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"], (x, y), dm)
+        assert [X, Y, Z] == rec["xyz"]
+        stored = open(os.path.join(FRAMES, f"canopy_y_{rec['ts']}.txt")).read().strip()
+        assert f"{Y:.4f}" == stored == rec["stored_in_reference"]
+
+
+def test_median_depth_windows(golden, rs720):
+    _, depth = load_frame(CANOPY_TS[0])
+    for rec in golden["median_depth"]:
+        d = O.median_depth_window(depth, rec["x"], rec["y"], rec["window"])
+        if rec["depth_m"] is None:
+            assert d is None
+        else:
+            assert d / 1000.0 == rec["depth_m"]
+            xyz = O.deproject_pixel_to_point(rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"], (rec["x"], rec["y"]),
+                                             d / 1000.0)
+            assert list(xyz) == rec["xyz"]
+
+
+def test_depth_to_meters(golden):
+    _, depth = load_frame(CANOPY_TS[0])
+    assert sha(O.depth_to_meters(depth, "mul_f32")) == golden["depth_to_meters"]["depth_m"]["sha256"]
+    allv = np.arange(65536, dtype=np.uint16).reshape(256, 256)
+    assert sha(O.depth_to_meters(allv, "mul_f32")) == golden["depth_to_meters"]["all_u16"]["sha256"]
+    # the three unit rules differ in the last ulp for many values
+    a = O.depth_to_meters(allv, "mul_f32")
+    b = O.depth_to_meters(allv, "div_f32")
+    assert a.dtype == b.dtype == np.float32 and (a != b).any()
+    assert np.abs(a.astype(np.float64) - b).max() < 1e-5
+
+
+@pytest.mark.parametrize("idx", range(5))
+def test_masked_cloud_real_frames(golden, rs720, idx):
+    ts = CANOPY_TS[idx]
+    color, depth = load_frame(ts)
+    dm = O.depth_to_meters(depth, "mul_f32")
+    recs = [r for r in golden["masked_cloud"] if r["ts"] == ts]
+    assert len(recs) == 3
+    for rec in recs:
+        h, w = depth.shape
+        mask = np.full((h, w), 255, np.uint8) if rec["variant"] == "all" else blob_mask(h, w, rec["mask_seed"])
+        P, C = O.create_masked_pointcloud(color, dm, mask, rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"],
+                                          invert_mask=rec["variant"] == "blob_inverted")
+        assert P.shape[0] == rec["n"]
+        assert sha(P) == rec["points"]["sha256"]  # float64, bit-exact, same order
+        assert sha(C) == rec["colors"]["sha256"]
+        # the fused-kernel contract reproduces the same cloud in its float64 mode
+        out = O.deproject_mask(depth, color, mask, fx=rs720["fx"], fy=rs720["fy"], cx=rs720["cx"], cy=rs720["cy"],
+                               invert_mask=rec["variant"] == "blob_inverted", out_dtype="f64")
+        assert sha(out["points"]) == rec["points"]["sha256"] and sha(out["colors"]) == rec["colors"]["sha256"]
+        if rec["variant"] == "all":
+            keep = O.distance_mask(P, 1.0)
+            assert int(keep.sum()) == rec["dist_lt_1m"]["kept"]
+            assert sha(np.packbits(keep)) == rec["dist_lt_1m"]["mask"]["sha256"]
+            assert sha(P[keep]) == rec["dist_lt_1m"]["points"]["sha256"]
+            fused = O.deproject_mask(depth, color, None, fx=rs720["fx"], fy=rs720["fy"], cx=rs720["cx"],
+                                     cy=rs720["cy"], r_max=1.0, out_dtype="f64")
+            assert sha(fused["points"]) == rec["dist_lt_1m"]["points"]["sha256"]
+            kz = O.z_clip_mask(P, 0.15, 8.0)
+            assert sha(np.packbits(kz)) == rec["zclip_0p15_8"]["mask"]["sha256"]
+            ka = O.aabb_mask(P, rec["aabb"]["min"], rec["aabb"]["max"])
+            assert int(ka.sum()) == rec["aabb"]["kept"] and sha(np.packbits(ka)) == rec["aabb"]["mask"]["sha256"]
+            # compiled loop form agrees with the numpy form
+            Pc, Cc = oracle_c.deproject_masked(depth, color, None, rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"])
+            assert sha(Pc) == rec["points"]["sha256"] and sha(Cc) == rec["colors"]["sha256"]
+
+
+def test_masked_cloud_float_depth_nan_inf(golden):
+    rngf = np.random.default_rng(11)
+    dm = (rngf.uniform(0.2, 4.0, (48, 64))).astype(np.float32)
+    dm[rngf.random((48, 64)) < 0.1] = np.nan
+    dm[rngf.random((48, 64)) < 0.05] = np.inf
+    dm[rngf.random((48, 64)) < 0.05] = -1.0
+    dm[rngf.random((48, 64)) < 0.1] = 0.0
+    col = rngf.integers(0, 256, (48, 64, 3), dtype=np.uint8)
+    msk = (rngf.random((48, 64)) < 0.7).astype(np.uint8) * 255
+    P, C = O.create_masked_pointcloud(col, dm, msk, 60.0, 61.0, 31.5, 23.25)
+    g = golden["masked_cloud_float_small"]
+    assert P.shape[0] == g["n"] and sha(P) == g["points"]["sha256"] and sha(C) == g["colors"]["sha256"]
+    out = O.deproject_mask(dm, col, msk, fx=60.0, fy=61.0, cx=31.5, cy=23.25, depth_kind="f32", out_dtype="f64")
+    assert sha(out["points"]) == g["points"]["sha256"]
+
+
+def test_final_view_median_and_pixel_to_3d(golden, rs720):
+    """final_view.py:132-146 -- median of finite positive float depths; (u-cx)/fx*Z order (within 1 ulp
+    of the kernel's (u-cx)*Z/fx order)."""
+    _, depth = load_frame(CANOPY_TS[0])
+    Zm = depth.astype(np.float32) * np.float32(0.001)
+    for rec in golden["final_view_median"]:
+        u, v, win = rec["u"], rec["v"], rec["win"]
+        r = max(1, win // 2)
+        patch = Zm[max(0, v - r):min(720, v + r + 1), max(0, u - r):min(1280, u + r + 1)]
+        patch = patch[np.isfinite(patch) & (patch > 0)]
+        z = float(np.median(patch)) if patch.size else 0.0
+        assert z == rec["z"]
+        x, y, zz = O.deproject_pixel_to_point(rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"], (float(u), float(v)), z)
+        assert np.allclose([x, y, zz], rec["p"], rtol=1e-15, atol=1e-15)
