@@ -116,6 +116,9 @@ typedef struct RvDeprojectParams {
 
 /* ---- context -------------------------------------------------------------- */
 int rv_abi_version(void);
+/* sizeof(RvCam) / sizeof(RvDeprojectParams) as compiled, so a foreign-language binding can verify its layout */
+int rv_sizeof_cam(void);
+int rv_sizeof_deproject_params(void);
 const char *rv_build_info(void); /* "sm_100a nvcc 12.9 ..." */
 int rv_create(int device, rv_ctx **out_ctx);
 int rv_destroy(rv_ctx *ctx);

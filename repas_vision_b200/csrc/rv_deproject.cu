@@ -1,0 +1,632 @@
+// rv_deproject.cu -- K1: depth units, ray table, fused deprojection + masks + stream
+// compaction, and the stand-alone cloud filter.
+//
+// Reference semantics (paths relative to the reference checkout):
+//   create_masked_pointcloud     femto_bolt_code/scripts/create_masked_ply.py:56-107
+//   depth_to_meters              femto_bolt_code/scripts/better_three_capture.py:118-125
+//   distance mask                realsense_d415i/capture_scripts/distance_masking_on_ply.py:12-19
+//   Z clip                       femto_bolt_code/scripts/view_point_cloud.py:109-116
+//   AABB crop                    femto_bolt_code/scripts/april_tag_bg_removal_pl.py:450-455
+//   rs2_deproject_pixel_to_point SURVEY.md Appendix B.3 (ray table)
+//
+// Data layout: a frame is a flat array of P = H*W pixels.  A tile is 2048 consecutive
+// pixels; warp w of a 256-thread CTA owns pixels [256w, 256w+256) of the tile and walks
+// them 32 at a time, so every warp-wide load and every compacted store is one contiguous
+// run.  Ordered compaction chains the tiles of a frame with a decoupled look-back
+// (rv_common.cuh); tiles are handed out by an atomic ticket so a tile's predecessors
+// are always already running.
+#include "rv_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kIters = 8;
+constexpr int kTile = kThreads * kIters;  // 2048 pixels
+
+struct DeprojArgs {
+  const void *depth;
+  const uint8_t *bgr;
+  const uint8_t *mask;
+  const double2 *rays;
+  void *out;
+  uint8_t *valid;
+  int32_t *src_index;
+  unsigned long long *counts;
+  unsigned long long *status;  // ws + 128 B
+  unsigned int *ticket;        // ws
+  int B, H, W, P;
+  int tiles_per_frame, total_tiles;
+  long long plane_stride, frame_stride;
+  double cx, cy, fx, fy, rfx, rfy;
+  double unit_scale, unit_rcp;
+  float unit_scale_f, unit_rcp_f;
+  float trunc_f;
+  int unit_rule;
+  double z_min, z_max;
+  double r2_thresh;  // keep iff (x*x+y*y)+z*z < r2_thresh  <=>  sqrt(.) < r_max
+  double amin[3], amax[3];
+  int use_mask, invert_mask, use_trunc, use_zclip, use_radius, use_aabb;
+  int color_255;
+};
+
+template <typename T>
+__device__ __forceinline__ T color_value(uint32_t k, int color_255);
+template <>
+__device__ __forceinline__ float color_value<float>(uint32_t k, int color_255) {
+  const float kf = (float)k;
+  return color_255 ? kf : rv_divf(kf, 255.0f, 0.003921568859368563f /* RN_f32(1/255) */);
+}
+template <>
+__device__ __forceinline__ double color_value<double>(uint32_t k, int color_255) {
+  const double kd = (double)k;
+  return color_255 ? kd : rv_div(kd, 255.0, 0.00392156862745098 /* RN(1/255) */);
+}
+
+template <typename T>
+__device__ __forceinline__ T quiet_nan();
+template <>
+__device__ __forceinline__ float quiet_nan<float>() {
+  return __int_as_float(0x7fc00000);
+}
+template <>
+__device__ __forceinline__ double quiet_nan<double>() {
+  return __longlong_as_double(0x7ff8000000000000ll);
+}
+
+// MODE: RvDeprojectMode.  DK: RvDepthKind.
+template <typename OutT, int DK, int MODE>
+__global__ void __launch_bounds__(kThreads) k_deproject(const DeprojArgs a) {
+  constexpr bool kOrdered = MODE == RV_MODE_COMPACT_ORDERED;
+  constexpr bool kCompact = MODE == RV_MODE_COMPACT_ORDERED || MODE == RV_MODE_COMPACT_UNORDERED;
+  __shared__ uint32_t s_warp_tot[kWarps];
+  __shared__ int s_tile;
+  __shared__ unsigned long long s_base;
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lt = rv_lanemask_lt();
+  OutT *const out = reinterpret_cast<OutT *>(a.out);
+
+  for (int round = 0;; ++round) {
+    int tile;
+    if (kOrdered) {
+      if (threadIdx.x == 0) s_tile = (int)atomicAdd(a.ticket, 1u);
+      __syncthreads();
+      tile = s_tile;
+    } else {
+      tile = blockIdx.x + round * gridDim.x;
+    }
+    if (tile >= a.total_tiles) break;
+    const int b = tile / a.tiles_per_frame;
+    const int t = tile - b * a.tiles_per_frame;
+    const int p0 = t * kTile + warp * (32 * kIters) + lane;  // first pixel of this lane
+    const long long fpix = (long long)b * a.P;               // frame offset in pixels
+
+    // ---------------- loads: everything this lane needs, issued before any use
+    uint32_t draw[kIters];
+    uint32_t craw[kIters];
+    uint32_t mraw[kIters];
+#pragma unroll
+    for (int j = 0; j < kIters; ++j) {
+      const int p = p0 + j * 32;
+      draw[j] = 0;
+      craw[j] = 0;
+      mraw[j] = 255;
+      if (p < a.P) {
+        const long long g = fpix + p;
+        if (DK == RV_DEPTH_U16)
+          draw[j] = __ldg(reinterpret_cast<const uint16_t *>(a.depth) + g);
+        else
+          draw[j] = __float_as_uint(__ldg(reinterpret_cast<const float *>(a.depth) + g));
+        if (a.use_mask) mraw[j] = __ldg(a.mask + g);
+        if (a.bgr) {
+          const uint8_t *c = a.bgr + 3 * g;
+          craw[j] = (uint32_t)__ldg(c) | ((uint32_t)__ldg(c + 1) << 8) | ((uint32_t)__ldg(c + 2) << 16);
+        }
+      }
+    }
+
+    // ---------------- geometry + predicates
+    int u = p0 % a.W;
+    int v = p0 / a.W;
+    OutT xs[kIters], ys[kIters], zs[kIters];
+    uint32_t ballots[kIters];
+    uint32_t warp_total = 0;
+#pragma unroll
+    for (int j = 0; j < kIters; ++j) {
+      const int p = p0 + j * 32;
+      float z32;
+      double z64;
+      bool ok;
+      if (DK == RV_DEPTH_U16) {
+        const float df = (float)draw[j];
+        if (a.unit_rule == RV_UNIT_MUL_F32) {
+          z32 = df * a.unit_scale_f;
+          z64 = (double)z32;
+        } else if (a.unit_rule == RV_UNIT_DIV_F32) {
+          z32 = rv_divf(df, a.unit_scale_f, a.unit_rcp_f);
+          z64 = (double)z32;
+        } else {
+          z64 = rv_div((double)draw[j], a.unit_scale, a.unit_rcp);
+          z32 = (float)z64;
+        }
+        ok = draw[j] != 0;
+      } else {
+        z32 = __uint_as_float(draw[j]);
+        z64 = (double)z32;
+        ok = (z32 > 0.0f) && (z32 < __int_as_float(0x7f800000));  // finite and positive
+      }
+      ok = ok && (p < a.P);
+      if (a.use_mask) ok = ok && (a.invert_mask ? (mraw[j] == 0) : (mraw[j] != 0));
+      if (a.use_trunc) ok = ok && !(z32 >= a.trunc_f);
+
+      double x64, y64;
+      if (a.rays) {
+        double2 r = make_double2(0.0, 0.0);
+        if (p < a.P) r = __ldg(a.rays + p);
+        x64 = z64 * r.x;
+        y64 = z64 * r.y;
+      } else {
+        x64 = rv_div(((double)u - a.cx) * z64, a.fx, a.rfx);
+        y64 = rv_div(((double)v - a.cy) * z64, a.fy, a.rfy);
+      }
+      const OutT xo = (OutT)x64, yo = (OutT)y64, zo = (OutT)z64;
+      if (a.use_zclip | a.use_radius | a.use_aabb) {
+        // predicates on the STORED values (exact up-casts for float32 storage)
+        const double X = (double)xo, Y = (double)yo, Z = (double)zo;
+        if (a.use_zclip) ok = ok && (Z >= a.z_min) && (Z <= a.z_max);
+        if (a.use_radius) ok = ok && (((X * X + Y * Y) + Z * Z) < a.r2_thresh);
+        if (a.use_aabb)
+          ok = ok && (X >= a.amin[0]) && (X <= a.amax[0]) && (Y >= a.amin[1]) && (Y <= a.amax[1]) &&
+               (Z >= a.amin[2]) && (Z <= a.amax[2]);
+      }
+      xs[j] = xo;
+      ys[j] = yo;
+      zs[j] = zo;
+      ballots[j] = __ballot_sync(0xffffffffu, ok);
+      warp_total += __popc(ballots[j]);
+      if (a.valid && p < a.P) a.valid[fpix + p] = ok ? 1 : 0;
+      u += 32;
+      while (u >= a.W) {
+        u -= a.W;
+        ++v;
+      }
+    }
+
+    // ---------------- tile totals, tile base
+    if (lane == 0) s_warp_tot[warp] = warp_total;
+    __syncthreads();
+    uint32_t warp_excl = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const uint32_t c = s_warp_tot[w];
+      warp_excl += (w < warp) ? c : 0u;
+      tile_total += c;
+    }
+    unsigned long long base = 0;
+    if (kOrdered) {
+      if (warp == 0) {
+        const uint32_t excl = rv_lookback(a.status, tile, t, tile_total);
+        if (lane == 0) {
+          s_base = excl;
+          if (t == a.tiles_per_frame - 1) a.counts[b] = (unsigned long long)excl + tile_total;
+        }
+      }
+      __syncthreads();
+      base = s_base;
+    } else if (MODE == RV_MODE_COMPACT_UNORDERED) {
+      if (threadIdx.x == 0) s_base = atomicAdd(a.counts + b, (unsigned long long)tile_total);
+      __syncthreads();
+      base = s_base;
+    } else {
+      if (threadIdx.x == 0 && tile_total) atomicAdd(a.counts + b, (unsigned long long)tile_total);
+    }
+
+    // ---------------- stores
+    const long long fout = (long long)b * a.frame_stride;
+    unsigned long long run = base + warp_excl;
+#pragma unroll
+    for (int j = 0; j < kIters; ++j) {
+      const int p = p0 + j * 32;
+      const bool ok = (ballots[j] >> lane) & 1u;
+      if (kCompact) {
+        const unsigned long long pos = run + __popc(ballots[j] & lt);
+        run += __popc(ballots[j]);
+        if (ok && pos < (unsigned long long)a.frame_stride) {
+          OutT *o = out + fout + pos;
+          o[0] = xs[j];
+          o[a.plane_stride] = ys[j];
+          o[2 * a.plane_stride] = zs[j];
+          if (a.bgr) {
+            o[3 * a.plane_stride] = color_value<OutT>((craw[j] >> 16) & 255u, a.color_255);
+            o[4 * a.plane_stride] = color_value<OutT>((craw[j] >> 8) & 255u, a.color_255);
+            o[5 * a.plane_stride] = color_value<OutT>(craw[j] & 255u, a.color_255);
+          }
+          if (a.src_index) a.src_index[fout + pos] = p;
+        }
+      } else if (p < a.P && p < a.frame_stride) {
+        OutT *o = out + fout + p;
+        const OutT bad = (MODE == RV_MODE_DENSE_NAN) ? quiet_nan<OutT>() : (OutT)0;
+        o[0] = ok ? xs[j] : bad;
+        o[a.plane_stride] = ok ? ys[j] : bad;
+        o[2 * a.plane_stride] = ok ? zs[j] : bad;
+        if (a.bgr) {
+          o[3 * a.plane_stride] = ok ? color_value<OutT>((craw[j] >> 16) & 255u, a.color_255) : (OutT)0;
+          o[4 * a.plane_stride] = ok ? color_value<OutT>((craw[j] >> 8) & 255u, a.color_255) : (OutT)0;
+          o[5 * a.plane_stride] = ok ? color_value<OutT>(craw[j] & 255u, a.color_255) : (OutT)0;
+        }
+        if (a.src_index) a.src_index[fout + p] = ok ? p : -1;
+      }
+    }
+    if (!kOrdered) __syncthreads();  // s_warp_tot / s_base are reused next round
+  }
+}
+
+// ------------------------------------------------------------------ depth units
+__global__ void __launch_bounds__(256) k_depth_to_meters(const uint16_t *__restrict__ d, long long n, int rule,
+                                                         double scale, double rcp, float scale_f, float rcp_f,
+                                                         float *__restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t r = d[i];
+    float z;
+    if (rule == RV_UNIT_MUL_F32)
+      z = (float)r * scale_f;
+    else if (rule == RV_UNIT_DIV_F32)
+      z = rv_divf((float)r, scale_f, rcp_f);
+    else
+      z = (float)rv_div((double)r, scale, rcp);
+    out[i] = z;
+  }
+}
+
+// -------------------------------------------------------------------- ray table
+// One-off per camera: float64 rs2_deproject_pixel_to_point normalised ray per pixel.
+__global__ void __launch_bounds__(256) k_ray_table(RvCam cam, double2 *__restrict__ table) {
+  const int n = cam.width * cam.height;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int u = i % cam.width, v = i / cam.width;
+  double x = ((double)u - cam.cx) / cam.fx;
+  double y = ((double)v - cam.cy) / cam.fy;
+  const double k1 = cam.dist[0], k2 = cam.dist[1], p1 = cam.dist[2], p2 = cam.dist[3], k3 = cam.dist[4];
+  if (cam.model == RV_DIST_INVERSE_BROWN_CONRADY) {
+    const double r2 = x * x + y * y;
+    const double f = 1.0 + k1 * r2 + k2 * r2 * r2 + k3 * r2 * r2 * r2;
+    const double ux = x * f + 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x);
+    const double uy = y * f + 2.0 * p2 * x * y + p1 * (r2 + 2.0 * y * y);
+    x = ux;
+    y = uy;
+  } else if (cam.model == RV_DIST_BROWN_CONRADY) {
+    const double xo = x, yo = y;
+    for (int it = 0; it < 10; ++it) {
+      const double r2 = x * x + y * y;
+      const double icdist = 1.0 / (1.0 + ((k3 * r2 + k2) * r2 + k1) * r2);
+      const double dx = 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x);
+      const double dy = 2.0 * p2 * x * y + p1 * (r2 + 2.0 * y * y);
+      x = (xo - dx) * icdist;
+      y = (yo - dy) * icdist;
+    }
+  }
+  table[i] = make_double2(x, y);
+}
+
+// ------------------------------------------------------------- cloud filter (a8/a9)
+struct FilterArgs {
+  const void *in;
+  void *out;
+  long long in_stride, out_stride, n;
+  unsigned long long *count;
+  unsigned long long *status;
+  unsigned int *ticket;
+  int total_tiles, has_color;
+  double z_min, z_max, r2_thresh, amin[3], amax[3];
+  int use_zclip, use_radius, use_aabb;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_filter_cloud(const FilterArgs a) {
+  __shared__ uint32_t s_warp_tot[kWarps];
+  __shared__ int s_tile;
+  __shared__ unsigned long long s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = rv_lanemask_lt();
+  const T *in = reinterpret_cast<const T *>(a.in);
+  T *out = reinterpret_cast<T *>(a.out);
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile >= a.total_tiles) break;
+    const long long i0 = (long long)tile * kTile + warp * (32 * kIters) + lane;
+    T x[kIters], y[kIters], z[kIters];
+    uint32_t ballots[kIters];
+    uint32_t warp_total = 0;
+#pragma unroll
+    for (int j = 0; j < kIters; ++j) {
+      const long long i = i0 + j * 32;
+      x[j] = y[j] = z[j] = (T)0;
+      if (i < a.n) {
+        x[j] = in[i];
+        y[j] = in[a.in_stride + i];
+        z[j] = in[2 * a.in_stride + i];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kIters; ++j) {
+      const long long i = i0 + j * 32;
+      const double X = (double)x[j], Y = (double)y[j], Z = (double)z[j];
+      bool ok = i < a.n;
+      if (a.use_zclip) ok = ok && (Z >= a.z_min) && (Z <= a.z_max);
+      if (a.use_radius) ok = ok && (((X * X + Y * Y) + Z * Z) < a.r2_thresh);
+      if (a.use_aabb)
+        ok = ok && (X >= a.amin[0]) && (X <= a.amax[0]) && (Y >= a.amin[1]) && (Y <= a.amax[1]) && (Z >= a.amin[2]) &&
+             (Z <= a.amax[2]);
+      ballots[j] = __ballot_sync(0xffffffffu, ok);
+      warp_total += __popc(ballots[j]);
+    }
+    if (lane == 0) s_warp_tot[warp] = warp_total;
+    __syncthreads();
+    uint32_t warp_excl = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const uint32_t c = s_warp_tot[w];
+      warp_excl += (w < warp) ? c : 0u;
+      tile_total += c;
+    }
+    if (warp == 0) {
+      const uint32_t excl = rv_lookback(a.status, tile, tile, tile_total);
+      if (lane == 0) {
+        s_base = excl;
+        if (tile == a.total_tiles - 1) *a.count = (unsigned long long)excl + tile_total;
+      }
+    }
+    __syncthreads();
+    unsigned long long run = s_base + warp_excl;
+#pragma unroll
+    for (int j = 0; j < kIters; ++j) {
+      const long long i = i0 + j * 32;
+      const bool ok = (ballots[j] >> lane) & 1u;
+      const unsigned long long pos = run + __popc(ballots[j] & lt);
+      run += __popc(ballots[j]);
+      if (ok) {
+        out[pos] = x[j];
+        out[a.out_stride + pos] = y[j];
+        out[2 * a.out_stride + pos] = z[j];
+        if (a.has_color) {
+          out[3 * a.out_stride + pos] = in[3 * a.in_stride + i];
+          out[4 * a.out_stride + pos] = in[4 * a.in_stride + i];
+          out[5 * a.out_stride + pos] = in[5 * a.in_stride + i];
+        }
+      }
+    }
+  }
+}
+
+// Largest double s with RN(sqrt(s)) < r  <=>  s < T: T is the smallest double whose
+// correctly rounded square root reaches r.  sqrt is monotone, so a short search around r*r finds it.
+double radius_threshold(double r) {
+  if (!(r > 0.0)) return 0.0;
+  double t = r * r;
+  while (sqrt(t) >= r) t = nextafter(t, 0.0);
+  while (sqrt(t) < r) t = nextafter(t, INFINITY);
+  return t;  // first value whose sqrt is >= r
+}
+
+template <typename OutT, int DK>
+void launch_mode(rv_ctx *ctx, const DeprojArgs &a, int mode, cudaStream_t st) {
+#define RV_GO(M)                                                                                   \
+  {                                                                                                \
+    auto k = k_deproject<OutT, DK, M>;                                                             \
+    const int grid = rv_persistent_grid(ctx, k, kThreads, 0, a.total_tiles);                       \
+    k<<<grid, kThreads, 0, st>>>(a);                                                               \
+  }
+  switch (mode) {
+    case RV_MODE_COMPACT_ORDERED: RV_GO(RV_MODE_COMPACT_ORDERED) break;
+    case RV_MODE_COMPACT_UNORDERED: RV_GO(RV_MODE_COMPACT_UNORDERED) break;
+    case RV_MODE_DENSE_ZERO: RV_GO(RV_MODE_DENSE_ZERO) break;
+    default: RV_GO(RV_MODE_DENSE_NAN) break;
+  }
+#undef RV_GO
+}
+
+}  // namespace
+
+extern "C" {
+
+int rv_depth_to_meters(rv_ctx *ctx, const uint16_t *d_depth, int64_t n, int unit_rule, double unit_scale, float *d_out,
+                       rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  if (n < 0 || (n > 0 && (!d_depth || !d_out))) RV_FAIL(ctx, RV_EINVAL, "rv_depth_to_meters: null pointer or n<0");
+  if (unit_rule < RV_UNIT_MUL_F32 || unit_rule > RV_UNIT_DIV_F64 || !(unit_scale > 0.0))
+    RV_FAIL(ctx, RV_EINVAL, "rv_depth_to_meters: bad unit rule / scale");
+  if (n == 0) return RV_OK;
+  const float sf = (float)unit_scale;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  k_depth_to_meters<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_depth, n, unit_rule, unit_scale, 1.0 / unit_scale, sf,
+                                                                  1.0f / sf, d_out);
+  RV_LAUNCHED(ctx);
+  return RV_OK;
+}
+
+int rv_build_ray_table(rv_ctx *ctx, const RvCam *cam, double *d_table, rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  if (!cam || !d_table || cam->width <= 0 || cam->height <= 0) RV_FAIL(ctx, RV_EINVAL, "rv_build_ray_table: bad camera");
+  if (!rv_aligned(d_table, 16)) RV_FAIL(ctx, RV_EALIGN, "rv_build_ray_table: table must be 16-byte aligned");
+  const int n = cam->width * cam->height;
+  k_ray_table<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*cam, reinterpret_cast<double2 *>(d_table));
+  RV_LAUNCHED(ctx);
+  return RV_OK;
+}
+
+size_t rv_deproject_workspace_bytes(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 128;
+  const long long P = (long long)H * W;
+  const long long tiles = (P + kTile - 1) / kTile * B;
+  return 128 + (size_t)tiles * 8;
+}
+
+int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, const uint8_t *d_mask,
+                      const double *d_ray_table, int B, int H, int W, const RvDeprojectParams *p, void *d_out,
+                      int64_t plane_stride, int64_t frame_stride, uint8_t *d_valid, int32_t *d_src_index,
+                      int64_t *d_counts, void *d_ws, size_t ws_bytes, rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  if (!p) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: params is null");
+  if (B < 0 || H <= 0 || W <= 0 || (long long)H * W > 0x7fffffffll)
+    RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad shape B=%d H=%d W=%d", B, H, W);
+  if (B == 0) return RV_OK;
+  if (!d_depth || !d_out || !d_counts) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: depth/out/counts must be non-null");
+  if (p->depth_kind != RV_DEPTH_U16 && p->depth_kind != RV_DEPTH_F32_METERS)
+    RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad depth_kind %d", p->depth_kind);
+  if (p->out_dtype != RV_F32 && p->out_dtype != RV_F64) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad out_dtype");
+  if (p->mode < RV_MODE_COMPACT_ORDERED || p->mode > RV_MODE_DENSE_NAN) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad mode");
+  if (p->depth_kind == RV_DEPTH_U16 &&
+      (p->unit_rule < RV_UNIT_MUL_F32 || p->unit_rule > RV_UNIT_DIV_F64 || !(p->unit_scale > 0.0)))
+    RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad unit rule / scale");
+  if (p->use_seg_mask && !d_mask) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: use_seg_mask set but mask is null");
+  if (p->cam.model != RV_DIST_NONE && p->cam.model != RV_DIST_MODIFIED_BROWN_CONRADY && !d_ray_table)
+    RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: distorted camera needs a ray table (rv_build_ray_table)");
+  if (!(p->cam.fx != 0.0) || !(p->cam.fy != 0.0)) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: fx/fy must be non-zero");
+  const long long P = (long long)H * W;
+  const bool dense = p->mode == RV_MODE_DENSE_ZERO || p->mode == RV_MODE_DENSE_NAN;
+  if (frame_stride <= 0 || plane_stride < (int64_t)B * frame_stride)
+    RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: plane_stride %lld < B*frame_stride", (long long)plane_stride);
+  if (dense && frame_stride < P) RV_FAIL(ctx, RV_ECAPACITY, "rv_deproject_mask: dense mode needs frame_stride >= H*W");
+  if (d_ray_table && !rv_aligned(d_ray_table, 16)) RV_FAIL(ctx, RV_EALIGN, "rv_deproject_mask: ray table alignment");
+  const size_t need = rv_deproject_workspace_bytes(B, H, W);
+  if (p->mode == RV_MODE_COMPACT_ORDERED) {
+    if (!d_ws || ws_bytes < need) RV_FAIL(ctx, RV_EWORKSPACE, "rv_deproject_mask: workspace %zu < %zu", ws_bytes, need);
+    if (!rv_aligned(d_ws, 8)) RV_FAIL(ctx, RV_EALIGN, "rv_deproject_mask: workspace alignment");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+
+  DeprojArgs a;
+  memset(&a, 0, sizeof(a));
+  a.depth = d_depth;
+  a.bgr = d_bgr;
+  a.mask = p->use_seg_mask ? d_mask : nullptr;
+  const bool use_rays = p->cam.model != RV_DIST_NONE && p->cam.model != RV_DIST_MODIFIED_BROWN_CONRADY;
+  a.rays = use_rays ? reinterpret_cast<const double2 *>(d_ray_table) : nullptr;
+  a.out = d_out;
+  a.valid = d_valid;
+  a.src_index = d_src_index;
+  a.counts = reinterpret_cast<unsigned long long *>(d_counts);
+  a.ticket = reinterpret_cast<unsigned int *>(d_ws);
+  a.status = d_ws ? reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(d_ws) + 128) : nullptr;
+  a.B = B;
+  a.H = H;
+  a.W = W;
+  a.P = (int)P;
+  a.tiles_per_frame = (int)((P + kTile - 1) / kTile);
+  const long long total = (long long)a.tiles_per_frame * B;
+  if (total > 0x7fffffffll) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: batch too large");
+  a.total_tiles = (int)total;
+  a.plane_stride = plane_stride;
+  a.frame_stride = frame_stride;
+  a.cx = p->cam.cx;
+  a.cy = p->cam.cy;
+  a.fx = p->cam.fx;
+  a.fy = p->cam.fy;
+  a.rfx = 1.0 / p->cam.fx;
+  a.rfy = 1.0 / p->cam.fy;
+  a.unit_rule = p->unit_rule;
+  a.unit_scale = p->unit_scale;
+  a.unit_rcp = 1.0 / p->unit_scale;
+  a.unit_scale_f = (float)p->unit_scale;
+  a.unit_rcp_f = 1.0f / a.unit_scale_f;
+  a.trunc_f = (float)p->depth_trunc;
+  a.z_min = p->z_min;
+  a.z_max = p->z_max;
+  a.r2_thresh = radius_threshold(p->r_max);
+  for (int i = 0; i < 3; ++i) {
+    a.amin[i] = p->aabb_min[i];
+    a.amax[i] = p->aabb_max[i];
+  }
+  a.use_mask = p->use_seg_mask ? 1 : 0;
+  a.invert_mask = p->invert_mask ? 1 : 0;
+  a.use_trunc = p->use_depth_trunc ? 1 : 0;
+  a.use_zclip = p->use_zclip ? 1 : 0;
+  a.use_radius = p->use_radius ? 1 : 0;
+  a.use_aabb = p->use_aabb ? 1 : 0;
+  a.color_255 = p->color_scale == RV_COLOR_255;
+
+  if (p->mode == RV_MODE_COMPACT_ORDERED) {
+    RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, need, st));
+  } else {
+    RV_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (size_t)B * sizeof(int64_t), st));
+  }
+  if (p->out_dtype == RV_F32) {
+    if (p->depth_kind == RV_DEPTH_U16)
+      launch_mode<float, RV_DEPTH_U16>(ctx, a, p->mode, st);
+    else
+      launch_mode<float, RV_DEPTH_F32_METERS>(ctx, a, p->mode, st);
+  } else {
+    if (p->depth_kind == RV_DEPTH_U16)
+      launch_mode<double, RV_DEPTH_U16>(ctx, a, p->mode, st);
+    else
+      launch_mode<double, RV_DEPTH_F32_METERS>(ctx, a, p->mode, st);
+  }
+  RV_LAUNCHED(ctx);
+  return RV_OK;
+}
+
+size_t rv_filter_workspace_bytes(int64_t n) {
+  if (n <= 0) return 128;
+  return 128 + (size_t)((n + kTile - 1) / kTile) * 8;
+}
+
+int rv_filter_cloud(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int dtype, int has_color,
+                    const RvDeprojectParams *p, void *d_out, int64_t out_plane_stride, int64_t *d_count, void *d_ws,
+                    size_t ws_bytes, rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  if (!p || !d_count) RV_FAIL(ctx, RV_EINVAL, "rv_filter_cloud: null params/count");
+  if (n < 0 || in_plane_stride < n) RV_FAIL(ctx, RV_EINVAL, "rv_filter_cloud: bad n / stride");
+  if (dtype != RV_F32 && dtype != RV_F64) RV_FAIL(ctx, RV_EINVAL, "rv_filter_cloud: bad dtype");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    RV_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+    return RV_OK;
+  }
+  if (!d_in || !d_out) RV_FAIL(ctx, RV_EINVAL, "rv_filter_cloud: null cloud pointer");
+  const size_t need = rv_filter_workspace_bytes(n);
+  if (!d_ws || ws_bytes < need) RV_FAIL(ctx, RV_EWORKSPACE, "rv_filter_cloud: workspace %zu < %zu", ws_bytes, need);
+  const long long tiles = (n + kTile - 1) / kTile;
+  if (tiles > 0x7fffffffll) RV_FAIL(ctx, RV_EINVAL, "rv_filter_cloud: cloud too large");
+  FilterArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = d_in;
+  a.out = d_out;
+  a.in_stride = in_plane_stride;
+  a.out_stride = out_plane_stride;
+  a.n = n;
+  a.count = reinterpret_cast<unsigned long long *>(d_count);
+  a.ticket = reinterpret_cast<unsigned int *>(d_ws);
+  a.status = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(d_ws) + 128);
+  a.total_tiles = (int)tiles;
+  a.has_color = has_color ? 1 : 0;
+  a.z_min = p->z_min;
+  a.z_max = p->z_max;
+  a.r2_thresh = radius_threshold(p->r_max);
+  for (int i = 0; i < 3; ++i) {
+    a.amin[i] = p->aabb_min[i];
+    a.amax[i] = p->aabb_max[i];
+  }
+  a.use_zclip = p->use_zclip ? 1 : 0;
+  a.use_radius = p->use_radius ? 1 : 0;
+  a.use_aabb = p->use_aabb ? 1 : 0;
+  RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, need, st));
+  if (dtype == RV_F32) {
+    auto k = k_filter_cloud<float>;
+    k<<<rv_persistent_grid(ctx, k, kThreads, 0, tiles), kThreads, 0, st>>>(a);
+  } else {
+    auto k = k_filter_cloud<double>;
+    k<<<rv_persistent_grid(ctx, k, kThreads, 0, tiles), kThreads, 0, st>>>(a);
+  }
+  RV_LAUNCHED(ctx);
+  return RV_OK;
+}
+
+}  // extern "C"

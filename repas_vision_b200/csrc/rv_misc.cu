@@ -1,0 +1,106 @@
+// rv_misc.cu -- the callers either side of the hot path: windowed median
+// depth look-ups and NV12 -> BGR colour decode.
+//
+//   get_depth_at_pixel   realsense_d415i/canopy_detection/canopy_return.py:279-317
+//   median_depth         femto_bolt_code/scripts/final_view.py:132-141
+//   frame_to_bgr_image   femto_bolt_code/scripts/better_three_capture.py:101-106
+//                        (cv2.cvtColor(nv12, cv2.COLOR_YUV2BGR_NV12): OpenCV's fixed-point
+//                        ITU-R BT.601 conversion, 20-bit coefficients)
+#include "rv_common.cuh"
+
+namespace {
+
+constexpr int kMaxHalf = 8;  // windows up to 17 x 17
+
+__global__ void __launch_bounds__(128) k_median_window(const uint16_t *__restrict__ depth, int H, int W,
+                                                       const int32_t *__restrict__ uv, long long n, int half,
+                                                       double *__restrict__ out) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  int x = uv[2 * q], y = uv[2 * q + 1];
+  x = min(max(x, 0), W - 1);  // the reference clamps the pixel into the image first
+  y = min(max(y, 0), H - 1);
+  const int y0 = max(0, y - half), y1 = min(H, y + half + 1);
+  const int x0 = max(0, x - half), x1 = min(W, x + half + 1);
+  uint16_t vals[(2 * kMaxHalf + 1) * (2 * kMaxHalf + 1)];
+  int k = 0;
+  for (int yy = y0; yy < y1; ++yy)
+    for (int xx = x0; xx < x1; ++xx) {
+      const uint16_t d = depth[(long long)yy * W + xx];
+      if (d) {  // insertion sort keeps vals ascending
+        int j = k++;
+        while (j > 0 && vals[j - 1] > d) {
+          vals[j] = vals[j - 1];
+          --j;
+        }
+        vals[j] = d;
+      }
+    }
+  double r = __longlong_as_double(0x7ff8000000000000ll);
+  if (k > 0) r = (k & 1) ? (double)vals[k >> 1] : ((double)vals[(k >> 1) - 1] + (double)vals[k >> 1]) / 2.0;
+  out[q] = r;
+}
+
+__device__ __forceinline__ uint32_t sat8(int v) { return (uint32_t)min(max(v, 0), 255); }
+
+// one thread = 2 x 2 luma block sharing one (U,V) pair
+__global__ void __launch_bounds__(256) k_nv12_to_bgr(const uint8_t *__restrict__ nv12, int B, int H, int W,
+                                                     uint8_t *__restrict__ bgr) {
+  const int hw = W >> 1, hh = H >> 1;
+  const long long total = (long long)B * hh * hw;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int f = (int)(i / ((long long)hh * hw));
+    const int r = (int)(i - (long long)f * hh * hw);
+    const int by = r / hw, bx = r - by * hw;
+    const uint8_t *src = nv12 + (long long)f * (H + hh) * W;
+    uint8_t *dst = bgr + (long long)f * H * W * 3;
+    const int u = (int)src[(long long)(H + by) * W + 2 * bx] - 128;
+    const int v = (int)src[(long long)(H + by) * W + 2 * bx + 1] - 128;
+    const int ruv = (1 << 19) + 1673527 * v;
+    const int guv = (1 << 19) - 852492 * v - 409993 * u;
+    const int buv = (1 << 19) + 2116026 * u;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int yy = 2 * by + dy, xx = 2 * bx + dx;
+        const int y = max(0, (int)src[(long long)yy * W + xx] - 16) * 1220542;
+        uint8_t *o = dst + ((long long)yy * W + xx) * 3;
+        o[0] = (uint8_t)sat8((y + buv) >> 20);
+        o[1] = (uint8_t)sat8((y + guv) >> 20);
+        o[2] = (uint8_t)sat8((y + ruv) >> 20);
+      }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int rv_median_depth_window(rv_ctx *ctx, const uint16_t *d_depth, int H, int W, const int32_t *d_uv, int64_t n,
+                           int window, double *d_out, rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  if (H <= 0 || W <= 0 || n < 0) RV_FAIL(ctx, RV_EINVAL, "rv_median_depth_window: bad shape");
+  if (window < 1 || window / 2 > kMaxHalf) RV_FAIL(ctx, RV_EINVAL, "rv_median_depth_window: window must be 1..%d", 2 * kMaxHalf + 1);
+  if (n == 0) return RV_OK;
+  if (!d_depth || !d_uv || !d_out) RV_FAIL(ctx, RV_EINVAL, "rv_median_depth_window: null pointer");
+  k_median_window<<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_depth, H, W, d_uv, n, window / 2, d_out);
+  RV_LAUNCHED(ctx);
+  return RV_OK;
+}
+
+int rv_nv12_to_bgr(rv_ctx *ctx, const uint8_t *d_nv12, int B, int H, int W, uint8_t *d_bgr, rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  if (B < 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) RV_FAIL(ctx, RV_EINVAL, "rv_nv12_to_bgr: H and W must be even and positive");
+  if (B == 0) return RV_OK;
+  if (!d_nv12 || !d_bgr) RV_FAIL(ctx, RV_EINVAL, "rv_nv12_to_bgr: null pointer");
+  long long blocks = ((long long)B * (H / 2) * (W / 2) + 255) / 256;
+  const long long cap = (long long)ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  k_nv12_to_bgr<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_nv12, B, H, W, d_bgr);
+  RV_LAUNCHED(ctx);
+  return RV_OK;
+}
+
+}  // extern "C"
