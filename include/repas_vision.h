@@ -84,7 +84,10 @@ enum RvDeprojectMode {
   RV_MODE_COMPACT_ORDERED = 0,   /* row-major order of valid pixels, == numpy `[valid]` (create_masked_ply.py:89-100) */
   RV_MODE_COMPACT_UNORDERED = 1, /* tiles land in arrival order; order inside a 2048-pixel tile is kept              */
   RV_MODE_DENSE_ZERO = 2,        /* one record per pixel, zeros where invalid (rs.pointcloud / Orbbec RGB_POINT)     */
-  RV_MODE_DENSE_NAN = 3          /* one record per pixel, NaN xyz where invalid (Open3D project_valid_depth_only=False) */
+  RV_MODE_DENSE_NAN = 3,         /* one record per pixel, NaN xyz where invalid (Open3D project_valid_depth_only=False) */
+  RV_MODE_COMPACT_PACKED = 4     /* COMPACT_ORDERED with the frames of the batch back to back: frame b occupies
+                                    [offsets[b], offsets[b+1]) of every plane; d_counts receives the B+1 offsets and
+                                    frame_stride is ignored (one contiguous device->host copy per plane)            */
 };
 
 enum RvColorScale {
@@ -176,7 +179,7 @@ int rv_build_ray_table(rv_ctx *ctx, const RvCam *cam, double *d_table, rv_stream
  *            plane, dense modes H*W.  frame_stride is the per-frame capacity.
  *  d_valid   [B,H,W] uint8 (1 = kept) or NULL
  *  d_src_index  same addressing as one plane, int32 source pixel index of each output point, or NULL
- *  d_counts  [B] int64 kept points per frame (written in every mode)
+ *  d_counts  [B] int64 kept points per frame (written in every mode); [B+1] exclusive offsets in COMPACT_PACKED
  *  d_ws      rv_deproject_workspace_bytes(B,H,W) bytes
  * Points beyond frame_stride are not written; counts[b] still reports the true
  * number so the caller can detect RV_ECAPACITY after synchronising. */

@@ -18,7 +18,7 @@ RV_F32, RV_F64 = 0, 1
 DIST_MODELS = {"none": 0, "brown_conrady": 1, "inverse_brown_conrady": 2, "modified_brown_conrady": 3}
 UNIT_RULES = {"mul_f32": 0, "div_f32": 1, "div_f64": 2}
 DEPTH_KINDS = {"u16": 0, "f32": 1}
-MODES = {"compact_ordered": 0, "compact_unordered": 1, "dense_zero": 2, "dense_nan": 3}
+MODES = {"compact_ordered": 0, "compact_unordered": 1, "dense_zero": 2, "dense_nan": 3, "compact_packed": 4}
 COLOR_SCALES = {"unit": 0, "255": 1}
 
 c_i32, c_i64, c_f64, c_vp = C.c_int32, C.c_int64, C.c_double, C.c_void_p

@@ -1,0 +1,275 @@
+"""Torch-tensor front of the C ABI: pointer extraction, workspace allocation, stream hand-off.
+
+PyTorch is plumbing here (device memory from its caching allocator, the current stream);
+every computation is a kernel of librepasvision.so reached through include/repas_vision.h.
+There is no fallback: without the library or an sm_100 device these raise RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .calibration import Camera
+
+_TORCH_DT = {"f32": torch.float32, "f64": torch.float64}
+_RV_DT = {torch.float32: _lib.RV_F32, torch.float64: _lib.RV_F64}
+
+
+def require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("repas_vision_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"repas_vision_b200 computes on CUDA devices only, got {dev}")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def ctx_for(t_or_dev) -> _lib.Context:
+    dev = t_or_dev.device if isinstance(t_or_dev, torch.Tensor) else t_or_dev
+    return _lib.context(dev.index)
+
+
+def stream_ptr(dev: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def ptr(t) -> C.c_void_p:
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+def workspace(nbytes: int, dev: torch.device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+
+
+def cam_struct(cam: Camera, width=None, height=None) -> _lib.RvCam:
+    return _lib.make_cam(cam.fx, cam.fy, cam.cx, cam.cy, cam.width if width is None else width,
+                         cam.height if height is None else height, cam.dist, cam.model)
+
+
+def to_device(a, dev: torch.device, dtype=None) -> torch.Tensor:
+    """numpy / torch (any device) -> contiguous tensor on dev.  No copy for a conforming CUDA tensor."""
+    if isinstance(a, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    elif isinstance(a, torch.Tensor):
+        t = a
+    else:
+        t = torch.as_tensor(np.asarray(a))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if t.device != dev:
+        t = t.to(dev, non_blocking=True)
+    return t.contiguous()
+
+
+# ---------------------------------------------------------------------------- K1
+def deproject(depth, bgr, mask, cam: Camera, *, depth_kind, unit_rule="mul_f32", unit_scale=None, invert_mask=False,
+              depth_trunc=None, z_clip=None, r_max=None, aabb=None, mode="compact_ordered", out_dtype="f32",
+              color_scale="unit", want_valid=False, want_src_index=False, frame_capacity=None, out=None,
+              rays=None):
+    """depth [B,H,W] (uint16 or float32), bgr [B,H,W,3] uint8 or None, mask [B,H,W] uint8 or None, all on one
+    CUDA device.  Returns dict(data [6 or 3, B*cap], counts [B] int64, cap, valid, src_index)."""
+    dev = depth.device
+    ctx = ctx_for(dev)
+    B, H, W = depth.shape
+    P = H * W
+    p = _lib.RvDeprojectParams()
+    p.cam = cam_struct(cam, W, H)
+    p.depth_kind = _lib.DEPTH_KINDS[depth_kind]
+    p.unit_rule = _lib.UNIT_RULES[unit_rule]
+    p.unit_scale = float(unit_scale) if unit_scale is not None else (0.001 if unit_rule == "mul_f32" else 1000.0)
+    p.use_seg_mask = int(mask is not None)
+    p.invert_mask = int(bool(invert_mask))
+    p.use_depth_trunc = int(depth_trunc is not None)
+    p.depth_trunc = float(depth_trunc or 0.0)
+    p.use_zclip = int(z_clip is not None)
+    if z_clip is not None:
+        p.z_min = -np.inf if z_clip[0] is None else float(z_clip[0])
+        p.z_max = np.inf if z_clip[1] is None else float(z_clip[1])
+    p.use_radius = int(r_max is not None)
+    p.r_max = float(r_max or 0.0)
+    p.use_aabb = int(aabb is not None)
+    if aabb is not None:
+        for i in range(3):
+            p.aabb_min[i] = float(aabb[0][i])
+            p.aabb_max[i] = float(aabb[1][i])
+    p.mode = _lib.MODES[mode]
+    p.out_dtype = _lib.RV_F32 if out_dtype == "f32" else _lib.RV_F64
+    p.color_scale = _lib.COLOR_SCALES[color_scale]
+    cap = int(frame_capacity) if frame_capacity is not None else P
+    planes = 6 if bgr is not None else 3
+    packed = mode == "compact_packed"
+    plane_stride = B * cap
+    if out is None:
+        out = torch.empty((planes, plane_stride), dtype=_TORCH_DT[out_dtype], device=dev)
+    else:
+        if out.dtype != _TORCH_DT[out_dtype] or out.device != dev or out.dim() != 2 or out.shape[0] < planes \
+                or out.shape[1] < plane_stride or not out.is_contiguous():
+            raise ValueError("out must be a contiguous [planes, >= B*capacity] tensor of the output dtype on the input device")
+        plane_stride = out.shape[1]
+    counts = torch.empty(B + 1 if packed else B, dtype=torch.int64, device=dev)
+    valid = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if want_valid else None
+    src = torch.empty(plane_stride, dtype=torch.int32, device=dev) if want_src_index else None
+    if cam.distorted and cam.model != "modified_brown_conrady" and rays is None:
+        rays = ray_table(cam, H, W, dev)
+    ws_bytes = ctx.lib.rv_deproject_workspace_bytes(B, H, W)
+    ws = workspace(ws_bytes, dev)
+    ctx.check(ctx.lib.rv_deproject_mask(ctx.handle, ptr(depth), ptr(bgr), ptr(mask), ptr(rays), B, H, W, C.byref(p),
+                                        ptr(out), plane_stride, cap, ptr(valid), ptr(src), ptr(counts), ptr(ws),
+                                        ws.numel(), stream_ptr(dev)))
+    return dict(data=out, counts=counts, cap=cap, valid=valid, src_index=src, planes=planes, plane_stride=plane_stride)
+
+
+_ray_cache: dict = {}
+
+
+def ray_table(cam: Camera, H: int, W: int, dev: torch.device) -> torch.Tensor:
+    key = (cam.fx, cam.fy, cam.cx, cam.cy, tuple(cam.dist), cam.model, H, W, dev.index)
+    t = _ray_cache.get(key)
+    if t is None:
+        ctx = ctx_for(dev)
+        t = torch.empty((H, W, 2), dtype=torch.float64, device=dev)
+        cs = cam_struct(cam, W, H)
+        ctx.check(ctx.lib.rv_build_ray_table(ctx.handle, C.byref(cs), ptr(t), stream_ptr(dev)))
+        if len(_ray_cache) > 16:
+            _ray_cache.clear()
+        _ray_cache[key] = t
+    return t
+
+
+def depth_to_meters(depth_u16: torch.Tensor, rule="mul_f32", scale=None) -> torch.Tensor:
+    dev = depth_u16.device
+    ctx = ctx_for(dev)
+    out = torch.empty(depth_u16.shape, dtype=torch.float32, device=dev)
+    s = float(scale) if scale is not None else (0.001 if rule == "mul_f32" else 1000.0)
+    ctx.check(ctx.lib.rv_depth_to_meters(ctx.handle, ptr(depth_u16), depth_u16.numel(), _lib.UNIT_RULES[rule], s, ptr(out),
+                                         stream_ptr(dev)))
+    return out
+
+
+# ---------------------------------------------------------------------------- K2
+def register(depth: torch.Tensor, dcam: Camera, ccam: Camera, R_colmajor, t, depth_units=0.001, want_winner=False,
+             chunk_frames=None):
+    """depth [B,Hd,Wd] uint16 -> (aligned [B,Hc,Wc] uint16, winner [B,Hc,Wc] int32 or None)."""
+    dev = depth.device
+    ctx = ctx_for(dev)
+    B, Hd, Wd = depth.shape
+    Hc, Wc = ccam.height, ccam.width
+    out = torch.empty((B, Hc, Wc), dtype=torch.uint16, device=dev)
+    win = torch.empty((B, Hc, Wc), dtype=torch.int32, device=dev) if want_winner else None
+    nb = ctx.lib.rv_register_workspace_bytes(B if chunk_frames is None else min(B, chunk_frames), Hc, Wc)
+    ws = workspace(nb, dev)
+    R = (C.c_float * 9)(*[float(v) for v in np.asarray(R_colmajor, dtype=np.float32).reshape(9)])
+    tt = (C.c_float * 3)(*[float(v) for v in np.asarray(t, dtype=np.float32).reshape(3)])
+    dc, cc = cam_struct(dcam, Wd, Hd), cam_struct(ccam)
+    ctx.check(ctx.lib.rv_register_depth_to_color(ctx.handle, ptr(depth), B, C.byref(dc), C.byref(cc), R, tt,
+                                                 C.c_float(depth_units), ptr(out), ptr(win), ptr(ws), ws.numel(),
+                                                 stream_ptr(dev)))
+    return out, win
+
+
+# --------------------------------------------------------------------- cloud ops
+def filter_cloud(data: torch.Tensor, n: int, has_color: bool, *, z_clip=None, r_max=None, aabb=None):
+    dev = data.device
+    ctx = ctx_for(dev)
+    p = _lib.RvDeprojectParams()
+    p.use_zclip = int(z_clip is not None)
+    if z_clip is not None:
+        p.z_min = -np.inf if z_clip[0] is None else float(z_clip[0])
+        p.z_max = np.inf if z_clip[1] is None else float(z_clip[1])
+    p.use_radius = int(r_max is not None)
+    p.r_max = float(r_max or 0.0)
+    p.use_aabb = int(aabb is not None)
+    if aabb is not None:
+        for i in range(3):
+            p.aabb_min[i] = float(aabb[0][i])
+            p.aabb_max[i] = float(aabb[1][i])
+    out = torch.empty((data.shape[0], max(n, 1)), dtype=data.dtype, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = workspace(ctx.lib.rv_filter_workspace_bytes(n), dev)
+    ctx.check(ctx.lib.rv_filter_cloud(ctx.handle, ptr(data), data.shape[1], n, _RV_DT[data.dtype], int(has_color), C.byref(p),
+                                      ptr(out), out.shape[1], ptr(count), ptr(ws), ws.numel(), stream_ptr(dev)))
+    return out, count
+
+
+def transform_merge(views, Ts, has_color: bool, out_dtype=None, want_bounds=False):
+    """views: list of (data [planes, stride], n).  Ts: list of 4x4.  Returns (merged [planes, total], total, bounds)."""
+    dev = views[0][0].device
+    ctx = ctx_for(dev)
+    in_dt = views[0][0].dtype
+    if any(v[0].dtype != in_dt for v in views):
+        raise ValueError("all views must share one dtype")
+    out_dt = in_dt if out_dtype is None else _TORCH_DT[out_dtype]
+    nv = len(views)
+    total = int(sum(v[1] for v in views))
+    planes = 6 if has_color else 3
+    out = torch.empty((planes, max(total, 1)), dtype=out_dt, device=dev)
+    ptrs = (C.c_void_p * nv)(*[v[0].data_ptr() for v in views])
+    strides = (C.c_int64 * nv)(*[v[0].shape[1] for v in views])
+    ns = (C.c_int64 * nv)(*[int(v[1]) for v in views])
+    Tflat = np.ascontiguousarray(np.stack([np.asarray(T, dtype=np.float64).reshape(4, 4) for T in Ts])).reshape(-1)
+    Tc = (C.c_double * (16 * nv))(*Tflat.tolist())
+    bounds = None
+    if want_bounds:
+        bounds = torch.empty(6, dtype=torch.float64, device=dev)
+        ctx.check(ctx.lib.rv_bounds_init(ctx.handle, ptr(bounds), stream_ptr(dev)))
+    ctx.check(ctx.lib.rv_transform_merge(ctx.handle, nv, ptrs, strides, ns, Tc, _RV_DT[in_dt], int(has_color), ptr(out),
+                                         out.shape[1], _RV_DT[out_dt], ptr(bounds), stream_ptr(dev)))
+    return out, total, bounds
+
+
+def voxel_downsample(data: torch.Tensor, n: int, has_color: bool, voxel_size: float, *, bounds=None, out_dtype=None,
+                     want_keys=False, want_counts=False, out_capacity=None):
+    """Returns dict(data [planes, cap], m (int64 tensor[1]), keys [3,cap] int32 | None, counts [cap] | None)."""
+    dev = data.device
+    ctx = ctx_for(dev)
+    out_dt = data.dtype if out_dtype is None else _TORCH_DT[out_dtype]
+    cap = int(n if out_capacity is None else out_capacity)
+    planes = 6 if has_color else 3
+    out = torch.empty((planes, max(cap, 1)), dtype=out_dt, device=dev)
+    keys = torch.empty((3, max(cap, 1)), dtype=torch.int32, device=dev) if want_keys else None
+    cnts = torch.empty(max(cap, 1), dtype=torch.int32, device=dev) if want_counts else None
+    m = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = workspace(ctx.lib.rv_voxel_workspace_bytes(n), dev)
+    if not (float(voxel_size) > 0.0):
+        raise ValueError("voxel_size <= 0")
+    ctx.check(ctx.lib.rv_voxel_downsample(ctx.handle, ptr(data), data.shape[1], n, _RV_DT[data.dtype], int(has_color),
+                                          float(voxel_size), ptr(bounds), ptr(out), out.shape[1], _RV_DT[out_dt],
+                                          min(cap, out.shape[1]) if cap > 0 else 0, ptr(keys), ptr(cnts), ptr(m), ptr(ws),
+                                          ws.numel(), stream_ptr(dev)))
+    return dict(data=out, m=m, keys=keys, counts=cnts, cap=out.shape[1])
+
+
+def pack_ply_records(data: torch.Tensor, n: int, has_color: bool, color_scale="unit", coord_dtype="f32") -> torch.Tensor:
+    dev = data.device
+    ctx = ctx_for(dev)
+    rec = 3 * (4 if coord_dtype == "f32" else 8) + 3
+    out = torch.empty(max(n, 1) * rec, dtype=torch.uint8, device=dev)
+    ctx.check(ctx.lib.rv_pack_ply_records(ctx.handle, ptr(data), data.shape[1], n, _RV_DT[data.dtype], int(has_color),
+                                          _lib.COLOR_SCALES[color_scale], _lib.RV_F32 if coord_dtype == "f32" else _lib.RV_F64,
+                                          ptr(out), stream_ptr(dev)))
+    return out[:n * rec]
+
+
+def median_depth_window(depth_u16: torch.Tensor, uv: torch.Tensor, window: int) -> torch.Tensor:
+    dev = depth_u16.device
+    ctx = ctx_for(dev)
+    H, W = depth_u16.shape
+    n = uv.shape[0]
+    out = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+    ctx.check(ctx.lib.rv_median_depth_window(ctx.handle, ptr(depth_u16), H, W, ptr(uv), n, int(window), ptr(out),
+                                             stream_ptr(dev)))
+    return out[:n]
+
+
+def nv12_to_bgr(nv12: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    dev = nv12.device
+    ctx = ctx_for(dev)
+    B = nv12.shape[0]
+    out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
+    ctx.check(ctx.lib.rv_nv12_to_bgr(ctx.handle, ptr(nv12), B, H, W, ptr(out), stream_ptr(dev)))
+    return out

@@ -1,0 +1,436 @@
+"""User-facing RGB-D -> point-cloud functions with the reference scripts' call shapes.
+
+numpy in -> numpy-backed results, torch CUDA in -> results stay on that device (zero copy).
+All arithmetic runs in the sm_100a kernels of librepasvision.so; this module only validates
+shapes, moves buffers and mirrors the reference's argument meaning and error behaviour:
+
+* depth_to_meters ............. femto_bolt_code/scripts/better_three_capture.py:118-125
+* create_masked_pointcloud .... femto_bolt_code/scripts/create_masked_ply.py:56-107
+* create_from_rgbd_image ...... Open3D 0.19 RGBDImage + PointCloud.create_from_rgbd_image
+* PointCloud.transform / + / voxel_down_sample / select_by_index ... Open3D legacy PointCloud (Appendix B.1), call sites
+  final_view_with_cad.py:333, mpa_icp_export.py:174, view_point_cloud.py:116-120
+* PointCloud.select_within_distance ... realsense_d415i/capture_scripts/distance_masking_on_ply.py:9-23
+* PointCloud.clip_z ........... femto_bolt_code/scripts/view_point_cloud.py:109-116
+* PointCloud.crop_aabb ........ femto_bolt_code/scripts/april_tag_bg_removal_pl.py:450-468
+* register_depth_to_color ..... AlignFilter / rs.align call sites (better_three_capture.py:169,188;
+  capture_aligned_all.py:75,197), semantics SURVEY Appendix B.3
+* get_depth_at_pixel / median_depth ... canopy_return.py:279-317, final_view.py:132-141
+* fuse_views .................. SURVEY Appendix D.4 (four_pose_captures composition)
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _ops
+from .calibration import Camera
+
+_NP_DT = {"f32": np.float32, "f64": np.float64}
+
+
+def _as_camera(cam=None, fx=None, fy=None, cx=None, cy=None, width=0, height=0) -> Camera:
+    if isinstance(cam, Camera):
+        return cam
+    if isinstance(cam, dict):
+        return Camera(cam["fx"], cam["fy"], cam["cx"], cam["cy"], cam.get("width", 0), cam.get("height", 0),
+                      tuple(cam.get("dist", (0, 0, 0, 0, 0))), cam.get("model", "none"))
+    return Camera(float(fx), float(fy), float(cx), float(cy), int(width), int(height))
+
+
+def _is_torch_cuda(a) -> bool:
+    return isinstance(a, torch.Tensor) and a.is_cuda
+
+
+class PointCloud:
+    """Coloured cloud held on the GPU as structure-of-arrays planes x,y,z[,r,g,b].
+
+    Mirrors the slice of Open3D's legacy PointCloud the reference uses: `.points` / `.colors`
+    ((N,3) float64 numpy, like np.asarray(pcd.points)), `transform`, `+`, `voxel_down_sample`,
+    `select_by_index`, `is_empty`, `has_colors`.  `.xyz` / `.rgb` expose the device planes ([3,N] torch views).
+    """
+
+    def __init__(self, data: torch.Tensor | None = None, n: int = 0, has_color: bool = True, device=None):
+        if data is None:
+            dev = _ops.require_cuda(device)
+            data = torch.empty((6 if has_color else 3, 1), dtype=torch.float64, device=dev)
+            n = 0
+        self._data = data
+        self._n = int(n)
+        self._has_color = bool(has_color) and data.shape[0] >= 6
+
+    # ---- construction
+    @classmethod
+    def from_arrays(cls, points, colors=None, device=None, dtype="f64") -> "PointCloud":
+        dev = points.device if _is_torch_cuda(points) else _ops.require_cuda(device)
+        tdt = torch.float64 if dtype == "f64" else torch.float32
+        p = _ops.to_device(points, dev, tdt)
+        if p.dim() != 2 or p.shape[1] != 3:
+            raise ValueError("points must have shape (N, 3)")
+        n = p.shape[0]
+        planes = 6 if colors is not None else 3
+        data = torch.empty((planes, max(n, 1)), dtype=tdt, device=dev)
+        data[:3, :n] = p.t()
+        if colors is not None:
+            c = _ops.to_device(colors, dev, tdt)
+            if c.shape != p.shape:
+                raise ValueError("colors must match points in shape")
+            data[3:6, :n] = c.t()
+        return cls(data, n, colors is not None)
+
+    # ---- views
+    def __len__(self):
+        return self._n
+
+    @property
+    def device(self):
+        return self._data.device
+
+    @property
+    def dtype(self):
+        return self._data.dtype
+
+    @property
+    def xyz(self) -> torch.Tensor:
+        return self._data[:3, :self._n]
+
+    @property
+    def rgb(self):
+        return self._data[3:6, :self._n] if self._has_color else None
+
+    @property
+    def points(self) -> np.ndarray:
+        return self.xyz.t().to(torch.float64).cpu().numpy()
+
+    @property
+    def colors(self) -> np.ndarray:
+        if not self._has_color:
+            return np.zeros((0, 3))
+        return self.rgb.t().to(torch.float64).cpu().numpy()
+
+    def has_colors(self) -> bool:
+        return self._has_color and self._n > 0
+
+    def has_points(self) -> bool:
+        return self._n > 0
+
+    def is_empty(self) -> bool:
+        return self._n == 0
+
+    def get_min_bound(self) -> np.ndarray:
+        return self.xyz.to(torch.float64).min(dim=1).values.cpu().numpy() if self._n else np.zeros(3)
+
+    def get_max_bound(self) -> np.ndarray:
+        return self.xyz.to(torch.float64).max(dim=1).values.cpu().numpy() if self._n else np.zeros(3)
+
+    def __repr__(self):
+        return f"PointCloud with {self._n} points."
+
+    # ---- Open3D-shaped operations
+    def transform(self, T) -> "PointCloud":
+        """In place, returns self (Open3D semantics): p' = (T [p,1])[:3] / (T [p,1])[3] in float64."""
+        T = np.asarray(T, dtype=np.float64)
+        if T.shape != (4, 4):
+            raise ValueError(f"Expected 4x4 matrix, got shape {T.shape}")
+        if self._n:
+            out, total, _ = _ops.transform_merge([(self._data, self._n)], [T], self._has_color)
+            self._data = out
+        return self
+
+    def transformed(self, T) -> "PointCloud":
+        return PointCloud(self._data, self._n, self._has_color).transform(T) if self._n else self
+
+    def __add__(self, other: "PointCloud") -> "PointCloud":
+        return merge([self, other])
+
+    def voxel_down_sample(self, voxel_size: float, return_keys: bool = False):
+        """Open3D PointCloud.voxel_down_sample: mean position / colour per occupied voxel of the grid anchored
+        at min_bound - voxel_size/2.  Output order is unspecified (as in Open3D).  RuntimeError for
+        voxel_size <= 0 or a grid whose index would overflow, as Open3D raises."""
+        if not (float(voxel_size) > 0.0):
+            raise RuntimeError("[Open3D-compatible] voxel_size <= 0.")
+        if self._n == 0:
+            return (self, np.zeros((0, 3), np.int32), np.zeros(0, np.int32)) if return_keys else self
+        r = _ops.voxel_downsample(self._data, self._n, self._has_color, float(voxel_size), want_keys=return_keys,
+                                  want_counts=return_keys)
+        m = int(r["m"].item())
+        if m < 0:
+            raise RuntimeError("[Open3D-compatible] voxel_size is too small.")
+        pc = PointCloud(r["data"], m, self._has_color)
+        if return_keys:
+            return pc, r["keys"][:, :m].t().cpu().numpy(), r["counts"][:m].cpu().numpy()
+        return pc
+
+    def select_by_index(self, indices, invert: bool = False) -> "PointCloud":
+        idx = torch.as_tensor(np.asarray(indices), dtype=torch.int64, device=self.device)
+        if invert:
+            keep = torch.ones(self._n, dtype=torch.bool, device=self.device)
+            keep[idx] = False
+            idx = torch.nonzero(keep).reshape(-1)
+        return PointCloud(self._data[:, :self._n].index_select(1, idx).contiguous(), idx.numel(), self._has_color)
+
+    # ---- the reference's cloud predicates, fused into one ordered compaction kernel
+    def _filtered(self, **kw) -> "PointCloud":
+        if self._n == 0:
+            return self
+        out, count = _ops.filter_cloud(self._data, self._n, self._has_color, **kw)
+        return PointCloud(out, int(count.item()), self._has_color)
+
+    def select_within_distance(self, max_distance: float = 1.0) -> "PointCloud":
+        """keep ||p||_2 < max_distance (strict), float64 on the stored coordinates."""
+        return self._filtered(r_max=float(max_distance))
+
+    def clip_z(self, z_min=None, z_max=None) -> "PointCloud":
+        """keep z_min <= Z <= z_max, inclusive; either bound may be None."""
+        if z_min is None and z_max is None:
+            return self
+        return self._filtered(z_clip=(z_min, z_max))
+
+    def crop_aabb(self, min_bound, max_bound) -> "PointCloud":
+        """keep min_bound <= p <= max_bound per axis, inclusive."""
+        return self._filtered(aabb=(np.asarray(min_bound, dtype=np.float64), np.asarray(max_bound, dtype=np.float64)))
+
+
+def merge(clouds) -> PointCloud:
+    """Concatenation in list order (Open3D `+`)."""
+    clouds = [c for c in clouds]
+    if not clouds:
+        raise ValueError("merge needs at least one cloud")
+    has_color = all(c._has_color for c in clouds)
+    eye = np.eye(4)
+    views = [(c._data, c._n) for c in clouds]
+    out, total, _ = _ops.transform_merge(views, [eye] * len(views), has_color)
+    return PointCloud(out, total, has_color)
+
+
+# --------------------------------------------------------------------------- a1/a2
+def depth_to_meters(depth_raw, rule: str = "mul_f32", scale=None):
+    """(raw, depth_m, scale): uint16 depth -> float32 metres, `raw.astype(float32) * 0.001` by default.
+
+    The reference takes an SDK frame and views its buffer as uint16[H,W]; here the array is passed directly."""
+    s = float(scale) if scale is not None else (0.001 if rule == "mul_f32" else 1000.0)
+    if _is_torch_cuda(depth_raw):
+        if depth_raw.dtype != torch.uint16:
+            raise RuntimeError(f"depth must be uint16, got {depth_raw.dtype}")
+        return depth_raw, _ops.depth_to_meters(depth_raw.contiguous(), rule, s), s
+    raw = np.asarray(depth_raw)
+    if raw.dtype != np.uint16:
+        raise RuntimeError(f"depth must be uint16, got {raw.dtype}")
+    dev = _ops.require_cuda()
+    out = _ops.depth_to_meters(_ops.to_device(raw, dev), rule, s)
+    return raw, out.cpu().numpy(), s
+
+
+# --------------------------------------------------------------------------- a3
+def _prep_frame_inputs(rgb, depth, mask, dev):
+    """Validate one frame's arrays the way create_masked_ply.py:134-139 does and upload them as [1,...] tensors."""
+    d = depth if isinstance(depth, torch.Tensor) else np.asarray(depth)
+    if d.ndim != 2:
+        raise RuntimeError(f"depth must be HxW, got shape {tuple(d.shape)}")
+    H, W = d.shape
+    if rgb is not None:
+        c = rgb if isinstance(rgb, torch.Tensor) else np.asarray(rgb)
+        if tuple(c.shape) != (H, W, 3):
+            raise RuntimeError(f"Color/depth size mismatch: color {tuple(c.shape[:2])}, depth {(H, W)}")
+    if mask is not None:
+        m = mask if isinstance(mask, torch.Tensor) else np.asarray(mask)
+        if tuple(m.shape) != (H, W):
+            raise RuntimeError(f"Mask/depth size mismatch: mask {tuple(m.shape)}, depth {(H, W)}")
+    if isinstance(d, torch.Tensor):
+        kind = "u16" if d.dtype == torch.uint16 else "f32"
+        dt = _ops.to_device(d, dev, None if kind == "u16" else torch.float32)
+    else:
+        kind = "u16" if d.dtype == np.uint16 else "f32"
+        dt = _ops.to_device(d if kind == "u16" else d.astype(np.float32, copy=False), dev)
+    ct = None if rgb is None else _ops.to_device(rgb, dev, torch.uint8)
+    mt = None if mask is None else _ops.to_device(mask, dev, torch.uint8)
+    return (dt[None], None if ct is None else ct[None], None if mt is None else mt[None], kind, H, W)
+
+
+def create_masked_pointcloud(rgb, depth_m, mask, fx, fy, cx, cy, invert_mask: bool = False, *, dtype: str = "f64",
+                             unit_rule: str = "mul_f32", depth_scale=None, max_distance=None, z_clip=None, aabb=None,
+                             camera: Camera | None = None) -> PointCloud:
+    """Coloured cloud of the masked pixels with finite positive depth, in row-major pixel order.
+
+    rgb: HxWx3 uint8 BGR; depth_m: HxW float metres aligned to colour (a uint16 raw-depth image is also
+    accepted and converted with `unit_rule` / `depth_scale`); mask: HxW uint8 (>0 = object, or ==0 when
+    invert_mask).  x=(u-cx)*z/fx, y=(v-cy)*z/fy in float64; colours RGB/255.  dtype="f64" reproduces the
+    reference's float64 arrays bit for bit; "f32" stores float32 planes (within 1 ulp of the float64 values).
+    The keyword-only predicates fuse the reference's later filters into the same kernel."""
+    dev = depth_m.device if _is_torch_cuda(depth_m) else _ops.require_cuda()
+    d, c, m, kind, H, W = _prep_frame_inputs(rgb, depth_m, mask, dev)
+    cam = camera if camera is not None else Camera(float(fx), float(fy), float(cx), float(cy), W, H)
+    r = _ops.deproject(d, c, m, cam, depth_kind=kind, unit_rule=unit_rule, unit_scale=depth_scale,
+                       invert_mask=invert_mask, r_max=max_distance, z_clip=z_clip, aabb=aabb, mode="compact_ordered",
+                       out_dtype=dtype)
+    return PointCloud(r["data"], int(r["counts"][0].item()), c is not None)
+
+
+def create_from_rgbd_image(color, depth, intrinsic, extrinsic=None, *, depth_scale: float = 1000.0,
+                           depth_trunc: float = 3.0, project_valid_depth_only: bool = True, dtype: str = "f64"):
+    """Open3D-shaped: RGBDImage.create_from_color_and_depth(depth_scale, depth_trunc, convert_rgb_to_intensity=False)
+    followed by PointCloud.create_from_rgbd_image(intrinsic, extrinsic).  color is BGR uint8 (cv2 order).
+    With project_valid_depth_only=False the cloud is dense (H*W points, NaN where invalid)."""
+    cam = _as_camera(intrinsic)
+    dev = depth.device if _is_torch_cuda(depth) else _ops.require_cuda()
+    d, c, _, kind, H, W = _prep_frame_inputs(color, depth, None, dev)
+    if kind != "u16":
+        raise RuntimeError("create_from_rgbd_image expects a uint16 depth image")
+    mode = "compact_ordered" if project_valid_depth_only else "dense_nan"
+    r = _ops.deproject(d, c, None, cam, depth_kind="u16", unit_rule="div_f32", unit_scale=float(depth_scale),
+                       depth_trunc=float(depth_trunc), mode=mode, out_dtype=dtype)
+    n = int(r["counts"][0].item()) if project_valid_depth_only else H * W
+    pc = PointCloud(r["data"], n, c is not None)
+    if extrinsic is not None:
+        pc.transform(np.linalg.inv(np.asarray(extrinsic, dtype=np.float64)))
+    return pc
+
+
+class CloudBatch:
+    """Result of a batched deprojection: planes [6 or 3, B*cap] with frame b at columns [b*cap, b*cap+counts[b])."""
+
+    def __init__(self, r: dict, B: int, H: int, W: int, has_color: bool, dense: bool):
+        self.data, self.counts, self.cap = r["data"], r["counts"], r["cap"]
+        self.valid, self.src_index = r["valid"], r["src_index"]
+        self.B, self.H, self.W, self.has_color, self.dense = B, H, W, has_color, dense
+        self._counts_host = None
+
+    def counts_host(self) -> np.ndarray:
+        if self._counts_host is None:
+            self._counts_host = self.counts.cpu().numpy()
+        return self._counts_host
+
+    def frame(self, b: int) -> PointCloud:
+        n = self.H * self.W if self.dense else int(self.counts_host()[b])
+        n = min(n, self.cap)
+        return PointCloud(self.data[:, b * self.cap:b * self.cap + max(n, 1)], n, self.has_color)
+
+    def __len__(self):
+        return self.B
+
+
+def deproject_batch(depth, bgr, camera, mask=None, *, unit_rule: str = "mul_f32", depth_scale=None, invert_mask=False,
+                    depth_trunc=None, max_distance=None, z_clip=None, aabb=None, mode: str = "compact_ordered",
+                    dtype: str = "f32", color_scale: str = "unit", want_valid=False, want_src_index=False,
+                    frame_capacity=None, out=None) -> CloudBatch:
+    """Batched form of create_masked_pointcloud: depth [B,H,W] (uint16 raw or float32 metres), bgr [B,H,W,3] uint8,
+    mask [B,H,W] uint8 or None.  One kernel launch for the whole batch."""
+    cam = _as_camera(camera)
+    dev = depth.device if _is_torch_cuda(depth) else _ops.require_cuda()
+    d = _ops.to_device(depth, dev)
+    if d.dim() != 3:
+        raise RuntimeError(f"depth must be [B,H,W], got {tuple(d.shape)}")
+    if d.dtype == torch.uint16:
+        kind = "u16"
+    else:
+        kind = "f32"
+        d = d.to(torch.float32)
+    B, H, W = d.shape
+    c = None if bgr is None else _ops.to_device(bgr, dev, torch.uint8)
+    if c is not None and tuple(c.shape) != (B, H, W, 3):
+        raise RuntimeError(f"Color/depth size mismatch: color {tuple(c.shape)}, depth {(B, H, W)}")
+    m = None if mask is None else _ops.to_device(mask, dev, torch.uint8)
+    if m is not None and tuple(m.shape) != (B, H, W):
+        raise RuntimeError(f"Mask/depth size mismatch: mask {tuple(m.shape)}, depth {(B, H, W)}")
+    r = _ops.deproject(d, c, m, cam, depth_kind=kind, unit_rule=unit_rule, unit_scale=depth_scale, invert_mask=invert_mask,
+                       depth_trunc=depth_trunc, r_max=max_distance, z_clip=z_clip, aabb=aabb, mode=mode, out_dtype=dtype,
+                       color_scale=color_scale, want_valid=want_valid, want_src_index=want_src_index,
+                       frame_capacity=frame_capacity, out=out)
+    return CloudBatch(r, B, H, W, c is not None, mode.startswith("dense"))
+
+
+# --------------------------------------------------------------------------- a6
+def register_depth_to_color(depth, depth_camera, color_camera, R=None, t=None, *, depth_units: float = 0.001,
+                            rotation_layout: str = "row_major", return_winner: bool = False):
+    """Depth image(s) in the depth camera's geometry -> uint16 depth on the colour pixel grid, nearest surface wins
+    (what AlignFilter(COLOR_STREAM).process / rs.align(rs.stream.color).process return for the depth stream).
+
+    depth: [Hd,Wd] or [B,Hd,Wd] uint16.  R, t: depth -> colour rigid transform; R as a 3x3 in `rotation_layout`
+    ("row_major" mathematical matrix, or "col_major" = librealsense's flat storage).  Identity when omitted."""
+    dcam, ccam = _as_camera(depth_camera), _as_camera(color_camera)
+    single = (depth.dim() if isinstance(depth, torch.Tensor) else np.asarray(depth).ndim) == 2
+    dev = depth.device if _is_torch_cuda(depth) else _ops.require_cuda()
+    d = _ops.to_device(depth, dev)
+    if d.dtype != torch.uint16:
+        raise RuntimeError(f"depth must be uint16, got {d.dtype}")
+    if single:
+        d = d[None]
+    if ccam.width <= 0 or ccam.height <= 0:
+        raise RuntimeError("color_camera needs width/height")
+    Rm = np.eye(3) if R is None else np.asarray(R, dtype=np.float64).reshape(3, 3)
+    Rcol = Rm.T.reshape(9) if rotation_layout == "row_major" else Rm.reshape(9)
+    tt = np.zeros(3) if t is None else np.asarray(t, dtype=np.float64).reshape(3)
+    out, win = _ops.register(d, dcam, ccam, Rcol, tt, depth_units, return_winner)
+    numpy_out = not _is_torch_cuda(depth)
+    if single:
+        out = out[0]
+        win = None if win is None else win[0]
+    if numpy_out:
+        out = out.cpu().numpy()
+        win = None if win is None else win.cpu().numpy()
+    return (out, win) if return_winner else out
+
+
+# --------------------------------------------------------------------------- a2 (windowed median)
+def median_depth_windows(depth_raw, pixels, window: int = 5) -> np.ndarray:
+    """Median of the non-zero raw depths in clipped window x window neighbourhoods (raw units, float64; NaN = none)."""
+    dev = depth_raw.device if _is_torch_cuda(depth_raw) else _ops.require_cuda()
+    d = _ops.to_device(depth_raw, dev)
+    if d.dtype != torch.uint16 or d.dim() != 2:
+        raise RuntimeError("depth must be a uint16 HxW image")
+    uv = _ops.to_device(np.asarray(pixels, dtype=np.int32).reshape(-1, 2), dev)
+    return _ops.median_depth_window(d, uv, window).cpu().numpy()
+
+
+def get_depth_at_pixel(depth_raw, x: int, y: int, window_size: int = 5):
+    """canopy_return.py:279-317: median of valid depths around (x, y) in metres (raw / 1000.0), None if no valid depth."""
+    v = float(median_depth_windows(depth_raw, [(int(x), int(y))], window_size)[0])
+    if np.isnan(v):
+        return None
+    return v / 1000.0
+
+
+def deproject_pixel_to_point(intrinsics, pixel, depth_value):
+    """canopy_return.py:183-206 single pixel, float64 on the host (three flops; not worth a launch)."""
+    cam = intrinsics
+    fx, fy = float(cam.fx), float(cam.fy)
+    ppx = float(getattr(cam, "ppx", getattr(cam, "cx", 0.0)))
+    ppy = float(getattr(cam, "ppy", getattr(cam, "cy", 0.0)))
+    x, y = pixel
+    return ((x - ppx) * depth_value / fx, (y - ppy) * depth_value / fy, depth_value)
+
+
+# --------------------------------------------------------------------------- config 4
+def fuse_views(clouds, T_cam_tag_list, voxel_size: float = 0.005, *, return_keys: bool = False):
+    """Four-pose fusion: move view i by inv(T_cam_tag_i) into the shared tag frame, concatenate in view order,
+    voxel_down_sample(voxel_size).  Returns the fused PointCloud (and voxel keys / counts when asked)."""
+    from .pose import world_from_camera
+    if len(clouds) != len(T_cam_tag_list) or not clouds:
+        raise ValueError("need one pose per cloud")
+    has_color = all(c._has_color for c in clouds)
+    Ts = [world_from_camera(T) for T in T_cam_tag_list]
+    out, total, bounds = _ops.transform_merge([(c._data, c._n) for c in clouds], Ts, has_color, want_bounds=True)
+    merged = PointCloud(out, total, has_color)
+    if total == 0:
+        return (merged, np.zeros((0, 3), np.int32), np.zeros(0, np.int32)) if return_keys else merged
+    r = _ops.voxel_downsample(out, total, has_color, float(voxel_size), bounds=bounds, want_keys=return_keys,
+                              want_counts=return_keys)
+    m = int(r["m"].item())
+    if m < 0:
+        raise RuntimeError("[Open3D-compatible] voxel_size is too small.")
+    pc = PointCloud(r["data"], m, has_color)
+    if return_keys:
+        return pc, r["keys"][:, :m].t().cpu().numpy(), r["counts"][:m].cpu().numpy()
+    return pc
+
+
+def nv12_to_bgr(nv12, height: int, width: int):
+    """cv2.cvtColor(nv12.reshape(H*3//2, W), COLOR_YUV2BGR_NV12) for [B, H*3/2, W] (or one [H*3/2, W]) uint8 frames."""
+    dev = nv12.device if _is_torch_cuda(nv12) else _ops.require_cuda()
+    a = _ops.to_device(nv12, dev, torch.uint8)
+    single = a.dim() == 2
+    if single:
+        a = a[None]
+    out = _ops.nv12_to_bgr(a, int(height), int(width))
+    if single:
+        out = out[0]
+    return out if _is_torch_cuda(nv12) else out.cpu().numpy()

@@ -315,6 +315,7 @@ extern "C" {
 
 int rv_bounds_init(rv_ctx *ctx, double *d_bounds, rv_stream stream) {
   if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
   if (!d_bounds) RV_FAIL(ctx, RV_EINVAL, "rv_bounds_init: null pointer");
   k_bounds_init<<<1, 32, 0, (cudaStream_t)stream>>>(d_bounds);
   RV_LAUNCHED(ctx);
@@ -325,6 +326,7 @@ int rv_transform_merge(rv_ctx *ctx, int n_views, const void *const *d_in, const 
                        const int64_t *n, const double *T, int in_dtype, int has_color, void *d_out,
                        int64_t out_plane_stride, int out_dtype, double *d_bounds, rv_stream stream) {
   if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
   if (n_views < 0 || (n_views > 0 && (!d_in || !in_plane_stride || !n || !T)))
     RV_FAIL(ctx, RV_EINVAL, "rv_transform_merge: null argument");
   if ((in_dtype != RV_F32 && in_dtype != RV_F64) || (out_dtype != RV_F32 && out_dtype != RV_F64))
@@ -374,6 +376,7 @@ int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, 
                         int64_t out_capacity, int32_t *d_keys, int32_t *d_counts_out, int64_t *d_m, void *d_ws,
                         size_t ws_bytes, rv_stream stream) {
   if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
   if (!(voxel_size > 0.0)) RV_FAIL(ctx, RV_EINVAL, "rv_voxel_downsample: voxel_size <= 0");
   if (n < 0 || in_plane_stride < n || !d_m) RV_FAIL(ctx, RV_EINVAL, "rv_voxel_downsample: bad n / stride / m");
   if ((in_dtype != RV_F32 && in_dtype != RV_F64) || (out_dtype != RV_F32 && out_dtype != RV_F64))
@@ -445,6 +448,7 @@ int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, 
 int rv_pack_ply_records(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int in_dtype, int has_color,
                         int color_scale, int coord_dtype, uint8_t *d_records, rv_stream stream) {
   if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
   if (n < 0 || in_plane_stride < n) RV_FAIL(ctx, RV_EINVAL, "rv_pack_ply_records: bad n / stride");
   if ((in_dtype != RV_F32 && in_dtype != RV_F64) || (coord_dtype != RV_F32 && coord_dtype != RV_F64))
     RV_FAIL(ctx, RV_EINVAL, "rv_pack_ply_records: bad dtype");

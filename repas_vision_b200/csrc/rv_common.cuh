@@ -39,6 +39,18 @@ struct rv_ctx {
     if (e__ != cudaSuccess) RV_FAIL(ctx, RV_ECUDA, "kernel launch: %s", cudaGetErrorString(e__)); \
   } while (0)
 
+// Entry points launch on the context's device whatever the caller's current device is, and restore it.
+struct RvDeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit RvDeviceGuard(const rv_ctx *ctx) {
+    if (ctx && cudaGetDevice(&prev) == cudaSuccess && prev != ctx->device) switched = cudaSetDevice(ctx->device) == cudaSuccess;
+  }
+  ~RvDeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
 static inline bool rv_aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
 // ---------------------------------------------------------------- exact division

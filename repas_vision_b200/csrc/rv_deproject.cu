@@ -77,8 +77,9 @@ __device__ __forceinline__ double quiet_nan<double>() {
 // MODE: RvDeprojectMode.  DK: RvDepthKind.
 template <typename OutT, int DK, int MODE>
 __global__ void __launch_bounds__(kThreads) k_deproject(const DeprojArgs a) {
-  constexpr bool kOrdered = MODE == RV_MODE_COMPACT_ORDERED;
-  constexpr bool kCompact = MODE == RV_MODE_COMPACT_ORDERED || MODE == RV_MODE_COMPACT_UNORDERED;
+  constexpr bool kPacked = MODE == RV_MODE_COMPACT_PACKED;
+  constexpr bool kOrdered = MODE == RV_MODE_COMPACT_ORDERED || kPacked;
+  constexpr bool kCompact = kOrdered || MODE == RV_MODE_COMPACT_UNORDERED;
   __shared__ uint32_t s_warp_tot[kWarps];
   __shared__ int s_tile;
   __shared__ unsigned long long s_base;
@@ -207,10 +208,16 @@ __global__ void __launch_bounds__(kThreads) k_deproject(const DeprojArgs a) {
     unsigned long long base = 0;
     if (kOrdered) {
       if (warp == 0) {
-        const uint32_t excl = rv_lookback(a.status, tile, t, tile_total);
+        // per-frame chains restart at every frame; the packed chain runs through the whole batch
+        const uint32_t excl = rv_lookback(a.status, tile, kPacked ? tile : t, tile_total);
         if (lane == 0) {
           s_base = excl;
-          if (t == a.tiles_per_frame - 1) a.counts[b] = (unsigned long long)excl + tile_total;
+          if (kPacked) {
+            if (t == 0) a.counts[b] = excl;  // exclusive offset of frame b
+            if (tile == a.total_tiles - 1) a.counts[a.B] = (unsigned long long)excl + tile_total;
+          } else if (t == a.tiles_per_frame - 1) {
+            a.counts[b] = (unsigned long long)excl + tile_total;
+          }
         }
       }
       __syncthreads();
@@ -224,7 +231,8 @@ __global__ void __launch_bounds__(kThreads) k_deproject(const DeprojArgs a) {
     }
 
     // ---------------- stores
-    const long long fout = (long long)b * a.frame_stride;
+    const long long fout = kPacked ? 0ll : (long long)b * a.frame_stride;
+    const unsigned long long cap = kPacked ? (unsigned long long)a.plane_stride : (unsigned long long)a.frame_stride;
     unsigned long long run = base + warp_excl;
 #pragma unroll
     for (int j = 0; j < kIters; ++j) {
@@ -233,7 +241,7 @@ __global__ void __launch_bounds__(kThreads) k_deproject(const DeprojArgs a) {
       if (kCompact) {
         const unsigned long long pos = run + __popc(ballots[j] & lt);
         run += __popc(ballots[j]);
-        if (ok && pos < (unsigned long long)a.frame_stride) {
+        if (ok && pos < cap) {
           OutT *o = out + fout + pos;
           o[0] = xs[j];
           o[a.plane_stride] = ys[j];
@@ -425,6 +433,7 @@ void launch_mode(rv_ctx *ctx, const DeprojArgs &a, int mode, cudaStream_t st) {
   switch (mode) {
     case RV_MODE_COMPACT_ORDERED: RV_GO(RV_MODE_COMPACT_ORDERED) break;
     case RV_MODE_COMPACT_UNORDERED: RV_GO(RV_MODE_COMPACT_UNORDERED) break;
+    case RV_MODE_COMPACT_PACKED: RV_GO(RV_MODE_COMPACT_PACKED) break;
     case RV_MODE_DENSE_ZERO: RV_GO(RV_MODE_DENSE_ZERO) break;
     default: RV_GO(RV_MODE_DENSE_NAN) break;
   }
@@ -438,6 +447,7 @@ extern "C" {
 int rv_depth_to_meters(rv_ctx *ctx, const uint16_t *d_depth, int64_t n, int unit_rule, double unit_scale, float *d_out,
                        rv_stream stream) {
   if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
   if (n < 0 || (n > 0 && (!d_depth || !d_out))) RV_FAIL(ctx, RV_EINVAL, "rv_depth_to_meters: null pointer or n<0");
   if (unit_rule < RV_UNIT_MUL_F32 || unit_rule > RV_UNIT_DIV_F64 || !(unit_scale > 0.0))
     RV_FAIL(ctx, RV_EINVAL, "rv_depth_to_meters: bad unit rule / scale");
@@ -454,6 +464,7 @@ int rv_depth_to_meters(rv_ctx *ctx, const uint16_t *d_depth, int64_t n, int unit
 
 int rv_build_ray_table(rv_ctx *ctx, const RvCam *cam, double *d_table, rv_stream stream) {
   if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
   if (!cam || !d_table || cam->width <= 0 || cam->height <= 0) RV_FAIL(ctx, RV_EINVAL, "rv_build_ray_table: bad camera");
   if (!rv_aligned(d_table, 16)) RV_FAIL(ctx, RV_EALIGN, "rv_build_ray_table: table must be 16-byte aligned");
   const int n = cam->width * cam->height;
@@ -474,6 +485,7 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
                       int64_t plane_stride, int64_t frame_stride, uint8_t *d_valid, int32_t *d_src_index,
                       int64_t *d_counts, void *d_ws, size_t ws_bytes, rv_stream stream) {
   if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
   if (!p) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: params is null");
   if (B < 0 || H <= 0 || W <= 0 || (long long)H * W > 0x7fffffffll)
     RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad shape B=%d H=%d W=%d", B, H, W);
@@ -482,7 +494,7 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
   if (p->depth_kind != RV_DEPTH_U16 && p->depth_kind != RV_DEPTH_F32_METERS)
     RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad depth_kind %d", p->depth_kind);
   if (p->out_dtype != RV_F32 && p->out_dtype != RV_F64) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad out_dtype");
-  if (p->mode < RV_MODE_COMPACT_ORDERED || p->mode > RV_MODE_DENSE_NAN) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad mode");
+  if (p->mode < RV_MODE_COMPACT_ORDERED || p->mode > RV_MODE_COMPACT_PACKED) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad mode");
   if (p->depth_kind == RV_DEPTH_U16 &&
       (p->unit_rule < RV_UNIT_MUL_F32 || p->unit_rule > RV_UNIT_DIV_F64 || !(p->unit_scale > 0.0)))
     RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad unit rule / scale");
@@ -492,12 +504,15 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
   if (!(p->cam.fx != 0.0) || !(p->cam.fy != 0.0)) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: fx/fy must be non-zero");
   const long long P = (long long)H * W;
   const bool dense = p->mode == RV_MODE_DENSE_ZERO || p->mode == RV_MODE_DENSE_NAN;
-  if (frame_stride <= 0 || plane_stride < (int64_t)B * frame_stride)
+  const bool packed = p->mode == RV_MODE_COMPACT_PACKED;
+  if (packed ? plane_stride <= 0 : (frame_stride <= 0 || plane_stride < (int64_t)B * frame_stride))
     RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: plane_stride %lld < B*frame_stride", (long long)plane_stride);
+  if (packed && (long long)B * H * W > 0xffffffffll) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: packed batches hold < 2^32 pixels");
   if (dense && frame_stride < P) RV_FAIL(ctx, RV_ECAPACITY, "rv_deproject_mask: dense mode needs frame_stride >= H*W");
   if (d_ray_table && !rv_aligned(d_ray_table, 16)) RV_FAIL(ctx, RV_EALIGN, "rv_deproject_mask: ray table alignment");
   const size_t need = rv_deproject_workspace_bytes(B, H, W);
-  if (p->mode == RV_MODE_COMPACT_ORDERED) {
+  const bool ordered = p->mode == RV_MODE_COMPACT_ORDERED || packed;
+  if (ordered) {
     if (!d_ws || ws_bytes < need) RV_FAIL(ctx, RV_EWORKSPACE, "rv_deproject_mask: workspace %zu < %zu", ws_bytes, need);
     if (!rv_aligned(d_ws, 8)) RV_FAIL(ctx, RV_EALIGN, "rv_deproject_mask: workspace alignment");
   }
@@ -553,7 +568,7 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
   a.use_aabb = p->use_aabb ? 1 : 0;
   a.color_255 = p->color_scale == RV_COLOR_255;
 
-  if (p->mode == RV_MODE_COMPACT_ORDERED) {
+  if (ordered) {
     RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, need, st));
   } else {
     RV_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (size_t)B * sizeof(int64_t), st));
@@ -582,6 +597,7 @@ int rv_filter_cloud(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int6
                     const RvDeprojectParams *p, void *d_out, int64_t out_plane_stride, int64_t *d_count, void *d_ws,
                     size_t ws_bytes, rv_stream stream) {
   if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
   if (!p || !d_count) RV_FAIL(ctx, RV_EINVAL, "rv_filter_cloud: null params/count");
   if (n < 0 || in_plane_stride < n) RV_FAIL(ctx, RV_EINVAL, "rv_filter_cloud: bad n / stride");
   if (dtype != RV_F32 && dtype != RV_F64) RV_FAIL(ctx, RV_EINVAL, "rv_filter_cloud: bad dtype");

@@ -81,6 +81,7 @@ extern "C" {
 int rv_median_depth_window(rv_ctx *ctx, const uint16_t *d_depth, int H, int W, const int32_t *d_uv, int64_t n,
                            int window, double *d_out, rv_stream stream) {
   if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
   if (H <= 0 || W <= 0 || n < 0) RV_FAIL(ctx, RV_EINVAL, "rv_median_depth_window: bad shape");
   if (window < 1 || window / 2 > kMaxHalf) RV_FAIL(ctx, RV_EINVAL, "rv_median_depth_window: window must be 1..%d", 2 * kMaxHalf + 1);
   if (n == 0) return RV_OK;
@@ -92,6 +93,7 @@ int rv_median_depth_window(rv_ctx *ctx, const uint16_t *d_depth, int H, int W, c
 
 int rv_nv12_to_bgr(rv_ctx *ctx, const uint8_t *d_nv12, int B, int H, int W, uint8_t *d_bgr, rv_stream stream) {
   if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
   if (B < 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) RV_FAIL(ctx, RV_EINVAL, "rv_nv12_to_bgr: H and W must be even and positive");
   if (B == 0) return RV_OK;
   if (!d_nv12 || !d_bgr) RV_FAIL(ctx, RV_EINVAL, "rv_nv12_to_bgr: null pointer");

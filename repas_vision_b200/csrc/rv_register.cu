@@ -178,6 +178,7 @@ int rv_register_depth_to_color(rv_ctx *ctx, const uint16_t *d_depth, int B, cons
                                const RvCam *color_cam, const float *R_colmajor, const float *t, float depth_units,
                                uint16_t *d_out, int32_t *d_winner, void *d_ws, size_t ws_bytes, rv_stream stream) {
   if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
   if (!depth_cam || !color_cam || !R_colmajor || !t) RV_FAIL(ctx, RV_EINVAL, "rv_register: null camera / extrinsics");
   if (B < 0 || depth_cam->width <= 0 || depth_cam->height <= 0 || color_cam->width <= 0 || color_cam->height <= 0)
     RV_FAIL(ctx, RV_EINVAL, "rv_register: bad shape");

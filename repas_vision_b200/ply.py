@@ -1,0 +1,127 @@
+"""PLY output compatible with the reference's viewers (o3d.io.read_point_cloud) and a reader for round trips.
+
+* write_point_cloud ... o3d.io.write_point_cloud call sites femto_bolt_code/scripts/create_masked_ply.py:177,
+  april_tag_bg_removal_pl.py:535-537 (write_ascii=False, compressed=False); layout per SURVEY Appendix B.1:
+  binary little-endian, `property double x/y/z` (Open3D's default) then `uchar red/green/blue` =
+  round(clamp(c,0,1)*255).  coord="float" gives the 15-byte records the SDK writers emit
+  (better_three_capture.py:242, capture_aligned_all.py:262).
+* read_point_cloud .... the 31 o3d.io.read_point_cloud call sites (e.g. view_point_cloud.py:104): float or double
+  coordinates, optional uchar colours (-> /255.0), ascii or binary little-endian; other vertex properties are skipped.
+
+The vertex records are packed on the GPU (rv_pack_ply_records) so a cloud crosses PCIe once, already in file layout.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import _ops
+from .cloud import PointCloud
+
+_NP_T = {"float": "<f4", "float32": "<f4", "double": "<f8", "float64": "<f8", "uchar": "u1", "uint8": "u1",
+         "char": "i1", "int8": "i1", "short": "<i2", "int16": "<i2", "ushort": "<u2", "uint16": "<u2",
+         "int": "<i4", "int32": "<i4", "uint": "<u4", "uint32": "<u4"}
+
+
+def ply_header(n: int, has_color: bool, coord: str = "double", ascii_: bool = False) -> bytes:
+    lines = ["ply", "format ascii 1.0" if ascii_ else "format binary_little_endian 1.0", "comment Created by Open3D",
+             f"element vertex {n}", f"property {coord} x", f"property {coord} y", f"property {coord} z"]
+    if has_color:
+        lines += ["property uchar red", "property uchar green", "property uchar blue"]
+    lines.append("end_header")
+    return ("\n".join(lines) + "\n").encode("ascii")
+
+
+def cloud_to_ply_records(pcd: PointCloud, coord: str = "double") -> np.ndarray:
+    """uint8 [N, record_bytes] vertex records in file layout, packed on the device."""
+    cdt = "f64" if coord == "double" else "f32"
+    rec = 3 * (8 if cdt == "f64" else 4) + 3
+    if len(pcd) == 0:
+        return np.zeros((0, rec if pcd._has_color else rec - 3), np.uint8)
+    raw = _ops.pack_ply_records(pcd._data, len(pcd), pcd._has_color, "unit", cdt).cpu().numpy().reshape(len(pcd), rec)
+    return raw if pcd._has_color else np.ascontiguousarray(raw[:, :rec - 3])
+
+
+def write_point_cloud(filename, pointcloud: PointCloud, write_ascii: bool = False, compressed: bool = False,
+                      print_progress: bool = False, coord: str = "double") -> bool:
+    """Returns True on success like Open3D; `compressed` has no effect on PLY (as in Open3D)."""
+    if coord not in ("double", "float"):
+        raise ValueError("coord must be 'double' or 'float'")
+    filename = os.fspath(filename)
+    n = len(pointcloud)
+    rec = cloud_to_ply_records(pointcloud, coord)
+    with open(filename, "wb") as f:
+        f.write(ply_header(n, pointcloud._has_color, coord, write_ascii))
+        if not write_ascii:
+            f.write(rec.tobytes())
+        else:
+            cw = 8 if coord == "double" else 4
+            xyz = np.ascontiguousarray(rec[:, :3 * cw]).view("<f8" if cw == 8 else "<f4").reshape(n, 3)
+            rgb = rec[:, 3 * cw:3 * cw + 3] if pointcloud._has_color else None
+            fmt = "%.10f" if cw == 8 else "%.9g"
+            for i in range(n):
+                row = " ".join(fmt % v for v in xyz[i])
+                if rgb is not None:
+                    row += " %d %d %d" % tuple(int(v) for v in rgb[i])
+                f.write((row + "\n").encode("ascii"))
+    return True
+
+
+def read_ply_vertices(filename):
+    """(header lines, structured numpy array of the vertex element)."""
+    with open(os.fspath(filename), "rb") as f:
+        data = f.read()
+    marker = b"end_header\n"
+    if not data.startswith(b"ply") or marker not in data:
+        raise RuntimeError(f"not a PLY file: {filename}")
+    end = data.index(marker) + len(marker)
+    header = data[:end].decode("ascii", "replace").splitlines()
+    fmt, n, props, in_vertex, before_vertex = None, 0, [], False, 0
+    for line in header[1:]:
+        tok = line.split()
+        if not tok:
+            continue
+        if tok[0] == "format":
+            fmt = tok[1]
+        elif tok[0] == "element":
+            if tok[1] == "vertex":
+                in_vertex, n = True, int(tok[2])
+            else:
+                if not props:
+                    before_vertex += int(tok[2])
+                in_vertex = False
+        elif tok[0] == "property" and in_vertex:
+            if tok[1] == "list":
+                raise RuntimeError("list properties on the vertex element are not supported")
+            props.append((tok[2], _NP_T[tok[1]]))
+    if before_vertex:
+        raise RuntimeError("elements before `vertex` are not supported")
+    dt = np.dtype(props)
+    if fmt == "binary_little_endian":
+        arr = np.frombuffer(data, dtype=dt, count=n, offset=end)
+    elif fmt == "ascii":
+        rows = np.loadtxt(data[end:].decode("ascii").splitlines()[:n], ndmin=2) if n else np.zeros((0, len(props)))
+        arr = np.zeros(n, dtype=dt)
+        for i, (name, _) in enumerate(props):
+            arr[name] = rows[:, i]
+    else:
+        raise RuntimeError(f"unsupported PLY format: {fmt}")
+    return header, arr
+
+
+def read_point_cloud(filename, device=None, dtype: str = "f64") -> PointCloud:
+    """PLY -> PointCloud on the GPU.  A missing file gives an empty cloud with a warning, as Open3D does."""
+    filename = os.fspath(filename)
+    if not os.path.exists(filename):
+        print(f"[Open3D-compatible WARNING] Read PLY failed: unable to open file: {filename}")
+        return PointCloud(None, 0, False, device=device)
+    _, arr = read_ply_vertices(filename)
+    names = arr.dtype.names or ()
+    if not all(k in names for k in ("x", "y", "z")):
+        raise RuntimeError("PLY vertex element has no x/y/z")
+    pts = np.stack([arr["x"], arr["y"], arr["z"]], axis=1).astype(np.float64)
+    cols = None
+    if all(k in names for k in ("red", "green", "blue")):
+        cols = np.stack([arr["red"], arr["green"], arr["blue"]], axis=1).astype(np.float64) / 255.0
+    return PointCloud.from_arrays(pts, cols, device=device, dtype=dtype)

@@ -1,0 +1,255 @@
+"""K3/K4 parity on the B200: 4x4 pose transform + merge, hash voxel grid, four-pose fusion, PLY records and the
+windowed-median / NV12 helpers, through the C ABI against the CPU oracle.
+
+Bars: voxel keys and per-voxel point counts bit-exact as a SET (Open3D's output order is unspecified, SURVEY
+Appendix B.1); centroids / mean colours within 1e-5 relative; transformed coordinates bit-exact in float64."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CAL, CANOPY_TS, load_frame, sha
+from synth import synth_batch
+
+pytestmark = pytest.mark.gpu
+
+CENTROID_RTOL = 1e-5  # BASELINE.json north_star
+
+
+@pytest.fixture(scope="module")
+def rv():
+    import torch
+    assert torch.cuda.is_available()
+    import repas_vision_b200 as rv
+    return rv
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle_np
+    return oracle_np
+
+
+def _rand_pose(rng, scale=0.5):
+    import cv2
+    R, _ = cv2.Rodrigues(rng.uniform(-1.5, 1.5, 3))
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = rng.uniform(-scale, scale, 3)
+    return T
+
+
+def _sorted_voxels(keys, cent, col, cnt):
+    order = np.lexsort((keys[:, 2], keys[:, 1], keys[:, 0]))
+    return keys[order], cent[order], None if col is None else col[order], cnt[order]
+
+
+def _check_voxels(got_pc, got_keys, got_counts, ref):
+    rk, rc, rcol, rn = ref  # oracle returns keys sorted lexicographically
+    gk, gc, gcol, gn = _sorted_voxels(got_keys, got_pc.points, got_pc.colors if got_pc.has_colors() else None, got_counts)
+    assert gk.shape == rk.shape and np.array_equal(gk, rk), "voxel key sets differ"
+    assert np.array_equal(gn, rn), "per-voxel point counts differ"
+    scale = np.maximum(np.abs(rc), 1e-3)
+    assert (np.abs(gc - rc) / scale).max() <= CENTROID_RTOL
+    if rcol is not None:
+        assert np.abs(gcol - rcol).max() <= CENTROID_RTOL
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_transform_matches_open3d_semantics(rv, O, dtype):
+    rng = np.random.default_rng(5)
+    P = rng.uniform(-2, 2, (100003, 3))
+    C = rng.random((100003, 3))
+    if dtype == "f32":
+        P, C = P.astype(np.float32), C.astype(np.float32)
+    T = _rand_pose(rng)
+    pc = rv.PointCloud.from_arrays(P, C, dtype=dtype)
+    out = pc.transform(T)
+    assert out is pc  # in place, returns self like Open3D
+    ref = O.transform(P, T)
+    if dtype == "f64":
+        assert np.array_equal(pc.points, ref)
+    else:
+        assert np.array_equal(pc.points.astype(np.float32), ref.astype(np.float32))
+    assert np.array_equal(pc.colors, C.astype(np.float64))
+    # projective last row (w != 1)
+    Tp = T.copy()
+    Tp[3] = [0.01, -0.02, 0.03, 1.1]
+    pc2 = rv.PointCloud.from_arrays(P.astype(np.float64), None).transform(Tp)
+    assert np.array_equal(pc2.points, O.transform(P.astype(np.float64), Tp))
+    with pytest.raises(ValueError):
+        pc.transform(np.eye(3))
+
+
+def test_merge_is_concatenation(rv):
+    rng = np.random.default_rng(6)
+    parts = [(rng.normal(size=(n, 3)), rng.random((n, 3))) for n in (1000, 1, 0, 777)]
+    clouds = [rv.PointCloud.from_arrays(p, c) for p, c in parts]
+    m = rv.merge(clouds)
+    assert np.array_equal(m.points, np.concatenate([p for p, _ in parts]))
+    assert np.array_equal(m.colors, np.concatenate([c for _, c in parts]))
+    s = clouds[0] + clouds[3]
+    assert len(s) == 1777 and np.array_equal(s.points[1000:], parts[3][0])
+
+
+@pytest.mark.parametrize("voxel", [0.005, 0.003, 0.05])
+def test_voxel_down_sample_real_frame(rv, O, rs720, voxel):
+    """mpa_icp_export.py:44,174 (5 mm), view_point_cloud.py example (3 mm) on a captured frame."""
+    color, depth = load_frame(CANOPY_TS[4])
+    pc = rv.create_masked_pointcloud(color, depth, None, rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"], max_distance=1.5)
+    P, C = pc.points, pc.colors
+    down, keys, counts = pc.voxel_down_sample(voxel, return_keys=True)
+    _check_voxels(down, keys, counts, O.voxel_down_sample(P, C, voxel))
+    assert counts.sum() == len(pc)
+
+
+def test_voxel_oracle_forms_agree_and_edge_cases(rv, O):
+    from oracle import oracle_c
+    rng = np.random.default_rng(8)
+    P = rng.uniform(-0.4, 0.4, (50000, 3))
+    P[:100] = P[0]  # duplicates
+    P[100:200] = np.round(P[100:200] / 0.01) * 0.01  # points exactly on voxel faces
+    C = rng.random((50000, 3))
+    ref = O.voxel_down_sample(P, C, 0.01)
+    ck, cc, ccol, cn = _sorted_voxels(*oracle_c.voxel_down_sample(P, C, 0.01))
+    assert np.array_equal(ck, ref[0]) and np.array_equal(cn, ref[3]) and np.allclose(cc, ref[1], rtol=0, atol=1e-15)
+    pc = rv.PointCloud.from_arrays(P, C)
+    down, keys, counts = pc.voxel_down_sample(0.01, return_keys=True)
+    _check_voxels(down, keys, counts, ref)
+    # no colours, float32 storage
+    pc32 = rv.PointCloud.from_arrays(P.astype(np.float32), None, dtype="f32")
+    d32, k32, n32 = pc32.voxel_down_sample(0.02, return_keys=True)
+    _check_voxels(d32, k32, n32, O.voxel_down_sample(P.astype(np.float32), None, 0.02))
+    # single point, empty cloud, bad sizes
+    one = rv.PointCloud.from_arrays(P[:1], C[:1]).voxel_down_sample(0.005)
+    assert len(one) == 1 and np.array_equal(one.points, P[:1])
+    assert len(rv.PointCloud.from_arrays(P[:0], C[:0]).voxel_down_sample(0.005)) == 0
+    with pytest.raises(RuntimeError):
+        pc.voxel_down_sample(0.0)
+    with pytest.raises(RuntimeError):
+        pc.voxel_down_sample(1e-9)  # index range overflow -> "voxel_size is too small"
+
+
+def test_four_pose_fusion(rv, O, rs720):
+    """BASELINE config 4: four views, solvePnP-style T_cam_tag poses, merged in the tag frame and voxelised at 5 mm."""
+    import torch
+    rng = np.random.default_rng(12)
+    depth, bgr = synth_batch(4, 720, 1280, seed0=40)
+    cam = rv.Camera(rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"], 1280, 720)
+    poses = []
+    for i in range(4):  # camera orbiting the tag at 0/90/180/270 degrees, 0.8 m away
+        a = np.deg2rad(90.0 * i)
+        R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+        T = np.eye(4)
+        T[:3, :3] = R
+        T[:3, 3] = [0.02 * i, -0.01, 0.8]
+        poses.append(T)
+    batch = rv.deproject_batch(torch.from_numpy(depth).cuda(), torch.from_numpy(bgr).cuda(), cam, max_distance=1.2, dtype="f64")
+    clouds = [batch.frame(i) for i in range(4)]
+    fused, keys, counts = rv.fuse_views(clouds, poses, 0.005, return_keys=True)
+    parts, cols = [], []
+    for i in range(4):
+        ref = O.deproject_mask(depth[i], bgr[i], None, fx=cam.fx, fy=cam.fy, cx=cam.cx, cy=cam.cy, r_max=1.2, out_dtype="f64")
+        parts.append(O.transform(ref["points"], O.invert_rigid(poses[i])))
+        cols.append(ref["colors"])
+    _check_voxels(fused, keys, counts, O.voxel_down_sample(np.concatenate(parts), np.concatenate(cols), 0.005))
+    assert counts.sum() == sum(len(c) for c in clouds)
+
+
+def test_pose_from_corners_feeds_fusion(rv, golden):
+    """final_view.py:171-225 on exactly projected corners: same winning order and pose as the reference produced."""
+    K = np.array(golden["solvepnp_K"])
+    for rec in golden["solvepnp"]:
+        _, rvec, tvec, err, label = rv.solve_pnp_with_best_obj_order(np.array(rec["corners_px"]), K, np.zeros((5, 1)),
+                                                                     golden["solvepnp_tag_size"])
+        assert label == rec["label"]
+        assert np.allclose(rvec.reshape(3), rec["rvec"], atol=1e-9) and np.allclose(tvec.reshape(3), rec["tvec"], atol=1e-9)
+        T = rv.pose_from_tag_corners(np.array(rec["corners_px"]), K, np.zeros((5, 1)), golden["solvepnp_tag_size"])
+        assert np.allclose(T, rec["T_cam_tag"], atol=1e-9)
+
+
+def test_ply_round_trip_and_layout(rv, O, rs720, tmp_path):
+    color, depth = load_frame(CANOPY_TS[0])
+    pc = rv.create_masked_pointcloud(color, depth, None, rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"], max_distance=1.0)
+    P, C = pc.points, pc.colors
+    for coord, npdt in (("double", "<f8"), ("float", "<f4")):
+        path = tmp_path / f"cloud_{coord}.ply"
+        assert rv.write_point_cloud(str(path), pc, coord=coord)
+        header, arr = O.read_ply_minimal(str(path))
+        assert header[1] == "format binary_little_endian 1.0" and f"element vertex {len(pc)}" in header
+        assert [h for h in header if h.startswith("property")] == [f"property {coord} x", f"property {coord} y",
+                                                                   f"property {coord} z", "property uchar red",
+                                                                   "property uchar green", "property uchar blue"]
+        assert np.array_equal(arr["x"], P[:, 0].astype(npdt)) and np.array_equal(arr["z"], P[:, 2].astype(npdt))
+        assert np.array_equal(arr["red"], np.round(C[:, 0] * 255).astype(np.uint8))
+        back = rv.read_point_cloud(str(path))
+        assert len(back) == len(pc)
+        if coord == "double":
+            assert np.array_equal(back.points, P)
+        assert np.array_equal(np.round(back.colors * 255), np.round(C * 255))
+    # colours survive exactly: uchar -> /255 -> *255 round trip for every byte value
+    ramp = np.arange(256, dtype=np.float64)[:, None].repeat(3, 1) / 255.0
+    pcr = rv.PointCloud.from_arrays(np.zeros((256, 3)), ramp)
+    rv.write_point_cloud(str(tmp_path / "ramp.ply"), pcr)
+    _, arr = O.read_ply_minimal(str(tmp_path / "ramp.ply"))
+    assert np.array_equal(arr["green"], np.arange(256, dtype=np.uint8))
+    # ascii variant parses with the independent reader too
+    small = rv.PointCloud.from_arrays(P[:50], C[:50])
+    rv.write_point_cloud(str(tmp_path / "a.ply"), small, write_ascii=True)
+    _, arr = O.read_ply_minimal(str(tmp_path / "a.ply"))
+    assert np.allclose(arr["y"], P[:50, 1], atol=1e-9)
+    # no colours
+    rv.write_point_cloud(str(tmp_path / "nc.ply"), rv.PointCloud.from_arrays(P[:10], None))
+    header, arr = O.read_ply_minimal(str(tmp_path / "nc.ply"))
+    assert arr.dtype.names == ("x", "y", "z") and np.array_equal(arr["x"], P[:10, 0])
+
+
+def test_median_depth_windows_and_canopy_known_answers(rv, golden, rs720):
+    """get_depth_at_pixel (canopy_return.py:279-317) on the GPU reproduces the reference's stored canopy_y goldens."""
+    _, depth0 = load_frame(CANOPY_TS[0])
+    recs = golden["median_depth"]
+    for win in (5, 11):
+        sel = [r for r in recs if r["window"] == win]
+        got = rv.median_depth_windows(depth0, [(r["x"], r["y"]) for r in sel], win)
+        for r, g in zip(sel, got):
+            if r["depth_m"] is None:
+                assert np.isnan(g)
+            else:
+                assert g / 1000.0 == r["depth_m"]
+    class Intr:
+        fx, fy, ppx, ppy = rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"]
+    for rec in golden["canopy"]:
+        _, depth = load_frame(rec["ts"])
+        x, y = rec["pixel"]
+        d = rv.get_depth_at_pixel(depth, x, y, 5)
+        if d is None or d <= 0:
+            d = rv.get_depth_at_pixel(depth, x, y, 11)
+        assert d == rec["depth_m"]
+        X, Y, Z = rv.deproject_pixel_to_point(Intr, (x, y), d)
+        assert [X, Y, Z] == rec["xyz"] and f"{Y:.4f}" == rec["stored_in_reference"]
+
+
+def test_nv12_to_bgr_matches_opencv(rv):
+    import cv2
+    rng = np.random.default_rng(2)
+    H, W = 72, 128
+    nv12 = rng.integers(0, 256, (3, H * 3 // 2, W), dtype=np.uint8)
+    got = rv.nv12_to_bgr(nv12, H, W)
+    for b in range(3):
+        ref = cv2.cvtColor(nv12[b], cv2.COLOR_YUV2BGR_NV12)
+        assert np.array_equal(got[b], ref)
+
+
+def test_exact_division_helper_against_numpy(rv):
+    """rv_div (reciprocal + two fused corrections) must equal IEEE division for the divisors this path uses: checked through
+    the kernels on all 65536 raw depths and all 256 colour bytes, for several focal lengths."""
+    import torch
+    from oracle import oracle_np as O
+    allv = np.arange(65536, dtype=np.uint16).reshape(64, 1024)
+    col = (np.arange(64 * 1024 * 3) % 256).astype(np.uint8).reshape(64, 1024, 3)
+    for fx, fy in ((912.350341796875, 911.7763061523438), (748.8987426757812, 748.3513793945312), (3.0, 7.0),
+                   (605.2845686, 605.44233933), (1.0000000000000002, 1.9999999999999998)):
+        for rule in ("mul_f32", "div_f32", "div_f64"):
+            pc = rv.create_masked_pointcloud(col, allv, None, fx, fy, 511.3, 31.7, unit_rule=rule)
+            ref = O.deproject_mask(allv, col, None, fx=fx, fy=fy, cx=511.3, cy=31.7, unit_rule=rule, out_dtype="f64")
+            assert np.array_equal(pc.points, ref["points"]) and np.array_equal(pc.colors, ref["colors"])

@@ -1,0 +1,275 @@
+"""K1 parity on the B200: deprojection + masks + stream compaction through the C ABI against the CPU oracle
+and against the golden vectors the reference's own functions produced (tests/golden/make_golden.py).
+
+Bars: valid mask, point order and float64 clouds bit-exact; float32 clouds bit-exact against the oracle's
+float32 contract and within 1e-5 m of the float64 reference values."""
+import functools
+
+import numpy as np
+import pytest
+
+from conftest import CANOPY_TS, blob_mask, load_frame, sha
+from synth import synth_batch, synth_color, synth_depth, synth_mask
+
+pytestmark = pytest.mark.gpu
+
+XYZ_TOL_M = 1e-5  # BASELINE.json north_star: within 1e-5 m absolute on xyz
+
+
+@pytest.fixture(scope="module")
+def rv():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import repas_vision_b200 as rv
+    return rv
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle_np
+    return oracle_np
+
+
+@functools.lru_cache(maxsize=None)
+def _dataset(B, H, W):
+    depth, bgr = synth_batch(B, H, W, seed0=1)
+    return depth, bgr, np.stack([synth_mask(H, W, 50 + i, cover=0.3) for i in range(B)])
+
+
+def _cloud_np(pc):
+    return pc.points, pc.colors
+
+
+@pytest.mark.parametrize("idx", range(5))
+def test_real_frames_float64_match_reference_goldens(rv, golden, rs720, idx):
+    """create_masked_pointcloud on the reference's captured frames: float64 points/colours hash-identical to what
+    femto_bolt_code/scripts/create_masked_ply.py:56-107 produced, plus the fused distance mask."""
+    ts = CANOPY_TS[idx]
+    color, depth = load_frame(ts)
+    _, dm, _ = rv.depth_to_meters(depth)
+    for rec in [r for r in golden["masked_cloud"] if r["ts"] == ts]:
+        h, w = depth.shape
+        mask = np.full((h, w), 255, np.uint8) if rec["variant"] == "all" else blob_mask(h, w, rec["mask_seed"])
+        pc = rv.create_masked_pointcloud(color, dm, mask, rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"],
+                                         invert_mask=rec["variant"] == "blob_inverted")
+        P, C = _cloud_np(pc)
+        assert len(pc) == rec["n"]
+        assert sha(P) == rec["points"]["sha256"]
+        assert sha(C) == rec["colors"]["sha256"]
+        # raw uint16 depth in, unit conversion fused: same cloud
+        pc16 = rv.create_masked_pointcloud(color, depth, mask, rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"],
+                                           invert_mask=rec["variant"] == "blob_inverted")
+        assert sha(pc16.points) == rec["points"]["sha256"]
+        if rec["variant"] == "all":
+            near = rv.create_masked_pointcloud(color, dm, mask, rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"],
+                                               max_distance=1.0)
+            assert len(near) == rec["dist_lt_1m"]["kept"]
+            assert sha(near.points) == rec["dist_lt_1m"]["points"]["sha256"]
+            # the stand-alone filters on the produced cloud (distance_masking_on_ply.py, view_point_cloud.py, AABB crop)
+            assert sha(pc.select_within_distance(1.0).points) == rec["dist_lt_1m"]["points"]["sha256"]
+            assert len(pc.clip_z(0.15, 8.0)) == rec["zclip_0p15_8"]["kept"]
+            assert len(pc.crop_aabb(rec["aabb"]["min"], rec["aabb"]["max"])) == rec["aabb"]["kept"]
+
+
+def test_float_depth_nan_inf_negative(rv, golden):
+    rngf = np.random.default_rng(11)
+    dm = (rngf.uniform(0.2, 4.0, (48, 64))).astype(np.float32)
+    dm[rngf.random((48, 64)) < 0.1] = np.nan
+    dm[rngf.random((48, 64)) < 0.05] = np.inf
+    dm[rngf.random((48, 64)) < 0.05] = -1.0
+    dm[rngf.random((48, 64)) < 0.1] = 0.0
+    col = rngf.integers(0, 256, (48, 64, 3), dtype=np.uint8)
+    msk = (rngf.random((48, 64)) < 0.7).astype(np.uint8) * 255
+    pc = rv.create_masked_pointcloud(col, dm, msk, 60.0, 61.0, 31.5, 23.25)
+    g = golden["masked_cloud_float_small"]
+    assert len(pc) == g["n"] and sha(pc.points) == g["points"]["sha256"] and sha(pc.colors) == g["colors"]["sha256"]
+
+
+CASES = [
+    dict(),
+    dict(r_max=1.0),
+    dict(z_clip=(0.15, 8.0)),
+    dict(z_clip=(None, 2.0), r_max=2.5),
+    dict(aabb=((-0.3, -0.25, 0.5), (0.35, 0.2, 1.2))),
+    dict(depth_trunc=3.0, unit_rule="div_f32"),
+    dict(unit_rule="div_f64", r_max=1.5),
+    dict(mask=True),
+    dict(mask=True, invert_mask=True, r_max=1.2),
+    dict(color_scale="255"),
+]
+
+
+@pytest.mark.parametrize("shape", [(720, 1280), (480, 640), (37, 53), (1, 2049)])
+@pytest.mark.parametrize("case", range(len(CASES)))
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_synthetic_frames_all_predicates(rv, O, rs720, shape, case, dtype):
+    """Every predicate combination of the fused kernel, ragged shapes included (tile tails, odd widths)."""
+    import torch
+    H, W = shape
+    kw = dict(CASES[case])
+    use_mask = kw.pop("mask", False)
+    B = 2 if H * W > 10000 else 5
+    depth, bgr, allmask = _dataset(B, H, W)
+    mask = allmask if use_mask else None
+    cam = rv.Camera(rs720["fx"] * W / 1280, rs720["fy"] * H / 720, rs720["cx"] * W / 1280, rs720["cy"] * H / 720, W, H)
+    okw = dict(kw)
+    if okw.get("z_clip") is not None:
+        okw["z_clip"] = tuple(v if v is not None else s * np.inf for v, s in zip(okw["z_clip"], (-1.0, 1.0)))
+    gk = dict(unit_rule=kw.get("unit_rule", "mul_f32"), invert_mask=kw.get("invert_mask", False),
+              depth_trunc=kw.get("depth_trunc"), max_distance=kw.get("r_max"), z_clip=kw.get("z_clip"), aabb=kw.get("aabb"),
+              color_scale=kw.get("color_scale", "unit"))
+    batch = rv.deproject_batch(torch.from_numpy(depth).cuda(), torch.from_numpy(bgr).cuda(), cam,
+                               None if mask is None else torch.from_numpy(mask).cuda(), dtype=dtype, want_valid=True,
+                               want_src_index=True, **gk)
+    counts = batch.counts_host()
+    for b in range(B):
+        ref = O.deproject_mask(depth[b], bgr[b], None if mask is None else mask[b], fx=cam.fx, fy=cam.fy, cx=cam.cx,
+                               cy=cam.cy, out_dtype=dtype, **okw)
+        n = ref["points"].shape[0]
+        assert counts[b] == n
+        assert np.array_equal(batch.valid[b].cpu().numpy().astype(bool), ref["valid"])  # bit-exact mask
+        f = batch.frame(b)
+        got = f.xyz.t().cpu().numpy()
+        assert np.array_equal(batch.src_index[b * batch.cap:b * batch.cap + n].cpu().numpy(), ref["src_index"])
+        assert got.dtype == ref["points"].dtype and np.array_equal(got, ref["points"])  # bit-exact, same order
+        assert np.array_equal(f.rgb.t().cpu().numpy(), ref["colors"])
+        ref64 = O.deproject_mask(depth[b], bgr[b], None if mask is None else mask[b], fx=cam.fx, fy=cam.fy, cx=cam.cx,
+                                 cy=cam.cy, out_dtype="f64", **{k: v for k, v in okw.items() if k in ("unit_rule", "invert_mask", "depth_trunc")})
+        # tolerance bar against the float64 values (same pixels selected by src_index)
+        sel = np.isin(ref64["src_index"], ref["src_index"])
+        assert np.abs(got.astype(np.float64) - ref64["points"][sel]).max(initial=0.0) <= XYZ_TOL_M
+
+
+@pytest.mark.parametrize("mode", ["compact_unordered", "dense_zero", "dense_nan"])
+def test_other_output_modes(rv, O, rs720, mode):
+    import torch
+    H, W, B = 480, 640, 4
+    depth, bgr = synth_batch(B, H, W, seed0=21)
+    cam = rv.Camera(608.2335815429688, 607.8508911132812, 312.52239990234375, 232.65150451660156, W, H)
+    batch = rv.deproject_batch(torch.from_numpy(depth).cuda(), torch.from_numpy(bgr).cuda(), cam, max_distance=1.0,
+                               unit_rule="div_f32", mode=mode, want_src_index=True)
+    counts = batch.counts_host()
+    for b in range(B):
+        ref = O.deproject_mask(depth[b], bgr[b], None, fx=cam.fx, fy=cam.fy, cx=cam.cx, cy=cam.cy, r_max=1.0,
+                               unit_rule="div_f32", out_dtype="f32")
+        n = ref["points"].shape[0]
+        assert counts[b] == n
+        blk = batch.data[:, b * batch.cap:(b + 1) * batch.cap].cpu().numpy()
+        src = batch.src_index[b * batch.cap:(b + 1) * batch.cap].cpu().numpy()
+        if mode == "compact_unordered":
+            order = np.argsort(src[:n], kind="stable")  # compare as a set keyed by source pixel
+            assert np.array_equal(src[:n][order], ref["src_index"])
+            assert np.array_equal(blk[:3, :n].T[order], ref["points"])
+            assert np.array_equal(blk[3:, :n].T[order], ref["colors"])
+        else:
+            flat = ref["valid"].reshape(-1)
+            assert np.array_equal(src >= 0, flat)
+            assert np.array_equal(blk[:3][:, flat].T, ref["points"])
+            assert np.array_equal(blk[3:][:, flat].T, ref["colors"])
+            inv = blk[:3][:, ~flat]
+            assert np.isnan(inv).all() if mode == "dense_nan" else (inv == 0).all()
+            assert (blk[3:][:, ~flat] == 0).all()
+
+
+@pytest.mark.parametrize("model", ["inverse_brown_conrady", "brown_conrady"])
+def test_distorted_camera_ray_table(rv, O, model):
+    """Checkerboard calibration with lens distortion (realtime_pose_estimation_april_tag.py:10-18): the float64 ray table
+    reproduces rs2_deproject_pixel_to_point and the kernel multiplies by it."""
+    import torch
+    H, W = 480, 640
+    dist = (0.04344582, 0.32076285, -0.00060687, -0.0004814, -1.40593456)
+    cam = rv.Camera(605.2845686, 605.44233933, 309.95995203, 229.79166863, W, H, dist, model)
+    depth, bgr = synth_batch(2, H, W, seed0=31)
+    rays = O.ray_table(cam.fx, cam.fy, cam.cx, cam.cy, dist, model, W, H)
+    from repas_vision_b200 import _ops
+    got_rays = _ops.ray_table(cam, H, W, torch.device("cuda", 0)).cpu().numpy()
+    assert np.array_equal(got_rays, rays)
+    for dtype in ("f32", "f64"):
+        batch = rv.deproject_batch(torch.from_numpy(depth).cuda(), torch.from_numpy(bgr).cuda(), cam, max_distance=1.5,
+                                   dtype=dtype)
+        for b in range(2):
+            ref = O.deproject_mask(depth[b], bgr[b], None, fx=cam.fx, fy=cam.fy, cx=cam.cx, cy=cam.cy, r_max=1.5,
+                                   out_dtype=dtype, rays=rays)
+            assert batch.counts_host()[b] == ref["points"].shape[0]
+            assert np.array_equal(batch.frame(b).xyz.t().cpu().numpy(), ref["points"])
+
+
+def test_create_from_rgbd_image_open3d_shape(rv, O, rs720):
+    color, depth = load_frame(CANOPY_TS[0])
+    pc = rv.create_from_rgbd_image(color, depth, rs720, depth_scale=1000.0, depth_trunc=3.0)
+    P, C = O.create_from_rgbd_image(color, depth, rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"], 1000.0, 3.0)
+    assert len(pc) == P.shape[0] and np.array_equal(pc.points, P) and np.array_equal(pc.colors, C)
+    E = np.eye(4)
+    E[:3, 3] = [0.1, -0.2, 0.05]
+    E[:3, :3] = [[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]]
+    pc2 = rv.create_from_rgbd_image(color, depth, rs720, extrinsic=E)
+    P2, _ = O.create_from_rgbd_image(color, depth, rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"], 1000.0, 3.0, extrinsic=E)
+    assert np.abs(pc2.points - P2).max() <= 1e-12
+    dense = rv.create_from_rgbd_image(color, depth, rs720, project_valid_depth_only=False)
+    assert len(dense) == 720 * 1280 and np.isnan(dense.points[:, 0]).sum() == 720 * 1280 - P.shape[0]
+
+
+def test_depth_to_meters_goldens(rv, golden):
+    _, depth = load_frame(CANOPY_TS[0])
+    raw, dm, scale = rv.depth_to_meters(depth)
+    assert scale == golden["depth_to_meters"]["scale"] and raw is depth or np.array_equal(raw, depth)
+    assert dm.dtype == np.float32 and sha(dm) == golden["depth_to_meters"]["depth_m"]["sha256"]
+    allv = np.arange(65536, dtype=np.uint16).reshape(256, 256)
+    assert sha(rv.depth_to_meters(allv)[1]) == golden["depth_to_meters"]["all_u16"]["sha256"]
+    from oracle import oracle_np as O
+    for rule in ("div_f32", "div_f64"):
+        ref = O.depth_to_meters(allv, rule).astype(np.float32)
+        assert np.array_equal(rv.depth_to_meters(allv, rule)[1], ref)
+
+
+def test_full_size_batch_properties(rv, rs720):
+    """BASELINE full-size shapes through size-independent properties: counts equal the valid-mask population, ordered
+    output is strictly increasing in source index, dense and compact agree, and a second run is identical."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    B, H, W = 64, 720, 1280
+    depth = torch.randint(0, 4000, (B, H, W), generator=g, device="cuda", dtype=torch.int32)
+    depth = torch.where(depth < 1500, torch.zeros_like(depth), depth).to(torch.uint16)
+    bgr = torch.randint(0, 256, (B, H, W, 3), generator=g, device="cuda", dtype=torch.uint8)
+    cam = rv.Camera(rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"], W, H)
+    a = rv.deproject_batch(depth, bgr, cam, max_distance=2.0, want_valid=True, want_src_index=True)
+    counts = a.counts.cpu()
+    assert torch.equal(counts, a.valid.view(B, -1).sum(dim=1, dtype=torch.int64).cpu())
+    for b in (0, B // 2, B - 1):
+        n = int(counts[b])
+        s = a.src_index[b * a.cap:b * a.cap + n]
+        assert bool((s[1:] > s[:-1]).all())
+        assert torch.equal(torch.nonzero(a.valid[b].view(-1)).view(-1).to(torch.int32), s)
+    d = rv.deproject_batch(depth, bgr, cam, max_distance=2.0, mode="dense_zero")
+    for b in (0, B - 1):
+        n = int(counts[b])
+        idx = a.src_index[b * a.cap:b * a.cap + n].long()
+        assert torch.equal(d.data[:, b * d.cap:(b + 1) * d.cap][:, idx], a.data[:, b * a.cap:b * a.cap + n])
+    a2 = rv.deproject_batch(depth, bgr, cam, max_distance=2.0)
+    assert torch.equal(a2.counts.cpu(), counts)
+    for b in (1, B - 2):
+        n = int(counts[b])
+        assert torch.equal(a2.data[:, b * a.cap:b * a.cap + n], a.data[:, b * a.cap:b * a.cap + n])
+
+
+def test_edge_cases_and_errors(rv, rs720):
+    import torch
+    cam = rv.Camera(500.0, 500.0, 3.5, 2.5, 8, 6)
+    z = np.zeros((6, 8), np.uint16)
+    c = np.zeros((6, 8, 3), np.uint8)
+    pc = rv.create_masked_pointcloud(c, z, np.full((6, 8), 255, np.uint8), 500.0, 500.0, 3.5, 2.5)
+    assert len(pc) == 0 and pc.is_empty() and pc.points.shape == (0, 3)
+    full = np.full((6, 8), 65535, np.uint16)
+    pc = rv.create_masked_pointcloud(c, full, np.full((6, 8), 255, np.uint8), 500.0, 500.0, 3.5, 2.5, dtype="f32")
+    assert len(pc) == 48 and np.allclose(pc.points[:, 2], np.float32(65535) * np.float32(0.001))
+    with pytest.raises(RuntimeError):
+        rv.create_masked_pointcloud(c[:5], z, None, 500.0, 500.0, 3.5, 2.5)
+    with pytest.raises(RuntimeError):
+        rv.create_masked_pointcloud(c, z, np.zeros((5, 8), np.uint8), 500.0, 500.0, 3.5, 2.5)
+    # capacity: counts stay truthful when the per-frame capacity is too small
+    b = rv.deproject_batch(torch.from_numpy(full[None]).cuda(), torch.from_numpy(c[None]).cuda(), cam, frame_capacity=10)
+    assert int(b.counts[0]) == 48
+    from repas_vision_b200 import _lib
+    ctx = _lib.context(0)
+    st = ctx.lib.rv_deproject_mask(ctx.handle, None, None, None, None, 1, 6, 8, None, None, 0, 0, None, None, None, None, 0, None)
+    assert st == _lib.RV_EINVAL and b"params" in ctx.lib.rv_last_error(ctx.handle)

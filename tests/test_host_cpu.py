@@ -1,0 +1,210 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/repas_vision.h declares,
+the host logic (calibration loaders, pose helper, PLY header, sharding) behaves like the reference's, and the
+product refuses to compute without a GPU instead of falling back."""
+import ctypes
+import json
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import CAL, GOLDEN, ROOT
+
+import __graft_entry__ as entry
+
+
+@pytest.fixture(scope="module")
+def built():
+    entry.build()
+    import repas_vision_b200 as rv
+    return rv
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "repas_vision.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rv_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    from repas_vision_b200 import _lib
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/repas_vision.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes prototype"
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.rv_abi_version() == 1
+    assert b"sm_100a" in lib.rv_build_info()
+    assert lib.rv_sizeof_cam() == ctypes.sizeof(_lib.RvCam)
+    assert lib.rv_sizeof_deproject_params() == ctypes.sizeof(_lib.RvDeprojectParams)
+    assert lib.rv_status_string(2) == b"output capacity exceeded"
+    # size queries are pure host functions
+    assert lib.rv_deproject_workspace_bytes(1, 720, 1280) == 128 + 450 * 8
+    assert lib.rv_register_workspace_bytes(64, 720, 1280) == 8 * 720 * 1280 * 8
+    assert lib.rv_voxel_workspace_bytes(1000) == 256 + 2048 * 64
+
+
+def test_shared_object_holds_only_sm100a_code(built):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", built.library_path()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_cpu_fallback(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    rv = built
+    z = np.ones((4, 4), np.float32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rv.create_masked_pointcloud(np.zeros((4, 4, 3), np.uint8), z, np.ones((4, 4), np.uint8), 1, 1, 0, 0)
+    with pytest.raises(RuntimeError):
+        rv.register_depth_to_color(np.zeros((4, 4), np.uint16), rv.Camera(1, 1, 0, 0, 4, 4), rv.Camera(1, 1, 0, 0, 4, 4))
+    from repas_vision_b200 import _lib
+    h = ctypes.c_void_p()
+    assert _lib.load().rv_create(0, ctypes.byref(h)) == _lib.RV_ECUDA
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "repas_vision_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
+
+
+def test_intrinsics_loaders_match_reference_outputs(built, golden, tmp_path):
+    rv = built
+    for name, rec in golden["intrinsics"].items():
+        vals = rv.load_color_intrinsics(os.path.join(CAL, name))
+        assert list(vals) == rec["load"]
+        assert list(rv.scale_intrinsics(*vals[:4], vals[4], vals[5], 640, 360)) == rec["scaled_640x360"]
+        assert list(rv.scale_intrinsics(*vals[:4], 0, 0, 640, 360)) == rec["scaled_noop"]
+    with pytest.raises(FileNotFoundError):
+        rv.load_color_intrinsics(tmp_path / "missing.json")
+    bad = tmp_path / "bad.json"
+    bad.write_text(json.dumps({"fx": 1, "fy": 1, "cx": 1}))
+    with pytest.raises(KeyError):
+        rv.load_color_intrinsics(bad)
+    nested = tmp_path / "nested.json"
+    nested.write_text(json.dumps({"color_intrinsics": {"fx": 2, "fy": 3, "cx": 4, "cy": 5}}))
+    assert rv.load_color_intrinsics(nested) == (2.0, 3.0, 4.0, 5.0, 0, 0)
+    K, dist, w, h = rv.load_intrinsics_json(os.path.join(CAL, "checkerboard_color_intrinsics_2025-08-26T183535.json"))
+    assert K.dtype == np.float32 and dist.shape == (5,) and (w, h) == (1280, 720)
+    K, dist, wh = rv.load_intrinsics(os.path.join(CAL, "factory_color_intrinsics_1280_720.json"))
+    assert K[0, 2] == 628.7836303710938 and wh == (1280, 720) and not dist.any()
+    cam = rv.load_camera(os.path.join(CAL, "checkerboard_color_intrinsics_2025-08-26T183535.json"))
+    assert cam.model == "brown_conrady" and cam.distorted and cam.dist[0] == 0.09217283086787045
+    cam = rv.load_camera(os.path.join(CAL, "factory_color_intrinsics_640_480.json"))
+    assert cam.model == "none" and cam.cx == 312.52239990234375 and (cam.width, cam.height) == (640, 480)
+    R, t = rv.read_depth_to_color_extrinsics(os.path.join(CAL, "factory_d2c_extrinsics.json"))
+    assert R.shape == (3, 3) and abs(t[0] - 0.014984656) < 1e-8
+    R, t = rv.load_extrinsics(os.path.join(CAL, "factory_extrinsics_d2c_2025-09-08T143506.json"))
+    assert np.array_equal(R, np.eye(3)) and not t.any()
+    T = rv.load_transform_matrix(os.path.join(CAL, "20250917_164430.txt"))
+    assert T.shape == (4, 4) and np.allclose(T[:3, :3] @ T[:3, :3].T, np.eye(3), atol=1e-5)
+    (tmp_path / "t3.txt").write_text("1 0 0\n0 1 0\n0 0 1\n")
+    with pytest.raises(ValueError):
+        rv.load_transform_matrix(tmp_path / "t3.txt")
+
+
+def test_pose_helper_matches_reference_goldens(built, golden):
+    rv = built
+    K = np.array(golden["solvepnp_K"])
+    for rec in golden["solvepnp"]:
+        _, rvec, tvec, err, label = rv.solve_pnp_with_best_obj_order(np.array(rec["corners_px"]), K, np.zeros((5, 1)),
+                                                                     golden["solvepnp_tag_size"])
+        assert label == rec["label"] and abs(err - rec["err_px"]) < 1e-9
+        assert np.allclose(rvec.reshape(3), rec["rvec"], atol=1e-9) and np.allclose(tvec.reshape(3), rec["tvec"], atol=1e-9)
+        T = rv.pose_from_tag_corners(np.array(rec["corners_px"]), K, np.zeros((5, 1)), golden["solvepnp_tag_size"])
+        assert np.allclose(T, rec["T_cam_tag"], atol=1e-9)
+        assert np.allclose(rv.world_from_camera(T) @ T, np.eye(4), atol=1e-12)
+
+
+def test_ply_header_and_reader(built, tmp_path):
+    from repas_vision_b200 import ply
+    from oracle import oracle_np as O
+    hdr = ply.ply_header(3, True, "double").decode()
+    assert hdr.splitlines()[:4] == ["ply", "format binary_little_endian 1.0", "comment Created by Open3D", "element vertex 3"]
+    assert hdr.endswith("end_header\n")
+    rec = np.zeros(3, dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("red", "u1"), ("green", "u1"), ("blue", "u1")])
+    rec["x"], rec["y"], rec["z"], rec["red"] = [1, 2, 3], [4, 5, 6], [7, 8, 9], [255, 0, 128]
+    p = tmp_path / "h.ply"
+    p.write_bytes(ply.ply_header(3, True, "float") + rec.tobytes())
+    header, arr = ply.read_ply_vertices(p)
+    _, arr2 = O.read_ply_minimal(str(p))
+    assert np.array_equal(arr, arr2) and arr["red"].tolist() == [255, 0, 128]
+    with pytest.raises(RuntimeError):
+        (tmp_path / "x.ply").write_bytes(b"not a ply")
+        ply.read_ply_vertices(tmp_path / "x.ply")
+
+
+def test_shard_range_partitions_exactly(built):
+    from repas_vision_b200.shard import shard_range
+    for total in (0, 1, 7, 8, 8192, 1023):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(8, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from repas_vision_b200 import shard
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        total = 11
+        a, b = shard.shard_range(total, rank, world)
+        local = torch.arange(a, b, dtype=torch.int64) * 10 + 1  # "counts" of this rank's frames
+        allc = shard.gather_counts(local, total)
+        data = torch.arange(6 * (rank + 2), dtype=torch.float64).reshape(6, rank + 2) + 100 * rank
+        merged, sizes = shard.gather_clouds(data, rank + 1, dst=0)
+        tmax = shard.max_over_ranks(1.0 + rank)
+        tsum = shard.sum_over_ranks(float(b - a))
+        q.put((rank, allc.tolist(), None if merged is None else merged.tolist(), sizes, tmax, tsum))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gathers(built):
+    """world_size 2 on CPU: the only collectives of the path (counts all-gather, variable-length cloud gather)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    expect_counts = [i * 10 + 1 for i in range(11)]
+    for rank, allc, merged, sizes, tmax, tsum in res:
+        assert allc == expect_counts and sizes == [1, 2] and tmax == 2.0 and tsum == 11.0
+    m0 = np.array(res[0][2])
+    assert m0.shape == (6, 3)
+    assert m0[:, 0].tolist() == [0.0, 2.0, 4.0, 6.0, 8.0, 10.0]  # rank 0: data[:, :1] of a [6,2] arange
+    assert m0[:, 1:].tolist() == (np.arange(18).reshape(6, 3)[:, :2] + 100).tolist()
+    assert res[1][2] is None
