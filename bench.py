@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--e2e-frames", type=int, default=512, help="frames per end-to-end step (pinned host buffers)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0 = auto)")
     ap.add_argument("--mode", default="compact_ordered", choices=["compact_ordered", "compact_unordered", "dense_zero"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "tma"], help="K1 kernel (A/B runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -289,7 +290,7 @@ def workload_config(a, world):
     return {"workload": "BASELINE configs[4]: synthetic 1280x720 RGB-D (u16 depth + BGR8) -> validity + ||p||<1.0 m mask -> "
                         "ordered compacted float32 SoA xyz+rgb cloud",
             "frames_per_gpu_per_step": a.frames, "global_batch": a.frames * world, "chunk_frames": a.chunk,
-            "resolution": [W, H], "mode": a.mode, "r_max_m": R_MAX, "unit_rule": "mul_f32",
+            "resolution": [W, H], "mode": a.mode, "kernel": a.kernel, "r_max_m": R_MAX, "unit_rule": "mul_f32",
             "l2": "inputs (1.18 GB per launch, 37.7 GB per step) exceed the 126 MB L2; no flush needed",
             "parallelism": f"frames sharded over {world} GPU(s), no collective on the hot path"}
 
@@ -331,7 +332,7 @@ def run_b200(a):
     ring = [torch.empty((6, chunk * P), dtype=torch.float32, device=dev) for _ in range(2)]
     torch.cuda.synchronize()
 
-    kw = dict(max_distance=R_MAX, mode=a.mode, dtype="f32")
+    kw = dict(max_distance=R_MAX, mode=a.mode, dtype="f32", kernel=a.kernel)
     launches_ctx = rv._lib.context(local)
 
     def one_step(events=None):

@@ -95,6 +95,11 @@ enum RvColorScale {
   RV_COLOR_255 = 1   /* raw 0..255 as floats (Orbbec RGB_POINT, better_three_capture.py:235-237) */
 };
 
+/* which K1 kernel runs: AUTO picks the TMA-fed pipeline when H*W % 16 == 0, W >= 32, the inputs are 16-byte
+ * aligned, there is no ray table and the mode is not COMPACT_UNORDERED; otherwise the generic kernel.  Both
+ * produce identical bytes (tests/test_gpu_deproject.py runs every case through both). */
+enum RvKernelSelect { RV_KERNEL_AUTO = 0, RV_KERNEL_GENERIC = 1, RV_KERNEL_TMA = 2 };
+
 typedef struct RvDeprojectParams {
   RvCam cam;            /* intrinsics of the grid the depth lives on (the colour camera after alignment) */
   int32_t depth_kind;   /* RvDepthKind */
@@ -114,7 +119,7 @@ typedef struct RvDeprojectParams {
   int32_t mode;        /* RvDeprojectMode */
   int32_t out_dtype;   /* RvDType of the six output planes */
   int32_t color_scale; /* RvColorScale */
-  int32_t reserved;
+  int32_t kernel_select; /* RvKernelSelect */
 } RvDeprojectParams;
 
 /* ---- context -------------------------------------------------------------- */

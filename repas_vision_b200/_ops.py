@@ -38,6 +38,14 @@ def stream_ptr(dev: torch.device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+def pstride(t: torch.Tensor) -> int:
+    """Plane stride (elements) of an SoA cloud tensor [planes, n]; column slices of a batch are fine, the points of a
+    plane must be contiguous."""
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError("cloud planes must be rows of a 2-D tensor with unit column stride")
+    return int(t.stride(0)) if t.shape[0] > 1 else int(t.shape[1])
+
+
 def ptr(t) -> C.c_void_p:
     return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
 
@@ -70,7 +78,7 @@ def to_device(a, dev: torch.device, dtype=None) -> torch.Tensor:
 def deproject(depth, bgr, mask, cam: Camera, *, depth_kind, unit_rule="mul_f32", unit_scale=None, invert_mask=False,
               depth_trunc=None, z_clip=None, r_max=None, aabb=None, mode="compact_ordered", out_dtype="f32",
               color_scale="unit", want_valid=False, want_src_index=False, frame_capacity=None, out=None,
-              rays=None):
+              rays=None, kernel="auto"):
     """depth [B,H,W] (uint16 or float32), bgr [B,H,W,3] uint8 or None, mask [B,H,W] uint8 or None, all on one
     CUDA device.  Returns dict(data [6 or 3, B*cap], counts [B] int64, cap, valid, src_index)."""
     dev = depth.device
@@ -100,6 +108,7 @@ def deproject(depth, bgr, mask, cam: Camera, *, depth_kind, unit_rule="mul_f32",
     p.mode = _lib.MODES[mode]
     p.out_dtype = _lib.RV_F32 if out_dtype == "f32" else _lib.RV_F64
     p.color_scale = _lib.COLOR_SCALES[color_scale]
+    p.kernel_select = _lib.KERNELS[kernel]
     cap = int(frame_capacity) if frame_capacity is not None else P
     planes = 6 if bgr is not None else 3
     packed = mode == "compact_packed"
@@ -191,7 +200,7 @@ def filter_cloud(data: torch.Tensor, n: int, has_color: bool, *, z_clip=None, r_
     out = torch.empty((data.shape[0], max(n, 1)), dtype=data.dtype, device=dev)
     count = torch.zeros(1, dtype=torch.int64, device=dev)
     ws = workspace(ctx.lib.rv_filter_workspace_bytes(n), dev)
-    ctx.check(ctx.lib.rv_filter_cloud(ctx.handle, ptr(data), data.shape[1], n, _RV_DT[data.dtype], int(has_color), C.byref(p),
+    ctx.check(ctx.lib.rv_filter_cloud(ctx.handle, ptr(data), pstride(data), n, _RV_DT[data.dtype], int(has_color), C.byref(p),
                                       ptr(out), out.shape[1], ptr(count), ptr(ws), ws.numel(), stream_ptr(dev)))
     return out, count
 
@@ -209,7 +218,7 @@ def transform_merge(views, Ts, has_color: bool, out_dtype=None, want_bounds=Fals
     planes = 6 if has_color else 3
     out = torch.empty((planes, max(total, 1)), dtype=out_dt, device=dev)
     ptrs = (C.c_void_p * nv)(*[v[0].data_ptr() for v in views])
-    strides = (C.c_int64 * nv)(*[v[0].shape[1] for v in views])
+    strides = (C.c_int64 * nv)(*[pstride(v[0]) for v in views])
     ns = (C.c_int64 * nv)(*[int(v[1]) for v in views])
     Tflat = np.ascontiguousarray(np.stack([np.asarray(T, dtype=np.float64).reshape(4, 4) for T in Ts])).reshape(-1)
     Tc = (C.c_double * (16 * nv))(*Tflat.tolist())
@@ -237,7 +246,7 @@ def voxel_downsample(data: torch.Tensor, n: int, has_color: bool, voxel_size: fl
     ws = workspace(ctx.lib.rv_voxel_workspace_bytes(n), dev)
     if not (float(voxel_size) > 0.0):
         raise ValueError("voxel_size <= 0")
-    ctx.check(ctx.lib.rv_voxel_downsample(ctx.handle, ptr(data), data.shape[1], n, _RV_DT[data.dtype], int(has_color),
+    ctx.check(ctx.lib.rv_voxel_downsample(ctx.handle, ptr(data), pstride(data), n, _RV_DT[data.dtype], int(has_color),
                                           float(voxel_size), ptr(bounds), ptr(out), out.shape[1], _RV_DT[out_dt],
                                           min(cap, out.shape[1]) if cap > 0 else 0, ptr(keys), ptr(cnts), ptr(m), ptr(ws),
                                           ws.numel(), stream_ptr(dev)))
@@ -249,7 +258,7 @@ def pack_ply_records(data: torch.Tensor, n: int, has_color: bool, color_scale="u
     ctx = ctx_for(dev)
     rec = 3 * (4 if coord_dtype == "f32" else 8) + 3
     out = torch.empty(max(n, 1) * rec, dtype=torch.uint8, device=dev)
-    ctx.check(ctx.lib.rv_pack_ply_records(ctx.handle, ptr(data), data.shape[1], n, _RV_DT[data.dtype], int(has_color),
+    ctx.check(ctx.lib.rv_pack_ply_records(ctx.handle, ptr(data), pstride(data), n, _RV_DT[data.dtype], int(has_color),
                                           _lib.COLOR_SCALES[color_scale], _lib.RV_F32 if coord_dtype == "f32" else _lib.RV_F64,
                                           ptr(out), stream_ptr(dev)))
     return out[:n * rec]

@@ -311,7 +311,7 @@ class CloudBatch:
 def deproject_batch(depth, bgr, camera, mask=None, *, unit_rule: str = "mul_f32", depth_scale=None, invert_mask=False,
                     depth_trunc=None, max_distance=None, z_clip=None, aabb=None, mode: str = "compact_ordered",
                     dtype: str = "f32", color_scale: str = "unit", want_valid=False, want_src_index=False,
-                    frame_capacity=None, out=None) -> CloudBatch:
+                    frame_capacity=None, out=None, kernel: str = "auto") -> CloudBatch:
     """Batched form of create_masked_pointcloud: depth [B,H,W] (uint16 raw or float32 metres), bgr [B,H,W,3] uint8,
     mask [B,H,W] uint8 or None.  One kernel launch for the whole batch."""
     cam = _as_camera(camera)
@@ -334,7 +334,7 @@ def deproject_batch(depth, bgr, camera, mask=None, *, unit_rule: str = "mul_f32"
     r = _ops.deproject(d, c, m, cam, depth_kind=kind, unit_rule=unit_rule, unit_scale=depth_scale, invert_mask=invert_mask,
                        depth_trunc=depth_trunc, r_max=max_distance, z_clip=z_clip, aabb=aabb, mode=mode, out_dtype=dtype,
                        color_scale=color_scale, want_valid=want_valid, want_src_index=want_src_index,
-                       frame_capacity=frame_capacity, out=out)
+                       frame_capacity=frame_capacity, out=out, kernel=kernel)
     return CloudBatch(r, B, H, W, c is not None, mode.startswith("dense"))
 
 

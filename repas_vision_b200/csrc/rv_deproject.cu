@@ -16,6 +16,7 @@
 // (rv_common.cuh); tiles are handed out by an atomic ticket so a tile's predecessors
 // are always already running.
 #include "rv_common.cuh"
+#include "rv_deproject_args.cuh"
 
 namespace {
 
@@ -24,31 +25,6 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kIters = 8;
 constexpr int kTile = kThreads * kIters;  // 2048 pixels
 
-struct DeprojArgs {
-  const void *depth;
-  const uint8_t *bgr;
-  const uint8_t *mask;
-  const double2 *rays;
-  void *out;
-  uint8_t *valid;
-  int32_t *src_index;
-  unsigned long long *counts;
-  unsigned long long *status;  // ws + 128 B
-  unsigned int *ticket;        // ws
-  int B, H, W, P;
-  int tiles_per_frame, total_tiles;
-  long long plane_stride, frame_stride;
-  double cx, cy, fx, fy, rfx, rfy;
-  double unit_scale, unit_rcp;
-  float unit_scale_f, unit_rcp_f;
-  float trunc_f;
-  int unit_rule;
-  double z_min, z_max;
-  double r2_thresh;  // keep iff (x*x+y*y)+z*z < r2_thresh  <=>  sqrt(.) < r_max
-  double amin[3], amax[3];
-  int use_mask, invert_mask, use_trunc, use_zclip, use_radius, use_aabb;
-  int color_255;
-};
 
 template <typename T>
 __device__ __forceinline__ T color_value(uint32_t k, int color_255);
@@ -422,6 +398,18 @@ double radius_threshold(double r) {
   return t;  // first value whose sqrt is >= r
 }
 
+// smallest float >= d / largest float <= d (NaN stays NaN: every comparison with it is false, as in float64)
+float float_at_least(double d) {
+  float f = (float)d;
+  if ((double)f < d) f = nextafterf(f, INFINITY);
+  return f;
+}
+float float_at_most(double d) {
+  float f = (float)d;
+  if ((double)f > d) f = nextafterf(f, -INFINITY);
+  return f;
+}
+
 template <typename OutT, int DK>
 void launch_mode(rv_ctx *ctx, const DeprojArgs &a, int mode, cudaStream_t st) {
 #define RV_GO(M)                                                                                   \
@@ -495,6 +483,7 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
     RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad depth_kind %d", p->depth_kind);
   if (p->out_dtype != RV_F32 && p->out_dtype != RV_F64) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad out_dtype");
   if (p->mode < RV_MODE_COMPACT_ORDERED || p->mode > RV_MODE_COMPACT_PACKED) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad mode");
+  if (p->kernel_select < RV_KERNEL_AUTO || p->kernel_select > RV_KERNEL_TMA) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad kernel_select");
   if (p->depth_kind == RV_DEPTH_U16 &&
       (p->unit_rule < RV_UNIT_MUL_F32 || p->unit_rule > RV_UNIT_DIV_F64 || !(p->unit_scale > 0.0)))
     RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad unit rule / scale");
@@ -567,13 +556,29 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
   a.use_radius = p->use_radius ? 1 : 0;
   a.use_aabb = p->use_aabb ? 1 : 0;
   a.color_255 = p->color_scale == RV_COLOR_255;
+  a.zmin_f = float_at_least(a.z_min);
+  a.zmax_f = float_at_most(a.z_max);
+  for (int i = 0; i < 3; ++i) {
+    a.amin_f[i] = float_at_least(a.amin[i]);
+    a.amax_f[i] = float_at_most(a.amax[i]);
+  }
+  a.fast_radius = a.r2_thresh > 1e-30 && a.r2_thresh < 1e30;
+  a.r2_lo_f = a.fast_radius ? float_at_most(a.r2_thresh * (1.0 - 9.5367431640625e-07)) : 0.0f;   // 2^-20 band
+  a.r2_hi_f = a.fast_radius ? float_at_least(a.r2_thresh * (1.0 + 9.5367431640625e-07)) : 0.0f;
+  const bool fast_ok = rv_deproject_fast_eligible(a, p->mode);
+  if (p->kernel_select == RV_KERNEL_TMA && !fast_ok)
+    RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: RV_KERNEL_TMA requested but the inputs are not eligible "
+                            "(H*W %% 16 == 0, W >= 32, 16-byte aligned inputs, no ray table, not COMPACT_UNORDERED)");
+  const bool use_fast = fast_ok && p->kernel_select != RV_KERNEL_GENERIC;
 
   if (ordered) {
     RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, need, st));
   } else {
     RV_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (size_t)B * sizeof(int64_t), st));
   }
-  if (p->out_dtype == RV_F32) {
+  if (use_fast) {
+    RV_CUDA(ctx, rv_deproject_fast_launch(ctx, a, p->mode, p->out_dtype, p->depth_kind, st));
+  } else if (p->out_dtype == RV_F32) {
     if (p->depth_kind == RV_DEPTH_U16)
       launch_mode<float, RV_DEPTH_U16>(ctx, a, p->mode, st);
     else

@@ -1,0 +1,420 @@
+// rv_deproject_tma.cu -- K1 fast path: the fused deprojection + masks + ordered compaction kernel as a
+// TMA-fed persistent pipeline (sm_100a).
+//
+// Same contract and arithmetic as k_deproject in rv_deproject.cu (reference semantics cited there:
+// create_masked_ply.py:56-107, better_three_capture.py:118-125, distance_masking_on_ply.py:12-19,
+// view_point_cloud.py:109-116, april_tag_bg_removal_pl.py:450-455); what changes is how bytes move:
+//
+//  * one producer warp per CTA takes tile tickets and issues 1-D bulk async copies (cp.async.bulk ->
+//    UBLKCP, the TMA engine) of the tile's depth / BGR / mask bytes into a kStages-deep shared-memory
+//    ring guarded by full/empty mbarriers, so ~3 tiles of loads per CTA are always in flight and no
+//    compute warp ever waits on a global load;
+//  * eight compute warps read the tile from shared memory (lane + 32 j ownership, so every ballot is a
+//    contiguous run of pixels and every compacted store instruction writes one contiguous run);
+//  * tiles are handed out frame-interleaved (ticket -> tile t of frame ticket % B), so the B per-frame
+//    prefix chains advance in parallel and a tile's predecessor finished a whole round earlier: its
+//    inclusive prefix is fetched by ONE load issued before the tile's arithmetic ("early peek"); the
+//    decoupled look-back of rv_common.cuh remains as the fallback when the peek finds no prefix yet;
+//  * the radius / z-clip / AABB decisions are taken on float32 values with thresholds rounded so that
+//    the decision equals the float64 predicate of the oracle bit for bit (exact float64 re-evaluation
+//    inside a 2^-20 band around the sphere).
+//
+// Eligibility (checked by rv_deproject_fast_eligible): H*W % 16 == 0, W >= 32, 16-byte aligned inputs,
+// no distortion ray table, mode != COMPACT_UNORDERED.  Everything else runs k_deproject.
+#include "rv_common.cuh"
+#include "rv_deproject_args.cuh"
+
+namespace {
+
+constexpr int kCW = 8;                  // compute warps
+constexpr int kCT = kCW * 32;           // compute threads
+constexpr int kThreadsT = kCT + 32;     // + producer warp
+constexpr int kItersT = 8;
+constexpr int kTileT = kCT * kItersT;   // 2048 pixels
+constexpr int kStages = 3;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// 1-D bulk copy global -> shared, completion reported to an mbarrier in bytes (TMA engine, no tensor map)
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }
+
+template <typename T>
+__device__ __forceinline__ T unit_color(uint32_t k, int color_255);
+// k / 255 with ONE residual correction: exhaustively exact for k = 0..255 in both precisions
+// (tests/test_gpu_cloud.py::test_exact_division_helper_against_numpy walks all 256 bytes).
+template <>
+__device__ __forceinline__ float unit_color<float>(uint32_t k, int color_255) {
+  const float kf = (float)k;
+  if (color_255) return kf;
+  const float c = 0.003921568859368563f;
+  const float q = kf * c;
+  return fmaf(fmaf(-q, 255.0f, kf), c, q);
+}
+template <>
+__device__ __forceinline__ double unit_color<double>(uint32_t k, int color_255) {
+  const double kd = (double)k;
+  if (color_255) return kd;
+  const double c = 0.00392156862745098;
+  const double q = kd * c;
+  return fma(fma(-q, 255.0, kd), c, q);
+}
+
+template <typename T>
+__device__ __forceinline__ T qnan();
+template <>
+__device__ __forceinline__ float qnan<float>() {
+  return __int_as_float(0x7fc00000);
+}
+template <>
+__device__ __forceinline__ double qnan<double>() {
+  return __longlong_as_double(0x7ff8000000000000ll);
+}
+
+template <typename OutT, int DK, int MODE>
+__global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproject_tma(const DeprojArgs a) {
+  constexpr bool kPacked = MODE == RV_MODE_COMPACT_PACKED;
+  constexpr bool kOrdered = MODE == RV_MODE_COMPACT_ORDERED || kPacked;
+  constexpr bool kF32 = sizeof(OutT) == 4;
+  constexpr int kDepthB = DK == RV_DEPTH_U16 ? 2 : 4;
+  constexpr int kStageBytes = kTileT * (kDepthB + 3 + 1);
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+  __shared__ __align__(8) uint64_t empty_bar[kStages];
+  __shared__ int s_tile[kStages];
+  __shared__ uint32_t s_warp_tot[kCW];
+  __shared__ uint32_t s_base;
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kCW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ticket -> (frame, tile-in-frame).  Per-frame chains: frame-interleaved.  Packed chain: frame-major.
+  const int tpf = a.tiles_per_frame;
+
+  // ============================================================ producer warp
+  if (warp == kCW) {
+    if (lane == 0) {
+      for (int it = 0;; ++it) {
+        const int s = it % kStages;
+        mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
+        const int ticket = (int)atomicAdd(a.ticket, 1u);
+        if (ticket >= a.total_tiles) {
+          s_tile[s] = -1;
+          mbar_arrive(&full_bar[s]);
+          break;
+        }
+        s_tile[s] = ticket;
+        int b, t;
+        if (kPacked) {
+          b = ticket / tpf;
+          t = ticket - b * tpf;
+        } else {
+          t = ticket / a.B;
+          b = ticket - t * a.B;
+        }
+        const int px0 = t * kTileT;
+        const int npx = min(kTileT, a.P - px0);
+        const long long g = (long long)b * a.P + px0;
+        unsigned char *st = smem + (size_t)s * kStageBytes;
+        uint32_t bytes = (uint32_t)npx * kDepthB;
+        if (a.bgr) bytes += (uint32_t)npx * 3;
+        if (a.use_mask) bytes += (uint32_t)npx;
+        mbar_arrive_expect_tx(&full_bar[s], bytes);
+        bulk_load(st, reinterpret_cast<const unsigned char *>(a.depth) + g * kDepthB, (uint32_t)npx * kDepthB, &full_bar[s]);
+        if (a.bgr) bulk_load(st + kTileT * kDepthB, a.bgr + g * 3, (uint32_t)npx * 3, &full_bar[s]);
+        if (a.use_mask) bulk_load(st + kTileT * (kDepthB + 3), a.mask + g, (uint32_t)npx, &full_bar[s]);
+      }
+    }
+    return;
+  }
+
+  // ============================================================ compute warps
+  const uint32_t lt = rv_lanemask_lt();
+  OutT *const out = reinterpret_cast<OutT *>(a.out);
+  const float inf_f = __int_as_float(0x7f800000);
+
+  for (int it = 0;; ++it) {
+    const int s = it % kStages;
+    mbar_wait(&full_bar[s], (it / kStages) & 1);
+    const int ticket = s_tile[s];
+    if (ticket < 0) break;
+    int b, t;
+    if (kPacked) {
+      b = ticket / tpf;
+      t = ticket - b * tpf;
+    } else {
+      t = ticket / a.B;
+      b = ticket - t * a.B;
+    }
+    const int tile = b * tpf + t;  // index into status[]
+    const int n_pred = kPacked ? tile : t;
+    const int px0 = t * kTileT;
+    const int npx = min(kTileT, a.P - px0);
+    const unsigned char *st = smem + (size_t)s * kStageBytes;
+    const uint8_t *s_bgr = st + kTileT * kDepthB;
+    const uint8_t *s_msk = st + kTileT * (kDepthB + 3);
+
+    // early peek: the predecessor's status word, requested before the arithmetic, consumed after it
+    unsigned long long peek = 0;
+    if (kOrdered && warp == 0 && lane == 0 && n_pred > 0) peek = rv_ld_relaxed(a.status + tile - 1);
+
+    const int li0 = warp * (32 * kItersT) + lane;  // index inside the tile
+    const int p0 = px0 + li0;                      // pixel index inside the frame
+    int v = p0 / a.W;
+    int u = p0 - v * a.W;
+
+    OutT xs[kItersT], ys[kItersT];
+    float zf[kItersT];
+    double zd[kItersT];  // only live when OutT is double
+    uint32_t ballots[kItersT];
+    uint32_t warp_total = 0;
+#pragma unroll
+    for (int j = 0; j < kItersT; ++j) {
+      const int li = li0 + j * 32;
+      const bool inb = li < npx;
+      float z32;
+      double z64;
+      bool ok;
+      if (DK == RV_DEPTH_U16) {
+        const uint32_t d = inb ? (uint32_t) reinterpret_cast<const uint16_t *>(st)[li] : 0u;
+        const float df = (float)d;
+        if (a.unit_rule == RV_UNIT_MUL_F32) {
+          z32 = df * a.unit_scale_f;
+          z64 = (double)z32;
+        } else if (a.unit_rule == RV_UNIT_DIV_F32) {
+          z32 = rv_divf(df, a.unit_scale_f, a.unit_rcp_f);
+          z64 = (double)z32;
+        } else {
+          z64 = rv_div((double)d, a.unit_scale, a.unit_rcp);
+          z32 = (float)z64;
+        }
+        ok = d != 0;
+      } else {
+        z32 = inb ? reinterpret_cast<const float *>(st)[li] : 0.0f;
+        z64 = (double)z32;
+        ok = (z32 > 0.0f) && (z32 < inf_f);
+      }
+      ok = ok && inb;
+      if (a.use_mask) {
+        const uint32_t m = inb ? (uint32_t)s_msk[li] : 0u;
+        ok = ok && (a.invert_mask ? (m == 0) : (m != 0));
+      }
+      if (a.use_trunc) ok = ok && !(z32 >= a.trunc_f);
+
+      const double x64 = rv_div(((double)u - a.cx) * z64, a.fx, a.rfx);
+      const double y64 = rv_div(((double)v - a.cy) * z64, a.fy, a.rfy);
+      const OutT xo = (OutT)x64, yo = (OutT)y64;
+      if (kF32) {
+        // float32 storage: compare the stored floats against thresholds rounded toward the kept side;
+        // identical to the float64 predicate on their exact up-casts
+        const float xf = (float)xo, yf = (float)yo;
+        if (a.use_zclip) ok = ok && (z32 >= a.zmin_f) && (z32 <= a.zmax_f);
+        if (a.use_aabb)
+          ok = ok && (xf >= a.amin_f[0]) && (xf <= a.amax_f[0]) && (yf >= a.amin_f[1]) && (yf <= a.amax_f[1]) &&
+               (z32 >= a.amin_f[2]) && (z32 <= a.amax_f[2]);
+        if (a.use_radius) {
+          bool in;
+          if (a.fast_radius) {
+            const float sf = fmaf(z32, z32, fmaf(yf, yf, xf * xf));
+            in = sf <= a.r2_lo_f;
+            if (!in && sf < a.r2_hi_f) {  // inside the 2^-20 band: the float64 sum decides
+              const double X = (double)xf, Y = (double)yf, Z = (double)z32;
+              in = ((X * X + Y * Y) + Z * Z) < a.r2_thresh;
+            }
+          } else {
+            const double X = (double)xf, Y = (double)yf, Z = (double)z32;
+            in = ((X * X + Y * Y) + Z * Z) < a.r2_thresh;
+          }
+          ok = ok && in;
+        }
+      } else {
+        const double X = (double)xo, Y = (double)yo, Z = z64;
+        if (a.use_zclip) ok = ok && (Z >= a.z_min) && (Z <= a.z_max);
+        if (a.use_radius) ok = ok && (((X * X + Y * Y) + Z * Z) < a.r2_thresh);
+        if (a.use_aabb)
+          ok = ok && (X >= a.amin[0]) && (X <= a.amax[0]) && (Y >= a.amin[1]) && (Y <= a.amax[1]) && (Z >= a.amin[2]) &&
+               (Z <= a.amax[2]);
+      }
+      xs[j] = xo;
+      ys[j] = yo;
+      zf[j] = z32;
+      zd[j] = z64;
+      ballots[j] = __ballot_sync(0xffffffffu, ok);
+      warp_total += __popc(ballots[j]);
+      if (a.valid && inb) a.valid[(long long)b * a.P + px0 + li] = ok ? 1 : 0;
+      u += 32;
+      if (u >= a.W) {
+        u -= a.W;
+        ++v;
+      }
+    }
+
+    // ---------------- tile totals, tile base
+    if (lane == 0) s_warp_tot[warp] = warp_total;
+    compute_bar();
+    uint32_t warp_excl = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < kCW; ++w) {
+      const uint32_t c = s_warp_tot[w];
+      warp_excl += (w < warp) ? c : 0u;
+      tile_total += c;
+    }
+    uint32_t base = 0;
+    if (kOrdered) {
+      if (warp == 0) {
+        uint32_t excl = 0;
+        peek = __shfl_sync(0xffffffffu, peek, 0);
+        if (n_pred == 0) {
+          if (lane == 0) rv_st_relaxed(a.status + tile, RV_ST_PREFIX | (unsigned long long)tile_total);
+        } else if ((peek >> 62) == 2) {
+          excl = (uint32_t)peek;
+          if (lane == 0) rv_st_relaxed(a.status + tile, RV_ST_PREFIX | (unsigned long long)(excl + tile_total));
+        } else {
+          excl = rv_lookback(a.status, tile, n_pred, tile_total);
+        }
+        if (lane == 0) {
+          s_base = excl;
+          if (kPacked) {
+            if (t == 0) a.counts[b] = excl;
+            if (tile == a.total_tiles - 1) a.counts[a.B] = (unsigned long long)excl + tile_total;
+          } else if (t == tpf - 1) {
+            a.counts[b] = (unsigned long long)excl + tile_total;
+          }
+        }
+      }
+      compute_bar();
+      base = s_base;
+    } else {
+      if (threadIdx.x == 0 && tile_total) atomicAdd(a.counts + b, (unsigned long long)tile_total);
+    }
+
+    // ---------------- stores (colours are converted here, for kept pixels only)
+    const long long fout = kPacked ? 0ll : (long long)b * a.frame_stride;
+    const unsigned long long cap = kPacked ? (unsigned long long)a.plane_stride : (unsigned long long)a.frame_stride;
+    OutT *const o0 = out + fout;
+    uint32_t run = base + warp_excl;
+#pragma unroll
+    for (int j = 0; j < kItersT; ++j) {
+      const int li = li0 + j * 32;
+      const bool ok = (ballots[j] >> lane) & 1u;
+      const OutT zo = kF32 ? (OutT)zf[j] : (OutT)zd[j];
+      if (kOrdered) {
+        if (ballots[j] == 0) continue;
+        const uint32_t pos = run + __popc(ballots[j] & lt);
+        run += __popc(ballots[j]);
+        if (ok && pos < cap) {
+          OutT *o = o0 + pos;
+          o[0] = xs[j];
+          o[a.plane_stride] = ys[j];
+          o[2 * a.plane_stride] = zo;
+          if (a.bgr) {
+            const uint8_t *c = s_bgr + 3 * li;
+            o[3 * a.plane_stride] = unit_color<OutT>(c[2], a.color_255);
+            o[4 * a.plane_stride] = unit_color<OutT>(c[1], a.color_255);
+            o[5 * a.plane_stride] = unit_color<OutT>(c[0], a.color_255);
+          }
+          if (a.src_index) a.src_index[fout + pos] = px0 + li;
+        }
+      } else if (li < npx && (long long)(px0 + li) < a.frame_stride) {
+        OutT *o = o0 + px0 + li;
+        const OutT bad = (MODE == RV_MODE_DENSE_NAN) ? qnan<OutT>() : (OutT)0;
+        o[0] = ok ? xs[j] : bad;
+        o[a.plane_stride] = ok ? ys[j] : bad;
+        o[2 * a.plane_stride] = ok ? zo : bad;
+        if (a.bgr) {
+          const uint8_t *c = s_bgr + 3 * li;
+          o[3 * a.plane_stride] = ok ? unit_color<OutT>(c[2], a.color_255) : (OutT)0;
+          o[4 * a.plane_stride] = ok ? unit_color<OutT>(c[1], a.color_255) : (OutT)0;
+          o[5 * a.plane_stride] = ok ? unit_color<OutT>(c[0], a.color_255) : (OutT)0;
+        }
+        if (a.src_index) a.src_index[fout + px0 + li] = ok ? px0 + li : -1;
+      }
+    }
+    // this warp is done with the stage's shared memory: hand it back to the producer
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+}
+
+template <typename OutT, int DK>
+cudaError_t launch_tma(const rv_ctx *ctx, const DeprojArgs &a, int mode, cudaStream_t st) {
+  constexpr int kDepthB = DK == RV_DEPTH_U16 ? 2 : 4;
+  const size_t smem = (size_t)kStages * kTileT * (kDepthB + 3 + 1);
+#define RV_GO(M)                                                                                           \
+  {                                                                                                        \
+    auto k = k_deproject_tma<OutT, DK, M>;                                                                 \
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    if (e != cudaSuccess) return e;                                                                        \
+    const int grid = rv_persistent_grid(ctx, k, kThreadsT, smem, a.total_tiles);                           \
+    k<<<grid, kThreadsT, smem, st>>>(a);                                                                   \
+  }
+  switch (mode) {
+    case RV_MODE_COMPACT_ORDERED: RV_GO(RV_MODE_COMPACT_ORDERED) break;
+    case RV_MODE_COMPACT_PACKED: RV_GO(RV_MODE_COMPACT_PACKED) break;
+    case RV_MODE_DENSE_ZERO: RV_GO(RV_MODE_DENSE_ZERO) break;
+    default: RV_GO(RV_MODE_DENSE_NAN) break;
+  }
+#undef RV_GO
+  return cudaSuccess;
+}
+
+}  // namespace
+
+bool rv_deproject_fast_eligible(const DeprojArgs &a, int mode) {
+  if (mode == RV_MODE_COMPACT_UNORDERED) return false;
+  if (a.rays) return false;
+  if (a.W < 32 || (a.P % 16) != 0) return false;
+  if (!rv_aligned(a.depth, 16) || (a.bgr && !rv_aligned(a.bgr, 16)) || (a.mask && !rv_aligned(a.mask, 16))) return false;
+  if (a.tiles_per_frame != (a.P + kTileT - 1) / kTileT) return false;
+  return true;
+}
+
+cudaError_t rv_deproject_fast_launch(const rv_ctx *ctx, const DeprojArgs &a, int mode, int out_dtype, int depth_kind,
+                                     cudaStream_t st) {
+  if (out_dtype == RV_F32) {
+    if (depth_kind == RV_DEPTH_U16) return launch_tma<float, RV_DEPTH_U16>(ctx, a, mode, st);
+    return launch_tma<float, RV_DEPTH_F32_METERS>(ctx, a, mode, st);
+  }
+  if (depth_kind == RV_DEPTH_U16) return launch_tma<double, RV_DEPTH_U16>(ctx, a, mode, st);
+  return launch_tma<double, RV_DEPTH_F32_METERS>(ctx, a, mode, st);
+}

@@ -99,11 +99,13 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("shape", [(720, 1280), (480, 640), (37, 53), (1, 2049)])
+@pytest.mark.parametrize("shape,kernel", [((720, 1280), "tma"), ((720, 1280), "generic"), ((480, 640), "tma"),
+                                          ((480, 640), "generic"), ((36, 48), "tma"), ((37, 53), "auto"), ((1, 2049), "auto")])
 @pytest.mark.parametrize("case", range(len(CASES)))
 @pytest.mark.parametrize("dtype", ["f32", "f64"])
-def test_synthetic_frames_all_predicates(rv, O, rs720, shape, case, dtype):
-    """Every predicate combination of the fused kernel, ragged shapes included (tile tails, odd widths)."""
+def test_synthetic_frames_all_predicates(rv, O, rs720, shape, kernel, case, dtype):
+    """Every predicate combination through BOTH K1 kernels (TMA-fed pipeline and generic), ragged shapes included
+    (tile tails, odd widths; those only run the generic kernel)."""
     import torch
     H, W = shape
     kw = dict(CASES[case])
@@ -120,7 +122,7 @@ def test_synthetic_frames_all_predicates(rv, O, rs720, shape, case, dtype):
               color_scale=kw.get("color_scale", "unit"))
     batch = rv.deproject_batch(torch.from_numpy(depth).cuda(), torch.from_numpy(bgr).cuda(), cam,
                                None if mask is None else torch.from_numpy(mask).cuda(), dtype=dtype, want_valid=True,
-                               want_src_index=True, **gk)
+                               want_src_index=True, kernel=kernel, **gk)
     counts = batch.counts_host()
     for b in range(B):
         ref = O.deproject_mask(depth[b], bgr[b], None if mask is None else mask[b], fx=cam.fx, fy=cam.fy, cx=cam.cx,
@@ -140,14 +142,15 @@ def test_synthetic_frames_all_predicates(rv, O, rs720, shape, case, dtype):
         assert np.abs(got.astype(np.float64) - ref64["points"][sel]).max(initial=0.0) <= XYZ_TOL_M
 
 
-@pytest.mark.parametrize("mode", ["compact_unordered", "dense_zero", "dense_nan"])
-def test_other_output_modes(rv, O, rs720, mode):
+@pytest.mark.parametrize("mode,kernel", [("compact_unordered", "auto"), ("dense_zero", "tma"), ("dense_zero", "generic"),
+                                         ("dense_nan", "tma"), ("dense_nan", "generic")])
+def test_other_output_modes(rv, O, rs720, mode, kernel):
     import torch
     H, W, B = 480, 640, 4
     depth, bgr = synth_batch(B, H, W, seed0=21)
     cam = rv.Camera(608.2335815429688, 607.8508911132812, 312.52239990234375, 232.65150451660156, W, H)
     batch = rv.deproject_batch(torch.from_numpy(depth).cuda(), torch.from_numpy(bgr).cuda(), cam, max_distance=1.0,
-                               unit_rule="div_f32", mode=mode, want_src_index=True)
+                               unit_rule="div_f32", mode=mode, want_src_index=True, kernel=kernel)
     counts = batch.counts_host()
     for b in range(B):
         ref = O.deproject_mask(depth[b], bgr[b], None, fx=cam.fx, fy=cam.fy, cx=cam.cx, cy=cam.cy, r_max=1.0,
@@ -273,3 +276,34 @@ def test_edge_cases_and_errors(rv, rs720):
     ctx = _lib.context(0)
     st = ctx.lib.rv_deproject_mask(ctx.handle, None, None, None, None, 1, 6, 8, None, None, 0, 0, None, None, None, None, 0, None)
     assert st == _lib.RV_EINVAL and b"params" in ctx.lib.rv_last_error(ctx.handle)
+
+
+@pytest.mark.parametrize("kernel", ["tma", "generic"])
+def test_packed_mode_and_host_pipeline(rv, O, rs720, kernel):
+    """COMPACT_PACKED (frames back to back, B+1 offsets) and the host-buffer pipeline built on it: numpy in, host clouds out."""
+    import torch
+    from repas_vision_b200 import _ops
+    from repas_vision_b200.pipeline import HostPipeline
+    H, W, B = 480, 640, 7
+    depth, bgr = synth_batch(B, H, W, seed0=61)
+    cam = rv.Camera(608.2335815429688, 607.8508911132812, 312.52239990234375, 232.65150451660156, W, H)
+    refs = [O.deproject_mask(depth[b], bgr[b], None, fx=cam.fx, fy=cam.fy, cx=cam.cx, cy=cam.cy, r_max=1.3, out_dtype="f32")
+            for b in range(B)]
+    r = _ops.deproject(torch.from_numpy(depth).cuda(), torch.from_numpy(bgr).cuda(), None, cam, depth_kind="u16", r_max=1.3,
+                       mode="compact_packed", kernel=kernel)
+    off = r["counts"].cpu().numpy()
+    assert off[0] == 0 and np.array_equal(np.diff(off), [x["points"].shape[0] for x in refs])
+    data = r["data"].cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(data[:3, off[b]:off[b + 1]].T, refs[b]["points"])
+        assert np.array_equal(data[3:, off[b]:off[b + 1]].T, refs[b]["colors"])
+    if kernel == "tma":
+        pipe = HostPipeline(cam, H, W, max_distance=1.3, chunk_frames=3)
+        res = pipe.run(depth, bgr)
+        assert np.array_equal(res.counts, np.diff(off)) and res.h2d_bytes == B * H * W * 5
+        for b in range(B):
+            xyz, rgb = res.frame(b)
+            assert np.array_equal(xyz.T, refs[b]["points"]) and np.array_equal(rgb.T, refs[b]["colors"])
+        assert np.array_equal(res.points(2), refs[2]["points"].astype(np.float64))
+        res2 = pipe.run(torch.from_numpy(depth).pin_memory(), torch.from_numpy(bgr).pin_memory())  # pinned inputs, reuse
+        assert np.array_equal(res2.counts, res.counts) and np.array_equal(res2.frame(B - 1)[0], res.frame(B - 1)[0])
