@@ -501,10 +501,10 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
   if (d_ray_table && !rv_aligned(d_ray_table, 16)) RV_FAIL(ctx, RV_EALIGN, "rv_deproject_mask: ray table alignment");
   const size_t need = rv_deproject_workspace_bytes(B, H, W);
   const bool ordered = p->mode == RV_MODE_COMPACT_ORDERED || packed;
-  if (ordered) {
-    if (!d_ws || ws_bytes < need) RV_FAIL(ctx, RV_EWORKSPACE, "rv_deproject_mask: workspace %zu < %zu", ws_bytes, need);
-    if (!rv_aligned(d_ws, 8)) RV_FAIL(ctx, RV_EALIGN, "rv_deproject_mask: workspace alignment");
-  }
+  // every mode takes the workspace: the ordered modes keep their prefix chains in it and the TMA pipeline hands
+  // out tiles through its ticket counter
+  if (!d_ws || ws_bytes < need) RV_FAIL(ctx, RV_EWORKSPACE, "rv_deproject_mask: workspace %zu < %zu", ws_bytes, need);
+  if (!rv_aligned(d_ws, 8)) RV_FAIL(ctx, RV_EALIGN, "rv_deproject_mask: workspace alignment");
   cudaStream_t st = (cudaStream_t)stream;
 
   DeprojArgs a;
@@ -574,6 +574,7 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
   if (ordered) {
     RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, need, st));
   } else {
+    RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, 128, st));  // ticket counter
     RV_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (size_t)B * sizeof(int64_t), st));
   }
   if (use_fast) {

@@ -31,7 +31,7 @@ constexpr int kCT = kCW * 32;           // compute threads
 constexpr int kThreadsT = kCT + 32;     // + producer warp
 constexpr int kItersT = 8;
 constexpr int kTileT = kCT * kItersT;   // 2048 pixels
-constexpr int kStages = 3;
+constexpr int kStages = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -59,6 +59,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+// 256 threads polling a barrier burn issue slots the arithmetic wants: back off between polls
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  do {
+    __nanosleep(64);
+  } while (!mbar_try_wait(bar, parity));
 }
 // 1-D bulk copy global -> shared, completion reported to an mbarrier in bytes (TMA engine, no tensor map)
 __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -100,11 +107,16 @@ __device__ __forceinline__ double qnan<double>() {
   return __longlong_as_double(0x7ff8000000000000ll);
 }
 
-template <typename OutT, int DK, int MODE>
+// SPEC selects how much of the predicate set is compiled in:
+//   0  uint16/float depth with the MUL_F32 unit rule, colour, validity only
+//   1  the same plus the radius mask (the canopy / BASELINE configuration)
+//   2  everything, decided by the run-time flags of DeprojArgs
+template <typename OutT, int DK, int MODE, int SPEC>
 __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproject_tma(const DeprojArgs a) {
   constexpr bool kPacked = MODE == RV_MODE_COMPACT_PACKED;
   constexpr bool kOrdered = MODE == RV_MODE_COMPACT_ORDERED || kPacked;
   constexpr bool kF32 = sizeof(OutT) == 4;
+  constexpr bool kGen = SPEC == 2;
   constexpr int kDepthB = DK == RV_DEPTH_U16 ? 2 : 4;
   constexpr int kStageBytes = kTileT * (kDepthB + 3 + 1);
 
@@ -112,7 +124,7 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
   __shared__ int s_tile[kStages];
-  __shared__ uint32_t s_warp_tot[kCW];
+  __shared__ uint32_t s_warp_tot[2][kCW];
   __shared__ uint32_t s_base;
 
   const int lane = threadIdx.x & 31;
@@ -128,16 +140,21 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   }
   __syncthreads();
 
-  // ticket -> (frame, tile-in-frame).  Per-frame chains: frame-interleaved.  Packed chain: frame-major.
   const int tpf = a.tiles_per_frame;
+  const int nB = a.B;
+  const int P = a.P;
+  const bool has_bgr = kGen ? (a.bgr != nullptr) : true;
+  const bool has_mask = kGen ? (a.use_mask != 0) : false;
 
   // ============================================================ producer warp
   if (warp == kCW) {
     if (lane == 0) {
+      // tickets are requested one tile ahead so the atomic's round trip hides behind the wait for a free stage
+      int ticket = (int)atomicAdd(a.ticket, 1u);
       for (int it = 0;; ++it) {
         const int s = it % kStages;
+        const int next = ticket < a.total_tiles ? (int)atomicAdd(a.ticket, 1u) : ticket;
         mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
-        const int ticket = (int)atomicAdd(a.ticket, 1u);
         if (ticket >= a.total_tiles) {
           s_tile[s] = -1;
           mbar_arrive(&full_bar[s]);
@@ -148,34 +165,42 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
         if (kPacked) {
           b = ticket / tpf;
           t = ticket - b * tpf;
-        } else {
-          t = ticket / a.B;
-          b = ticket - t * a.B;
+        } else {  // frame-interleaved: consecutive tickets belong to different per-frame chains
+          t = ticket / nB;
+          b = ticket - t * nB;
         }
         const int px0 = t * kTileT;
-        const int npx = min(kTileT, a.P - px0);
-        const long long g = (long long)b * a.P + px0;
+        const int npx = min(kTileT, P - px0);
+        const long long g = (long long)b * P + px0;
         unsigned char *st = smem + (size_t)s * kStageBytes;
         uint32_t bytes = (uint32_t)npx * kDepthB;
-        if (a.bgr) bytes += (uint32_t)npx * 3;
-        if (a.use_mask) bytes += (uint32_t)npx;
+        if (has_bgr) bytes += (uint32_t)npx * 3;
+        if (has_mask) bytes += (uint32_t)npx;
         mbar_arrive_expect_tx(&full_bar[s], bytes);
         bulk_load(st, reinterpret_cast<const unsigned char *>(a.depth) + g * kDepthB, (uint32_t)npx * kDepthB, &full_bar[s]);
-        if (a.bgr) bulk_load(st + kTileT * kDepthB, a.bgr + g * 3, (uint32_t)npx * 3, &full_bar[s]);
-        if (a.use_mask) bulk_load(st + kTileT * (kDepthB + 3), a.mask + g, (uint32_t)npx, &full_bar[s]);
+        if (has_bgr) bulk_load(st + kTileT * kDepthB, a.bgr + g * 3, (uint32_t)npx * 3, &full_bar[s]);
+        if (has_mask) bulk_load(st + kTileT * (kDepthB + 3), a.mask + g, (uint32_t)npx, &full_bar[s]);
+        ticket = next;
       }
     }
     return;
   }
 
   // ============================================================ compute warps
-  const uint32_t lt = rv_lanemask_lt();
-  OutT *const out = reinterpret_cast<OutT *>(a.out);
+  const uint32_t lt = (1u << lane) - 1u;
   const float inf_f = __int_as_float(0x7f800000);
+  const int W = a.W;
+  const double cx = a.cx, cy = a.cy, fx = a.fx, fy = a.fy, rfx = a.rfx, rfy = a.rfy;
+  const float unit_f = a.unit_scale_f;
+  const long long ps = a.plane_stride;
+  const bool use_radius = kGen ? (a.use_radius != 0) : (SPEC == 1);
+  const bool fast_radius = kGen ? (a.fast_radius != 0) : true;
+  const bool color_255 = kGen ? (a.color_255 != 0) : false;
+  const int unit_rule = kGen ? a.unit_rule : RV_UNIT_MUL_F32;
 
   for (int it = 0;; ++it) {
     const int s = it % kStages;
-    mbar_wait(&full_bar[s], (it / kStages) & 1);
+    mbar_wait_backoff(&full_bar[s], (it / kStages) & 1);
     const int ticket = s_tile[s];
     if (ticket < 0) break;
     int b, t;
@@ -183,13 +208,13 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
       b = ticket / tpf;
       t = ticket - b * tpf;
     } else {
-      t = ticket / a.B;
-      b = ticket - t * a.B;
+      t = ticket / nB;
+      b = ticket - t * nB;
     }
     const int tile = b * tpf + t;  // index into status[]
     const int n_pred = kPacked ? tile : t;
     const int px0 = t * kTileT;
-    const int npx = min(kTileT, a.P - px0);
+    const int npx = min(kTileT, P - px0);
     const unsigned char *st = smem + (size_t)s * kStageBytes;
     const uint8_t *s_bgr = st + kTileT * kDepthB;
     const uint8_t *s_msk = st + kTileT * (kDepthB + 3);
@@ -200,8 +225,8 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
 
     const int li0 = warp * (32 * kItersT) + lane;  // index inside the tile
     const int p0 = px0 + li0;                      // pixel index inside the frame
-    int v = p0 / a.W;
-    int u = p0 - v * a.W;
+    int v = p0 / W;
+    int u = p0 - v * W;
 
     OutT xs[kItersT], ys[kItersT];
     float zf[kItersT];
@@ -218,46 +243,49 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
       if (DK == RV_DEPTH_U16) {
         const uint32_t d = inb ? (uint32_t) reinterpret_cast<const uint16_t *>(st)[li] : 0u;
         const float df = (float)d;
-        if (a.unit_rule == RV_UNIT_MUL_F32) {
-          z32 = df * a.unit_scale_f;
+        if (unit_rule == RV_UNIT_MUL_F32) {
+          z32 = df * unit_f;
           z64 = (double)z32;
-        } else if (a.unit_rule == RV_UNIT_DIV_F32) {
-          z32 = rv_divf(df, a.unit_scale_f, a.unit_rcp_f);
+        } else if (unit_rule == RV_UNIT_DIV_F32) {
+          z32 = rv_divf(df, unit_f, a.unit_rcp_f);
           z64 = (double)z32;
         } else {
           z64 = rv_div((double)d, a.unit_scale, a.unit_rcp);
           z32 = (float)z64;
         }
-        ok = d != 0;
+        ok = d != 0;  // li >= npx reads as 0
       } else {
         z32 = inb ? reinterpret_cast<const float *>(st)[li] : 0.0f;
         z64 = (double)z32;
         ok = (z32 > 0.0f) && (z32 < inf_f);
       }
-      ok = ok && inb;
-      if (a.use_mask) {
-        const uint32_t m = inb ? (uint32_t)s_msk[li] : 0u;
-        ok = ok && (a.invert_mask ? (m == 0) : (m != 0));
+      if (kGen) {
+        if (has_mask) {
+          const uint32_t m = inb ? (uint32_t)s_msk[li] : 0u;
+          ok = ok && (a.invert_mask ? (m == 0) : (m != 0));
+        }
+        if (a.use_trunc) ok = ok && !(z32 >= a.trunc_f);
       }
-      if (a.use_trunc) ok = ok && !(z32 >= a.trunc_f);
 
-      const double x64 = rv_div(((double)u - a.cx) * z64, a.fx, a.rfx);
-      const double y64 = rv_div(((double)v - a.cy) * z64, a.fy, a.rfy);
+      const double x64 = rv_div(((double)u - cx) * z64, fx, rfx);
+      const double y64 = rv_div(((double)v - cy) * z64, fy, rfy);
       const OutT xo = (OutT)x64, yo = (OutT)y64;
       if (kF32) {
         // float32 storage: compare the stored floats against thresholds rounded toward the kept side;
         // identical to the float64 predicate on their exact up-casts
         const float xf = (float)xo, yf = (float)yo;
-        if (a.use_zclip) ok = ok && (z32 >= a.zmin_f) && (z32 <= a.zmax_f);
-        if (a.use_aabb)
-          ok = ok && (xf >= a.amin_f[0]) && (xf <= a.amax_f[0]) && (yf >= a.amin_f[1]) && (yf <= a.amax_f[1]) &&
-               (z32 >= a.amin_f[2]) && (z32 <= a.amax_f[2]);
-        if (a.use_radius) {
+        if (kGen) {
+          if (a.use_zclip) ok = ok && (z32 >= a.zmin_f) && (z32 <= a.zmax_f);
+          if (a.use_aabb)
+            ok = ok && (xf >= a.amin_f[0]) && (xf <= a.amax_f[0]) && (yf >= a.amin_f[1]) && (yf <= a.amax_f[1]) &&
+                 (z32 >= a.amin_f[2]) && (z32 <= a.amax_f[2]);
+        }
+        if (use_radius) {
           bool in;
-          if (a.fast_radius) {
+          if (fast_radius) {
             const float sf = fmaf(z32, z32, fmaf(yf, yf, xf * xf));
             in = sf <= a.r2_lo_f;
-            if (!in && sf < a.r2_hi_f) {  // inside the 2^-20 band: the float64 sum decides
+            if (sf > a.r2_lo_f && sf < a.r2_hi_f) {  // inside the 2^-20 band: the float64 sum decides
               const double X = (double)xf, Y = (double)yf, Z = (double)z32;
               in = ((X * X + Y * Y) + Z * Z) < a.r2_thresh;
             }
@@ -269,11 +297,13 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
         }
       } else {
         const double X = (double)xo, Y = (double)yo, Z = z64;
-        if (a.use_zclip) ok = ok && (Z >= a.z_min) && (Z <= a.z_max);
-        if (a.use_radius) ok = ok && (((X * X + Y * Y) + Z * Z) < a.r2_thresh);
-        if (a.use_aabb)
-          ok = ok && (X >= a.amin[0]) && (X <= a.amax[0]) && (Y >= a.amin[1]) && (Y <= a.amax[1]) && (Z >= a.amin[2]) &&
-               (Z <= a.amax[2]);
+        if (kGen) {
+          if (a.use_zclip) ok = ok && (Z >= a.z_min) && (Z <= a.z_max);
+          if (a.use_aabb)
+            ok = ok && (X >= a.amin[0]) && (X <= a.amax[0]) && (Y >= a.amin[1]) && (Y <= a.amax[1]) && (Z >= a.amin[2]) &&
+                 (Z <= a.amax[2]);
+        }
+        if (use_radius) ok = ok && (((X * X + Y * Y) + Z * Z) < a.r2_thresh);
       }
       xs[j] = xo;
       ys[j] = yo;
@@ -281,21 +311,22 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
       zd[j] = z64;
       ballots[j] = __ballot_sync(0xffffffffu, ok);
       warp_total += __popc(ballots[j]);
-      if (a.valid && inb) a.valid[(long long)b * a.P + px0 + li] = ok ? 1 : 0;
+      if (kGen && a.valid && inb) a.valid[(long long)b * P + px0 + li] = ok ? 1 : 0;
       u += 32;
-      if (u >= a.W) {
-        u -= a.W;
+      if (u >= W) {
+        u -= W;
         ++v;
       }
     }
 
     // ---------------- tile totals, tile base
-    if (lane == 0) s_warp_tot[warp] = warp_total;
+    uint32_t *const wt = s_warp_tot[it & 1];  // double-buffered: a warp may run one barrier ahead of the readers
+    if (lane == 0) wt[warp] = warp_total;
     compute_bar();
     uint32_t warp_excl = 0, tile_total = 0;
 #pragma unroll
     for (int w = 0; w < kCW; ++w) {
-      const uint32_t c = s_warp_tot[w];
+      const uint32_t c = wt[w];
       warp_excl += (w < warp) ? c : 0u;
       tile_total += c;
     }
@@ -316,7 +347,7 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
           s_base = excl;
           if (kPacked) {
             if (t == 0) a.counts[b] = excl;
-            if (tile == a.total_tiles - 1) a.counts[a.B] = (unsigned long long)excl + tile_total;
+            if (tile == a.total_tiles - 1) a.counts[nB] = (unsigned long long)excl + tile_total;
           } else if (t == tpf - 1) {
             a.counts[b] = (unsigned long long)excl + tile_total;
           }
@@ -330,44 +361,46 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
 
     // ---------------- stores (colours are converted here, for kept pixels only)
     const long long fout = kPacked ? 0ll : (long long)b * a.frame_stride;
-    const unsigned long long cap = kPacked ? (unsigned long long)a.plane_stride : (unsigned long long)a.frame_stride;
-    OutT *const o0 = out + fout;
+    const unsigned long long cap64 = kPacked ? (unsigned long long)ps : (unsigned long long)a.frame_stride;
+    const uint32_t cap = cap64 > 0xffffffffull ? 0xffffffffu : (uint32_t)cap64;
+    OutT *const o0 = reinterpret_cast<OutT *>(a.out) + fout;
     uint32_t run = base + warp_excl;
 #pragma unroll
     for (int j = 0; j < kItersT; ++j) {
       const int li = li0 + j * 32;
-      const bool ok = (ballots[j] >> lane) & 1u;
+      const uint32_t bal = ballots[j];
+      const bool ok = (bal >> lane) & 1u;
       const OutT zo = kF32 ? (OutT)zf[j] : (OutT)zd[j];
       if (kOrdered) {
-        if (ballots[j] == 0) continue;
-        const uint32_t pos = run + __popc(ballots[j] & lt);
-        run += __popc(ballots[j]);
+        if (bal == 0) continue;
+        const uint32_t pos = run + __popc(bal & lt);
+        run += __popc(bal);
         if (ok && pos < cap) {
           OutT *o = o0 + pos;
           o[0] = xs[j];
-          o[a.plane_stride] = ys[j];
-          o[2 * a.plane_stride] = zo;
-          if (a.bgr) {
+          o[ps] = ys[j];
+          o[2 * ps] = zo;
+          if (has_bgr) {
             const uint8_t *c = s_bgr + 3 * li;
-            o[3 * a.plane_stride] = unit_color<OutT>(c[2], a.color_255);
-            o[4 * a.plane_stride] = unit_color<OutT>(c[1], a.color_255);
-            o[5 * a.plane_stride] = unit_color<OutT>(c[0], a.color_255);
+            o[3 * ps] = unit_color<OutT>(c[2], color_255);
+            o[4 * ps] = unit_color<OutT>(c[1], color_255);
+            o[5 * ps] = unit_color<OutT>(c[0], color_255);
           }
-          if (a.src_index) a.src_index[fout + pos] = px0 + li;
+          if (kGen && a.src_index) a.src_index[fout + pos] = px0 + li;
         }
       } else if (li < npx && (long long)(px0 + li) < a.frame_stride) {
         OutT *o = o0 + px0 + li;
         const OutT bad = (MODE == RV_MODE_DENSE_NAN) ? qnan<OutT>() : (OutT)0;
         o[0] = ok ? xs[j] : bad;
-        o[a.plane_stride] = ok ? ys[j] : bad;
-        o[2 * a.plane_stride] = ok ? zo : bad;
-        if (a.bgr) {
+        o[ps] = ok ? ys[j] : bad;
+        o[2 * ps] = ok ? zo : bad;
+        if (has_bgr) {
           const uint8_t *c = s_bgr + 3 * li;
-          o[3 * a.plane_stride] = ok ? unit_color<OutT>(c[2], a.color_255) : (OutT)0;
-          o[4 * a.plane_stride] = ok ? unit_color<OutT>(c[1], a.color_255) : (OutT)0;
-          o[5 * a.plane_stride] = ok ? unit_color<OutT>(c[0], a.color_255) : (OutT)0;
+          o[3 * ps] = ok ? unit_color<OutT>(c[2], color_255) : (OutT)0;
+          o[4 * ps] = ok ? unit_color<OutT>(c[1], color_255) : (OutT)0;
+          o[5 * ps] = ok ? unit_color<OutT>(c[0], color_255) : (OutT)0;
         }
-        if (a.src_index) a.src_index[fout + px0 + li] = ok ? px0 + li : -1;
+        if (kGen && a.src_index) a.src_index[fout + px0 + li] = ok ? px0 + li : -1;
       }
     }
     // this warp is done with the stage's shared memory: hand it back to the producer
@@ -376,26 +409,41 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   }
 }
 
-template <typename OutT, int DK>
-cudaError_t launch_tma(const rv_ctx *ctx, const DeprojArgs &a, int mode, cudaStream_t st) {
+// SPEC 0/1 cover the plain configurations; anything else falls to the run-time-flag variant
+int pick_spec(const DeprojArgs &a, int depth_kind) {
+  const bool plain = a.bgr && !a.use_mask && !a.use_trunc && !a.use_zclip && !a.use_aabb && !a.valid && !a.src_index &&
+                     !a.color_255 && (depth_kind != RV_DEPTH_U16 || a.unit_rule == RV_UNIT_MUL_F32);
+  if (!plain) return 2;
+  if (!a.use_radius) return 0;
+  return a.fast_radius ? 1 : 2;
+}
+
+template <typename OutT, int DK, int MODE>
+cudaError_t launch_spec(const rv_ctx *ctx, const DeprojArgs &a, int spec, cudaStream_t st) {
   constexpr int kDepthB = DK == RV_DEPTH_U16 ? 2 : 4;
   const size_t smem = (size_t)kStages * kTileT * (kDepthB + 3 + 1);
-#define RV_GO(M)                                                                                           \
+#define RV_GO(S)                                                                                           \
   {                                                                                                        \
-    auto k = k_deproject_tma<OutT, DK, M>;                                                                 \
+    auto k = k_deproject_tma<OutT, DK, MODE, S>;                                                           \
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     if (e != cudaSuccess) return e;                                                                        \
     const int grid = rv_persistent_grid(ctx, k, kThreadsT, smem, a.total_tiles);                           \
     k<<<grid, kThreadsT, smem, st>>>(a);                                                                   \
   }
-  switch (mode) {
-    case RV_MODE_COMPACT_ORDERED: RV_GO(RV_MODE_COMPACT_ORDERED) break;
-    case RV_MODE_COMPACT_PACKED: RV_GO(RV_MODE_COMPACT_PACKED) break;
-    case RV_MODE_DENSE_ZERO: RV_GO(RV_MODE_DENSE_ZERO) break;
-    default: RV_GO(RV_MODE_DENSE_NAN) break;
-  }
+  if (spec == 0) RV_GO(0) else if (spec == 1) RV_GO(1) else RV_GO(2)
 #undef RV_GO
   return cudaSuccess;
+}
+
+template <typename OutT, int DK>
+cudaError_t launch_tma(const rv_ctx *ctx, const DeprojArgs &a, int mode, cudaStream_t st) {
+  const int spec = pick_spec(a, DK);
+  switch (mode) {
+    case RV_MODE_COMPACT_ORDERED: return launch_spec<OutT, DK, RV_MODE_COMPACT_ORDERED>(ctx, a, spec, st);
+    case RV_MODE_COMPACT_PACKED: return launch_spec<OutT, DK, RV_MODE_COMPACT_PACKED>(ctx, a, spec, st);
+    case RV_MODE_DENSE_ZERO: return launch_spec<OutT, DK, RV_MODE_DENSE_ZERO>(ctx, a, spec, st);
+    default: return launch_spec<OutT, DK, RV_MODE_DENSE_NAN>(ctx, a, spec, st);
+  }
 }
 
 }  // namespace
