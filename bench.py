@@ -382,7 +382,8 @@ def run_b200(a):
     full = [(e0.elapsed_time(e1), n) for e0, e1, n in events if n == chunk]
     k_ms = statistics.mean(t for t, _ in full)
     valid_frac = valid_per_step / (frames * P)
-    alg_bytes = chunk * (P * 5 + valid_frac * P * 24)
+    written_frac = 1.0 if a.mode.startswith("dense") else valid_frac  # dense modes write every pixel
+    alg_bytes = chunk * (P * 5 + written_frac * P * 24)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy, burst)"

@@ -64,7 +64,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   do {
-    __nanosleep(64);
+    __nanosleep(100);
   } while (!mbar_try_wait(bar, parity));
 }
 // 1-D bulk copy global -> shared, completion reported to an mbarrier in bytes (TMA engine, no tensor map)
@@ -74,6 +74,17 @@ __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint3
                : "memory");
 }
 __device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }
+
+// n / d for 0 <= n < 2^24 (exact int -> float) with a precomputed float reciprocal and one fix-up; callers fall
+// back to the integer divide above that range
+__device__ __forceinline__ int fast_div(int n, int d, float rcp, bool small) {
+  if (!small) return n / d;
+  int q = __float2int_rz(__int2float_rn(n) * rcp);
+  const int r = n - q * d;
+  if (r < 0) --q;
+  if (r >= d) ++q;
+  return q;
+}
 
 template <typename T>
 __device__ __forceinline__ T unit_color(uint32_t k, int color_255);
@@ -145,6 +156,8 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   const int P = a.P;
   const bool has_bgr = kGen ? (a.bgr != nullptr) : true;
   const bool has_mask = kGen ? (a.use_mask != 0) : false;
+  const bool small_idx = a.total_tiles < (1 << 24) && P < (1 << 24);
+  const float rcpB = 1.0f / (float)nB;
 
   // ============================================================ producer warp
   if (warp == kCW) {
@@ -154,7 +167,7 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
       for (int it = 0;; ++it) {
         const int s = it % kStages;
         const int next = ticket < a.total_tiles ? (int)atomicAdd(a.ticket, 1u) : ticket;
-        mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
+        mbar_wait_backoff(&empty_bar[s], ((it / kStages) & 1) ^ 1);
         if (ticket >= a.total_tiles) {
           s_tile[s] = -1;
           mbar_arrive(&full_bar[s]);
@@ -166,7 +179,7 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
           b = ticket / tpf;
           t = ticket - b * tpf;
         } else {  // frame-interleaved: consecutive tickets belong to different per-frame chains
-          t = ticket / nB;
+          t = fast_div(ticket, nB, rcpB, small_idx);
           b = ticket - t * nB;
         }
         const int px0 = t * kTileT;
@@ -190,6 +203,8 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   const uint32_t lt = (1u << lane) - 1u;
   const float inf_f = __int_as_float(0x7f800000);
   const int W = a.W;
+  const float rcpW = 1.0f / (float)W;
+  const double Wd = (double)W;
   const double cx = a.cx, cy = a.cy, fx = a.fx, fy = a.fy, rfx = a.rfx, rfy = a.rfy;
   const float unit_f = a.unit_scale_f;
   const long long ps = a.plane_stride;
@@ -208,7 +223,7 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
       b = ticket / tpf;
       t = ticket - b * tpf;
     } else {
-      t = ticket / nB;
+      t = fast_div(ticket, nB, rcpB, small_idx);
       b = ticket - t * nB;
     }
     const int tile = b * tpf + t;  // index into status[]
@@ -225,8 +240,10 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
 
     const int li0 = warp * (32 * kItersT) + lane;  // index inside the tile
     const int p0 = px0 + li0;                      // pixel index inside the frame
-    int v = p0 / W;
+    int v = fast_div(p0, W, rcpW, small_idx);
     int u = p0 - v * W;
+    // pixel coordinates as doubles, advanced with exact integer-valued additions (no int -> double conversions)
+    double ud = (double)u, vd = (double)v;
 
     OutT xs[kItersT], ys[kItersT];
     float zf[kItersT];
@@ -238,25 +255,23 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
       const int li = li0 + j * 32;
       const bool inb = li < npx;
       float z32;
-      double z64;
+      double z64 = 0.0;
       bool ok;
+      uint32_t draw = 0;
       if (DK == RV_DEPTH_U16) {
-        const uint32_t d = inb ? (uint32_t) reinterpret_cast<const uint16_t *>(st)[li] : 0u;
-        const float df = (float)d;
+        draw = inb ? (uint32_t) reinterpret_cast<const uint16_t *>(st)[li] : 0u;  // li >= npx reads as 0
+        const float df = (float)draw;
         if (unit_rule == RV_UNIT_MUL_F32) {
           z32 = df * unit_f;
-          z64 = (double)z32;
         } else if (unit_rule == RV_UNIT_DIV_F32) {
           z32 = rv_divf(df, unit_f, a.unit_rcp_f);
-          z64 = (double)z32;
         } else {
-          z64 = rv_div((double)d, a.unit_scale, a.unit_rcp);
+          z64 = rv_div((double)draw, a.unit_scale, a.unit_rcp);
           z32 = (float)z64;
         }
-        ok = d != 0;  // li >= npx reads as 0
+        ok = draw != 0;
       } else {
         z32 = inb ? reinterpret_cast<const float *>(st)[li] : 0.0f;
-        z64 = (double)z32;
         ok = (z32 > 0.0f) && (z32 < inf_f);
       }
       if (kGen) {
@@ -266,44 +281,52 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
         }
         if (a.use_trunc) ok = ok && !(z32 >= a.trunc_f);
       }
+      // cheap rejection before any float64 work: x^2 + y^2 + z^2 >= z^2, so a depth beyond the sphere is outside
+      // whatever x and y are (same float32 decision the full test below would reach, by monotone rounding)
+      if (kF32 && use_radius && fast_radius) ok = ok && (z32 * z32 < a.r2_hi_f);
 
-      const double x64 = rv_div(((double)u - cx) * z64, fx, rfx);
-      const double y64 = rv_div(((double)v - cy) * z64, fy, rfy);
-      const OutT xo = (OutT)x64, yo = (OutT)y64;
-      if (kF32) {
-        // float32 storage: compare the stored floats against thresholds rounded toward the kept side;
-        // identical to the float64 predicate on their exact up-casts
-        const float xf = (float)xo, yf = (float)yo;
-        if (kGen) {
-          if (a.use_zclip) ok = ok && (z32 >= a.zmin_f) && (z32 <= a.zmax_f);
-          if (a.use_aabb)
-            ok = ok && (xf >= a.amin_f[0]) && (xf <= a.amax_f[0]) && (yf >= a.amin_f[1]) && (yf <= a.amax_f[1]) &&
-                 (z32 >= a.amin_f[2]) && (z32 <= a.amax_f[2]);
-        }
-        if (use_radius) {
-          bool in;
-          if (fast_radius) {
-            const float sf = fmaf(z32, z32, fmaf(yf, yf, xf * xf));
-            in = sf <= a.r2_lo_f;
-            if (sf > a.r2_lo_f && sf < a.r2_hi_f) {  // inside the 2^-20 band: the float64 sum decides
+      OutT xo = (OutT)0, yo = (OutT)0;
+      if (__any_sync(0xffffffffu, ok)) {  // warp-uniform: 32 consecutive holes / far pixels cost no geometry
+        if (!(DK == RV_DEPTH_U16 && unit_rule == RV_UNIT_DIV_F64)) z64 = (double)z32;
+        const double x64 = rv_div((ud - cx) * z64, fx, rfx);
+        const double y64 = rv_div((vd - cy) * z64, fy, rfy);
+        xo = (OutT)x64;
+        yo = (OutT)y64;
+        if (kF32) {
+          // float32 storage: compare the stored floats against thresholds rounded toward the kept side;
+          // identical to the float64 predicate on their exact up-casts
+          const float xf = (float)xo, yf = (float)yo;
+          if (kGen) {
+            if (a.use_zclip) ok = ok && (z32 >= a.zmin_f) && (z32 <= a.zmax_f);
+            if (a.use_aabb)
+              ok = ok && (xf >= a.amin_f[0]) && (xf <= a.amax_f[0]) && (yf >= a.amin_f[1]) && (yf <= a.amax_f[1]) &&
+                   (z32 >= a.amin_f[2]) && (z32 <= a.amax_f[2]);
+          }
+          if (use_radius) {
+            bool in;
+            if (fast_radius) {
+              const float sf = fmaf(z32, z32, fmaf(yf, yf, xf * xf));
+              in = sf <= a.r2_lo_f;
+              if (sf > a.r2_lo_f && sf < a.r2_hi_f) {  // inside the 2^-20 band: the float64 sum decides
+                const double X = (double)xf, Y = (double)yf, Z = (double)z32;
+                in = ((X * X + Y * Y) + Z * Z) < a.r2_thresh;
+              }
+            } else {
               const double X = (double)xf, Y = (double)yf, Z = (double)z32;
               in = ((X * X + Y * Y) + Z * Z) < a.r2_thresh;
             }
-          } else {
-            const double X = (double)xf, Y = (double)yf, Z = (double)z32;
-            in = ((X * X + Y * Y) + Z * Z) < a.r2_thresh;
+            ok = ok && in;
           }
-          ok = ok && in;
+        } else {
+          const double X = (double)xo, Y = (double)yo, Z = z64;
+          if (kGen) {
+            if (a.use_zclip) ok = ok && (Z >= a.z_min) && (Z <= a.z_max);
+            if (a.use_aabb)
+              ok = ok && (X >= a.amin[0]) && (X <= a.amax[0]) && (Y >= a.amin[1]) && (Y <= a.amax[1]) && (Z >= a.amin[2]) &&
+                   (Z <= a.amax[2]);
+          }
+          if (use_radius) ok = ok && (((X * X + Y * Y) + Z * Z) < a.r2_thresh);
         }
-      } else {
-        const double X = (double)xo, Y = (double)yo, Z = z64;
-        if (kGen) {
-          if (a.use_zclip) ok = ok && (Z >= a.z_min) && (Z <= a.z_max);
-          if (a.use_aabb)
-            ok = ok && (X >= a.amin[0]) && (X <= a.amax[0]) && (Y >= a.amin[1]) && (Y <= a.amax[1]) && (Z >= a.amin[2]) &&
-                 (Z <= a.amax[2]);
-        }
-        if (use_radius) ok = ok && (((X * X + Y * Y) + Z * Z) < a.r2_thresh);
       }
       xs[j] = xo;
       ys[j] = yo;
@@ -313,9 +336,11 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
       warp_total += __popc(ballots[j]);
       if (kGen && a.valid && inb) a.valid[(long long)b * P + px0 + li] = ok ? 1 : 0;
       u += 32;
+      ud += 32.0;
       if (u >= W) {
         u -= W;
-        ++v;
+        ud -= Wd;
+        vd += 1.0;
       }
     }
 
