@@ -7,10 +7,15 @@
 //
 //  * one producer warp per CTA takes tile tickets and issues 1-D bulk async copies (cp.async.bulk ->
 //    UBLKCP, the TMA engine) of the tile's depth / BGR / mask bytes into a kStages-deep shared-memory
-//    ring guarded by full/empty mbarriers, so ~3 tiles of loads per CTA are always in flight and no
+//    ring guarded by full/empty mbarriers, so several tiles of loads per CTA are always in flight and no
 //    compute warp ever waits on a global load;
 //  * eight compute warps read the tile from shared memory (lane + 32 j ownership, so every ballot is a
-//    contiguous run of pixels and every compacted store instruction writes one contiguous run);
+//    contiguous run of pixels).  A group of 32 consecutive pixels with no candidate (holes, or depths
+//    already beyond the distance mask) costs ~10 instructions and no float64 work;
+//  * kept points are compacted into a per-warp shared-memory staging area (x, y, z and the packed BGR
+//    bytes), which frees the registers during the arithmetic and lets the input stage return to the
+//    producer before the prefix is known; once the tile's base offset is known each warp drains its
+//    run with fully coalesced stores (colours are converted to k/255 there, at 100 % lane use);
 //  * tiles are handed out frame-interleaved (ticket -> tile t of frame ticket % B), so the B per-frame
 //    prefix chains advance in parallel and a tile's predecessor finished a whole round earlier: its
 //    inclusive prefix is fetched by ONE load issued before the tile's arithmetic ("early peek"); the
@@ -30,8 +35,9 @@ constexpr int kCW = 8;                  // compute warps
 constexpr int kCT = kCW * 32;           // compute threads
 constexpr int kThreadsT = kCT + 32;     // + producer warp
 constexpr int kItersT = 8;
+constexpr int kWarpPx = 32 * kItersT;   // 256 pixels per warp per tile
 constexpr int kTileT = kCT * kItersT;   // 2048 pixels
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -56,16 +62,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
+// Waiting threads suspend in hardware for up to `hint_ns` and are woken by the completing arrive, instead of
+// burning issue slots on a poll loop (a plain try_wait returned within a few ns here, and 1 + 8 warps per CTA
+// polling cost ~20 % of all issued instructions).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
 }
-// 256 threads polling a barrier burn issue slots the arithmetic wants: back off between polls
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  do {
-    __nanosleep(100);
-  } while (!mbar_try_wait(bar, parity));
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+  }
 }
 // 1-D bulk copy global -> shared, completion reported to an mbarrier in bytes (TMA engine, no tensor map)
 __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -86,12 +102,12 @@ __device__ __forceinline__ int fast_div(int n, int d, float rcp, bool small) {
   return q;
 }
 
-template <typename T>
-__device__ __forceinline__ T unit_color(uint32_t k, int color_255);
 // k / 255 with ONE residual correction: exhaustively exact for k = 0..255 in both precisions
 // (tests/test_gpu_cloud.py::test_exact_division_helper_against_numpy walks all 256 bytes).
+template <typename T>
+__device__ __forceinline__ T unit_color(uint32_t k, bool color_255);
 template <>
-__device__ __forceinline__ float unit_color<float>(uint32_t k, int color_255) {
+__device__ __forceinline__ float unit_color<float>(uint32_t k, bool color_255) {
   const float kf = (float)k;
   if (color_255) return kf;
   const float c = 0.003921568859368563f;
@@ -99,7 +115,7 @@ __device__ __forceinline__ float unit_color<float>(uint32_t k, int color_255) {
   return fmaf(fmaf(-q, 255.0f, kf), c, q);
 }
 template <>
-__device__ __forceinline__ double unit_color<double>(uint32_t k, int color_255) {
+__device__ __forceinline__ double unit_color<double>(uint32_t k, bool color_255) {
   const double kd = (double)k;
   if (color_255) return kd;
   const double c = 0.00392156862745098;
@@ -118,6 +134,16 @@ __device__ __forceinline__ double qnan<double>() {
   return __longlong_as_double(0x7ff8000000000000ll);
 }
 
+template <typename OutT, int DK>
+struct Layout {
+  static constexpr int kDepthB = DK == RV_DEPTH_U16 ? 2 : 4;
+  static constexpr int kStageBytes = kTileT * (kDepthB + 3 + 1);
+  // per-warp staging: x, y, z (OutT), packed colour (u32), source index inside the tile (u16)
+  static constexpr int kWarpStage = kWarpPx * (3 * (int)sizeof(OutT) + 4 + 2);
+  static constexpr int kRingBytes = kStages * kStageBytes;
+  static constexpr int kSmem = kRingBytes + kCW * kWarpStage;
+};
+
 // SPEC selects how much of the predicate set is compiled in:
 //   0  uint16/float depth with the MUL_F32 unit rule, colour, validity only
 //   1  the same plus the radius mask (the canopy / BASELINE configuration)
@@ -128,13 +154,13 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   constexpr bool kOrdered = MODE == RV_MODE_COMPACT_ORDERED || kPacked;
   constexpr bool kF32 = sizeof(OutT) == 4;
   constexpr bool kGen = SPEC == 2;
-  constexpr int kDepthB = DK == RV_DEPTH_U16 ? 2 : 4;
-  constexpr int kStageBytes = kTileT * (kDepthB + 3 + 1);
+  using L = Layout<OutT, DK>;
+  constexpr int kDepthB = L::kDepthB;
 
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
-  __shared__ int s_tile[kStages];
+  __shared__ int4 s_info[kStages];  // {status index or -1, frame, tile in frame, pixels in tile}
   __shared__ uint32_t s_warp_tot[2][kCW];
   __shared__ uint32_t s_base;
 
@@ -157,26 +183,26 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   const bool has_bgr = kGen ? (a.bgr != nullptr) : true;
   const bool has_mask = kGen ? (a.use_mask != 0) : false;
   const bool small_idx = a.total_tiles < (1 << 24) && P < (1 << 24);
-  const float rcpB = 1.0f / (float)nB;
 
   // ============================================================ producer warp
   if (warp == kCW) {
     if (lane == 0) {
+      const float rcpB = 1.0f / (float)nB;
+      const float rcpT = 1.0f / (float)tpf;
       // tickets are requested one tile ahead so the atomic's round trip hides behind the wait for a free stage
       int ticket = (int)atomicAdd(a.ticket, 1u);
       for (int it = 0;; ++it) {
         const int s = it % kStages;
         const int next = ticket < a.total_tiles ? (int)atomicAdd(a.ticket, 1u) : ticket;
-        mbar_wait_backoff(&empty_bar[s], ((it / kStages) & 1) ^ 1);
+        mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
         if (ticket >= a.total_tiles) {
-          s_tile[s] = -1;
+          s_info[s] = make_int4(-1, 0, 0, 0);
           mbar_arrive(&full_bar[s]);
           break;
         }
-        s_tile[s] = ticket;
         int b, t;
-        if (kPacked) {
-          b = ticket / tpf;
+        if (kPacked) {  // one chain through the whole batch: frame-major
+          b = fast_div(ticket, tpf, rcpT, small_idx);
           t = ticket - b * tpf;
         } else {  // frame-interleaved: consecutive tickets belong to different per-frame chains
           t = fast_div(ticket, nB, rcpB, small_idx);
@@ -184,8 +210,9 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
         }
         const int px0 = t * kTileT;
         const int npx = min(kTileT, P - px0);
+        s_info[s] = make_int4(b * tpf + t, b, t, npx);
         const long long g = (long long)b * P + px0;
-        unsigned char *st = smem + (size_t)s * kStageBytes;
+        unsigned char *st = smem + (size_t)s * L::kStageBytes;
         uint32_t bytes = (uint32_t)npx * kDepthB;
         if (has_bgr) bytes += (uint32_t)npx * 3;
         if (has_mask) bytes += (uint32_t)npx;
@@ -203,8 +230,8 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   const uint32_t lt = (1u << lane) - 1u;
   const float inf_f = __int_as_float(0x7f800000);
   const int W = a.W;
+  const bool wide = W >= kWarpPx;  // at most one row wrap inside a warp's 256 pixels
   const float rcpW = 1.0f / (float)W;
-  const double Wd = (double)W;
   const double cx = a.cx, cy = a.cy, fx = a.fx, fy = a.fy, rfx = a.rfx, rfy = a.rfy;
   const float unit_f = a.unit_scale_f;
   const long long ps = a.plane_stride;
@@ -213,24 +240,24 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   const bool color_255 = kGen ? (a.color_255 != 0) : false;
   const int unit_rule = kGen ? a.unit_rule : RV_UNIT_MUL_F32;
 
+  // this warp's staging area
+  unsigned char *const wst = smem + L::kRingBytes + (size_t)warp * L::kWarpStage;
+  OutT *const sx = reinterpret_cast<OutT *>(wst);
+  OutT *const sy = sx + kWarpPx;
+  OutT *const sz = sy + kWarpPx;
+  uint32_t *const sc = reinterpret_cast<uint32_t *>(sz + kWarpPx);
+  uint16_t *const si = reinterpret_cast<uint16_t *>(sc + kWarpPx);
+
   for (int it = 0;; ++it) {
     const int s = it % kStages;
-    mbar_wait_backoff(&full_bar[s], (it / kStages) & 1);
-    const int ticket = s_tile[s];
-    if (ticket < 0) break;
-    int b, t;
-    if (kPacked) {
-      b = ticket / tpf;
-      t = ticket - b * tpf;
-    } else {
-      t = fast_div(ticket, nB, rcpB, small_idx);
-      b = ticket - t * nB;
-    }
-    const int tile = b * tpf + t;  // index into status[]
+    mbar_wait(&full_bar[s], (it / kStages) & 1);
+    const int4 info = s_info[s];
+    const int tile = info.x;  // index into status[]
+    if (tile < 0) break;
+    const int b = info.y, t = info.z, npx = info.w;
     const int n_pred = kPacked ? tile : t;
     const int px0 = t * kTileT;
-    const int npx = min(kTileT, P - px0);
-    const unsigned char *st = smem + (size_t)s * kStageBytes;
+    const unsigned char *st = smem + (size_t)s * L::kStageBytes;
     const uint8_t *s_bgr = st + kTileT * kDepthB;
     const uint8_t *s_msk = st + kTileT * (kDepthB + 3);
 
@@ -238,28 +265,22 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
     unsigned long long peek = 0;
     if (kOrdered && warp == 0 && lane == 0 && n_pred > 0) peek = rv_ld_relaxed(a.status + tile - 1);
 
-    const int li0 = warp * (32 * kItersT) + lane;  // index inside the tile
-    const int p0 = px0 + li0;                      // pixel index inside the frame
-    int v = fast_div(p0, W, rcpW, small_idx);
-    int u = p0 - v * W;
-    // pixel coordinates as doubles, advanced with exact integer-valued additions (no int -> double conversions)
-    double ud = (double)u, vd = (double)v;
+    const int lw0 = warp * kWarpPx;   // first pixel of this warp inside the tile
+    const int p0 = px0 + lw0 + lane;  // this lane's first pixel inside the frame
+    const int v0 = fast_div(p0, W, rcpW, small_idx);
+    const int u0 = p0 - v0 * W;
 
-    OutT xs[kItersT], ys[kItersT];
-    float zf[kItersT];
-    double zd[kItersT];  // only live when OutT is double
-    uint32_t ballots[kItersT];
-    uint32_t warp_total = 0;
+    uint32_t run = 0;  // points staged by this warp so far
 #pragma unroll
     for (int j = 0; j < kItersT; ++j) {
-      const int li = li0 + j * 32;
+      const int lj = j * 32 + lane;  // index inside the warp's 256 pixels
+      const int li = lw0 + lj;       // index inside the tile
       const bool inb = li < npx;
       float z32;
       double z64 = 0.0;
       bool ok;
-      uint32_t draw = 0;
       if (DK == RV_DEPTH_U16) {
-        draw = inb ? (uint32_t) reinterpret_cast<const uint16_t *>(st)[li] : 0u;  // li >= npx reads as 0
+        const uint32_t draw = inb ? (uint32_t) reinterpret_cast<const uint16_t *>(st)[li] : 0u;  // beyond the tile: 0
         const float df = (float)draw;
         if (unit_rule == RV_UNIT_MUL_F32) {
           z32 = df * unit_f;
@@ -282,14 +303,27 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
         if (a.use_trunc) ok = ok && !(z32 >= a.trunc_f);
       }
       // cheap rejection before any float64 work: x^2 + y^2 + z^2 >= z^2, so a depth beyond the sphere is outside
-      // whatever x and y are (same float32 decision the full test below would reach, by monotone rounding)
+      // whatever x and y are (the same float32 decision the full test below reaches, by monotone rounding)
       if (kF32 && use_radius && fast_radius) ok = ok && (z32 * z32 < a.r2_hi_f);
 
       OutT xo = (OutT)0, yo = (OutT)0;
+      uint32_t bal = 0;
       if (__any_sync(0xffffffffu, ok)) {  // warp-uniform: 32 consecutive holes / far pixels cost no geometry
+        int uj = u0 + j * 32, vj = v0;
+        if (wide) {
+          if (uj >= W) {
+            uj -= W;
+            ++vj;
+          }
+        } else {
+          while (uj >= W) {
+            uj -= W;
+            ++vj;
+          }
+        }
         if (!(DK == RV_DEPTH_U16 && unit_rule == RV_UNIT_DIV_F64)) z64 = (double)z32;
-        const double x64 = rv_div((ud - cx) * z64, fx, rfx);
-        const double y64 = rv_div((vd - cy) * z64, fy, rfy);
+        const double x64 = rv_div(((double)uj - cx) * z64, fx, rfx);
+        const double y64 = rv_div(((double)vj - cy) * z64, fy, rfy);
         xo = (OutT)x64;
         yo = (OutT)y64;
         if (kF32) {
@@ -327,24 +361,49 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
           }
           if (use_radius) ok = ok && (((X * X + Y * Y) + Z * Z) < a.r2_thresh);
         }
+        bal = __ballot_sync(0xffffffffu, ok);
+      } else {
+        ok = false;
       }
-      xs[j] = xo;
-      ys[j] = yo;
-      zf[j] = z32;
-      zd[j] = z64;
-      ballots[j] = __ballot_sync(0xffffffffu, ok);
-      warp_total += __popc(ballots[j]);
       if (kGen && a.valid && inb) a.valid[(long long)b * P + px0 + li] = ok ? 1 : 0;
-      u += 32;
-      ud += 32.0;
-      if (u >= W) {
-        u -= W;
-        ud -= Wd;
-        vd += 1.0;
+
+      // ---- stage: compact modes append the kept lanes, dense modes fill slot lj of every pixel
+      if (kOrdered) {
+        if (bal) {
+          const uint32_t pos = run + __popc(bal & lt);
+          run += __popc(bal);
+          if (ok) {
+            sx[pos] = xo;
+            sy[pos] = yo;
+            sz[pos] = kF32 ? (OutT)z32 : (OutT)z64;
+            if (has_bgr) {
+              const uint8_t *c = s_bgr + 3 * li;
+              sc[pos] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16);
+            }
+            if (kGen) si[pos] = (uint16_t)li;
+          }
+        }
+      } else {
+        const OutT bad = (MODE == RV_MODE_DENSE_NAN) ? qnan<OutT>() : (OutT)0;
+        sx[lj] = ok ? xo : bad;
+        sy[lj] = ok ? yo : bad;
+        sz[lj] = ok ? (kF32 ? (OutT)z32 : (OutT)z64) : bad;
+        uint32_t cpk = 0;
+        if (has_bgr && ok) {
+          const uint8_t *c = s_bgr + 3 * li;
+          cpk = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16);
+        }
+        sc[lj] = cpk;
+        if (kGen) si[lj] = ok ? (uint16_t)li : (uint16_t)0xffffu;
+        run += __popc(bal);
       }
     }
+    // the input stage is no longer needed: hand it back to the producer before the prefix is resolved
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
 
     // ---------------- tile totals, tile base
+    const uint32_t warp_total = run;
     uint32_t *const wt = s_warp_tot[it & 1];  // double-buffered: a warp may run one barrier ahead of the readers
     if (lane == 0) wt[warp] = warp_total;
     compute_bar();
@@ -384,53 +443,32 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
       if (threadIdx.x == 0 && tile_total) atomicAdd(a.counts + b, (unsigned long long)tile_total);
     }
 
-    // ---------------- stores (colours are converted here, for kept pixels only)
+    // ---------------- drain: this warp's staged run -> one contiguous run per plane
     const long long fout = kPacked ? 0ll : (long long)b * a.frame_stride;
     const unsigned long long cap64 = kPacked ? (unsigned long long)ps : (unsigned long long)a.frame_stride;
     const uint32_t cap = cap64 > 0xffffffffull ? 0xffffffffu : (uint32_t)cap64;
-    OutT *const o0 = reinterpret_cast<OutT *>(a.out) + fout;
-    uint32_t run = base + warp_excl;
-#pragma unroll
-    for (int j = 0; j < kItersT; ++j) {
-      const int li = li0 + j * 32;
-      const uint32_t bal = ballots[j];
-      const bool ok = (bal >> lane) & 1u;
-      const OutT zo = kF32 ? (OutT)zf[j] : (OutT)zd[j];
-      if (kOrdered) {
-        if (bal == 0) continue;
-        const uint32_t pos = run + __popc(bal & lt);
-        run += __popc(bal);
-        if (ok && pos < cap) {
-          OutT *o = o0 + pos;
-          o[0] = xs[j];
-          o[ps] = ys[j];
-          o[2 * ps] = zo;
-          if (has_bgr) {
-            const uint8_t *c = s_bgr + 3 * li;
-            o[3 * ps] = unit_color<OutT>(c[2], color_255);
-            o[4 * ps] = unit_color<OutT>(c[1], color_255);
-            o[5 * ps] = unit_color<OutT>(c[0], color_255);
-          }
-          if (kGen && a.src_index) a.src_index[fout + pos] = px0 + li;
-        }
-      } else if (li < npx && (long long)(px0 + li) < a.frame_stride) {
-        OutT *o = o0 + px0 + li;
-        const OutT bad = (MODE == RV_MODE_DENSE_NAN) ? qnan<OutT>() : (OutT)0;
-        o[0] = ok ? xs[j] : bad;
-        o[ps] = ok ? ys[j] : bad;
-        o[2 * ps] = ok ? zo : bad;
+    const uint32_t g0 = kOrdered ? base + warp_excl : (uint32_t)(px0 + lw0);
+    const int n = kOrdered ? (int)warp_total : max(0, min(kWarpPx, npx - lw0));
+    OutT *const o0 = reinterpret_cast<OutT *>(a.out) + fout + g0;
+    for (int k = lane; k < n; k += 32) {
+      if (g0 + (uint32_t)k < cap) {
+        OutT *o = o0 + k;
+        o[0] = sx[k];
+        o[ps] = sy[k];
+        o[2 * ps] = sz[k];
         if (has_bgr) {
-          const uint8_t *c = s_bgr + 3 * li;
-          o[3 * ps] = ok ? unit_color<OutT>(c[2], color_255) : (OutT)0;
-          o[4 * ps] = ok ? unit_color<OutT>(c[1], color_255) : (OutT)0;
-          o[5 * ps] = ok ? unit_color<OutT>(c[0], color_255) : (OutT)0;
+          const uint32_t c = sc[k];
+          o[3 * ps] = unit_color<OutT>((c >> 16) & 255u, color_255);
+          o[4 * ps] = unit_color<OutT>((c >> 8) & 255u, color_255);
+          o[5 * ps] = unit_color<OutT>(c & 255u, color_255);
         }
-        if (kGen && a.src_index) a.src_index[fout + px0 + li] = ok ? px0 + li : -1;
+        if (kGen && a.src_index) {
+          const uint32_t idx = si[k];
+          a.src_index[fout + g0 + k] = (!kOrdered && idx == 0xffffu) ? -1 : px0 + (int)idx;
+        }
       }
     }
-    // this warp is done with the stage's shared memory: hand it back to the producer
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[s]);
+    __syncwarp();  // the staging area is rewritten by the next tile
   }
 }
 
@@ -445,8 +483,7 @@ int pick_spec(const DeprojArgs &a, int depth_kind) {
 
 template <typename OutT, int DK, int MODE>
 cudaError_t launch_spec(const rv_ctx *ctx, const DeprojArgs &a, int spec, cudaStream_t st) {
-  constexpr int kDepthB = DK == RV_DEPTH_U16 ? 2 : 4;
-  const size_t smem = (size_t)kStages * kTileT * (kDepthB + 3 + 1);
+  const size_t smem = (size_t)Layout<OutT, DK>::kSmem;
 #define RV_GO(S)                                                                                           \
   {                                                                                                        \
     auto k = k_deproject_tma<OutT, DK, MODE, S>;                                                           \
