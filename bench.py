@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=8192, help="frames per GPU per step (BASELINE configs[4] batch)")
-    ap.add_argument("--chunk", type=int, default=256, help="frames per kernel launch (resident output ring slot)")
+    ap.add_argument("--chunk", type=int, default=1024, help="frames per kernel launch (resident output ring slot)")
     ap.add_argument("--e2e-frames", type=int, default=512, help="frames per end-to-end step (pinned host buffers)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0 = auto)")
     ap.add_argument("--mode", default="compact_ordered", choices=["compact_ordered", "compact_unordered", "dense_zero"])
@@ -291,7 +291,7 @@ def workload_config(a, world):
                         "ordered compacted float32 SoA xyz+rgb cloud",
             "frames_per_gpu_per_step": a.frames, "global_batch": a.frames * world, "chunk_frames": a.chunk,
             "resolution": [W, H], "mode": a.mode, "kernel": a.kernel, "r_max_m": R_MAX, "unit_rule": "mul_f32",
-            "l2": "inputs (1.18 GB per launch, 37.7 GB per step) exceed the 126 MB L2; no flush needed",
+            "l2": f"inputs ({a.chunk * P * 5 / 1e9:.2f} GB per launch, {a.frames * P * 5 / 1e9:.1f} GB per step) exceed the 126 MB L2; no flush needed",
             "parallelism": f"frames sharded over {world} GPU(s), no collective on the hot path"}
 
 
