@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
   __shared__ int4 s_info[kStages];  // {status index or -1, frame, tile in frame, pixels in tile}
-  __shared__ uint32_t s_warp_tot[2][kCW];
-  __shared__ uint32_t s_base;
+  __shared__ __align__(8) uint32_t s_gcnt[2][kCW * kItersT];  // kept points of the tile's 64 groups
+  __shared__ __align__(8) unsigned long long s_base[8];      // (iteration + 1) << 32 | base, one slot per iteration % 8
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -230,7 +230,6 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   const uint32_t lt = (1u << lane) - 1u;
   const float inf_f = __int_as_float(0x7f800000);
   const int W = a.W;
-  const bool wide = W >= kWarpPx;  // at most one row wrap inside a warp's 256 pixels
   const float rcpW = 1.0f / (float)W;
   const double cx = a.cx, cy = a.cy, fx = a.fx, fy = a.fy, rfx = a.rfx, rfy = a.rfy;
   const float unit_f = a.unit_scale_f;
@@ -240,13 +239,16 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   const bool color_255 = kGen ? (a.color_255 != 0) : false;
   const int unit_rule = kGen ? a.unit_rule : RV_UNIT_MUL_F32;
 
-  // this warp's staging area
+  // this warp's staging area: 8 groups x 32 slots
   unsigned char *const wst = smem + L::kRingBytes + (size_t)warp * L::kWarpStage;
   OutT *const sx = reinterpret_cast<OutT *>(wst);
   OutT *const sy = sx + kWarpPx;
   OutT *const sz = sy + kWarpPx;
   uint32_t *const sc = reinterpret_cast<uint32_t *>(sz + kWarpPx);
   uint16_t *const si = reinterpret_cast<uint16_t *>(sc + kWarpPx);
+
+  unsigned long long peek_nxt = 0;  // status word of the NEXT tile's predecessor, requested a whole tile early
+  int peek_nxt_tile = -1;
 
   for (int it = 0;; ++it) {
     const int s = it % kStages;
@@ -261,20 +263,30 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
     const uint8_t *s_bgr = st + kTileT * kDepthB;
     const uint8_t *s_msk = st + kTileT * (kDepthB + 3);
 
-    // early peek: the predecessor's status word, requested before the arithmetic, consumed after it
+    // early peek: every warp fetches the predecessor's status word itself (lane 0), so no CTA-wide hand-off of the
+    // base is needed when it already holds an inclusive prefix.  The load for the next tile is issued here too when
+    // that tile's descriptor has already landed, which hides its L2 round trip behind a whole tile of work.
     unsigned long long peek = 0;
-    if (kOrdered && warp == 0 && lane == 0 && n_pred > 0) peek = rv_ld_relaxed(a.status + tile - 1);
+    if (kOrdered && lane == 0) {
+      if (n_pred > 0) peek = (peek_nxt_tile == tile) ? peek_nxt : rv_ld_relaxed(a.status + tile - 1);
+      const int sn = (it + 1) % kStages;
+      peek_nxt_tile = -1;
+      if (mbar_try_wait(&full_bar[sn], ((it + 1) / kStages) & 1)) {
+        const int4 nx = s_info[sn];
+        if (nx.x >= 0 && (kPacked ? nx.x : nx.z) > 0) {
+          peek_nxt = rv_ld_relaxed(a.status + nx.x - 1);
+          peek_nxt_tile = nx.x;
+        }
+      }
+    }
 
-    const int lw0 = warp * kWarpPx;   // first pixel of this warp inside the tile
-    const int p0 = px0 + lw0 + lane;  // this lane's first pixel inside the frame
-    const int v0 = fast_div(p0, W, rcpW, small_idx);
-    const int u0 = p0 - v0 * W;
-
-    uint32_t run = 0;  // points staged by this warp so far
+    // 32-pixel groups are dealt round-robin to the warps (group q = 8 j + warp), so every warp sees the same mix of
+    // holes, far and near pixels and the tile barrier below is reached together
+    uint32_t my_cnt = 0;  // lane j keeps the kept-point count of this warp's j-th group
 #pragma unroll
     for (int j = 0; j < kItersT; ++j) {
-      const int lj = j * 32 + lane;  // index inside the warp's 256 pixels
-      const int li = lw0 + lj;       // index inside the tile
+      const int q = j * kCW + warp;
+      const int li = q * 32 + lane;  // index inside the tile
       const bool inb = li < npx;
       float z32;
       double z64 = 0.0;
@@ -309,18 +321,9 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
       OutT xo = (OutT)0, yo = (OutT)0;
       uint32_t bal = 0;
       if (__any_sync(0xffffffffu, ok)) {  // warp-uniform: 32 consecutive holes / far pixels cost no geometry
-        int uj = u0 + j * 32, vj = v0;
-        if (wide) {
-          if (uj >= W) {
-            uj -= W;
-            ++vj;
-          }
-        } else {
-          while (uj >= W) {
-            uj -= W;
-            ++vj;
-          }
-        }
+        const int p = px0 + li;
+        const int vj = fast_div(p, W, rcpW, small_idx);
+        const int uj = p - vj * W;
         if (!(DK == RV_DEPTH_U16 && unit_rule == RV_UNIT_DIV_F64)) z64 = (double)z32;
         const double x64 = rv_div(((double)uj - cx) * z64, fx, rfx);
         const double y64 = rv_div(((double)vj - cy) * z64, fy, rfy);
@@ -366,93 +369,112 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
         ok = false;
       }
       if (kGen && a.valid && inb) a.valid[(long long)b * P + px0 + li] = ok ? 1 : 0;
+      if (lane == j) my_cnt = __popc(bal);
 
-      // ---- stage: compact modes append the kept lanes, dense modes fill slot lj of every pixel
+      // ---- stage: compact modes pack the kept lanes of the group, dense modes fill every lane's slot
       if (kOrdered) {
-        if (bal) {
-          const uint32_t pos = run + __popc(bal & lt);
-          run += __popc(bal);
-          if (ok) {
-            sx[pos] = xo;
-            sy[pos] = yo;
-            sz[pos] = kF32 ? (OutT)z32 : (OutT)z64;
-            if (has_bgr) {
-              const uint8_t *c = s_bgr + 3 * li;
-              sc[pos] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16);
-            }
-            if (kGen) si[pos] = (uint16_t)li;
+        if (ok) {
+          const uint32_t pos = j * 32 + __popc(bal & lt);
+          sx[pos] = xo;
+          sy[pos] = yo;
+          sz[pos] = kF32 ? (OutT)z32 : (OutT)z64;
+          if (has_bgr) {
+            const uint8_t *c = s_bgr + 3 * li;
+            sc[pos] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16);
           }
+          if (kGen) si[pos] = (uint16_t)li;
         }
       } else {
         const OutT bad = (MODE == RV_MODE_DENSE_NAN) ? qnan<OutT>() : (OutT)0;
-        sx[lj] = ok ? xo : bad;
-        sy[lj] = ok ? yo : bad;
-        sz[lj] = ok ? (kF32 ? (OutT)z32 : (OutT)z64) : bad;
+        const int pos = j * 32 + lane;
+        sx[pos] = ok ? xo : bad;
+        sy[pos] = ok ? yo : bad;
+        sz[pos] = ok ? (kF32 ? (OutT)z32 : (OutT)z64) : bad;
         uint32_t cpk = 0;
         if (has_bgr && ok) {
           const uint8_t *c = s_bgr + 3 * li;
           cpk = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16);
         }
-        sc[lj] = cpk;
-        if (kGen) si[lj] = ok ? (uint16_t)li : (uint16_t)0xffffu;
-        run += __popc(bal);
+        sc[pos] = cpk;
+        if (kGen) si[pos] = ok ? (uint16_t)li : (uint16_t)0xffffu;
       }
     }
     // the input stage is no longer needed: hand it back to the producer before the prefix is resolved
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);
 
-    // ---------------- tile totals, tile base
-    const uint32_t warp_total = run;
-    uint32_t *const wt = s_warp_tot[it & 1];  // double-buffered: a warp may run one barrier ahead of the readers
-    if (lane == 0) wt[warp] = warp_total;
+    // ---------------- per-group counts -> exclusive offsets of all 64 groups of the tile
+    uint32_t *const gc = s_gcnt[it & 1];  // double-buffered: a warp may run one barrier ahead of the readers
+    if (lane < kItersT) gc[lane * kCW + warp] = my_cnt;
     compute_bar();
-    uint32_t warp_excl = 0, tile_total = 0;
+    const uint2 cpair = reinterpret_cast<const uint2 *>(gc)[lane];  // groups 2*lane, 2*lane + 1
+    uint32_t incl = cpair.x + cpair.y;
 #pragma unroll
-    for (int w = 0; w < kCW; ++w) {
-      const uint32_t c = wt[w];
-      warp_excl += (w < warp) ? c : 0u;
-      tile_total += c;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
     }
+    const uint32_t tile_total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t excl0 = incl - cpair.x - cpair.y;
+    // this warp's groups all have the parity of `warp`: pick the matching half of each pair once
+    const uint32_t off_sel = (warp & 1) ? excl0 + cpair.x : excl0;
+    const uint32_t cnt_sel = (warp & 1) ? cpair.y : cpair.x;
+
+    // ---------------- tile base
     uint32_t base = 0;
     if (kOrdered) {
-      if (warp == 0) {
-        uint32_t excl = 0;
-        peek = __shfl_sync(0xffffffffu, peek, 0);
-        if (n_pred == 0) {
-          if (lane == 0) rv_st_relaxed(a.status + tile, RV_ST_PREFIX | (unsigned long long)tile_total);
-        } else if ((peek >> 62) == 2) {
-          excl = (uint32_t)peek;
-          if (lane == 0) rv_st_relaxed(a.status + tile, RV_ST_PREFIX | (unsigned long long)(excl + tile_total));
-        } else {
-          excl = rv_lookback(a.status, tile, n_pred, tile_total);
-        }
-        if (lane == 0) {
-          s_base = excl;
-          if (kPacked) {
-            if (t == 0) a.counts[b] = excl;
-            if (tile == a.total_tiles - 1) a.counts[nB] = (unsigned long long)excl + tile_total;
-          } else if (t == tpf - 1) {
-            a.counts[b] = (unsigned long long)excl + tile_total;
-          }
+      const unsigned long long pk = __shfl_sync(0xffffffffu, peek, 0);
+      const bool hit = (pk >> 62) == 2;
+      if (n_pred == 0) {
+        base = 0;
+      } else if (hit) {
+        base = (uint32_t)pk;
+      } else if (warp == 0) {
+        base = rv_lookback(a.status, tile, n_pred, tile_total);  // publishes the aggregate, then the prefix
+      } else {
+        // rare: this warp's peek came too early; warp 0 posts the base of tile `it` in slot it % 8 tagged it + 1
+        volatile unsigned long long *slot = s_base + (it & 7);
+        unsigned long long v;
+        do {
+          v = *slot;
+        } while ((uint32_t)(v >> 32) != (uint32_t)(it + 1));
+        base = (uint32_t)v;
+      }
+      if (warp == 0 && lane == 0) {
+        if (n_pred == 0 || hit) rv_st_relaxed(a.status + tile, RV_ST_PREFIX | (unsigned long long)(base + tile_total));
+        *reinterpret_cast<volatile unsigned long long *>(s_base + (it & 7)) = ((unsigned long long)(it + 1) << 32) | base;
+        if (kPacked) {
+          if (t == 0) a.counts[b] = base;
+          if (tile == a.total_tiles - 1) a.counts[nB] = (unsigned long long)base + tile_total;
+        } else if (t == tpf - 1) {
+          a.counts[b] = (unsigned long long)base + tile_total;
         }
       }
-      compute_bar();
-      base = s_base;
     } else {
       if (threadIdx.x == 0 && tile_total) atomicAdd(a.counts + b, (unsigned long long)tile_total);
     }
 
-    // ---------------- drain: this warp's staged run -> one contiguous run per plane
+    // ---------------- drain: each group's packed run -> its contiguous place in every plane
     const long long fout = kPacked ? 0ll : (long long)b * a.frame_stride;
     const unsigned long long cap64 = kPacked ? (unsigned long long)ps : (unsigned long long)a.frame_stride;
     const uint32_t cap = cap64 > 0xffffffffull ? 0xffffffffu : (uint32_t)cap64;
-    const uint32_t g0 = kOrdered ? base + warp_excl : (uint32_t)(px0 + lw0);
-    const int n = kOrdered ? (int)warp_total : max(0, min(kWarpPx, npx - lw0));
-    OutT *const o0 = reinterpret_cast<OutT *>(a.out) + fout + g0;
-    for (int k = lane; k < n; k += 32) {
-      if (g0 + (uint32_t)k < cap) {
-        OutT *o = o0 + k;
+    OutT *const o0 = reinterpret_cast<OutT *>(a.out) + fout;
+#pragma unroll
+    for (int j = 0; j < kItersT; ++j) {
+      const int q = j * kCW + warp;
+      uint32_t n, g0;
+      if (kOrdered) {
+        n = __shfl_sync(0xffffffffu, cnt_sel, q >> 1);
+        g0 = base + __shfl_sync(0xffffffffu, off_sel, q >> 1);
+      } else {
+        n = (uint32_t)max(0, min(32, npx - q * 32));
+        g0 = (uint32_t)(px0 + q * 32);
+      }
+      if (n == 0) continue;
+      const uint32_t g = g0 + (uint32_t)lane;
+      if ((uint32_t)lane < n && g < cap) {
+        const int k = j * 32 + lane;
+        OutT *o = o0 + g;
         o[0] = sx[k];
         o[ps] = sy[k];
         o[2 * ps] = sz[k];
@@ -464,7 +486,7 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
         }
         if (kGen && a.src_index) {
           const uint32_t idx = si[k];
-          a.src_index[fout + g0 + k] = (!kOrdered && idx == 0xffffu) ? -1 : px0 + (int)idx;
+          a.src_index[fout + g] = (!kOrdered && idx == 0xffffu) ? -1 : px0 + (int)idx;
         }
       }
     }

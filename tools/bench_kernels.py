@@ -1,0 +1,128 @@
+#!/usr/bin/env python3
+"""Per-kernel timings of the rest of the hot path: registration, transform + merge,
+voxel grid, PLY records.  One JSON line per kernel with its algorithmic bytes and the fraction of the measured HBM peak.
+bench.py stays the headline (K1); this tool produces the numbers quoted in profiles/ for K2-K4.
+
+    python tools/bench_kernels.py [--reps 20]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import repas_vision_b200 as rv  # noqa: E402
+from repas_vision_b200 import _ops  # noqa: E402
+
+sys.path.insert(0, ROOT)
+from bench import synth_chunk, H, W, FX, FY, CX, CY  # noqa: E402
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def timed(fn, reps, flush):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.add_(1)  # 512 MB write: evicts the 126 MB L2 between repetitions
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def line(name, ms, alg_bytes, units, unit_name, extra=None):
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    d = {"kernel": name, "ms": ms, "algorithmic_bytes": alg_bytes, "achieved_GBps": gbs, "frac_of_measured_hbm_peak": gbs / peak(),
+         unit_name + "_per_s": units / (ms * 1e-3)}
+    if extra:
+        d.update(extra)
+    print(json.dumps(d))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=20)
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    flush = torch.zeros(128 << 20, dtype=torch.float32, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(7)
+
+    # ---- K2 registration: Femto ToF 640x480 (centre crop of the 640x576 intrinsics) -> 1280x720, 32 mm baseline, 6 deg pitch
+    B = 256
+    d720, _ = synth_chunk(B, gen, dev)
+    depth = d720[:, 120:600, 320:960].contiguous()
+    dcam = rv.Camera(504.3227233886719, 504.2591247558594, 320.16888427734375, 345.57403564453125 - 48.0, 640, 480)
+    ccam = rv.Camera(748.8987426757812, 748.3513793945312, 639.8699951171875, 361.9516906738281, 1280, 720)
+    ang = np.deg2rad(6.0)
+    R = np.array([[1, 0, 0], [0, np.cos(ang), -np.sin(ang)], [0, np.sin(ang), np.cos(ang)]])
+    t = np.array([0.032, -0.002, 0.004])
+    ms = timed(lambda: rv.register_depth_to_color(depth, dcam, ccam, R, t), a.reps, flush)
+    line("K2 register 640x480 -> 1280x720 (B=256)", ms, B * (640 * 480 * 2 + 1280 * 720 * 2), B, "frames")
+
+    # ---- K1 on the registered frames feeds K3/K4: four views, distance-masked
+    _, bgr = synth_chunk(4, gen, dev)
+    cam = rv.Camera(FX, FY, CX, CY, W, H)
+    batch = rv.deproject_batch(d720[:4].contiguous(), bgr, cam, max_distance=2.5, dtype="f32")
+    clouds = [batch.frame(i) for i in range(4)]
+    n = [len(c) for c in clouds]
+    poses = []
+    for i in range(4):
+        an = np.deg2rad(90.0 * i)
+        T = np.eye(4)
+        T[:3, :3] = [[np.cos(an), 0, np.sin(an)], [0, 1, 0], [-np.sin(an), 0, np.cos(an)]]
+        T[:3, 3] = [0.02 * i, -0.01, 0.8]
+        poses.append(rv.world_from_camera(T))
+    views = [(c._data, c._n) for c in clouds]
+    ms = timed(lambda: _ops.transform_merge(views, poses, True, want_bounds=True), a.reps, flush)
+    N = sum(n)
+    line("K3 transform+merge 4 views f32", ms, N * 24 * 2, N, "points", {"points": N})
+
+    merged, total, bounds = _ops.transform_merge(views, poses, True, want_bounds=True)
+    for vs in (0.005, 0.02):
+        r = _ops.voxel_downsample(merged, total, True, vs, bounds=bounds)
+        m = int(r["m"].item())
+        ms = timed(lambda: _ops.voxel_downsample(merged, total, True, vs, bounds=bounds), a.reps, flush)
+        line(f"K4 voxel_down_sample {vs * 1000:.0f} mm f32", ms, total * 24 + m * 24, total, "points", {"points": total, "voxels": m})
+
+    ms = timed(lambda: _ops.pack_ply_records(merged, total, True, "unit", "f32"), a.reps, flush)
+    line("PLY records float xyz + uchar rgb", ms, total * 24 + total * 15, total, "points")
+
+    # ---- K1 variants for reference: all-valid dense-capacity compact (upper bound) and VGA canopy config (BASELINE configs[1])
+    B = 256
+    d, c = synth_chunk(B, gen, dev)
+    full = torch.where(d == 0, torch.full_like(d, 900), d)
+    out = torch.empty((6, B * H * W), dtype=torch.float32, device=dev)
+    ms = timed(lambda: rv.deproject_batch(full, c, cam, out=out), a.reps, flush)
+    line("K1 720p all pixels valid, ordered compact (B=256)", ms, B * H * W * 29, B, "frames")
+    ms = timed(lambda: rv.deproject_batch(d, c, cam, out=out), a.reps, flush)
+    kept = float(rv.deproject_batch(d, c, cam, out=out).counts.sum().item()) / (B * H * W)
+    line("K1 720p validity mask only, ordered compact (B=256)", ms, B * H * W * (5 + 24 * kept), B, "frames", {"kept": kept})
+    Bv = 1024
+    dv = d[:, :480, :640].contiguous().repeat(4, 1, 1)
+    cv = c[:, :480, :640].contiguous().repeat(4, 1, 1, 1)
+    camv = rv.Camera(608.2335815429688, 607.8508911132812, 312.52239990234375, 232.65150451660156, 640, 480)
+    outv = torch.empty((6, Bv * 480 * 640), dtype=torch.float32, device=dev)
+    ms = timed(lambda: rv.deproject_batch(dv, cv, camv, max_distance=1.0, unit_rule="div_f32", out=outv), a.reps, flush)
+    kept = float(rv.deproject_batch(dv, cv, camv, max_distance=1.0, unit_rule="div_f32", out=outv).counts.sum().item()) / (Bv * 480 * 640)
+    line("K1 VGA canopy config (BASELINE configs[1], 1024 frames, /1000 rule, 1 m mask)", ms, Bv * 480 * 640 * (5 + 24 * kept), Bv,
+         "frames", {"kept": kept})
+
+
+if __name__ == "__main__":
+    main()
