@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (threadIdx.x < 8) s_base[threadIdx.x] = 0ull;  // tags start at 1: shared memory left by an earlier launch never matches
   __syncthreads();
 
   const int tpf = a.tiles_per_frame;
@@ -268,7 +269,11 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
     // that tile's descriptor has already landed, which hides its L2 round trip behind a whole tile of work.
     unsigned long long peek = 0;
     if (kOrdered && lane == 0) {
-      if (n_pred > 0) peek = (peek_nxt_tile == tile) ? peek_nxt : rv_ld_relaxed(a.status + tile - 1);
+      if (n_pred > 0) {
+        // a prefetched word that does not hold a prefix yet is stale by now: ask again
+        const bool have = peek_nxt_tile == tile && (peek_nxt >> 62) == 2;
+        peek = have ? peek_nxt : rv_ld_relaxed(a.status + tile - 1);
+      }
       const int sn = (it + 1) % kStages;
       peek_nxt_tile = -1;
       if (mbar_try_wait(&full_bar[sn], ((it + 1) / kStages) & 1)) {

@@ -106,7 +106,8 @@ def main():
     # ---- K1 variants for reference: all-valid dense-capacity compact (upper bound) and VGA canopy config (BASELINE configs[1])
     B = 256
     d, c = synth_chunk(B, gen, dev)
-    full = torch.where(d == 0, torch.full_like(d, 900), d)
+    di = d.to(torch.int32)
+    full = torch.where(di == 0, torch.full_like(di, 900), di).to(torch.uint16)
     out = torch.empty((6, B * H * W), dtype=torch.float32, device=dev)
     ms = timed(lambda: rv.deproject_batch(full, c, cam, out=out), a.reps, flush)
     line("K1 720p all pixels valid, ordered compact (B=256)", ms, B * H * W * 29, B, "frames")
