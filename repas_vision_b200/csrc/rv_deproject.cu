@@ -565,6 +565,22 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
   a.fast_radius = a.r2_thresh > 1e-30 && a.r2_thresh < 1e30;
   a.r2_lo_f = a.fast_radius ? float_at_most(a.r2_thresh * (1.0 - 9.5367431640625e-07)) : 0.0f;   // 2^-20 band
   a.r2_hi_f = a.fast_radius ? float_at_least(a.r2_thresh * (1.0 + 9.5367431640625e-07)) : 0.0f;
+  // smallest raw depth whose z alone already fails the float32 sphere test (z*z >= r2_hi): monotone in d, bisection
+  a.d_cand = 65536u;
+  if (a.use_radius && a.fast_radius && p->depth_kind == RV_DEPTH_U16) {
+    auto z_of = [&](unsigned d) -> float {
+      if (a.unit_rule == RV_UNIT_MUL_F32) return (float)d * a.unit_scale_f;
+      if (a.unit_rule == RV_UNIT_DIV_F32) return (float)d / a.unit_scale_f;
+      return (float)((double)d / a.unit_scale);
+    };
+    unsigned lo = 0, hi = 65536;  // invariant: beyond(lo) false (or lo == 0), beyond(hi) true (or hi == 65536)
+    while (hi - lo > 1) {
+      const unsigned mid = (lo + hi) / 2;
+      const float z = z_of(mid);
+      if (z * z >= a.r2_hi_f) hi = mid; else lo = mid;
+    }
+    a.d_cand = hi;
+  }
   const bool fast_ok = rv_deproject_fast_eligible(a, p->mode);
   if (p->kernel_select == RV_KERNEL_TMA && !fast_ok)
     RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: RV_KERNEL_TMA requested but the inputs are not eligible "

@@ -32,6 +32,7 @@ struct DeprojArgs {
   float amin_f[3], amax_f[3];  // same rounding for the box
   float r2_lo_f, r2_hi_f;      // below lo: inside for sure; at or above hi: outside for sure; between: float64 decides
   int fast_radius;
+  unsigned int d_cand;  // uint16 depths in [1, d_cand) can still be inside the sphere; 65536 when there is no radius mask
 };
 
 // fast path (rv_deproject_tma.cu)

@@ -160,9 +160,11 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
-  __shared__ int4 s_info[kStages];  // {status index or -1, frame, tile in frame, pixels in tile}
+  __shared__ __align__(8) uint64_t base_bar[8];               // slow path: warp 0 posts the tile base
+  __shared__ int4 s_info[kStages];                            // {status index or -1, frame, tile in frame, pixels in tile}
   __shared__ __align__(8) uint32_t s_gcnt[2][kCW * kItersT];  // kept points of the tile's 64 groups
-  __shared__ __align__(8) unsigned long long s_base[8];      // (iteration + 1) << 32 | base, one slot per iteration % 8
+  __shared__ __align__(8) unsigned long long s_peek[2];       // predecessor status word seen by warp 0
+  __shared__ uint32_t s_base[8];
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -173,9 +175,10 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], kCW);
     }
+#pragma unroll
+    for (int s = 0; s < 8; ++s) mbar_init(&base_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < 8) s_base[threadIdx.x] = 0ull;  // tags start at 1: shared memory left by an earlier launch never matches
   __syncthreads();
 
   const int tpf = a.tiles_per_frame;
@@ -231,6 +234,7 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   const uint32_t lt = (1u << lane) - 1u;
   const float inf_f = __int_as_float(0x7f800000);
   const int W = a.W;
+  const bool wide = W >= 600;  // u0 + 7*256 then wraps at most three times ((W - 1 + 1792) / W < 4)
   const float rcpW = 1.0f / (float)W;
   const double cx = a.cx, cy = a.cy, fx = a.fx, fy = a.fy, rfx = a.rfx, rfy = a.rfy;
   const float unit_f = a.unit_scale_f;
@@ -239,6 +243,8 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   const bool fast_radius = kGen ? (a.fast_radius != 0) : true;
   const bool color_255 = kGen ? (a.color_255 != 0) : false;
   const int unit_rule = kGen ? a.unit_rule : RV_UNIT_MUL_F32;
+  // raw depths in [1, dcand) are candidates; dcand folds "z alone is already beyond the sphere" into an integer compare
+  const uint32_t dcand_m1 = ((kF32 && use_radius && fast_radius) ? a.d_cand : 65536u) - 1u;
 
   // this warp's staging area: 8 groups x 32 slots
   unsigned char *const wst = smem + L::kRingBytes + (size_t)warp * L::kWarpStage;
@@ -248,7 +254,7 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   uint32_t *const sc = reinterpret_cast<uint32_t *>(sz + kWarpPx);
   uint16_t *const si = reinterpret_cast<uint16_t *>(sc + kWarpPx);
 
-  unsigned long long peek_nxt = 0;  // status word of the NEXT tile's predecessor, requested a whole tile early
+  unsigned long long peek_nxt = 0;  // warp 0 lane 0: status word of the NEXT tile's predecessor, requested a tile early
   int peek_nxt_tile = -1;
 
   for (int it = 0;; ++it) {
@@ -260,18 +266,16 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
     const int b = info.y, t = info.z, npx = info.w;
     const int n_pred = kPacked ? tile : t;
     const int px0 = t * kTileT;
-    const unsigned char *st = smem + (size_t)s * L::kStageBytes;
+    unsigned char *st = smem + (size_t)s * L::kStageBytes;
     const uint8_t *s_bgr = st + kTileT * kDepthB;
     const uint8_t *s_msk = st + kTileT * (kDepthB + 3);
 
-    // early peek: every warp fetches the predecessor's status word itself (lane 0), so no CTA-wide hand-off of the
-    // base is needed when it already holds an inclusive prefix.  The load for the next tile is issued here too when
-    // that tile's descriptor has already landed, which hides its L2 round trip behind a whole tile of work.
+    // early peek (warp 0, lane 0): the predecessor's status word.  The request for the NEXT tile is issued here as well
+    // when that tile's descriptor has already landed, which hides its L2 round trip behind a whole tile of work.
     unsigned long long peek = 0;
-    if (kOrdered && lane == 0) {
+    if (kOrdered && warp == 0 && lane == 0) {
       if (n_pred > 0) {
-        // a prefetched word that does not hold a prefix yet is stale by now: ask again
-        const bool have = peek_nxt_tile == tile && (peek_nxt >> 62) == 2;
+        const bool have = peek_nxt_tile == tile && (peek_nxt >> 62) == 2;  // a word without a prefix is stale by now
         peek = have ? peek_nxt : rv_ld_relaxed(a.status + tile - 1);
       }
       const int sn = (it + 1) % kStages;
@@ -285,50 +289,80 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
       }
     }
 
+    // a partial last tile: zero the depth of this warp's own pixels beyond the frame so the loop needs no bounds test
+    if (npx < kTileT) {
+#pragma unroll
+      for (int j = 0; j < kItersT; ++j) {
+        const int li = (j * kCW + warp) * 32 + lane;
+        if (li >= npx) {
+          if (DK == RV_DEPTH_U16) reinterpret_cast<uint16_t *>(st)[li] = 0;
+          else reinterpret_cast<float *>(st)[li] = 0.0f;
+        }
+      }
+      __syncwarp();
+    }
+
     // 32-pixel groups are dealt round-robin to the warps (group q = 8 j + warp), so every warp sees the same mix of
-    // holes, far and near pixels and the tile barrier below is reached together
-    uint32_t my_cnt = 0;  // lane j keeps the kept-point count of this warp's j-th group
+    // holes, far and near pixels and reaches the tile barrier together
+    const int p0 = px0 + warp * 32 + lane;  // this lane's pixel in group j = 0
+    const int v0 = fast_div(p0, W, rcpW, small_idx);
+    const int u0 = p0 - v0 * W;
+    uint32_t cnt_lo = 0, cnt_hi = 0;  // kept points of groups 0-3 / 4-7, one byte each (warp-uniform)
 #pragma unroll
     for (int j = 0; j < kItersT; ++j) {
       const int q = j * kCW + warp;
       const int li = q * 32 + lane;  // index inside the tile
-      const bool inb = li < npx;
-      float z32;
+      float z32 = 0.0f;
       double z64 = 0.0;
+      uint32_t draw = 0;
       bool ok;
       if (DK == RV_DEPTH_U16) {
-        const uint32_t draw = inb ? (uint32_t) reinterpret_cast<const uint16_t *>(st)[li] : 0u;  // beyond the tile: 0
-        const float df = (float)draw;
-        if (unit_rule == RV_UNIT_MUL_F32) {
-          z32 = df * unit_f;
-        } else if (unit_rule == RV_UNIT_DIV_F32) {
-          z32 = rv_divf(df, unit_f, a.unit_rcp_f);
-        } else {
-          z64 = rv_div((double)draw, a.unit_scale, a.unit_rcp);
-          z32 = (float)z64;
-        }
-        ok = draw != 0;
+        draw = reinterpret_cast<const uint16_t *>(st)[li];
+        ok = (draw - 1u) < dcand_m1;  // draw != 0 && draw < dcand
       } else {
-        z32 = inb ? reinterpret_cast<const float *>(st)[li] : 0.0f;
+        z32 = reinterpret_cast<const float *>(st)[li];
         ok = (z32 > 0.0f) && (z32 < inf_f);
+        if (kF32 && use_radius && fast_radius) ok = ok && (z32 * z32 < a.r2_hi_f);
       }
-      if (kGen) {
-        if (has_mask) {
-          const uint32_t m = inb ? (uint32_t)s_msk[li] : 0u;
-          ok = ok && (a.invert_mask ? (m == 0) : (m != 0));
-        }
-        if (a.use_trunc) ok = ok && !(z32 >= a.trunc_f);
+      if (kGen && has_mask) {
+        const uint32_t m = s_msk[li];
+        ok = ok && (a.invert_mask ? (m == 0) : (m != 0));
       }
-      // cheap rejection before any float64 work: x^2 + y^2 + z^2 >= z^2, so a depth beyond the sphere is outside
-      // whatever x and y are (the same float32 decision the full test below reaches, by monotone rounding)
-      if (kF32 && use_radius && fast_radius) ok = ok && (z32 * z32 < a.r2_hi_f);
 
       OutT xo = (OutT)0, yo = (OutT)0;
       uint32_t bal = 0;
       if (__any_sync(0xffffffffu, ok)) {  // warp-uniform: 32 consecutive holes / far pixels cost no geometry
-        const int p = px0 + li;
-        const int vj = fast_div(p, W, rcpW, small_idx);
-        const int uj = p - vj * W;
+        if (DK == RV_DEPTH_U16) {
+          const float df = (float)draw;
+          if (unit_rule == RV_UNIT_MUL_F32) {
+            z32 = df * unit_f;
+          } else if (unit_rule == RV_UNIT_DIV_F32) {
+            z32 = rv_divf(df, unit_f, a.unit_rcp_f);
+          } else {
+            z64 = rv_div((double)draw, a.unit_scale, a.unit_rcp);
+            z32 = (float)z64;
+          }
+        }
+        if (kGen && a.use_trunc) ok = ok && !(z32 >= a.trunc_f);
+        int uj = u0 + j * kWarpPx, vj = v0;
+        if (wide) {
+          if (uj >= W) {
+            uj -= W;
+            ++vj;
+          }
+          if (uj >= W) {
+            uj -= W;
+            ++vj;
+          }
+          if (uj >= W) {
+            uj -= W;
+            ++vj;
+          }
+        } else {
+          const int p = p0 + j * kWarpPx;
+          vj = fast_div(p, W, rcpW, small_idx);
+          uj = p - vj * W;
+        }
         if (!(DK == RV_DEPTH_U16 && unit_rule == RV_UNIT_DIV_F64)) z64 = (double)z32;
         const double x64 = rv_div(((double)uj - cx) * z64, fx, rfx);
         const double y64 = rv_div(((double)vj - cy) * z64, fy, rfy);
@@ -370,15 +404,10 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
           if (use_radius) ok = ok && (((X * X + Y * Y) + Z * Z) < a.r2_thresh);
         }
         bal = __ballot_sync(0xffffffffu, ok);
-      } else {
-        ok = false;
-      }
-      if (kGen && a.valid && inb) a.valid[(long long)b * P + px0 + li] = ok ? 1 : 0;
-      if (lane == j) my_cnt = __popc(bal);
-
-      // ---- stage: compact modes pack the kept lanes of the group, dense modes fill every lane's slot
-      if (kOrdered) {
-        if (ok) {
+        if (j < 4) cnt_lo |= (uint32_t)__popc(bal) << (8 * j);
+        else cnt_hi |= (uint32_t)__popc(bal) << (8 * (j - 4));
+        // ---- stage the kept lanes of the group, packed (compact modes)
+        if (kOrdered && ok) {
           const uint32_t pos = j * 32 + __popc(bal & lt);
           sx[pos] = xo;
           sy[pos] = yo;
@@ -390,6 +419,10 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
           if (kGen) si[pos] = (uint16_t)li;
         }
       } else {
+        ok = false;
+      }
+      if (kGen && a.valid && li < npx) a.valid[(long long)b * P + px0 + li] = ok ? 1 : 0;
+      if (!kOrdered) {  // dense modes fill every lane's slot
         const OutT bad = (MODE == RV_MODE_DENSE_NAN) ? qnan<OutT>() : (OutT)0;
         const int pos = j * 32 + lane;
         sx[pos] = ok ? xo : bad;
@@ -405,12 +438,14 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
       }
     }
     // the input stage is no longer needed: hand it back to the producer before the prefix is resolved
+    if (npx < kTileT) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // our zero fill vs the next bulk copy
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);
 
     // ---------------- per-group counts -> exclusive offsets of all 64 groups of the tile
     uint32_t *const gc = s_gcnt[it & 1];  // double-buffered: a warp may run one barrier ahead of the readers
-    if (lane < kItersT) gc[lane * kCW + warp] = my_cnt;
+    if (lane < kItersT) gc[lane * kCW + warp] = ((lane < 4 ? cnt_lo : cnt_hi) >> (8 * (lane & 3))) & 0xffu;
+    if (kOrdered && warp == 0 && lane == 0) s_peek[it & 1] = peek;
     compute_bar();
     const uint2 cpair = reinterpret_cast<const uint2 *>(gc)[lane];  // groups 2*lane, 2*lane + 1
     uint32_t incl = cpair.x + cpair.y;
@@ -420,34 +455,34 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
       if (lane >= o) incl += up;
     }
     const uint32_t tile_total = __shfl_sync(0xffffffffu, incl, 31);
-    const uint32_t excl0 = incl - cpair.x - cpair.y;
     // this warp's groups all have the parity of `warp`: pick the matching half of each pair once
-    const uint32_t off_sel = (warp & 1) ? excl0 + cpair.x : excl0;
-    const uint32_t cnt_sel = (warp & 1) ? cpair.y : cpair.x;
+    const uint32_t off_sel = incl - cpair.y - ((warp & 1) ? 0u : cpair.x);
 
     // ---------------- tile base
     uint32_t base = 0;
     if (kOrdered) {
-      const unsigned long long pk = __shfl_sync(0xffffffffu, peek, 0);
+      const unsigned long long pk = s_peek[it & 1];
       const bool hit = (pk >> 62) == 2;
-      if (n_pred == 0) {
-        base = 0;
-      } else if (hit) {
-        base = (uint32_t)pk;
-      } else if (warp == 0) {
-        base = rv_lookback(a.status, tile, n_pred, tile_total);  // publishes the aggregate, then the prefix
-      } else {
-        // rare: this warp's peek came too early; warp 0 posts the base of tile `it` in slot it % 8 tagged it + 1
-        volatile unsigned long long *slot = s_base + (it & 7);
-        unsigned long long v;
-        do {
-          v = *slot;
-        } while ((uint32_t)(v >> 32) != (uint32_t)(it + 1));
-        base = (uint32_t)v;
+      if (n_pred > 0) {
+        if (hit) {
+          base = (uint32_t)pk;
+        } else if (warp == 0) {
+          base = rv_lookback(a.status, tile, n_pred, tile_total);  // publishes the aggregate, then the prefix
+          if (lane == 0) {
+            s_base[it & 7] = base;
+            mbar_arrive(&base_bar[it & 7]);
+          }
+        } else {
+          // the predecessor is still in flight in another CTA: sleep until warp 0 has walked the chain
+          mbar_wait(&base_bar[it & 7], (uint32_t)(it >> 3) & 1u);
+          base = s_base[it & 7];
+        }
       }
       if (warp == 0 && lane == 0) {
-        if (n_pred == 0 || hit) rv_st_relaxed(a.status + tile, RV_ST_PREFIX | (unsigned long long)(base + tile_total));
-        *reinterpret_cast<volatile unsigned long long *>(s_base + (it & 7)) = ((unsigned long long)(it + 1) << 32) | base;
+        if (n_pred == 0 || hit) {
+          rv_st_relaxed(a.status + tile, RV_ST_PREFIX | (unsigned long long)(base + tile_total));
+          mbar_arrive(&base_bar[it & 7]);  // keep the slot's phase in step with the iteration count
+        }
         if (kPacked) {
           if (t == 0) a.counts[b] = base;
           if (tile == a.total_tiles - 1) a.counts[nB] = (unsigned long long)base + tile_total;
@@ -460,38 +495,41 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
     }
 
     // ---------------- drain: each group's packed run -> its contiguous place in every plane
-    const long long fout = kPacked ? 0ll : (long long)b * a.frame_stride;
-    const unsigned long long cap64 = kPacked ? (unsigned long long)ps : (unsigned long long)a.frame_stride;
-    const uint32_t cap = cap64 > 0xffffffffull ? 0xffffffffu : (uint32_t)cap64;
-    OutT *const o0 = reinterpret_cast<OutT *>(a.out) + fout;
+    if (!kOrdered || (cnt_lo | cnt_hi) != 0) {
+      const long long fout = kPacked ? 0ll : (long long)b * a.frame_stride;
+      const unsigned long long cap64 = kPacked ? (unsigned long long)ps : (unsigned long long)a.frame_stride;
+      const uint32_t cap = cap64 > 0xffffffffull ? 0xffffffffu : (uint32_t)cap64;
+      OutT *const o0 = reinterpret_cast<OutT *>(a.out) + fout;
 #pragma unroll
-    for (int j = 0; j < kItersT; ++j) {
-      const int q = j * kCW + warp;
-      uint32_t n, g0;
-      if (kOrdered) {
-        n = __shfl_sync(0xffffffffu, cnt_sel, q >> 1);
-        g0 = base + __shfl_sync(0xffffffffu, off_sel, q >> 1);
-      } else {
-        n = (uint32_t)max(0, min(32, npx - q * 32));
-        g0 = (uint32_t)(px0 + q * 32);
-      }
-      if (n == 0) continue;
-      const uint32_t g = g0 + (uint32_t)lane;
-      if ((uint32_t)lane < n && g < cap) {
-        const int k = j * 32 + lane;
-        OutT *o = o0 + g;
-        o[0] = sx[k];
-        o[ps] = sy[k];
-        o[2 * ps] = sz[k];
-        if (has_bgr) {
-          const uint32_t c = sc[k];
-          o[3 * ps] = unit_color<OutT>((c >> 16) & 255u, color_255);
-          o[4 * ps] = unit_color<OutT>((c >> 8) & 255u, color_255);
-          o[5 * ps] = unit_color<OutT>(c & 255u, color_255);
+      for (int j = 0; j < kItersT; ++j) {
+        const int q = j * kCW + warp;
+        uint32_t n, g0;
+        if (kOrdered) {
+          n = ((j < 4 ? cnt_lo : cnt_hi) >> (8 * (j & 3))) & 0xffu;
+          if (n == 0) continue;
+          g0 = base + __shfl_sync(0xffffffffu, off_sel, q >> 1);
+        } else {
+          n = (uint32_t)max(0, min(32, npx - q * 32));
+          if (n == 0) continue;
+          g0 = (uint32_t)(px0 + q * 32);
         }
-        if (kGen && a.src_index) {
-          const uint32_t idx = si[k];
-          a.src_index[fout + g] = (!kOrdered && idx == 0xffffu) ? -1 : px0 + (int)idx;
+        const uint32_t g = g0 + (uint32_t)lane;
+        if ((uint32_t)lane < n && g < cap) {
+          const int k = j * 32 + lane;
+          OutT *o = o0 + g;
+          o[0] = sx[k];
+          o[ps] = sy[k];
+          o[2 * ps] = sz[k];
+          if (has_bgr) {
+            const uint32_t c = sc[k];
+            o[3 * ps] = unit_color<OutT>((c >> 16) & 255u, color_255);
+            o[4 * ps] = unit_color<OutT>((c >> 8) & 255u, color_255);
+            o[5 * ps] = unit_color<OutT>(c & 255u, color_255);
+          }
+          if (kGen && a.src_index) {
+            const uint32_t idx = si[k];
+            a.src_index[fout + g] = (!kOrdered && idx == 0xffffu) ? -1 : px0 + (int)idx;
+          }
         }
       }
     }
