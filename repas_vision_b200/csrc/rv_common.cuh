@@ -119,9 +119,11 @@ __device__ __forceinline__ uint32_t rv_lookback(unsigned long long *status, int 
   for (;;) {
     unsigned long long s = RV_ST_PREFIX;  // lanes past the chain head read as "prefix 0"
     if (lane < remaining) {
-      do {
+      s = rv_ld_relaxed(status + (look - lane));
+      while ((s >> 62) == 0) {  // predecessor still computing in another CTA: poll gently, the issue slots are needed
+        __nanosleep(256);
         s = rv_ld_relaxed(status + (look - lane));
-      } while ((s >> 62) == 0);
+      }
     }
     const uint32_t pmask = __ballot_sync(0xffffffffu, (s >> 62) == 2);
     const int first = pmask ? (__ffs(pmask) - 1) : 32;

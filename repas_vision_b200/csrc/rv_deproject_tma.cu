@@ -37,7 +37,13 @@ constexpr int kThreadsT = kCT + 32;     // + producer warp
 constexpr int kItersT = 8;
 constexpr int kWarpPx = 32 * kItersT;   // 256 pixels per warp per tile
 constexpr int kTileT = kCT * kItersT;   // 2048 pixels
-constexpr int kStages = 3;
+#ifndef RV_K1_STAGES
+#define RV_K1_STAGES 3
+#endif
+#ifndef RV_K1_TICKET_AHEAD
+#define RV_K1_TICKET_AHEAD 1
+#endif
+constexpr int kStages = RV_K1_STAGES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -194,11 +200,13 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
       const float rcpB = 1.0f / (float)nB;
       const float rcpT = 1.0f / (float)tpf;
       // tickets are requested one tile ahead so the atomic's round trip hides behind the wait for a free stage
-      int ticket = (int)atomicAdd(a.ticket, 1u);
+      int ticket = RV_K1_TICKET_AHEAD ? (int)atomicAdd(a.ticket, 1u) : 0;
       for (int it = 0;; ++it) {
         const int s = it % kStages;
-        const int next = ticket < a.total_tiles ? (int)atomicAdd(a.ticket, 1u) : ticket;
+        int next = 0;
+        if (RV_K1_TICKET_AHEAD) next = ticket < a.total_tiles ? (int)atomicAdd(a.ticket, 1u) : ticket;
         mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
+        if (!RV_K1_TICKET_AHEAD) ticket = (int)atomicAdd(a.ticket, 1u);
         if (ticket >= a.total_tiles) {
           s_info[s] = make_int4(-1, 0, 0, 0);
           mbar_arrive(&full_bar[s]);
