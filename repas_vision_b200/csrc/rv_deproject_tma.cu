@@ -7,8 +7,10 @@
 //
 //  * one producer warp per CTA takes tile tickets and issues 1-D bulk async copies (cp.async.bulk ->
 //    UBLKCP, the TMA engine) of the tile's depth / BGR / mask bytes into a kStages-deep shared-memory
-//    ring guarded by full/empty mbarriers, so several tiles of loads per CTA are always in flight and no
-//    compute warp ever waits on a global load;
+//    ring guarded by full/empty mbarriers, so the next tile's loads are in flight while this one is
+//    computed.  The ring is kept shallow (2 stages, ticket taken when the stage frees) on purpose: a
+//    ticket held in a deep queue delays the prefix chain of its frame for every CTA behind it (measured:
+//    3 stages + ticket prefetch 420 k frames/s, 2 stages without 500 k at 1024 frames per launch);
 //  * eight compute warps read the tile from shared memory (lane + 32 j ownership, so every ballot is a
 //    contiguous run of pixels).  A group of 32 consecutive pixels with no candidate (holes, or depths
 //    already beyond the distance mask) costs ~10 instructions and no float64 work;
@@ -38,10 +40,10 @@ constexpr int kItersT = 8;
 constexpr int kWarpPx = 32 * kItersT;   // 256 pixels per warp per tile
 constexpr int kTileT = kCT * kItersT;   // 2048 pixels
 #ifndef RV_K1_STAGES
-#define RV_K1_STAGES 3
+#define RV_K1_STAGES 2
 #endif
 #ifndef RV_K1_TICKET_AHEAD
-#define RV_K1_TICKET_AHEAD 1
+#define RV_K1_TICKET_AHEAD 0
 #endif
 constexpr int kStages = RV_K1_STAGES;
 
