@@ -142,27 +142,48 @@ __device__ __forceinline__ double qnan<double>() {
   return __longlong_as_double(0x7ff8000000000000ll);
 }
 
-template <typename OutT, int DK>
+template <typename OutT, int DK, bool kGen>
 struct Layout {
   static constexpr int kDepthB = DK == RV_DEPTH_U16 ? 2 : 4;
-  static constexpr int kStageBytes = kTileT * (kDepthB + 3 + 1);
-  // per-warp staging: x, y, z (OutT), packed colour (u32), source index inside the tile (u16)
-  static constexpr int kWarpStage = kWarpPx * (3 * (int)sizeof(OutT) + 4 + 2);
+  // the segmentation-mask bytes and the source-index column exist only in the run-time-flag variant
+  static constexpr int kStageBytes = kTileT * (kDepthB + 3 + (kGen ? 1 : 0));
+  // per-warp staging: x, y, z (OutT), packed colour (u32) [, source index inside the tile (u16)]
+  static constexpr int kWarpStage = kWarpPx * (3 * (int)sizeof(OutT) + 4 + (kGen ? 2 : 0));
   static constexpr int kRingBytes = kStages * kStageBytes;
   static constexpr int kSmem = kRingBytes + kCW * kWarpStage;
+  // resident CTAs per SM the shared memory allows (227 KB usable, ~1.5 KB static + reserved per CTA)
+  static constexpr int kOcc = (227 * 1024) / (kSmem + 1536) > 4 ? 4 : (227 * 1024) / (kSmem + 1536);
 };
+
+// k / 255 in float32, correctly rounded for every byte: 1/255 split into hi + lo so that fma(k, hi, k * lo) carries
+// ~48 bits (tests/test_gpu_cloud.py::test_exact_division_helper_against_numpy walks all 256 bytes)
+__device__ __forceinline__ float unit_color_f(float kf) {
+  const float hi = 0.003921568859368563f;       // RN(1/255)
+  const float lo = -2.319175823606301e-10f;    // RN(1/255 - hi)
+  return fmaf(kf, hi, kf * lo);
+}
+
+// store to a global address + compile-time byte offset (keeps the address arithmetic out of the unrolled drain)
+template <int OFF>
+__device__ __forceinline__ void st_global(unsigned long long addr, float v) {
+  asm volatile("st.global.f32 [%0+%1], %2;" ::"l"(addr), "n"(OFF), "f"(v) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void st_global(unsigned long long addr, double v) {
+  asm volatile("st.global.f64 [%0+%1], %2;" ::"l"(addr), "n"(OFF), "d"(v) : "memory");
+}
 
 // SPEC selects how much of the predicate set is compiled in:
 //   0  uint16/float depth with the MUL_F32 unit rule, colour, validity only
 //   1  the same plus the radius mask (the canopy / BASELINE configuration)
 //   2  everything, decided by the run-time flags of DeprojArgs
 template <typename OutT, int DK, int MODE, int SPEC>
-__global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproject_tma(const DeprojArgs a) {
+__global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)) k_deproject_tma(const DeprojArgs a) {
   constexpr bool kPacked = MODE == RV_MODE_COMPACT_PACKED;
   constexpr bool kOrdered = MODE == RV_MODE_COMPACT_ORDERED || kPacked;
   constexpr bool kF32 = sizeof(OutT) == 4;
   constexpr bool kGen = SPEC == 2;
-  using L = Layout<OutT, DK>;
+  using L = Layout<OutT, DK, kGen>;
   constexpr int kDepthB = L::kDepthB;
 
   extern __shared__ __align__(128) unsigned char smem[];
@@ -170,7 +191,7 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   __shared__ __align__(8) uint64_t empty_bar[kStages];
   __shared__ __align__(8) uint64_t base_bar[8];               // slow path: warp 0 posts the tile base
   __shared__ int4 s_info[kStages];                            // {status index or -1, frame, tile in frame, pixels in tile}
-  __shared__ __align__(8) uint32_t s_gcnt[2][kCW * kItersT];  // kept points of the tile's 64 groups
+  __shared__ __align__(16) uint32_t s_tot[2][kCW];            // kept points of the tile's eight warp runs
   __shared__ __align__(8) unsigned long long s_peek[2];       // predecessor status word seen by warp 0
   __shared__ uint32_t s_base[8];
 
@@ -233,7 +254,7 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
         mbar_arrive_expect_tx(&full_bar[s], bytes);
         bulk_load(st, reinterpret_cast<const unsigned char *>(a.depth) + g * kDepthB, (uint32_t)npx * kDepthB, &full_bar[s]);
         if (has_bgr) bulk_load(st + kTileT * kDepthB, a.bgr + g * 3, (uint32_t)npx * 3, &full_bar[s]);
-        if (has_mask) bulk_load(st + kTileT * (kDepthB + 3), a.mask + g, (uint32_t)npx, &full_bar[s]);
+        if (kGen && has_mask) bulk_load(st + kTileT * (kDepthB + 3), a.mask + g, (uint32_t)npx, &full_bar[s]);
         ticket = next;
       }
     }
@@ -244,7 +265,7 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   const uint32_t lt = (1u << lane) - 1u;
   const float inf_f = __int_as_float(0x7f800000);
   const int W = a.W;
-  const bool wide = W >= 600;  // u0 + 7*256 then wraps at most three times ((W - 1 + 1792) / W < 4)
+  const bool wide = W >= kWarpPx;  // a warp's 256-pixel run then crosses at most one row boundary
   const float rcpW = 1.0f / (float)W;
   const double cx = a.cx, cy = a.cy, fx = a.fx, fy = a.fy, rfx = a.rfx, rfy = a.rfy;
   const float unit_f = a.unit_scale_f;
@@ -256,13 +277,13 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
   // raw depths in [1, dcand) are candidates; dcand folds "z alone is already beyond the sphere" into an integer compare
   const uint32_t dcand_m1 = ((kF32 && use_radius && fast_radius) ? a.d_cand : 65536u) - 1u;
 
-  // this warp's staging area: 8 groups x 32 slots
+  // this warp's staging area: room for its whole 256-pixel run
   unsigned char *const wst = smem + L::kRingBytes + (size_t)warp * L::kWarpStage;
   OutT *const sx = reinterpret_cast<OutT *>(wst);
   OutT *const sy = sx + kWarpPx;
   OutT *const sz = sy + kWarpPx;
   uint32_t *const sc = reinterpret_cast<uint32_t *>(sz + kWarpPx);
-  uint16_t *const si = reinterpret_cast<uint16_t *>(sc + kWarpPx);
+  uint16_t *const si = reinterpret_cast<uint16_t *>(sc + kWarpPx);  // kGen only
 
   unsigned long long peek_nxt = 0;  // warp 0 lane 0: status word of the NEXT tile's predecessor, requested a tile early
   int peek_nxt_tile = -1;
@@ -282,8 +303,8 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
 
     // early peek (warp 0, lane 0): the predecessor's status word.  The request for the NEXT tile is issued here as well
     // when that tile's descriptor has already landed, which hides its L2 round trip behind a whole tile of work.
-    unsigned long long peek = 0;
     if (kOrdered && warp == 0 && lane == 0) {
+      unsigned long long peek = 0;
       if (n_pred > 0) {
         const bool have = peek_nxt_tile == tile && (peek_nxt >> 62) == 2;  // a word without a prefix is stale by now
         peek = have ? peek_nxt : rv_ld_relaxed(a.status + tile - 1);
@@ -297,13 +318,16 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
           peek_nxt_tile = nx.x;
         }
       }
+      s_peek[it & 1] = peek;  // read by every warp after the tile barrier
     }
 
+    // each warp owns 256 consecutive pixels of the tile, so its kept points are ONE contiguous run of the output
+    const int w0 = warp * kWarpPx;
     // a partial last tile: zero the depth of this warp's own pixels beyond the frame so the loop needs no bounds test
     if (npx < kTileT) {
 #pragma unroll
       for (int j = 0; j < kItersT; ++j) {
-        const int li = (j * kCW + warp) * 32 + lane;
+        const int li = w0 + j * 32 + lane;
         if (li >= npx) {
           if (DK == RV_DEPTH_U16) reinterpret_cast<uint16_t *>(st)[li] = 0;
           else reinterpret_cast<float *>(st)[li] = 0.0f;
@@ -312,16 +336,13 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
       __syncwarp();
     }
 
-    // 32-pixel groups are dealt round-robin to the warps (group q = 8 j + warp), so every warp sees the same mix of
-    // holes, far and near pixels and reaches the tile barrier together
-    const int p0 = px0 + warp * 32 + lane;  // this lane's pixel in group j = 0
+    const int p0 = px0 + w0 + lane;  // this lane's pixel in group j = 0
     const int v0 = fast_div(p0, W, rcpW, small_idx);
     const int u0 = p0 - v0 * W;
-    uint32_t cnt_lo = 0, cnt_hi = 0;  // kept points of groups 0-3 / 4-7, one byte each (warp-uniform)
+    uint32_t run = 0;  // kept points of this warp so far (warp-uniform)
 #pragma unroll
     for (int j = 0; j < kItersT; ++j) {
-      const int q = j * kCW + warp;
-      const int li = q * 32 + lane;  // index inside the tile
+      const int li = w0 + j * 32 + lane;  // index inside the tile
       float z32 = 0.0f;
       double z64 = 0.0;
       uint32_t draw = 0;
@@ -340,7 +361,6 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
       }
 
       OutT xo = (OutT)0, yo = (OutT)0;
-      uint32_t bal = 0;
       if (__any_sync(0xffffffffu, ok)) {  // warp-uniform: 32 consecutive holes / far pixels cost no geometry
         if (DK == RV_DEPTH_U16) {
           const float df = (float)draw;
@@ -354,22 +374,14 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
           }
         }
         if (kGen && a.use_trunc) ok = ok && !(z32 >= a.trunc_f);
-        int uj = u0 + j * kWarpPx, vj = v0;
+        int uj = u0 + j * 32, vj = v0;
         if (wide) {
           if (uj >= W) {
             uj -= W;
             ++vj;
           }
-          if (uj >= W) {
-            uj -= W;
-            ++vj;
-          }
-          if (uj >= W) {
-            uj -= W;
-            ++vj;
-          }
         } else {
-          const int p = p0 + j * kWarpPx;
+          const int p = p0 + j * 32;
           vj = fast_div(p, W, rcpW, small_idx);
           uj = p - vj * W;
         }
@@ -413,12 +425,10 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
           }
           if (use_radius) ok = ok && (((X * X + Y * Y) + Z * Z) < a.r2_thresh);
         }
-        bal = __ballot_sync(0xffffffffu, ok);
-        if (j < 4) cnt_lo |= (uint32_t)__popc(bal) << (8 * j);
-        else cnt_hi |= (uint32_t)__popc(bal) << (8 * (j - 4));
-        // ---- stage the kept lanes of the group, packed (compact modes)
+        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+        // ---- stage the kept lanes behind the warp's earlier groups (compact modes)
         if (kOrdered && ok) {
-          const uint32_t pos = j * 32 + __popc(bal & lt);
+          const uint32_t pos = run + __popc(bal & lt);
           sx[pos] = xo;
           sy[pos] = yo;
           sz[pos] = kF32 ? (OutT)z32 : (OutT)z64;
@@ -428,6 +438,7 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
           }
           if (kGen) si[pos] = (uint16_t)li;
         }
+        run += __popc(bal);
       } else {
         ok = false;
       }
@@ -450,30 +461,24 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
     // the input stage is no longer needed: hand it back to the producer before the prefix is resolved
     if (npx < kTileT) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // our zero fill vs the next bulk copy
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[s]);
-
-    // ---------------- per-group counts -> exclusive offsets of all 64 groups of the tile
-    uint32_t *const gc = s_gcnt[it & 1];  // double-buffered: a warp may run one barrier ahead of the readers
-    if (lane < kItersT) gc[lane * kCW + warp] = ((lane < 4 ? cnt_lo : cnt_hi) >> (8 * (lane & 3))) & 0xffu;
-    if (kOrdered && warp == 0 && lane == 0) s_peek[it & 1] = peek;
-    compute_bar();
-    const uint2 cpair = reinterpret_cast<const uint2 *>(gc)[lane];  // groups 2*lane, 2*lane + 1
-    uint32_t incl = cpair.x + cpair.y;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += up;
+    if (lane == 0) {
+      mbar_arrive(&empty_bar[s]);
+      s_tot[it & 1][warp] = run;  // double-buffered: a warp may run one barrier ahead of the readers
     }
-    const uint32_t tile_total = __shfl_sync(0xffffffffu, incl, 31);
-    // this warp's groups all have the parity of `warp`: pick the matching half of each pair once
-    const uint32_t off_sel = incl - cpair.y - ((warp & 1) ? 0u : cpair.x);
+    compute_bar();
+
+    // ---------------- the eight run totals -> this warp's offset inside the tile and the tile total
+    const uint32_t t8 = lane < kCW ? s_tot[it & 1][lane] : 0u;
+    const uint32_t tile_total = __reduce_add_sync(0xffffffffu, t8);
+    const uint32_t off = __reduce_add_sync(0xffffffffu, lane < warp ? t8 : 0u);
 
     // ---------------- tile base
     uint32_t base = 0;
     if (kOrdered) {
-      const unsigned long long pk = s_peek[it & 1];
-      const bool hit = (pk >> 62) == 2;
+      bool hit = false;
       if (n_pred > 0) {
+        const unsigned long long pk = s_peek[it & 1];
+        hit = (pk >> 62) == 2;
         if (hit) {
           base = (uint32_t)pk;
         } else if (warp == 0) {
@@ -504,41 +509,46 @@ __global__ void __launch_bounds__(kThreadsT, sizeof(OutT) == 4 ? 3 : 2) k_deproj
       if (threadIdx.x == 0 && tile_total) atomicAdd(a.counts + b, (unsigned long long)tile_total);
     }
 
-    // ---------------- drain: each group's packed run -> its contiguous place in every plane
-    if (!kOrdered || (cnt_lo | cnt_hi) != 0) {
+    // ---------------- drain: the warp's packed run -> its contiguous place in every plane, all lanes busy
+    {
       const long long fout = kPacked ? 0ll : (long long)b * a.frame_stride;
       const unsigned long long cap64 = kPacked ? (unsigned long long)ps : (unsigned long long)a.frame_stride;
       const uint32_t cap = cap64 > 0xffffffffull ? 0xffffffffu : (uint32_t)cap64;
       OutT *const o0 = reinterpret_cast<OutT *>(a.out) + fout;
+      const uint32_t n = kOrdered ? run : (uint32_t)max(0, min(kWarpPx, npx - w0));
+      const uint32_t g0 = kOrdered ? base + off : (uint32_t)(px0 + w0);
+      if (n != 0) {
+        // plane pointers once per tile; the unrolled iterations below then address with immediates only
+        const unsigned long long pb = (unsigned long long)ps * sizeof(OutT);
+        const unsigned long long ox = (unsigned long long)__cvta_generic_to_global(o0 + g0 + lane);
+        const unsigned long long oy = ox + pb, oz = oy + pb, orr = oz + pb, og = orr + pb, ob = og + pb;
+        const uint32_t room = g0 < cap ? cap - g0 : 0u;  // output slots left in this frame (capacity overflow is reported)
+        const uint32_t m = n < room ? n : room;
 #pragma unroll
-      for (int j = 0; j < kItersT; ++j) {
-        const int q = j * kCW + warp;
-        uint32_t n, g0;
-        if (kOrdered) {
-          n = ((j < 4 ? cnt_lo : cnt_hi) >> (8 * (j & 3))) & 0xffu;
-          if (n == 0) continue;
-          g0 = base + __shfl_sync(0xffffffffu, off_sel, q >> 1);
-        } else {
-          n = (uint32_t)max(0, min(32, npx - q * 32));
-          if (n == 0) continue;
-          g0 = (uint32_t)(px0 + q * 32);
-        }
-        const uint32_t g = g0 + (uint32_t)lane;
-        if ((uint32_t)lane < n && g < cap) {
+        for (int j = 0; j < kItersT; ++j) {
+          if ((uint32_t)(j * 32) >= m) break;  // warp-uniform
           const int k = j * 32 + lane;
-          OutT *o = o0 + g;
-          o[0] = sx[k];
-          o[ps] = sy[k];
-          o[2 * ps] = sz[k];
-          if (has_bgr) {
-            const uint32_t c = sc[k];
-            o[3 * ps] = unit_color<OutT>((c >> 16) & 255u, color_255);
-            o[4 * ps] = unit_color<OutT>((c >> 8) & 255u, color_255);
-            o[5 * ps] = unit_color<OutT>(c & 255u, color_255);
-          }
-          if (kGen && a.src_index) {
-            const uint32_t idx = si[k];
-            a.src_index[fout + g] = (!kOrdered && idx == 0xffffu) ? -1 : px0 + (int)idx;
+          constexpr int kStep = 32 * (int)sizeof(OutT);
+          if ((uint32_t)k < m) {
+            st_global<0>(ox + j * kStep, sx[k]);
+            st_global<0>(oy + j * kStep, sy[k]);
+            st_global<0>(oz + j * kStep, sz[k]);
+            if (has_bgr) {
+              const uint32_t c = sc[k];
+              if (kF32 && !kGen) {
+                st_global<0>(orr + j * kStep, (OutT)unit_color_f((float)((c >> 16) & 255u)));
+                st_global<0>(og + j * kStep, (OutT)unit_color_f((float)((c >> 8) & 255u)));
+                st_global<0>(ob + j * kStep, (OutT)unit_color_f((float)(c & 255u)));
+              } else {
+                st_global<0>(orr + j * kStep, unit_color<OutT>((c >> 16) & 255u, color_255));
+                st_global<0>(og + j * kStep, unit_color<OutT>((c >> 8) & 255u, color_255));
+                st_global<0>(ob + j * kStep, unit_color<OutT>(c & 255u, color_255));
+              }
+            }
+            if (kGen && a.src_index) {
+              const uint32_t idx = si[k];
+              a.src_index[fout + g0 + k] = (!kOrdered && idx == 0xffffu) ? -1 : px0 + (int)idx;
+            }
           }
         }
       }
@@ -558,9 +568,9 @@ int pick_spec(const DeprojArgs &a, int depth_kind) {
 
 template <typename OutT, int DK, int MODE>
 cudaError_t launch_spec(const rv_ctx *ctx, const DeprojArgs &a, int spec, cudaStream_t st) {
-  const size_t smem = (size_t)Layout<OutT, DK>::kSmem;
 #define RV_GO(S)                                                                                           \
   {                                                                                                        \
+    const size_t smem = (size_t)Layout<OutT, DK, S == 2>::kSmem;                                           \
     auto k = k_deproject_tma<OutT, DK, MODE, S>;                                                           \
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
     if (e != cudaSuccess) return e;                                                                        \

@@ -37,7 +37,8 @@ CamF to_camf(const RvCam &c) {
 
 struct RegArgs {
   const uint16_t *depth;
-  unsigned long long *keys;
+  unsigned long long *keys;  // winners requested: (raw depth << 32) | source index
+  unsigned int *keys32;      // depth only: raw depth, 0xffffffff = empty
   uint16_t *out;
   int32_t *winner;
   CamF dcam, ccam;
@@ -114,6 +115,7 @@ __device__ __forceinline__ bool map_corner(const RegArgs &a, float px, float py,
   return round_pix(pix[0], ix) && round_pix(pix[1], iy);
 }
 
+template <bool kWinner>
 __global__ void __launch_bounds__(256) k_reg_scatter(const RegArgs a) {
   const int Wd = a.dcam.width, Hd = a.dcam.height;
   const int Wc = a.ccam.width, Hc = a.ccam.height;
@@ -131,20 +133,53 @@ __global__ void __launch_bounds__(256) k_reg_scatter(const RegArgs a) {
     if (!map_corner(a, (float)dx - 0.5f, (float)dy - 0.5f, d, x0, y0)) continue;
     if (!map_corner(a, (float)dx + 0.5f, (float)dy + 0.5f, d, x1, y1)) continue;
     if (x0 < 0 || y0 < 0 || x1 >= Wc || y1 >= Hc) continue;
-    const unsigned long long key = ((unsigned long long)z << 32) | (unsigned int)src;
-    unsigned long long *kf = a.keys + (long long)f * Wc * Hc;
-    for (int y = y0; y <= y1; ++y)
-      for (int x = x0; x <= x1; ++x) atomicMin(kf + (long long)y * Wc + x, key);
+    if (kWinner) {
+      const unsigned long long key = ((unsigned long long)z << 32) | (unsigned int)src;
+      unsigned long long *kf = a.keys + (long long)f * Wc * Hc;
+      for (int y = y0; y <= y1; ++y)
+        for (int x = x0; x <= x1; ++x) atomicMin(kf + (long long)y * Wc + x, key);
+    } else {
+      unsigned int *kf = a.keys32 + (long long)f * Wc * Hc;
+      for (int y = y0; y <= y1; ++y)
+        for (int x = x0; x <= x1; ++x) atomicMin(kf + (long long)y * Wc + x, z);
+    }
   }
 }
 
-__global__ void __launch_bounds__(256) k_reg_resolve(const unsigned long long *__restrict__ keys, long long n,
+// The resolve pass also puts the key plane back to "empty", so the next chunk of frames needs no memset.
+__global__ void __launch_bounds__(256) k_reg_resolve32(unsigned int *__restrict__ keys, long long n, uint16_t *__restrict__ out) {
+  // eight colour pixels per thread: two 16-byte key loads, one 16-byte depth store
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long octs = n >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < octs; i += stride) {
+    uint4 *kp = reinterpret_cast<uint4 *>(keys + 8 * i);
+    const uint4 k0 = kp[0], k1 = kp[1];
+    const uint4 e = make_uint4(~0u, ~0u, ~0u, ~0u);
+    kp[0] = e;
+    kp[1] = e;
+    uint4 o;
+    o.x = (k0.x == ~0u ? 0u : k0.x) | ((k0.y == ~0u ? 0u : k0.y) << 16);
+    o.y = (k0.z == ~0u ? 0u : k0.z) | ((k0.w == ~0u ? 0u : k0.w) << 16);
+    o.z = (k1.x == ~0u ? 0u : k1.x) | ((k1.y == ~0u ? 0u : k1.y) << 16);
+    o.w = (k1.z == ~0u ? 0u : k1.z) | ((k1.w == ~0u ? 0u : k1.w) << 16);
+    *reinterpret_cast<uint4 *>(out + 8 * i) = o;
+  }
+  const long long tail0 = octs << 3;
+  for (long long i = tail0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned int k = keys[i];
+    keys[i] = ~0u;
+    out[i] = k == ~0u ? 0 : (uint16_t)k;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_reg_resolve(unsigned long long *__restrict__ keys, long long n,
                                                      uint16_t *__restrict__ out, int32_t *__restrict__ winner) {
   // two colour pixels per thread: one 16-byte key load, one 32-bit depth store
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long pairs = n >> 1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
     const ulonglong2 k = *reinterpret_cast<const ulonglong2 *>(keys + 2 * i);
+    *reinterpret_cast<ulonglong2 *>(keys + 2 * i) = make_ulonglong2(~0ull, ~0ull);
     const bool e0 = k.x == ~0ull, e1 = k.y == ~0ull;
     const uint32_t z0 = e0 ? 0u : (uint32_t)(k.x >> 32), z1 = e1 ? 0u : (uint32_t)(k.y >> 32);
     *reinterpret_cast<uint32_t *>(out + 2 * i) = z0 | (z1 << 16);
@@ -157,6 +192,7 @@ __global__ void __launch_bounds__(256) k_reg_resolve(const unsigned long long *_
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const unsigned long long k = keys[n - 1];
+    keys[n - 1] = ~0ull;
     out[n - 1] = k == ~0ull ? 0 : (uint16_t)(k >> 32);
     if (winner) winner[n - 1] = k == ~0ull ? -1 : (int)(uint32_t)k;
   }
@@ -189,12 +225,16 @@ int rv_register_depth_to_color(rv_ctx *ctx, const uint16_t *d_depth, int B, cons
   if (Pd > 0x7fffffffll || Pc > 0x7fffffffll) RV_FAIL(ctx, RV_EINVAL, "rv_register: image too large");
   if (!d_ws || ws_bytes < (size_t)Pc * 8) RV_FAIL(ctx, RV_EWORKSPACE, "rv_register: workspace %zu < %zu", ws_bytes, (size_t)Pc * 8);
   if (!rv_aligned(d_ws, 16)) RV_FAIL(ctx, RV_EALIGN, "rv_register: workspace must be 16-byte aligned");
-  if (!rv_aligned(d_out, 4) || (d_winner && !rv_aligned(d_winner, 8)))
-    RV_FAIL(ctx, RV_EALIGN, "rv_register: out must be 4-byte and winner 8-byte aligned");
+  if (!rv_aligned(d_out, 16) || (d_winner && !rv_aligned(d_winner, 8)))
+    RV_FAIL(ctx, RV_EALIGN, "rv_register: out must be 16-byte and winner 8-byte aligned");
   if ((Pc & 1) && B > 1) RV_FAIL(ctx, RV_EINVAL, "rv_register: odd colour pixel count needs B == 1");
   cudaStream_t st = (cudaStream_t)stream;
-  long long chunk = (long long)(ws_bytes / ((size_t)Pc * 8));
+  const bool want_winner = d_winner != nullptr;
+  const size_t key_bytes = want_winner ? 8 : 4;  // depth-only registration packs nothing but the raw depth
+  long long chunk = (long long)(ws_bytes / ((size_t)Pc * key_bytes));
+  if (chunk > kChunkFrames * (want_winner ? 1 : 2)) chunk = kChunkFrames * (want_winner ? 1 : 2);
   if (chunk > B) chunk = B;
+  if ((Pc & 7) && B > 1 && !want_winner) RV_FAIL(ctx, RV_EINVAL, "rv_register: colour pixel count must be a multiple of 8 for B > 1");
 
   RegArgs a;
   memset(&a, 0, sizeof(a));
@@ -204,21 +244,31 @@ int rv_register_depth_to_color(rv_ctx *ctx, const uint16_t *d_depth, int B, cons
   for (int i = 0; i < 3; ++i) a.t[i] = t[i];
   a.depth_units = depth_units;
   a.keys = reinterpret_cast<unsigned long long *>(d_ws);
+  a.keys32 = reinterpret_cast<unsigned int *>(d_ws);
   const int max_blocks = ctx->sm_count * 8;
+  // one memset for the whole call: every resolve pass leaves the plane empty for the next chunk
+  RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0xff, (size_t)chunk * Pc * key_bytes, st));
   for (long long f0 = 0; f0 < B; f0 += chunk) {
     const int nf = (int)((B - f0) < chunk ? (B - f0) : chunk);
-    RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0xff, (size_t)nf * Pc * 8, st));
     a.depth = d_depth + f0 * Pd;
     a.frames = nf;
     long long blocks = (Pd * nf + 255) / 256;
     if (blocks > max_blocks) blocks = max_blocks;
-    k_reg_scatter<<<(int)blocks, 256, 0, st>>>(a);
+    if (want_winner) k_reg_scatter<true><<<(int)blocks, 256, 0, st>>>(a);
+    else k_reg_scatter<false><<<(int)blocks, 256, 0, st>>>(a);
     RV_LAUNCHED(ctx);
     const long long n = Pc * nf;
-    blocks = ((n >> 1) + 255) / 256;
-    if (blocks > max_blocks) blocks = max_blocks;
-    if (blocks < 1) blocks = 1;
-    k_reg_resolve<<<(int)blocks, 256, 0, st>>>(a.keys, n, d_out + f0 * Pc, d_winner ? d_winner + f0 * Pc : nullptr);
+    if (want_winner) {
+      blocks = ((n >> 1) + 255) / 256;
+      if (blocks > max_blocks) blocks = max_blocks;
+      if (blocks < 1) blocks = 1;
+      k_reg_resolve<<<(int)blocks, 256, 0, st>>>(a.keys, n, d_out + f0 * Pc, d_winner + f0 * Pc);
+    } else {
+      blocks = ((n >> 3) + 255) / 256;
+      if (blocks > max_blocks) blocks = max_blocks;
+      if (blocks < 1) blocks = 1;
+      k_reg_resolve32<<<(int)blocks, 256, 0, st>>>(a.keys32, n, d_out + f0 * Pc);
+    }
     RV_LAUNCHED(ctx);
   }
   return RV_OK;
