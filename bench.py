@@ -394,7 +394,8 @@ def run_b200(a):
     tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))  # ncu capture of one launch; scaled to this run's frames per launch
+            traffic = float(tj["dram_bytes_per_launch"]) * chunk / float(tj["frames_per_launch"])
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "k_deproject", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -157,8 +157,11 @@ int rv_depth_to_meters(rv_ctx *ctx, const uint16_t *d_depth, int64_t n, int unit
  *  d_out        [B,Hc,Wc] uint16, 0 where no depth pixel lands
  *  d_winner     [B,Hc,Wc] int32 source index (y*Wd+x) of the winning depth pixel,
  *               lowest index on ties, -1 where empty; may be NULL
- *  d_ws         workspace of rv_register_workspace_bytes(B,Hc,Wc) bytes, 16-B aligned */
-size_t rv_register_workspace_bytes(int B, int Hc, int Wc);
+ *  d_ws         workspace of rv_register_workspace_bytes(B,Hd,Wd,Hc,Wc) bytes, 16-B aligned: per frame of a
+ *               16-frame chunk the 8-byte colour rectangle of every depth pixel, the bounding box of every
+ *               32-pixel row segment and one fixed-capacity segment list per 64x32 colour tile (a workspace
+ *               that holds at least one frame's share is accepted; the batch is then walked in smaller chunks) */
+size_t rv_register_workspace_bytes(int B, int Hd, int Wd, int Hc, int Wc);
 int rv_register_depth_to_color(rv_ctx *ctx, const uint16_t *d_depth, int B, const RvCam *depth_cam,
                                const RvCam *color_cam, const float *R_colmajor, const float *t, float depth_units,
                                uint16_t *d_out, int32_t *d_winner, void *d_ws, size_t ws_bytes, rv_stream stream);

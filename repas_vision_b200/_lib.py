@@ -51,7 +51,7 @@ SIGNATURES = {
     "rv_sm_count": (C.c_int, [c_vp]),
     "rv_launch_count": (c_i64, [c_vp]),
     "rv_depth_to_meters": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_f64, c_vp, c_vp]),
-    "rv_register_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "rv_register_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "rv_register_depth_to_color": (C.c_int, [c_vp, c_vp, C.c_int, C.POINTER(RvCam), C.POINTER(RvCam),
                                              C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, c_vp, c_vp, c_vp,
                                              C.c_size_t, c_vp]),

@@ -170,7 +170,7 @@ def register(depth: torch.Tensor, dcam: Camera, ccam: Camera, R_colmajor, t, dep
     Hc, Wc = ccam.height, ccam.width
     out = torch.empty((B, Hc, Wc), dtype=torch.uint16, device=dev)
     win = torch.empty((B, Hc, Wc), dtype=torch.int32, device=dev) if want_winner else None
-    nb = ctx.lib.rv_register_workspace_bytes(B if chunk_frames is None else min(B, chunk_frames), Hc, Wc)
+    nb = ctx.lib.rv_register_workspace_bytes(B if chunk_frames is None else min(B, chunk_frames), Hd, Wd, Hc, Wc)
     ws = workspace(nb, dev)
     R = (C.c_float * 9)(*[float(v) for v in np.asarray(R_colmajor, dtype=np.float32).reshape(9)])
     tt = (C.c_float * 3)(*[float(v) for v in np.asarray(t, dtype=np.float32).reshape(3)])

@@ -45,7 +45,10 @@ def test_library_exports_every_declared_symbol(built):
     assert lib.rv_status_string(2) == b"output capacity exceeded"
     # size queries are pure host functions
     assert lib.rv_deproject_workspace_bytes(1, 720, 1280) == 128 + 450 * 8
-    assert lib.rv_register_workspace_bytes(64, 720, 1280) == 8 * 720 * 1280 * 8
+    # per frame: 8 B per depth pixel, 8 B per 32-pixel row segment, counter + 256-entry list per 64x32 colour tile
+    per_frame = 640 * 480 * 8 + 480 * 20 * 8 + 2048 + 20 * 23 * 256 * 4  # each part is a multiple of 256 B here
+    tables = (640 + 480) * 2 * 4  # normalised corner coordinates per column / row, 256-byte multiple here
+    assert lib.rv_register_workspace_bytes(64, 480, 640, 720, 1280) == tables + 16 * per_frame
     assert lib.rv_voxel_workspace_bytes(1000) == 256 + 2048 * 64
 
 
