@@ -12,11 +12,16 @@
 namespace {
 
 // ------------------------------------------------------------------ transform + merge
-struct XformArgs {
+constexpr int kXformViews = 8;  // views per launch (blockIdx.y); the four_pose_captures fusion is one launch
+struct XformView {
   const void *in;
-  void *out;
-  long long in_stride, out_stride, n, out_offset;
+  long long in_stride, n, out_offset;
   double T[16];
+};
+struct XformArgs {
+  XformView view[kXformViews];
+  void *out;
+  long long out_stride;
   double *bounds;  // 6 doubles or null
   int has_color;
 };
@@ -66,9 +71,10 @@ __device__ __forceinline__ void block_bounds_commit(double lo[3], double hi[3], 
 }
 
 template <typename InT, typename OutT>
-__global__ void __launch_bounds__(256) k_transform(const XformArgs a) {
+__global__ void __launch_bounds__(256) k_transform(const __grid_constant__ XformArgs args) {
+  const XformView &a = args.view[blockIdx.y];
   const InT *in = reinterpret_cast<const InT *>(a.in);
-  OutT *out = reinterpret_cast<OutT *>(a.out) + a.out_offset;
+  OutT *out = reinterpret_cast<OutT *>(args.out) + a.out_offset;
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
   double lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -88,14 +94,14 @@ __global__ void __launch_bounds__(256) k_transform(const XformArgs a) {
     }
     const OutT ox = (OutT)px, oy = (OutT)py, oz = (OutT)pz;
     out[i] = ox;
-    out[a.out_stride + i] = oy;
-    out[2 * a.out_stride + i] = oz;
-    if (a.has_color) {
-      out[3 * a.out_stride + i] = (OutT)in[3 * a.in_stride + i];
-      out[4 * a.out_stride + i] = (OutT)in[4 * a.in_stride + i];
-      out[5 * a.out_stride + i] = (OutT)in[5 * a.in_stride + i];
+    out[args.out_stride + i] = oy;
+    out[2 * args.out_stride + i] = oz;
+    if (args.has_color) {
+      out[3 * args.out_stride + i] = (OutT)in[3 * a.in_stride + i];
+      out[4 * args.out_stride + i] = (OutT)in[4 * a.in_stride + i];
+      out[5 * args.out_stride + i] = (OutT)in[5 * a.in_stride + i];
     }
-    if (a.bounds) {  // bounds of the STORED merged cloud
+    if (args.bounds) {  // bounds of the STORED merged cloud
       const double sx = (double)ox, sy = (double)oy, sz = (double)oz;
       lo[0] = sx < lo[0] ? sx : lo[0];
       lo[1] = sy < lo[1] ? sy : lo[1];
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(256) k_transform(const XformArgs a) {
       hi[2] = sz > hi[2] ? sz : hi[2];
     }
   }
-  if (a.bounds) block_bounds_commit(lo, hi, a.bounds);
+  if (args.bounds) block_bounds_commit(lo, hi, args.bounds);
 }
 
 __global__ void k_bounds_init(double *b) {
@@ -131,20 +137,39 @@ __global__ void __launch_bounds__(256) k_bounds(const T *__restrict__ in, long l
 }
 
 // --------------------------------------------------------------------- voxel grid
-// Workspace: [header 256 B][table: capacity x 64-byte slots]
+// Workspace: [header 256 B][per-part counters: 2048 x 8 B][hash slots: capacity x 16 B][records: n x 64 B][list: n x 4 B]
+//
+// The hash table holds only keys (16-byte slots: packed key + the index of the voxel's record), so clearing it and probing
+// it touch a quarter of the bytes a table of full records would, and nothing else is ever cleared.  Points arrive in
+// pixel order, so consecutive points usually share a voxel: each warp first folds runs of equal keys with a segmented
+// shuffle reduction, and only the head of a run goes to memory.  A run head
+//   * writes its partial sums to the record with its own point index (plain stores, no allocation counter),
+//   * tries to claim the slot of its key with ONE compare-and-swap: the winner's record becomes the voxel's record
+//     ("creator"); a head that finds the key already there is a "joiner",
+//   * creators and joiners are appended to the two ends of the CTA's own stretch of the list (the cloud is cut into one
+//     contiguous part per CTA), positions from shared-memory counters: no global counter anywhere.
+// k_voxel_merge then adds every joiner's record into its voxel's record with float64 atomics (the kernel boundary is
+// the only ordering the scheme needs: no fences, no spinning on another thread's publication), and k_voxel_emit writes
+// part p's creators behind the creators of parts 0..p-1 (a 2048-entry prefix sum per CTA).
 struct VoxHeader {
   double bounds[6];
-  unsigned long long n_out;  // voxel counter (compaction)
-  int error;                 // 1: a voxel index does not fit 21 bits / extent check failed
+  int error;  // 1: a voxel index does not fit 21 bits / extent check failed
   int pad;
 };
-struct __align__(64) VoxSlot {
+constexpr int kVoxMaxParts = 2048;
+constexpr size_t kVoxHead = 256 + (size_t)kVoxMaxParts * 8;  // header + per-part {creators, joiners}
+struct __align__(16) VoxSlot {
   unsigned long long key;  // 0 = empty, else packed(ix,iy,iz) + 1
+  unsigned int idx1;       // creator's record index + 1
+  unsigned int pad;
+};
+struct __align__(64) VoxAcc {
+  unsigned long long key;
   unsigned int count;
   unsigned int pad;
   double sum[6];
 };
-static_assert(sizeof(VoxSlot) == 64, "slot must be one 64-byte record");
+static_assert(sizeof(VoxSlot) == 16 && sizeof(VoxAcc) == 64, "slot / record layout");
 
 struct VoxArgs {
   const void *in;
@@ -154,6 +179,10 @@ struct VoxArgs {
   const double *bounds;  // device
   VoxHeader *hdr;
   VoxSlot *table;
+  VoxAcc *acc;
+  unsigned int *list;  // part p owns list[p * span, ...): creators from its front, joiners from its back (record indices)
+  uint2 *parts;        // per part {creators, joiners}
+  long long span;      // points per part, a multiple of 32
   unsigned long long cap_mask;
 };
 
@@ -182,41 +211,115 @@ __global__ void __launch_bounds__(256) k_voxel_insert(const VoxArgs a) {
       return;
     }
   }
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-    const double x = (double)in[i], y = (double)in[a.in_stride + i], z = (double)in[2 * a.in_stride + i];
-    // key = floor((p - origin) / voxel), IEEE division via the exact-reciprocal helper
-    const long long ix = (long long)floor(rv_div(x - ox, a.voxel, a.rvoxel));
-    const long long iy = (long long)floor(rv_div(y - oy, a.voxel, a.rvoxel));
-    const long long iz = (long long)floor(rv_div(z - oz, a.voxel, a.rvoxel));
-    const unsigned long long key =
-        (((unsigned long long)ix & 0x1fffff) << 42 | ((unsigned long long)iy & 0x1fffff) << 21 | ((unsigned long long)iz & 0x1fffff)) + 1ull;
-    unsigned long long h = vox_hash(key) & a.cap_mask;
-    for (;;) {
-      VoxSlot *s = a.table + h;
-      unsigned long long cur = s->key;
-      if (cur == 0) cur = atomicCAS(&s->key, 0ull, key);
-      if (cur == 0 || cur == key) {
-        atomicAdd(&s->count, 1u);
-        atomicAdd(&s->sum[0], x);
-        atomicAdd(&s->sum[1], y);
-        atomicAdd(&s->sum[2], z);
-        if (a.has_color) {
-          atomicAdd(&s->sum[3], (double)in[3 * a.in_stride + i]);
-          atomicAdd(&s->sum[4], (double)in[4 * a.in_stride + i]);
-          atomicAdd(&s->sum[5], (double)in[5 * a.in_stride + i]);
-        }
-        break;
+  const int lane = threadIdx.x & 31;
+  __shared__ unsigned int s_create, s_join;
+  if (threadIdx.x == 0) s_create = s_join = 0;
+  __syncthreads();
+  const long long p0 = (long long)blockIdx.x * a.span;                  // this CTA's part of the cloud
+  const long long p1 = p0 + a.span < a.n ? p0 + a.span : a.n;           // (empty when p0 >= n)
+  for (long long i = p0 + threadIdx.x; i < p0 + a.span && i - lane < p1; i += blockDim.x) {  // whole warps: full shuffles
+    const bool valid = i < p1;
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    unsigned long long key = 0;  // lanes past the end form one run that is never written
+    if (valid) {
+      v[0] = (double)in[i], v[1] = (double)in[a.in_stride + i], v[2] = (double)in[2 * a.in_stride + i];
+      if (a.has_color) {
+        v[3] = (double)in[3 * a.in_stride + i];
+        v[4] = (double)in[4 * a.in_stride + i];
+        v[5] = (double)in[5 * a.in_stride + i];
       }
-      h = (h + 1) & a.cap_mask;
+      // key = floor((p - origin) / voxel), IEEE division via the exact-reciprocal helper
+      const long long ix = (long long)floor(rv_div(v[0] - ox, a.voxel, a.rvoxel));
+      const long long iy = (long long)floor(rv_div(v[1] - oy, a.voxel, a.rvoxel));
+      const long long iz = (long long)floor(rv_div(v[2] - oz, a.voxel, a.rvoxel));
+      key = (((unsigned long long)ix & 0x1fffff) << 42 | ((unsigned long long)iy & 0x1fffff) << 21 | ((unsigned long long)iz & 0x1fffff)) + 1ull;
+    }
+    // ---- fold runs of equal keys inside the warp (segmented reduction towards the first lane of each run)
+    const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = lane == 0 || key != prev;
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    const uint32_t after = lane == 31 ? 0u : (heads >> (lane + 1));
+    const int run = after ? __ffs(after) : 32 - lane;  // lanes from this one to the end of its run
+    const int ncol = a.has_color ? 6 : 3;
+    const int longest = __reduce_max_sync(0xffffffffu, run);  // steps needed: log2 of the longest run in the warp (often 2-4 points)
+#pragma unroll 1
+    for (int d = 1; d < longest; d <<= 1) {
+      const bool take = d < run;  // lane + d still belongs to this lane's run
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        if (c < ncol) {
+          const double o = __shfl_down_sync(0xffffffffu, v[c], d);
+          if (take) v[c] += o;
+        }
+      }
+    }
+    // ---- one record and one slot probe per run
+    const bool lead = head && valid;
+    bool created = false;
+    if (lead) {
+      VoxAcc *acc = a.acc + i;
+      acc->key = key;
+      acc->count = (unsigned int)run;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc->sum[c] = v[c];
+      unsigned long long h = vox_hash(key) & a.cap_mask;
+      for (;;) {
+        VoxSlot *s = a.table + h;
+        const unsigned long long cur = atomicCAS(&s->key, 0ull, key);  // the table is at most a quarter full: usually empty
+        if (cur == 0) {
+          s->idx1 = (unsigned int)i + 1u;  // read by the next kernel
+          created = true;
+          break;
+        }
+        if (cur == key) break;
+        h = (h + 1) & a.cap_mask;
+      }
+    }
+    // ---- creators to the front of the part's stretch of the list, joiners to its back
+    const uint32_t cb = __ballot_sync(0xffffffffu, created);
+    const uint32_t jb = __ballot_sync(0xffffffffu, lead && !created);
+    unsigned int cbase = 0, jbase = 0;
+    if (lane == 0) {
+      if (cb) cbase = atomicAdd(&s_create, (unsigned int)__popc(cb));
+      if (jb) jbase = atomicAdd(&s_join, (unsigned int)__popc(jb));
+    }
+    cbase = __shfl_sync(0xffffffffu, cbase, 0);
+    jbase = __shfl_sync(0xffffffffu, jbase, 0);
+    if (created) a.list[p0 + cbase + __popc(cb & rv_lanemask_lt())] = (unsigned int)i;
+    else if (lead) a.list[p1 - 1 - (long long)(jbase + __popc(jb & rv_lanemask_lt()))] = (unsigned int)i;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) a.parts[blockIdx.x] = make_uint2(s_create, s_join);
+}
+
+// every joiner's record is added to the record of its voxel's creator
+__global__ void __launch_bounds__(256) k_voxel_merge(const VoxArgs a) {
+  const long long p0 = (long long)blockIdx.x * a.span;
+  const long long p1 = p0 + a.span < a.n ? p0 + a.span : a.n;
+  const unsigned int nj = a.parts[blockIdx.x].y;
+  for (unsigned int j = threadIdx.x; j < nj; j += blockDim.x) {
+    const VoxAcc r = a.acc[a.list[p1 - 1 - j]];
+    unsigned long long h = vox_hash(r.key) & a.cap_mask;
+    while (a.table[h].key != r.key) h = (h + 1) & a.cap_mask;
+    VoxAcc *acc = a.acc + (a.table[h].idx1 - 1u);
+    atomicAdd(&acc->count, r.count);
+    atomicAdd(&acc->sum[0], r.sum[0]);
+    atomicAdd(&acc->sum[1], r.sum[1]);
+    atomicAdd(&acc->sum[2], r.sum[2]);
+    if (a.has_color) {
+      atomicAdd(&acc->sum[3], r.sum[3]);
+      atomicAdd(&acc->sum[4], r.sum[4]);
+      atomicAdd(&acc->sum[5], r.sum[5]);
     }
   }
 }
 
 struct VoxOutArgs {
-  VoxHeader *hdr;
-  const VoxSlot *table;
-  unsigned long long capacity;
+  const VoxHeader *hdr;
+  const VoxAcc *acc;
+  const unsigned int *list;
+  const uint2 *parts;
+  long long span;
   void *out;
   long long out_stride, out_capacity;
   int32_t *keys;
@@ -225,45 +328,53 @@ struct VoxOutArgs {
   int has_color;
 };
 
+// CTA p writes the voxels part p created, behind those of parts 0..p-1: mean = sum / count (one IEEE division for
+// 1 / count, then the exact-quotient correction of rv_div per component)
 template <typename OutT>
 __global__ void __launch_bounds__(256) k_voxel_emit(const VoxOutArgs a) {
   OutT *out = reinterpret_cast<OutT *>(a.out);
-  const int lane = threadIdx.x & 31;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  // whole warps iterate together so the ballot below is always full
-  const long long cap_round = (long long)((a.capacity + 31) & ~31ull);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cap_round; i += stride) {
-    const bool live = (unsigned long long)i < a.capacity && a.table[i].key != 0;
-    const uint32_t bal = __ballot_sync(0xffffffffu, live);
-    if (!bal) continue;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&a.hdr->n_out, (unsigned long long)__popc(bal));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (!live) continue;
-    const long long o = (long long)(base + __popc(bal & rv_lanemask_lt()));
-    if (o >= a.out_capacity) continue;
-    const VoxSlot s = a.table[i];
-    const double c = (double)s.count;
-    out[o] = (OutT)(s.sum[0] / c);
-    out[a.out_stride + o] = (OutT)(s.sum[1] / c);
-    out[2 * a.out_stride + o] = (OutT)(s.sum[2] / c);
+  __shared__ unsigned long long s_red[2][8];
+  unsigned long long before = 0, total = 0;
+  for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) {
+    const unsigned long long c = a.parts[q].x;
+    total += c;
+    if (q < (int)blockIdx.x) before += c;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    before += __shfl_xor_sync(0xffffffffu, before, o);
+    total += __shfl_xor_sync(0xffffffffu, total, o);
+  }
+  if ((threadIdx.x & 31) == 0) s_red[0][threadIdx.x >> 5] = before, s_red[1][threadIdx.x >> 5] = total;
+  __syncthreads();
+  before = total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) before += s_red[0][w], total += s_red[1][w];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.m = a.hdr->error ? -1ll : (long long)total;
+  if (a.hdr->error) return;
+  const unsigned int mine = a.parts[blockIdx.x].x;
+  const unsigned int *list = a.list + (long long)blockIdx.x * a.span;
+  for (unsigned int k = threadIdx.x; k < mine; k += blockDim.x) {
+    const long long o = (long long)(before + k);
+    if (o >= a.out_capacity) break;
+    const VoxAcc s = a.acc[list[k]];
+    const double c = (double)s.count, rc = 1.0 / c;
+    out[o] = (OutT)rv_div(s.sum[0], c, rc);
+    out[a.out_stride + o] = (OutT)rv_div(s.sum[1], c, rc);
+    out[2 * a.out_stride + o] = (OutT)rv_div(s.sum[2], c, rc);
     if (a.has_color) {
-      out[3 * a.out_stride + o] = (OutT)(s.sum[3] / c);
-      out[4 * a.out_stride + o] = (OutT)(s.sum[4] / c);
-      out[5 * a.out_stride + o] = (OutT)(s.sum[5] / c);
+      out[3 * a.out_stride + o] = (OutT)rv_div(s.sum[3], c, rc);
+      out[4 * a.out_stride + o] = (OutT)rv_div(s.sum[4], c, rc);
+      out[5 * a.out_stride + o] = (OutT)rv_div(s.sum[5], c, rc);
     }
     if (a.keys) {
-      const unsigned long long k = s.key - 1ull;
-      a.keys[o] = (int32_t)((k >> 42) & 0x1fffff);
-      a.keys[a.out_capacity + o] = (int32_t)((k >> 21) & 0x1fffff);
-      a.keys[2 * a.out_capacity + o] = (int32_t)(k & 0x1fffff);
+      const unsigned long long kk = s.key - 1ull;
+      a.keys[o] = (int32_t)((kk >> 42) & 0x1fffff);
+      a.keys[a.out_capacity + o] = (int32_t)((kk >> 21) & 0x1fffff);
+      a.keys[2 * a.out_capacity + o] = (int32_t)(kk & 0x1fffff);
     }
     if (a.counts) a.counts[o] = (int32_t)s.count;
   }
-}
-
-__global__ void k_voxel_finish(const VoxHeader *hdr, long long *m) {
-  *m = hdr->error ? -1ll : (long long)hdr->n_out;
 }
 
 unsigned long long vox_capacity(long long n) {
@@ -341,34 +452,42 @@ int rv_transform_merge(rv_ctx *ctx, int n_views, const void *const *d_in, const 
   if (total > 0 && !d_out) RV_FAIL(ctx, RV_EINVAL, "rv_transform_merge: null output");
   cudaStream_t st = (cudaStream_t)stream;
   long long off = 0;
-  for (int v = 0; v < n_views; ++v) {
-    if (n[v] == 0) continue;
-    if (!d_in[v]) RV_FAIL(ctx, RV_EINVAL, "rv_transform_merge: view %d is null", v);
+  for (int v0 = 0; v0 < n_views; v0 += kXformViews) {
     XformArgs a;
     memset(&a, 0, sizeof(a));
-    a.in = d_in[v];
     a.out = d_out;
-    a.in_stride = in_plane_stride[v];
     a.out_stride = out_plane_stride;
-    a.n = n[v];
-    a.out_offset = off;
-    memcpy(a.T, T + 16 * v, sizeof(a.T));
     a.bounds = d_bounds;
     a.has_color = has_color ? 1 : 0;
-    const int grid = grid_for(ctx, n[v]);
+    int nv = 0;
+    long long nmax = 0;
+    for (int v = v0; v < n_views && v < v0 + kXformViews; ++v) {
+      if (n[v] > 0) {
+        if (!d_in[v]) RV_FAIL(ctx, RV_EINVAL, "rv_transform_merge: view %d is null", v);
+        XformView &w = a.view[nv++];
+        w.in = d_in[v];
+        w.in_stride = in_plane_stride[v];
+        w.n = n[v];
+        w.out_offset = off;
+        memcpy(w.T, T + 16 * v, sizeof(w.T));
+        nmax = n[v] > nmax ? n[v] : nmax;
+      }
+      off += n[v];
+    }
+    if (nv == 0) continue;
+    const dim3 grid((unsigned)grid_for(ctx, nmax, nv > 1 ? 4 : 8), (unsigned)nv);
     if (in_dtype == RV_F32 && out_dtype == RV_F32) k_transform<float, float><<<grid, 256, 0, st>>>(a);
     else if (in_dtype == RV_F32) k_transform<float, double><<<grid, 256, 0, st>>>(a);
     else if (out_dtype == RV_F32) k_transform<double, float><<<grid, 256, 0, st>>>(a);
     else k_transform<double, double><<<grid, 256, 0, st>>>(a);
     RV_LAUNCHED(ctx);
-    off += n[v];
   }
   return RV_OK;
 }
 
 size_t rv_voxel_workspace_bytes(int64_t n) {
   if (n < 0) n = 0;
-  return 256 + (size_t)vox_capacity(n) * sizeof(VoxSlot);
+  return kVoxHead + (size_t)vox_capacity(n) * sizeof(VoxSlot) + (size_t)n * sizeof(VoxAcc) + (((size_t)n * 4 + 63) & ~(size_t)63);
 }
 
 int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int in_dtype, int has_color,
@@ -378,6 +497,7 @@ int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, 
   if (!ctx) return RV_EINVAL;
   RvDeviceGuard dev_guard(ctx);
   if (!(voxel_size > 0.0)) RV_FAIL(ctx, RV_EINVAL, "rv_voxel_downsample: voxel_size <= 0");
+  if (n >= 0xffffffffll) RV_FAIL(ctx, RV_EINVAL, "rv_voxel_downsample: more than 2^32 - 2 points");
   if (n < 0 || in_plane_stride < n || !d_m) RV_FAIL(ctx, RV_EINVAL, "rv_voxel_downsample: bad n / stride / m");
   if ((in_dtype != RV_F32 && in_dtype != RV_F64) || (out_dtype != RV_F32 && out_dtype != RV_F64))
     RV_FAIL(ctx, RV_EINVAL, "rv_voxel_downsample: bad dtype");
@@ -393,8 +513,11 @@ int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, 
   if (!rv_aligned(d_ws, 64)) RV_FAIL(ctx, RV_EALIGN, "rv_voxel_downsample: workspace must be 64-byte aligned");
   const unsigned long long cap = vox_capacity(n);
   VoxHeader *hdr = reinterpret_cast<VoxHeader *>(d_ws);
-  VoxSlot *table = reinterpret_cast<VoxSlot *>(reinterpret_cast<char *>(d_ws) + 256);
-  RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, need, st));
+  uint2 *parts = reinterpret_cast<uint2 *>(reinterpret_cast<char *>(d_ws) + 256);
+  VoxSlot *table = reinterpret_cast<VoxSlot *>(reinterpret_cast<char *>(d_ws) + kVoxHead);
+  VoxAcc *acc = reinterpret_cast<VoxAcc *>(reinterpret_cast<char *>(d_ws) + kVoxHead + cap * sizeof(VoxSlot));
+  unsigned int *list = reinterpret_cast<unsigned int *>(acc + n);
+  RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, kVoxHead + cap * sizeof(VoxSlot), st));  // header, counters, key slots; records are written, not cleared
   const double *bounds = d_bounds;
   if (!bounds) {
     k_bounds_init<<<1, 32, 0, st>>>(hdr->bounds);
@@ -416,31 +539,39 @@ int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, 
   a.bounds = bounds;
   a.hdr = hdr;
   a.table = table;
+  a.acc = acc;
+  a.list = list;
   a.cap_mask = cap - 1;
+  int parts_n;
   {
-    const int g = grid_for(ctx, n);
-    if (in_dtype == RV_F32) k_voxel_insert<float><<<g, 256, 0, st>>>(a);
-    else k_voxel_insert<double><<<g, 256, 0, st>>>(a);
-    RV_LAUNCHED(ctx);
+    auto kf = k_voxel_insert<float>;
+    auto kd = k_voxel_insert<double>;
+    parts_n = in_dtype == RV_F32 ? rv_persistent_grid(ctx, kf, 256, 0, (n + 255) / 256) : rv_persistent_grid(ctx, kd, 256, 0, (n + 255) / 256);
+    if (parts_n > kVoxMaxParts) parts_n = kVoxMaxParts;
+    a.span = (((n + parts_n - 1) / parts_n) + 31) & ~31ll;
+    a.parts = parts;
+    if (in_dtype == RV_F32) kf<<<parts_n, 256, 0, st>>>(a);
+    else kd<<<parts_n, 256, 0, st>>>(a);
   }
+  RV_LAUNCHED(ctx);
+  k_voxel_merge<<<parts_n, 256, 0, st>>>(a);
+  RV_LAUNCHED(ctx);
   VoxOutArgs o;
   memset(&o, 0, sizeof(o));
   o.hdr = hdr;
-  o.table = table;
-  o.capacity = cap;
+  o.acc = acc;
+  o.list = list;
+  o.parts = parts;
+  o.span = a.span;
   o.out = d_out;
   o.out_stride = out_plane_stride;
   o.out_capacity = out_capacity;
   o.keys = d_keys;
   o.counts = d_counts_out;
+  o.m = reinterpret_cast<long long *>(d_m);
   o.has_color = has_color ? 1 : 0;
-  {
-    const int g = grid_for(ctx, (long long)cap);
-    if (out_dtype == RV_F32) k_voxel_emit<float><<<g, 256, 0, st>>>(o);
-    else k_voxel_emit<double><<<g, 256, 0, st>>>(o);
-    RV_LAUNCHED(ctx);
-  }
-  k_voxel_finish<<<1, 1, 0, st>>>(hdr, reinterpret_cast<long long *>(d_m));
+  if (out_dtype == RV_F32) k_voxel_emit<float><<<parts_n, 256, 0, st>>>(o);
+  else k_voxel_emit<double><<<parts_n, 256, 0, st>>>(o);
   RV_LAUNCHED(ctx);
   return RV_OK;
 }

@@ -45,6 +45,9 @@ constexpr int kTileT = kCT * kItersT;   // 2048 pixels
 #ifndef RV_K1_TICKET_AHEAD
 #define RV_K1_TICKET_AHEAD 0
 #endif
+#ifndef RV_K1_TICKET_BATCH
+#define RV_K1_TICKET_BATCH 4  // consecutive tickets taken per atomic: the shared counter is touched once per BATCH tiles
+#endif
 constexpr int kStages = RV_K1_STAGES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -224,12 +227,21 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
       const float rcpT = 1.0f / (float)tpf;
       // tickets are requested one tile ahead so the atomic's round trip hides behind the wait for a free stage
       int ticket = RV_K1_TICKET_AHEAD ? (int)atomicAdd(a.ticket, 1u) : 0;
+      int left = 0;  // tickets still unused from the last batch
       for (int it = 0;; ++it) {
         const int s = it % kStages;
         int next = 0;
         if (RV_K1_TICKET_AHEAD) next = ticket < a.total_tiles ? (int)atomicAdd(a.ticket, 1u) : ticket;
         mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
-        if (!RV_K1_TICKET_AHEAD) ticket = (int)atomicAdd(a.ticket, 1u);
+        if (!RV_K1_TICKET_AHEAD) {
+          if (left == 0) {
+            ticket = (int)atomicAdd(a.ticket, (unsigned int)RV_K1_TICKET_BATCH);
+            left = RV_K1_TICKET_BATCH;
+          } else {
+            ++ticket;
+          }
+          --left;
+        }
         if (ticket >= a.total_tiles) {
           s_info[s] = make_int4(-1, 0, 0, 0);
           mbar_arrive(&full_bar[s]);
@@ -255,7 +267,7 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
         bulk_load(st, reinterpret_cast<const unsigned char *>(a.depth) + g * kDepthB, (uint32_t)npx * kDepthB, &full_bar[s]);
         if (has_bgr) bulk_load(st + kTileT * kDepthB, a.bgr + g * 3, (uint32_t)npx * 3, &full_bar[s]);
         if (kGen && has_mask) bulk_load(st + kTileT * (kDepthB + 3), a.mask + g, (uint32_t)npx, &full_bar[s]);
-        ticket = next;
+        if (RV_K1_TICKET_AHEAD) ticket = next;
       }
     }
     return;

@@ -1,6 +1,9 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-timeout 300 python tools/bench_kernels.py > gpurun_out/k2v2_kernels.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_reg -c 4 -f -o gpurun_out/k2_v2 python tools/bench_kernels.py --reps 1 > gpurun_out/ncu_k2.log 2>&1
+for cfg in "0 4" "0 16" "1 4" "0 2"; do
+  set -- $cfg
+  RV_NVCC_EXTRA="-DRV_K1_TWO_PHASE=$1 -DRV_K1_TICKET_BATCH=$2" python -m repas_vision_b200._build --force > gpurun_out/build_tmp.log 2>&1 || echo BUILD FAILED $cfg
+  timeout 300 python bench.py --no-e2e --no-cpu-baseline --steps 5 > gpurun_out/tb_p$1_b$2_c2048.log 2>&1
+  timeout 300 python bench.py --no-e2e --no-cpu-baseline --steps 5 --chunk 1024 > gpurun_out/tb_p$1_b$2_c1024.log 2>&1
+done
 echo done
