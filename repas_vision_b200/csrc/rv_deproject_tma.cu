@@ -234,9 +234,11 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
         if (RV_K1_TICKET_AHEAD) next = ticket < a.total_tiles ? (int)atomicAdd(a.ticket, 1u) : ticket;
         mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
         if (!RV_K1_TICKET_AHEAD) {
+          // (packed mode is ONE chain through the batch: consecutive tickets depend on each other, so they are taken singly)
+          constexpr int kBatch = kPacked ? 1 : RV_K1_TICKET_BATCH;
           if (left == 0) {
-            ticket = (int)atomicAdd(a.ticket, (unsigned int)RV_K1_TICKET_BATCH);
-            left = RV_K1_TICKET_BATCH;
+            ticket = (int)atomicAdd(a.ticket, (unsigned int)kBatch);
+            left = kBatch;
           } else {
             ++ticket;
           }
