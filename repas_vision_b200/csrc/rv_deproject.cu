@@ -24,6 +24,7 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kIters = 8;
 constexpr int kTile = kThreads * kIters;  // 2048 pixels
+static_assert(kTile == kGenericTilePx, "rv_deproject_args.cuh sizes the workspace from this tile");
 
 
 template <typename T>
@@ -464,7 +465,7 @@ int rv_build_ray_table(rv_ctx *ctx, const RvCam *cam, double *d_table, rv_stream
 size_t rv_deproject_workspace_bytes(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 128;
   const long long P = (long long)H * W;
-  const long long tiles = (P + kTile - 1) / kTile * B;
+  const long long tiles = (P + kMinTilePx - 1) / kMinTilePx * B;
   return 128 + (size_t)tiles * 8;
 }
 
@@ -524,10 +525,7 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
   a.H = H;
   a.W = W;
   a.P = (int)P;
-  a.tiles_per_frame = (int)((P + kTile - 1) / kTile);
-  const long long total = (long long)a.tiles_per_frame * B;
-  if (total > 0x7fffffffll) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: batch too large");
-  a.total_tiles = (int)total;
+  if ((P + kMinTilePx - 1) / kMinTilePx * (long long)B > 0x7fffffffll) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: batch too large");
   a.plane_stride = plane_stride;
   a.frame_stride = frame_stride;
   a.cx = p->cam.cx;
@@ -586,9 +584,12 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
     RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: RV_KERNEL_TMA requested but the inputs are not eligible "
                             "(H*W %% 16 == 0, W >= 32, 16-byte aligned inputs, no ray table, not COMPACT_UNORDERED)");
   const bool use_fast = fast_ok && p->kernel_select != RV_KERNEL_GENERIC;
+  const int tile_px = use_fast ? kFastTilePx : kTile;
+  a.tiles_per_frame = (int)((P + tile_px - 1) / tile_px);
+  a.total_tiles = a.tiles_per_frame * B;
 
   if (ordered) {
-    RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, need, st));
+    RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, 128 + (size_t)a.total_tiles * 8, st));  // ticket counter + one status word per tile
   } else {
     RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, 128, st));  // ticket counter
     RV_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (size_t)B * sizeof(int64_t), st));

@@ -35,7 +35,14 @@ struct DeprojArgs {
   unsigned int d_cand;  // uint16 depths in [1, d_cand) can still be inside the sphere; 65536 when there is no radius mask
 };
 
-// fast path (rv_deproject_tma.cu)
+// fast path (rv_deproject_tma.cu): RV_K1_CW compute warps per CTA, 256 pixels each per tile
+#ifndef RV_K1_CW
+#define RV_K1_CW 8
+#endif
+constexpr int kFastTilePx = RV_K1_CW * 256;
+constexpr int kGenericTilePx = 2048;
+constexpr int kMinTilePx = kFastTilePx < kGenericTilePx ? kFastTilePx : kGenericTilePx;  // sizes the workspace
+
 bool rv_deproject_fast_eligible(const DeprojArgs &a, int mode);
 cudaError_t rv_deproject_fast_launch(const rv_ctx *ctx, const DeprojArgs &a, int mode, int out_dtype, int depth_kind,
                                      cudaStream_t st);

@@ -33,7 +33,7 @@
 
 namespace {
 
-constexpr int kCW = 8;                  // compute warps
+constexpr int kCW = RV_K1_CW;            // compute warps
 constexpr int kCT = kCW * 32;           // compute threads
 constexpr int kThreadsT = kCT + 32;     // + producer warp
 constexpr int kItersT = 8;
@@ -155,7 +155,9 @@ struct Layout {
   static constexpr int kRingBytes = kStages * kStageBytes;
   static constexpr int kSmem = kRingBytes + kCW * kWarpStage;
   // resident CTAs per SM the shared memory allows (227 KB usable, ~1.5 KB static + reserved per CTA)
-  static constexpr int kOcc = (227 * 1024) / (kSmem + 1536) > 4 ? 4 : (227 * 1024) / (kSmem + 1536);
+  static constexpr int kOccSmem = (227 * 1024) / (kSmem + 1536);
+  static constexpr int kOccCap = 32 / kCW;  // 32 compute warps per SM: 4 CTAs of 8 warps (or 8 CTAs of 4)
+  static constexpr int kOcc = kOccSmem > kOccCap ? kOccCap : kOccSmem;
 };
 
 // k / 255 in float32, correctly rounded for every byte: 1/255 split into hi + lo so that fma(k, hi, k * lo) carries
@@ -614,7 +616,6 @@ bool rv_deproject_fast_eligible(const DeprojArgs &a, int mode) {
   if (a.rays) return false;
   if (a.W < 32 || (a.P % 16) != 0) return false;
   if (!rv_aligned(a.depth, 16) || (a.bgr && !rv_aligned(a.bgr, 16)) || (a.mask && !rv_aligned(a.mask, 16))) return false;
-  if (a.tiles_per_frame != (a.P + kTileT - 1) / kTileT) return false;
   return true;
 }
 
