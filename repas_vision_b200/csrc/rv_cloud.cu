@@ -271,7 +271,10 @@ __global__ void __launch_bounds__(256) k_voxel_insert(const VoxArgs a) {
           created = true;
           break;
         }
-        if (cur == key) break;
+        if (cur == key) {
+          acc->pad = (unsigned int)h;  // joiner: where its voxel's slot is (capacity <= 2^32), so the merge pass does not probe again
+          break;
+        }
         h = (h + 1) & a.cap_mask;
       }
     }
@@ -292,16 +295,52 @@ __global__ void __launch_bounds__(256) k_voxel_insert(const VoxArgs a) {
   if (threadIdx.x == 0) a.parts[blockIdx.x] = make_uint2(s_create, s_join);
 }
 
-// every joiner's record is added to the record of its voxel's creator
-__global__ void __launch_bounds__(256) k_voxel_merge(const VoxArgs a) {
-  const long long p0 = (long long)blockIdx.x * a.span;
-  const long long p1 = p0 + a.span < a.n ? p0 + a.span : a.n;
-  const unsigned int nj = a.parts[blockIdx.x].y;
-  for (unsigned int j = threadIdx.x; j < nj; j += blockDim.x) {
-    const VoxAcc r = a.acc[a.list[p1 - 1 - j]];
-    unsigned long long h = vox_hash(r.key) & a.cap_mask;
-    while (a.table[h].key != r.key) h = (h + 1) & a.cap_mask;
-    VoxAcc *acc = a.acc + (a.table[h].idx1 - 1u);
+// every joiner's record is added to the record of its voxel's creator; the joiners of all parts are dealt evenly to
+// the threads of the grid (prefix sum of the per-part counts in shared memory, binary search per joiner)
+__global__ void __launch_bounds__(256) k_voxel_merge(const VoxArgs a, int n_parts) {
+  __shared__ unsigned int s_pre[kVoxMaxParts + 1];  // exclusive prefix of the joiner counts
+  __shared__ unsigned int s_warp[8];
+  // block-wide exclusive scan, eight parts per thread
+  unsigned int v[8], sum = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int q = threadIdx.x * 8 + k;
+    v[k] = q < n_parts ? a.parts[q].y : 0u;
+    sum += v[k];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  unsigned int wbase = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w)
+    if (w < warp) wbase += s_warp[w];
+  unsigned int run = wbase + incl - sum;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    s_pre[threadIdx.x * 8 + k] = run;
+    run += v[k];
+  }
+  if (threadIdx.x == 255) s_pre[kVoxMaxParts] = run;
+  __syncthreads();
+  const unsigned int total = s_pre[kVoxMaxParts];
+  const unsigned int stride = gridDim.x * blockDim.x;
+  for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += stride) {
+    int lo = 0, hi = kVoxMaxParts;  // last part whose prefix is <= j
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_pre[mid] <= j) lo = mid; else hi = mid;
+    }
+    const long long p0 = (long long)lo * a.span;
+    const long long p1 = p0 + a.span < a.n ? p0 + a.span : a.n;
+    const VoxAcc r = a.acc[a.list[p1 - 1 - (long long)(j - s_pre[lo])]];
+    VoxAcc *acc = a.acc + (a.table[r.pad].idx1 - 1u);
     atomicAdd(&acc->count, r.count);
     atomicAdd(&acc->sum[0], r.sum[0]);
     atomicAdd(&acc->sum[1], r.sum[1]);
@@ -546,15 +585,16 @@ int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, 
   {
     auto kf = k_voxel_insert<float>;
     auto kd = k_voxel_insert<double>;
-    parts_n = in_dtype == RV_F32 ? rv_persistent_grid(ctx, kf, 256, 0, (n + 255) / 256) : rv_persistent_grid(ctx, kd, 256, 0, (n + 255) / 256);
-    if (parts_n > kVoxMaxParts) parts_n = kVoxMaxParts;
+    // parts of at least 1024 points, up to 2048 of them: two to three waves of small CTAs keep the tail of the kernel short
+    parts_n = (int)((n + 1023) / 1024 < kVoxMaxParts ? (n + 1023) / 1024 : kVoxMaxParts);
+    if (parts_n < 1) parts_n = 1;
     a.span = (((n + parts_n - 1) / parts_n) + 31) & ~31ll;
     a.parts = parts;
     if (in_dtype == RV_F32) kf<<<parts_n, 256, 0, st>>>(a);
     else kd<<<parts_n, 256, 0, st>>>(a);
   }
   RV_LAUNCHED(ctx);
-  k_voxel_merge<<<parts_n, 256, 0, st>>>(a);
+  k_voxel_merge<<<grid_for(ctx, n / 2 + 1, 8), 256, 0, st>>>(a, parts_n);  // joiners < points; grid-stride over the real count
   RV_LAUNCHED(ctx);
   VoxOutArgs o;
   memset(&o, 0, sizeof(o));
