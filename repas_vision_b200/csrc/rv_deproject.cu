@@ -582,7 +582,7 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
   const bool fast_ok = rv_deproject_fast_eligible(a, p->mode);
   if (p->kernel_select == RV_KERNEL_TMA && !fast_ok)
     RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: RV_KERNEL_TMA requested but the inputs are not eligible "
-                            "(H*W %% 16 == 0, W >= 32, 16-byte aligned inputs, no ray table, not COMPACT_UNORDERED)");
+                            "(H*W %% 16 == 0, W >= 32, 16-byte aligned inputs, not COMPACT_UNORDERED)");
   const bool use_fast = fast_ok && p->kernel_select != RV_KERNEL_GENERIC;
   const int tile_px = use_fast ? kFastTilePx : kTile;
   a.tiles_per_frame = (int)((P + tile_px - 1) / tile_px);

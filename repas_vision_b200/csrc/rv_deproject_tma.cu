@@ -27,7 +27,7 @@
 //    inside a 2^-20 band around the sphere).
 //
 // Eligibility (checked by rv_deproject_fast_eligible): H*W % 16 == 0, W >= 32, 16-byte aligned inputs,
-// no distortion ray table, mode != COMPACT_UNORDERED.  Everything else runs k_deproject.
+// mode != COMPACT_UNORDERED.  Everything else runs k_deproject.
 #include "rv_common.cuh"
 #include "rv_deproject_args.cuh"
 
@@ -182,6 +182,7 @@ __device__ __forceinline__ void st_global(unsigned long long addr, double v) {
 //   0  uint16/float depth with the MUL_F32 unit rule, colour, validity only
 //   1  the same plus the radius mask (the canopy / BASELINE configuration)
 //   2  everything, decided by the run-time flags of DeprojArgs
+//   3  as 1 with the DIV_F32 unit rule (f32(d) / 1000: the RealSense canopy scripts)
 template <typename OutT, int DK, int MODE, int SPEC>
 __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)) k_deproject_tma(const DeprojArgs a) {
   constexpr bool kPacked = MODE == RV_MODE_COMPACT_PACKED;
@@ -286,10 +287,10 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
   const double cx = a.cx, cy = a.cy, fx = a.fx, fy = a.fy, rfx = a.rfx, rfy = a.rfy;
   const float unit_f = a.unit_scale_f;
   const long long ps = a.plane_stride;
-  const bool use_radius = kGen ? (a.use_radius != 0) : (SPEC == 1);
+  const bool use_radius = kGen ? (a.use_radius != 0) : (SPEC == 1 || SPEC == 3);
   const bool fast_radius = kGen ? (a.fast_radius != 0) : true;
   const bool color_255 = kGen ? (a.color_255 != 0) : false;
-  const int unit_rule = kGen ? a.unit_rule : RV_UNIT_MUL_F32;
+  const int unit_rule = kGen ? a.unit_rule : (SPEC == 3 ? RV_UNIT_DIV_F32 : RV_UNIT_MUL_F32);
   // raw depths in [1, dcand) are candidates; dcand folds "z alone is already beyond the sphere" into an integer compare
   const uint32_t dcand_m1 = ((kF32 && use_radius && fast_radius) ? a.d_cand : 65536u) - 1u;
 
@@ -402,8 +403,16 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
           uj = p - vj * W;
         }
         if (!(DK == RV_DEPTH_U16 && unit_rule == RV_UNIT_DIV_F64)) z64 = (double)z32;
-        const double x64 = rv_div(((double)uj - cx) * z64, fx, rfx);
-        const double y64 = rv_div(((double)vj - cy) * z64, fy, rfy);
+        double x64, y64;
+        if (kGen && a.rays) {  // distorted camera: the normalised ray of every pixel comes from the (L2-resident) table
+          double2 r = make_double2(0.0, 0.0);
+          if (li < npx) r = __ldg(a.rays + px0 + li);
+          x64 = z64 * r.x;
+          y64 = z64 * r.y;
+        } else {
+          x64 = rv_div(((double)uj - cx) * z64, fx, rfx);
+          y64 = rv_div(((double)vj - cy) * z64, fy, rfy);
+        }
         xo = (OutT)x64;
         yo = (OutT)y64;
         if (kF32) {
@@ -575,11 +584,15 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
 
 // SPEC 0/1 cover the plain configurations; anything else falls to the run-time-flag variant
 int pick_spec(const DeprojArgs &a, int depth_kind) {
-  const bool plain = a.bgr && !a.use_mask && !a.use_trunc && !a.use_zclip && !a.use_aabb && !a.valid && !a.src_index &&
-                     !a.color_255 && (depth_kind != RV_DEPTH_U16 || a.unit_rule == RV_UNIT_MUL_F32);
+  const bool plain = a.bgr && !a.rays && !a.use_mask && !a.use_trunc && !a.use_zclip && !a.use_aabb && !a.valid && !a.src_index &&
+                     !a.color_255;
   if (!plain) return 2;
-  if (!a.use_radius) return 0;
-  return a.fast_radius ? 1 : 2;
+  const bool mul = depth_kind != RV_DEPTH_U16 || a.unit_rule == RV_UNIT_MUL_F32;
+  const bool div = depth_kind == RV_DEPTH_U16 && a.unit_rule == RV_UNIT_DIV_F32;
+  if (mul && !a.use_radius) return 0;
+  if (mul && a.fast_radius) return 1;
+  if (div && a.use_radius && a.fast_radius) return 3;  // the canopy configuration: f32(d) / 1000 and a distance mask
+  return 2;
 }
 
 template <typename OutT, int DK, int MODE>
@@ -593,7 +606,7 @@ cudaError_t launch_spec(const rv_ctx *ctx, const DeprojArgs &a, int spec, cudaSt
     const int grid = rv_persistent_grid(ctx, k, kThreadsT, smem, a.total_tiles);                           \
     k<<<grid, kThreadsT, smem, st>>>(a);                                                                   \
   }
-  if (spec == 0) RV_GO(0) else if (spec == 1) RV_GO(1) else RV_GO(2)
+  if (spec == 0) RV_GO(0) else if (spec == 1) RV_GO(1) else if (spec == 3 && DK == RV_DEPTH_U16) RV_GO(3) else RV_GO(2)
 #undef RV_GO
   return cudaSuccess;
 }
@@ -613,7 +626,6 @@ cudaError_t launch_tma(const rv_ctx *ctx, const DeprojArgs &a, int mode, cudaStr
 
 bool rv_deproject_fast_eligible(const DeprojArgs &a, int mode) {
   if (mode == RV_MODE_COMPACT_UNORDERED) return false;
-  if (a.rays) return false;
   if (a.W < 32 || (a.P % 16) != 0) return false;
   if (!rv_aligned(a.depth, 16) || (a.bgr && !rv_aligned(a.bgr, 16)) || (a.mask && !rv_aligned(a.mask, 16))) return false;
   return true;

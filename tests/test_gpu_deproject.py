@@ -174,8 +174,9 @@ def test_other_output_modes(rv, O, rs720, mode, kernel):
             assert (blk[3:][:, ~flat] == 0).all()
 
 
+@pytest.mark.parametrize("kernel", ["generic", "tma"])
 @pytest.mark.parametrize("model", ["inverse_brown_conrady", "brown_conrady"])
-def test_distorted_camera_ray_table(rv, O, model):
+def test_distorted_camera_ray_table(rv, O, model, kernel):
     """Checkerboard calibration with lens distortion (realtime_pose_estimation_april_tag.py:10-18): the float64 ray table
     reproduces rs2_deproject_pixel_to_point and the kernel multiplies by it."""
     import torch
@@ -189,12 +190,13 @@ def test_distorted_camera_ray_table(rv, O, model):
     assert np.array_equal(got_rays, rays)
     for dtype in ("f32", "f64"):
         batch = rv.deproject_batch(torch.from_numpy(depth).cuda(), torch.from_numpy(bgr).cuda(), cam, max_distance=1.5,
-                                   dtype=dtype)
+                                   dtype=dtype, kernel=kernel)
         for b in range(2):
             ref = O.deproject_mask(depth[b], bgr[b], None, fx=cam.fx, fy=cam.fy, cx=cam.cx, cy=cam.cy, r_max=1.5,
                                    out_dtype=dtype, rays=rays)
             assert batch.counts_host()[b] == ref["points"].shape[0]
             assert np.array_equal(batch.frame(b).xyz.t().cpu().numpy(), ref["points"])
+            assert np.array_equal(batch.frame(b).rgb.t().cpu().numpy(), ref["colors"])
 
 
 def test_create_from_rgbd_image_open3d_shape(rv, O, rs720):
