@@ -75,6 +75,20 @@ def main():
     ms = timed(lambda: rv.register_depth_to_color(depth, dcam, ccam, R, t), a.reps, flush)
     line("K2 register 640x480 -> 1280x720 (B=256)", ms, B * (640 * 480 * 2 + 1280 * 720 * 2), B, "frames")
 
+    # ---- BASELINE configs[2] as a pipeline: register 256 ToF frames into the colour grid, then deproject + 1 m mask
+    _, bgr256 = synth_chunk(B, gen, dev)
+    out6 = torch.empty((6, B * H * W), dtype=torch.float32, device=dev)
+
+    def reg_then_deproject():
+        al, _ = _ops.register(depth, dcam, ccam, np.asarray(R).T.reshape(9), t)
+        return rv.deproject_batch(al, bgr256, ccam, max_distance=1.0, out=out6)
+
+    ms = timed(reg_then_deproject, a.reps, flush)
+    kept = float(reg_then_deproject().counts.sum().item()) / (B * H * W)
+    line("K2 -> K1 pipeline: register 640x480 into 720p, deproject + 1 m mask (B=256)", ms,
+         B * (640 * 480 * 2 + 1280 * 720 * 2) + B * H * W * (5 + 24 * kept), B, "frames", {"kept": kept})
+    del out6, bgr256
+
     # ---- K1 on the registered frames feeds K3/K4: four views, distance-masked
     _, bgr = synth_chunk(4, gen, dev)
     cam = rv.Camera(FX, FY, CX, CY, W, H)
@@ -99,6 +113,12 @@ def main():
         m = int(r["m"].item())
         ms = timed(lambda: _ops.voxel_downsample(merged, total, True, vs, bounds=bounds), a.reps, flush)
         line(f"K4 voxel_down_sample {vs * 1000:.0f} mm f32", ms, total * 24 + m * 24, total, "points", {"points": total, "voxels": m})
+
+    # ---- BASELINE configs[3] as one call: transform 4 views into the tag frame, merge, 5 mm voxel grid (device-resident)
+    cam_T = [np.linalg.inv(np.asarray(p).reshape(4, 4)) for p in poses]
+    ms = timed(lambda: rv.fuse_views(clouds, cam_T, 0.005), a.reps, flush)
+    line("fuse_views: 4 views -> tag frame -> merge -> 5 mm voxel grid (one int64 read back)", ms, N * 24 * 2 + N * 24, N, "points",
+         {"points": N, "views_per_s": 4.0 / (ms * 1e-3)})
 
     ms = timed(lambda: _ops.pack_ply_records(merged, total, True, "unit", "f32"), a.reps, flush)
     line("PLY records float xyz + uchar rgb", ms, total * 24 + total * 15, total, "points")
