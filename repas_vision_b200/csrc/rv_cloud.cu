@@ -137,10 +137,11 @@ __global__ void __launch_bounds__(256) k_bounds(const T *__restrict__ in, long l
 }
 
 // --------------------------------------------------------------------- voxel grid
-// Workspace: [header 256 B][per-part counters: 2048 x 8 B][hash slots: capacity x 16 B][records: n x 64 B][list: n x 4 B]
+// Workspace: [header 256 B][per-part counters: 2048 x 8 B][keys: capacity x 8 B][record index: capacity x 4 B][records: n x 64 B][list: n x 4 B]
 //
-// The hash table holds only keys (16-byte slots: packed key + the index of the voxel's record), so clearing it and probing
-// it touch a quarter of the bytes a table of full records would, and nothing else is ever cleared.  Points arrive in
+// The hash table holds only 8-byte keys (1.5 n slots, any size: the hash is mapped with a multiply-high), so clearing it
+// and probing it touch an eighth of the bytes a table of full records would and the whole table stays in the L2; the record
+// index of each slot lives in a parallel array that is written by the slot's creator and never cleared.  Points arrive in
 // pixel order, so consecutive points usually share a voxel: each warp first folds runs of equal keys with a segmented
 // shuffle reduction, and only the head of a run goes to memory.  A run head
 //   * writes its partial sums to the record with its own point index (plain stores, no allocation counter),
@@ -158,18 +159,13 @@ struct VoxHeader {
 };
 constexpr int kVoxMaxParts = 2048;
 constexpr size_t kVoxHead = 256 + (size_t)kVoxMaxParts * 8;  // header + per-part {creators, joiners}
-struct __align__(16) VoxSlot {
-  unsigned long long key;  // 0 = empty, else packed(ix,iy,iz) + 1
-  unsigned int idx1;       // creator's record index + 1
-  unsigned int pad;
-};
 struct __align__(64) VoxAcc {
   unsigned long long key;
   unsigned int count;
   unsigned int pad;
   double sum[6];
 };
-static_assert(sizeof(VoxSlot) == 16 && sizeof(VoxAcc) == 64, "slot / record layout");
+static_assert(sizeof(VoxAcc) == 64, "record layout");
 
 struct VoxArgs {
   const void *in;
@@ -178,12 +174,13 @@ struct VoxArgs {
   double voxel, rvoxel;
   const double *bounds;  // device
   VoxHeader *hdr;
-  VoxSlot *table;
+  unsigned long long *keys;  // 0 = empty, else packed(ix,iy,iz) + 1
+  unsigned int *slot_rec;    // record index of the slot's creator (valid where keys[] != 0 once k_voxel_insert is done)
   VoxAcc *acc;
   unsigned int *list;  // part p owns list[p * span, ...): creators from its front, joiners from its back (record indices)
   uint2 *parts;        // per part {creators, joiners}
   long long span;      // points per part, a multiple of 32
-  unsigned long long cap_mask;
+  unsigned int cap;
 };
 
 __device__ __forceinline__ unsigned long long vox_hash(unsigned long long k) {
@@ -262,20 +259,19 @@ __global__ void __launch_bounds__(256) k_voxel_insert(const VoxArgs a) {
       acc->count = (unsigned int)run;
 #pragma unroll
       for (int c = 0; c < 6; ++c) acc->sum[c] = v[c];
-      unsigned long long h = vox_hash(key) & a.cap_mask;
+      unsigned int h = __umulhi((unsigned int)(vox_hash(key) >> 32), a.cap);  // uniform over [0, cap)
       for (;;) {
-        VoxSlot *s = a.table + h;
-        const unsigned long long cur = atomicCAS(&s->key, 0ull, key);  // the table is at most a quarter full: usually empty
+        const unsigned long long cur = atomicCAS(a.keys + h, 0ull, key);  // the table is at most two thirds full: usually empty
         if (cur == 0) {
-          s->idx1 = (unsigned int)i + 1u;  // read by the next kernel
+          a.slot_rec[h] = (unsigned int)i;  // read by the next kernel
           created = true;
           break;
         }
         if (cur == key) {
-          acc->pad = (unsigned int)h;  // joiner: where its voxel's slot is (capacity <= 2^32), so the merge pass does not probe again
+          acc->pad = h;  // joiner: where its voxel's slot is, so the merge pass does not probe again
           break;
         }
-        h = (h + 1) & a.cap_mask;
+        if (++h == a.cap) h = 0;
       }
     }
     // ---- creators to the front of the part's stretch of the list, joiners to its back
@@ -340,7 +336,7 @@ __global__ void __launch_bounds__(256) k_voxel_merge(const VoxArgs a, int n_part
     const long long p0 = (long long)lo * a.span;
     const long long p1 = p0 + a.span < a.n ? p0 + a.span : a.n;
     const VoxAcc r = a.acc[a.list[p1 - 1 - (long long)(j - s_pre[lo])]];
-    VoxAcc *acc = a.acc + (a.table[r.pad].idx1 - 1u);
+    VoxAcc *acc = a.acc + a.slot_rec[r.pad];
     atomicAdd(&acc->count, r.count);
     atomicAdd(&acc->sum[0], r.sum[0]);
     atomicAdd(&acc->sum[1], r.sum[1]);
@@ -416,10 +412,9 @@ __global__ void __launch_bounds__(256) k_voxel_emit(const VoxOutArgs a) {
   }
 }
 
-unsigned long long vox_capacity(long long n) {
-  unsigned long long c = 1024;
-  while (c < (unsigned long long)n * 2ull) c <<= 1;
-  return c;
+unsigned long long vox_capacity(long long n) {  // 1.5 slots per point, a multiple of 32
+  unsigned long long c = ((unsigned long long)n * 3ull / 2ull + 31ull) & ~31ull;
+  return c < 1024 ? 1024 : c;
 }
 
 // --------------------------------------------------------------------- PLY records
@@ -526,7 +521,7 @@ int rv_transform_merge(rv_ctx *ctx, int n_views, const void *const *d_in, const 
 
 size_t rv_voxel_workspace_bytes(int64_t n) {
   if (n < 0) n = 0;
-  return kVoxHead + (size_t)vox_capacity(n) * sizeof(VoxSlot) + (size_t)n * sizeof(VoxAcc) + (((size_t)n * 4 + 63) & ~(size_t)63);
+  return kVoxHead + (size_t)vox_capacity(n) * 12 + (size_t)n * sizeof(VoxAcc) + (((size_t)n * 4 + 63) & ~(size_t)63);
 }
 
 int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int in_dtype, int has_color,
@@ -536,7 +531,7 @@ int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, 
   if (!ctx) return RV_EINVAL;
   RvDeviceGuard dev_guard(ctx);
   if (!(voxel_size > 0.0)) RV_FAIL(ctx, RV_EINVAL, "rv_voxel_downsample: voxel_size <= 0");
-  if (n >= 0xffffffffll) RV_FAIL(ctx, RV_EINVAL, "rv_voxel_downsample: more than 2^32 - 2 points");
+  if (n >= 0xa0000000ll) RV_FAIL(ctx, RV_EINVAL, "rv_voxel_downsample: more than 2.6e9 points");  // 1.5 n slots in 32 bits
   if (n < 0 || in_plane_stride < n || !d_m) RV_FAIL(ctx, RV_EINVAL, "rv_voxel_downsample: bad n / stride / m");
   if ((in_dtype != RV_F32 && in_dtype != RV_F64) || (out_dtype != RV_F32 && out_dtype != RV_F64))
     RV_FAIL(ctx, RV_EINVAL, "rv_voxel_downsample: bad dtype");
@@ -553,10 +548,12 @@ int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, 
   const unsigned long long cap = vox_capacity(n);
   VoxHeader *hdr = reinterpret_cast<VoxHeader *>(d_ws);
   uint2 *parts = reinterpret_cast<uint2 *>(reinterpret_cast<char *>(d_ws) + 256);
-  VoxSlot *table = reinterpret_cast<VoxSlot *>(reinterpret_cast<char *>(d_ws) + kVoxHead);
-  VoxAcc *acc = reinterpret_cast<VoxAcc *>(reinterpret_cast<char *>(d_ws) + kVoxHead + cap * sizeof(VoxSlot));
+  char *w = reinterpret_cast<char *>(d_ws) + kVoxHead;
+  unsigned long long *keys = reinterpret_cast<unsigned long long *>(w);
+  unsigned int *slot_rec = reinterpret_cast<unsigned int *>(w + cap * 8);
+  VoxAcc *acc = reinterpret_cast<VoxAcc *>(w + cap * 12);  // cap % 32 == 0: 64-byte aligned
   unsigned int *list = reinterpret_cast<unsigned int *>(acc + n);
-  RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, kVoxHead + cap * sizeof(VoxSlot), st));  // header, counters, key slots; records are written, not cleared
+  RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, kVoxHead + cap * 8, st));  // header, counters, keys; everything else is written, not cleared
   const double *bounds = d_bounds;
   if (!bounds) {
     k_bounds_init<<<1, 32, 0, st>>>(hdr->bounds);
@@ -577,10 +574,11 @@ int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, 
   a.rvoxel = 1.0 / voxel_size;
   a.bounds = bounds;
   a.hdr = hdr;
-  a.table = table;
+  a.keys = keys;
+  a.slot_rec = slot_rec;
   a.acc = acc;
   a.list = list;
-  a.cap_mask = cap - 1;
+  a.cap = (unsigned int)cap;
   int parts_n;
   {
     auto kf = k_voxel_insert<float>;
