@@ -235,6 +235,8 @@ int rv_transform_merge(rv_ctx *ctx, int n_views, const void *const *d_in, const 
  *  d_keys       [3, out_capacity] int32 voxel indices, or NULL
  *  d_counts_out [out_capacity] int32 points per voxel, or NULL
  *  d_m          one int64: number of voxels (true number even if > out_capacity)
+ *  d_ws         rv_voxel_workspace_bytes(n) bytes, 64-B aligned: 1.5 n eight-byte hash keys (+ 4 B record index each),
+ *               one 64-byte record and one list entry per point; only the keys are cleared by the call
  * Each voxel index must fit 21 bits (extent/voxel < 2^21); otherwise d_m is set to -1. */
 size_t rv_voxel_workspace_bytes(int64_t n);
 int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int in_dtype,
