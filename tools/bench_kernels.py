@@ -145,5 +145,29 @@ def main():
          "frames", {"kept": kept})
 
 
+    # ---- BASELINE configs[0]: ONE frame, numpy in -> numpy out through the scripts' call shape (host copies included)
+    import time
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from synth import synth_color, synth_depth
+    rgb1 = synth_color(H, W, 3)
+    dm1 = synth_depth(H, W, 3).astype(np.float32) * np.float32(0.001)
+    msk1 = np.full((H, W), 255, np.uint8)
+
+    def one_frame():
+        pc = rv.create_masked_pointcloud(rgb1, dm1, msk1, FX, FY, CX, CY)
+        return pc.points, pc.colors  # (N,3) float64 on the host, like np.asarray(pcd.points)
+
+    for _ in range(3):
+        one_frame()
+    ts = []
+    for _ in range(10):
+        t0 = time.perf_counter()
+        pts, _ = one_frame()
+        ts.append(time.perf_counter() - t0)
+    ms = float(np.median(ts)) * 1e3
+    print(json.dumps({"kernel": "configs[0]: create_masked_pointcloud, one 720p frame, numpy float64 in/out (host wall clock)",
+                      "ms": ms, "points": int(pts.shape[0]), "frames_per_s": 1e3 / ms}))
+
+
 if __name__ == "__main__":
     main()
