@@ -252,6 +252,16 @@ int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, 
 int rv_pack_ply_records(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int in_dtype,
                         int has_color, int color_scale, int coord_dtype, uint8_t *d_records, rv_stream stream);
 
+/* the inverse, for o3d.io.read_point_cloud (view_point_cloud.py:104 and 30 more call sites): the vertex element of a
+ * binary little-endian PLY, uploaded as it lies in the file, unpacked on the device into SoA planes.
+ *  d_records     n records of record_bytes each (any other vertex properties are skipped)
+ *  xyz_offset    byte offsets of x, y, z inside a record; coord_dtype RV_F32 / RV_F64 as stored in the file
+ *  rgb_offset    byte offsets of the uchar red, green, blue, or NULL: colours become k / 255.0 (Open3D's conversion)
+ *  d_out         three or six planes of out_dtype, out_plane_stride elements apart */
+int rv_unpack_ply_records(rv_ctx *ctx, const uint8_t *d_records, int64_t n, int record_bytes, const int32_t *xyz_offset,
+                          int coord_dtype, const int32_t *rgb_offset, void *d_out, int64_t out_plane_stride,
+                          int out_dtype, rv_stream stream);
+
 /* ---- a2 (next): windowed median depth ------------------------------
  * replaces get_depth_at_pixel (canopy_return.py:279-317) and median_depth
  * (final_view.py:132-141): median of the non-zero raw depths in a win x win

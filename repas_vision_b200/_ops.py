@@ -264,6 +264,21 @@ def pack_ply_records(data: torch.Tensor, n: int, has_color: bool, color_scale="u
     return out[:n * rec]
 
 
+def unpack_ply_records(records: torch.Tensor, n: int, record_bytes: int, xyz_offset, coord_dtype: str, rgb_offset,
+                       out_dtype: str = "f64") -> torch.Tensor:
+    """uint8 vertex records as they lie in a binary PLY (on the GPU) -> SoA planes [3 or 6, n]."""
+    dev = records.device
+    ctx = ctx_for(dev)
+    planes = 6 if rgb_offset is not None else 3
+    out = torch.empty((planes, max(n, 1)), dtype=torch.float64 if out_dtype == "f64" else torch.float32, device=dev)
+    xo = (C.c_int32 * 3)(*[int(v) for v in xyz_offset])
+    ro = (C.c_int32 * 3)(*[int(v) for v in rgb_offset]) if rgb_offset is not None else None
+    ctx.check(ctx.lib.rv_unpack_ply_records(ctx.handle, ptr(records), n, int(record_bytes), xo,
+                                            _lib.RV_F32 if coord_dtype == "f32" else _lib.RV_F64, ro, ptr(out), pstride(out),
+                                            _RV_DT[out.dtype], stream_ptr(dev)))
+    return out
+
+
 def median_depth_window(depth_u16: torch.Tensor, uv: torch.Tensor, window: int) -> torch.Tensor:
     dev = depth_u16.device
     ctx = ctx_for(dev)

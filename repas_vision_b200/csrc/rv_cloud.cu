@@ -446,6 +446,38 @@ __global__ void __launch_bounds__(256) k_pack_ply(const InT *__restrict__ in, lo
   }
 }
 
+struct UnpackArgs {
+  const uint8_t *rec;
+  long long n, out_stride;
+  int record_bytes;
+  int xyz_off[3], rgb_off[3];
+  int has_color;
+};
+
+template <typename CoordT, typename OutT>
+__global__ void __launch_bounds__(256) k_unpack_ply(const UnpackArgs a, OutT *__restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    const uint8_t *r = a.rec + i * a.record_bytes;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      uint8_t b[sizeof(CoordT)];  // records are packed: fields are not aligned
+#pragma unroll
+      for (int k = 0; k < (int)sizeof(CoordT); ++k) b[k] = r[a.xyz_off[c] + k];
+      CoordT v;
+      memcpy(&v, b, sizeof(CoordT));
+      out[c * a.out_stride + i] = (OutT)v;
+    }
+    if (a.has_color) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double k = (double)r[a.rgb_off[c]];
+        out[(3 + c) * a.out_stride + i] = (OutT)rv_div(k, 255.0, 0.00392156862745098);  // k / 255.0 in float64, as Open3D
+      }
+    }
+  }
+}
+
 int grid_for(const rv_ctx *ctx, long long n, int per_sm = 8) {
   long long blocks = (n + 255) / 256;
   const long long cap = (long long)ctx->sm_count * per_sm;
@@ -634,6 +666,42 @@ int rv_pack_ply_records(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, 
     k_pack_ply<double, float><<<g, 256, 0, st>>>(reinterpret_cast<const double *>(d_in), in_plane_stride, n, has_color, c255, d_records);
   else
     k_pack_ply<double, double><<<g, 256, 0, st>>>(reinterpret_cast<const double *>(d_in), in_plane_stride, n, has_color, c255, d_records);
+  RV_LAUNCHED(ctx);
+  return RV_OK;
+}
+
+int rv_unpack_ply_records(rv_ctx *ctx, const uint8_t *d_records, int64_t n, int record_bytes, const int32_t *xyz_offset,
+                          int coord_dtype, const int32_t *rgb_offset, void *d_out, int64_t out_plane_stride,
+                          int out_dtype, rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
+  if (n < 0 || out_plane_stride < n || record_bytes <= 0 || !xyz_offset) RV_FAIL(ctx, RV_EINVAL, "rv_unpack_ply_records: bad n / stride / record");
+  if ((coord_dtype != RV_F32 && coord_dtype != RV_F64) || (out_dtype != RV_F32 && out_dtype != RV_F64))
+    RV_FAIL(ctx, RV_EINVAL, "rv_unpack_ply_records: bad dtype");
+  const int cw = coord_dtype == RV_F32 ? 4 : 8;
+  for (int c = 0; c < 3; ++c) {
+    if (xyz_offset[c] < 0 || xyz_offset[c] + cw > record_bytes) RV_FAIL(ctx, RV_EINVAL, "rv_unpack_ply_records: coordinate offset outside the record");
+    if (rgb_offset && (rgb_offset[c] < 0 || rgb_offset[c] >= record_bytes)) RV_FAIL(ctx, RV_EINVAL, "rv_unpack_ply_records: colour offset outside the record");
+  }
+  if (n == 0) return RV_OK;
+  if (!d_records || !d_out) RV_FAIL(ctx, RV_EINVAL, "rv_unpack_ply_records: null pointer");
+  UnpackArgs a;
+  memset(&a, 0, sizeof(a));
+  a.rec = d_records;
+  a.n = n;
+  a.out_stride = out_plane_stride;
+  a.record_bytes = record_bytes;
+  for (int c = 0; c < 3; ++c) {
+    a.xyz_off[c] = xyz_offset[c];
+    a.rgb_off[c] = rgb_offset ? rgb_offset[c] : 0;
+  }
+  a.has_color = rgb_offset ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = grid_for(ctx, n);
+  if (coord_dtype == RV_F32 && out_dtype == RV_F32) k_unpack_ply<float, float><<<g, 256, 0, st>>>(a, reinterpret_cast<float *>(d_out));
+  else if (coord_dtype == RV_F32) k_unpack_ply<float, double><<<g, 256, 0, st>>>(a, reinterpret_cast<double *>(d_out));
+  else if (out_dtype == RV_F32) k_unpack_ply<double, float><<<g, 256, 0, st>>>(a, reinterpret_cast<float *>(d_out));
+  else k_unpack_ply<double, double><<<g, 256, 0, st>>>(a, reinterpret_cast<double *>(d_out));
   RV_LAUNCHED(ctx);
   return RV_OK;
 }

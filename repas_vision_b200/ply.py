@@ -8,7 +8,8 @@
 * read_point_cloud .... the 31 o3d.io.read_point_cloud call sites (e.g. view_point_cloud.py:104): float or double
   coordinates, optional uchar colours (-> /255.0), ascii or binary little-endian; other vertex properties are skipped.
 
-The vertex records are packed on the GPU (rv_pack_ply_records) so a cloud crosses PCIe once, already in file layout.
+The vertex records are packed on the GPU (rv_pack_ply_records) so a cloud crosses PCIe once, already in file layout;
+reading a binary file is the mirror image (rv_unpack_ply_records).
 """
 from __future__ import annotations
 
@@ -110,12 +111,71 @@ def read_ply_vertices(filename):
     return header, arr
 
 
+def _binary_vertex_layout(filename):
+    """For a binary little-endian PLY whose first element is `vertex` with float/double x, y, z (same type) and, if
+    present, uchar red/green/blue: (data offset, n, record bytes, xyz offsets, 'f32'|'f64', rgb offsets or None).
+    Anything else returns None and takes the host reader."""
+    with open(filename, "rb") as f:
+        head = f.read(1 << 16)
+    marker = b"end_header\n"
+    if not head.startswith(b"ply") or marker not in head:
+        return None
+    end = head.index(marker) + len(marker)
+    fmt, n, props, in_vertex, seen_vertex = None, 0, [], False, False
+    for line in head[:end].decode("ascii", "replace").splitlines()[1:]:
+        tok = line.split()
+        if not tok:
+            continue
+        if tok[0] == "format":
+            fmt = tok[1]
+        elif tok[0] == "element":
+            if tok[1] == "vertex" and not seen_vertex and not props:
+                in_vertex, seen_vertex, n = True, True, int(tok[2])
+            elif not seen_vertex:
+                return None  # an element before the vertices
+            else:
+                in_vertex = False
+        elif tok[0] == "property" and in_vertex:
+            if tok[1] == "list" or tok[1] not in _NP_T:
+                return None
+            props.append((tok[2], tok[1]))
+    if fmt != "binary_little_endian" or not seen_vertex:
+        return None
+    off, offsets, types = 0, {}, {}
+    for name, t in props:
+        offsets[name], types[name] = off, np.dtype(_NP_T[t])
+        off += types[name].itemsize
+    if not all(k in offsets for k in "xyz"):
+        return None
+    ct = {types[k].str for k in "xyz"}
+    if ct not in ({"<f4"}, {"<f8"}):
+        return None
+    rgb = None
+    if all(k in offsets for k in ("red", "green", "blue")):
+        if any(types[k].str != "|u1" for k in ("red", "green", "blue")):
+            return None
+        rgb = [offsets["red"], offsets["green"], offsets["blue"]]
+    return end, n, off, [offsets[k] for k in "xyz"], "f32" if ct == {"<f4"} else "f64", rgb
+
+
 def read_point_cloud(filename, device=None, dtype: str = "f64") -> PointCloud:
-    """PLY -> PointCloud on the GPU.  A missing file gives an empty cloud with a warning, as Open3D does."""
+    """PLY -> PointCloud on the GPU.  A missing file gives an empty cloud with a warning, as Open3D does.  Binary files
+    are uploaded as they lie on disk and their vertex records are unpacked on the device (rv_unpack_ply_records); ascii
+    files and unusual layouts are parsed on the host."""
     filename = os.fspath(filename)
     if not os.path.exists(filename):
         print(f"[Open3D-compatible WARNING] Read PLY failed: unable to open file: {filename}")
         return PointCloud(None, 0, False, device=device)
+    layout = _binary_vertex_layout(filename)
+    if layout is not None and layout[1] > 0:
+        import torch
+        start, n, rec, xyz_off, cdt, rgb_off = layout
+        raw = np.fromfile(filename, dtype=np.uint8, count=n * rec, offset=start)
+        if raw.size != n * rec:
+            raise RuntimeError(f"PLY file is truncated: {filename}")
+        dev = _ops.require_cuda(device)
+        planes = _ops.unpack_ply_records(torch.from_numpy(raw).to(dev), n, rec, xyz_off, cdt, rgb_off, dtype)
+        return PointCloud(planes, n, rgb_off is not None)
     _, arr = read_ply_vertices(filename)
     names = arr.dtype.names or ()
     if not all(k in names for k in ("x", "y", "z")):

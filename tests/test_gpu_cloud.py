@@ -156,6 +156,41 @@ def test_four_pose_fusion(rv, O, rs720):
     assert counts.sum() == sum(len(c) for c in clouds)
 
 
+def test_voxel_grid_full_size_properties(rv):
+    """A 3.2 M-point cloud (several CTA parts, many joiners) through size-independent properties: the per-voxel counts sum
+    to N, sum(count * centroid) reproduces the sum of the points, and the key set equals torch.unique of the float64 keys
+    computed independently on the device."""
+    import torch
+    from repas_vision_b200 import _ops
+    g = torch.Generator(device="cuda").manual_seed(99)
+    n = 3_200_017
+    # points on a noisy surface in scan order (runs of equal voxels) plus uniform clutter (isolated voxels)
+    u = torch.arange(n, device="cuda", dtype=torch.float64)
+    surf = torch.stack([(u % 2000) * 0.0007 - 0.7, torch.floor(u / 2000) * 0.0009 - 0.7,
+                        0.8 + 0.001 * torch.randn(n, generator=g, device="cuda", dtype=torch.float64)])
+    clutter = torch.rand((3, n), generator=g, device="cuda", dtype=torch.float64) * 2.0 - 1.0
+    pick = torch.rand(n, generator=g, device="cuda") < 0.2
+    xyz = torch.where(pick[None, :], clutter, surf).contiguous()
+    rgb = torch.rand((3, n), generator=g, device="cuda", dtype=torch.float64)
+    data = torch.cat([xyz, rgb]).contiguous()
+    for voxel in (0.005, 0.03):
+        r = _ops.voxel_downsample(data, n, True, voxel, want_keys=True, want_counts=True)
+        m = int(r["m"].item())
+        cnt = r["counts"][:m].to(torch.int64)
+        assert int(cnt.sum()) == n
+        cent = r["data"][:, :m]
+        tot = (cent * cnt[None, :].to(torch.float64)).sum(dim=1)
+        ref = data.sum(dim=1)
+        assert torch.all((tot - ref).abs() <= 1e-9 * ref.abs().clamp(min=1.0))
+        origin = xyz.min(dim=1).values - voxel * 0.5
+        k = torch.floor((xyz - origin[:, None]) / voxel).to(torch.int64)
+        packed = (k[0] << 42) | (k[1] << 21) | k[2]
+        uniq, ucnt = torch.unique(packed, return_counts=True)
+        got = (r["keys"][0, :m].to(torch.int64) << 42) | (r["keys"][1, :m].to(torch.int64) << 21) | r["keys"][2, :m].to(torch.int64)
+        order = torch.argsort(got)
+        assert m == uniq.numel() and torch.equal(got[order], uniq) and torch.equal(cnt[order], ucnt)
+
+
 def test_pose_from_corners_feeds_fusion(rv, golden):
     """final_view.py:171-225 on exactly projected corners: same winning order and pose as the reference produced."""
     K = np.array(golden["solvepnp_K"])
@@ -166,6 +201,52 @@ def test_pose_from_corners_feeds_fusion(rv, golden):
         assert np.allclose(rvec.reshape(3), rec["rvec"], atol=1e-9) and np.allclose(tvec.reshape(3), rec["tvec"], atol=1e-9)
         T = rv.pose_from_tag_corners(np.array(rec["corners_px"]), K, np.zeros((5, 1)), golden["solvepnp_tag_size"])
         assert np.allclose(T, rec["T_cam_tag"], atol=1e-9)
+
+
+def test_ply_device_decode_matches_host_parser(rv, O, tmp_path):
+    """read_point_cloud unpacks binary vertex records on the GPU: same arrays as the independent host reader, for float and
+    double coordinates, with and without colours, and with extra vertex properties / a face element that must be skipped."""
+    from repas_vision_b200 import ply as plymod
+    rng = np.random.default_rng(12)
+    n = 4099
+    P = rng.normal(size=(n, 3)) * 0.4
+    Cb = rng.integers(0, 256, size=(n, 3), dtype=np.uint8)
+    for coord in ("double", "float"):
+        path = tmp_path / f"c_{coord}.ply"
+        rv.write_point_cloud(str(path), rv.PointCloud.from_arrays(P, Cb.astype(np.float64) / 255.0), coord=coord)
+        assert plymod._binary_vertex_layout(str(path)) is not None
+        got = rv.read_point_cloud(str(path))
+        _, arr = O.read_ply_minimal(str(path))
+        ref = np.stack([arr["x"], arr["y"], arr["z"]], 1).astype(np.float64)
+        assert np.array_equal(got.points, ref)
+        assert np.array_equal(got.colors, np.stack([arr["red"], arr["green"], arr["blue"]], 1).astype(np.float64) / 255.0)
+        got32 = rv.read_point_cloud(str(path), dtype="f32")
+        assert np.array_equal(got32.points, ref.astype(np.float32).astype(np.float64))
+    # a hand-written file: normals and an alpha byte between the fields, colours before the coordinates, faces after
+    dt = np.dtype([("red", "u1"), ("nx", "<f4"), ("x", "<f4"), ("y", "<f4"), ("green", "u1"), ("z", "<f4"), ("alpha", "u1"),
+                   ("blue", "u1")])
+    rec = np.zeros(n, dt)
+    rec["x"], rec["y"], rec["z"] = P[:, 0], P[:, 1], P[:, 2]
+    rec["red"], rec["green"], rec["blue"] = Cb[:, 0], Cb[:, 1], Cb[:, 2]
+    rec["nx"], rec["alpha"] = 0.5, 7
+    names = {"u1": "uchar", "<f4": "float"}
+    head = ["ply", "format binary_little_endian 1.0", f"element vertex {n}"]
+    head += [f"property {names[dt[k].str.lstrip('|')]} {k}" for k in dt.names]
+    head += ["element face 1", "property list uchar int vertex_indices", "end_header"]
+    path = tmp_path / "odd.ply"
+    with open(path, "wb") as f:
+        f.write(("\n".join(head) + "\n").encode())
+        f.write(rec.tobytes())
+        f.write(bytes([3]) + np.array([0, 1, 2], "<i4").tobytes())
+    assert plymod._binary_vertex_layout(str(path))[2] == dt.itemsize
+    got = rv.read_point_cloud(str(path))
+    assert np.array_equal(got.points, np.stack([rec["x"], rec["y"], rec["z"]], 1).astype(np.float64))
+    assert np.array_equal(got.colors, Cb.astype(np.float64) / 255.0)
+    # no colours
+    path = tmp_path / "nc.ply"
+    rv.write_point_cloud(str(path), rv.PointCloud.from_arrays(P[:33], None))
+    got = rv.read_point_cloud(str(path))
+    assert not got.has_colors() and np.array_equal(got.points, P[:33])
 
 
 def test_ply_round_trip_and_layout(rv, O, rs720, tmp_path):

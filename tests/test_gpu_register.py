@@ -123,3 +123,27 @@ def test_batch_larger_than_one_chunk_and_idempotence(rv):
             assert np.array_equal(o[b + 4 * rep], ro)
     # a second pass over an already aligned image (equal cameras, identity extrinsics) still matches the oracle
     _check(rv, ro, ccam, ccam, np.eye(3), np.zeros(3))
+
+
+def test_full_size_batch_properties(rv):
+    """BASELINE configs[2] at batch size (64 x 640x480 -> 1280x720) through size-independent properties: every filled
+    colour pixel holds exactly the depth of the source pixel named as its winner, empty pixels have no winner, the
+    depth-only call equals the call with winners, and a frame gives the same image wherever it sits in the batch."""
+    import torch
+    dcam, ccam = _femto(rv)
+    dcam = rv.Camera(dcam.fx, dcam.fy, dcam.cx, dcam.cy - 48.0, 640, 480)
+    R, t = _pose(6.0, 0.032)
+    base = np.stack([synth_depth(480, 640, 300 + i) for i in range(8)])
+    depth = torch.from_numpy(np.concatenate([base] * 8)).cuda()  # 64 frames: four 16-frame chunks
+    out, win = rv.register_depth_to_color(depth, dcam, ccam, R, t, return_winner=True)
+    assert out.is_cuda and tuple(out.shape) == (64, 720, 1280)
+    filled = win >= 0
+    assert torch.equal(filled, out != 0)
+    src = depth.view(64, -1).to(torch.int32)
+    taken = torch.gather(src, 1, win.view(64, -1).clamp(min=0).to(torch.int64)).view(64, 720, 1280)
+    assert torch.equal(torch.where(filled, taken, torch.zeros_like(taken)), out.to(torch.int32))
+    assert float(filled.float().mean()) > 0.2
+    only = rv.register_depth_to_color(depth, dcam, ccam, R, t)
+    assert torch.equal(only, out)
+    for rep in range(1, 8):
+        assert torch.equal(out[rep * 8:(rep + 1) * 8], out[:8]) and torch.equal(win[rep * 8:(rep + 1) * 8], win[:8])

@@ -211,3 +211,26 @@ def test_two_rank_gloo_gathers(built):
     assert m0[:, 0].tolist() == [0.0, 2.0, 4.0, 6.0, 8.0, 10.0]  # rank 0: data[:, :1] of a [6,2] arange
     assert m0[:, 1:].tolist() == (np.arange(18).reshape(6, 3)[:, :2] + 100).tolist()
     assert res[1][2] is None
+
+
+def test_binary_ply_layout_parser(tmp_path):
+    """Host half of the device-side PLY decode: offsets of x, y, z / red, green, blue inside a packed vertex record."""
+    from repas_vision_b200 import ply
+    p = tmp_path / "a.ply"
+    head = ("ply\nformat binary_little_endian 1.0\ncomment x\nelement vertex 2\nproperty double x\nproperty double y\n"
+            "property double z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n").encode()
+    p.write_bytes(head + bytes(2 * 27))
+    assert ply._binary_vertex_layout(str(p)) == (len(head), 2, 27, [0, 8, 16], "f64", [24, 25, 26])
+    q = tmp_path / "b.ply"
+    head = ("ply\nformat binary_little_endian 1.0\nelement vertex 1\nproperty uchar blue\nproperty float z\nproperty float nx\n"
+            "property float x\nproperty float y\nelement face 0\nproperty list uchar int vertex_indices\nend_header\n").encode()
+    q.write_bytes(head + bytes(17))
+    assert ply._binary_vertex_layout(str(q)) == (len(head), 1, 17, [9, 13, 1], "f32", None)  # no red/green: no colours
+    for bad in ("format ascii 1.0\nelement vertex 1\nproperty float x\nproperty float y\nproperty float z\n",
+                "format binary_little_endian 1.0\nelement vertex 1\nproperty float x\nproperty double y\nproperty float z\n",
+                "format binary_little_endian 1.0\nelement face 1\nproperty list uchar int vertex_indices\nelement vertex 1\n"
+                "property float x\nproperty float y\nproperty float z\n",
+                "format binary_little_endian 1.0\nelement vertex 1\nproperty int x\nproperty int y\nproperty int z\n"):
+        r = tmp_path / "c.ply"
+        r.write_bytes(("ply\n" + bad + "end_header\n").encode() + bytes(64))
+        assert ply._binary_vertex_layout(str(r)) is None  # the host reader takes these
