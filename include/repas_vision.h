@@ -262,6 +262,24 @@ int rv_unpack_ply_records(rv_ctx *ctx, const uint8_t *d_records, int64_t n, int 
                           int coord_dtype, const int32_t *rgb_offset, void *d_out, int64_t out_plane_stride,
                           int out_dtype, rv_stream stream);
 
+/* ---- next, SURVEY 8f-4: statistical outlier removal ------------------------------
+ * replaces pcd.remove_statistical_outlier(nb_neighbors=20, std_ratio=2.0) (create_masked_ply.py:168-170); semantics of
+ * Open3D 0.19 PointCloud::RemoveStatisticalOutliers: avg[i] = mean of sqrt(squared distance) over the k nearest
+ * neighbours of point i INCLUDING itself (float64), cloud_mean / std_dev over the avg > 0 summed in index order with
+ * Bessel's correction, keep i <=> 0 < avg[i] < cloud_mean + std_ratio * std_dev.
+ *  rv_knn_mean_distance         exact k-nearest search on a hash grid (1 <= k <= 64); d_mean [n] float64
+ *  rv_statistical_outlier_mask  d_keep [n] uint8; d_stats 4 doubles: cloud_mean, std_dev, threshold, points counted
+ *  rv_select_by_mask            ordered compaction of the cloud by a uint8 mask; d_index (NULL or [n] int64) receives the
+ *                               source index of every kept point (Open3D's `ind`); workspace rv_filter_workspace_bytes(n) */
+size_t rv_knn_workspace_bytes(int64_t n);
+int rv_knn_mean_distance(rv_ctx *ctx, const void *d_xyz, int64_t plane_stride, int64_t n, int dtype, int k, double *d_mean,
+                         void *d_ws, size_t ws_bytes, rv_stream stream);
+int rv_statistical_outlier_mask(rv_ctx *ctx, const double *d_mean, int64_t n, double std_ratio, uint8_t *d_keep,
+                                double *d_stats, rv_stream stream);
+int rv_select_by_mask(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int dtype, int has_color,
+                      const uint8_t *d_keep, void *d_out, int64_t out_plane_stride, int64_t *d_count, int64_t *d_index,
+                      void *d_ws, size_t ws_bytes, rv_stream stream);
+
 /* ---- a2 (next): windowed median depth ------------------------------
  * replaces get_depth_at_pixel (canopy_return.py:279-317) and median_depth
  * (final_view.py:132-141): median of the non-zero raw depths in a win x win

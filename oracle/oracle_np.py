@@ -415,6 +415,56 @@ def register_depth_to_color_gather(depth_u16, dcam, ccam, R_colmajor, t, depth_u
     return aligned, winner
 
 
+# ------------------------------------------------------- statistical outlier removal
+def knn_mean_distance(points, k, chunk=512):
+    """avg[i] of Open3D RemoveStatisticalOutliers: mean of sqrt(d2) over the k nearest neighbours of point i, itself
+    included (KDTreeFlann::SearchKNN returns them ascending); brute force in float64, d2 = (dx*dx + dy*dy) + dz*dz."""
+    P = np.asarray(points, dtype=np.float64)
+    n = P.shape[0]
+    kk = min(int(k), n)
+    out = np.empty(n, np.float64)
+    for i0 in range(0, n, chunk):
+        q = P[i0:i0 + chunk]
+        dx = q[:, None, 0] - P[None, :, 0]
+        dy = q[:, None, 1] - P[None, :, 1]
+        dz = q[:, None, 2] - P[None, :, 2]
+        d2 = (dx * dx + dy * dy) + dz * dz
+        near = np.sort(np.partition(d2, kk - 1, axis=1)[:, :kk], axis=1)
+        r = np.sqrt(near)
+        acc = np.zeros(q.shape[0])
+        for j in range(kk):  # std::accumulate: left to right
+            acc = acc + r[:, j]
+        out[i0:i0 + chunk] = acc / kk
+    return out
+
+
+def statistical_outlier_indices(avg, std_ratio):
+    """Index-ordered sums of PointCloud::RemoveStatisticalOutliers (Open3D 0.19): returns (indices, mean, std, threshold)."""
+    avg = np.asarray(avg, np.float64)
+    valid = int((avg >= 0).sum())
+    cloud_mean = 0.0
+    for v in avg.tolist():
+        if v > 0:
+            cloud_mean = cloud_mean + v
+    cloud_mean /= valid
+    sq = 0.0
+    for v in avg.tolist():
+        if v > 0:
+            sq = sq + (v - cloud_mean) * (v - cloud_mean)
+    with np.errstate(all="ignore"):
+        std = float(np.sqrt(np.float64(sq) / np.float64(valid - 1)))
+    thr = cloud_mean + std_ratio * std
+    ind = np.nonzero((avg > 0) & (avg < thr))[0]
+    return ind, cloud_mean, std, thr
+
+
+def remove_statistical_outlier(points, nb_neighbors=20, std_ratio=2.0):
+    """create_masked_ply.py:169 -> (kept indices, avg distances)."""
+    avg = knn_mean_distance(points, nb_neighbors)
+    ind, _, _, _ = statistical_outlier_indices(avg, std_ratio)
+    return ind, avg
+
+
 # ----------------------------------------------------------------------- PLY read
 def read_ply_minimal(path):
     """Independent minimal PLY vertex reader (binary LE / ascii) used to check the

@@ -15,7 +15,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO_PATH = os.path.join(HERE, "librepasvision.so")
-SOURCES = ["rv_abi.cu", "rv_deproject.cu", "rv_deproject_tma.cu", "rv_register.cu", "rv_cloud.cu", "rv_misc.cu"]
+SOURCES = ["rv_abi.cu", "rv_deproject.cu", "rv_deproject_tma.cu", "rv_register.cu", "rv_cloud.cu", "rv_neighbors.cu",
+           "rv_misc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

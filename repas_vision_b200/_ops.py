@@ -279,6 +279,44 @@ def unpack_ply_records(records: torch.Tensor, n: int, record_bytes: int, xyz_off
     return out
 
 
+def knn_mean_distance(data: torch.Tensor, n: int, k: int) -> torch.Tensor:
+    """Mean distance of every point to its k nearest neighbours, itself included (float64 [n])."""
+    dev = data.device
+    ctx = ctx_for(dev)
+    out = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+    nb = ctx.lib.rv_knn_workspace_bytes(n)
+    ws = workspace(nb, dev)
+    ctx.check(ctx.lib.rv_knn_mean_distance(ctx.handle, ptr(data), pstride(data), n, _RV_DT[data.dtype], int(k), ptr(out),
+                                           ptr(ws), ws.numel(), stream_ptr(dev)))
+    return out[:n]
+
+
+def statistical_outlier_mask(mean: torch.Tensor, std_ratio: float):
+    """(keep uint8 [n], stats float64 [4] = cloud mean, std dev, threshold, points counted)."""
+    dev = mean.device
+    ctx = ctx_for(dev)
+    n = int(mean.numel())
+    keep = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    stats = torch.zeros(4, dtype=torch.float64, device=dev)
+    ctx.check(ctx.lib.rv_statistical_outlier_mask(ctx.handle, ptr(mean), n, float(std_ratio), ptr(keep), ptr(stats),
+                                                  stream_ptr(dev)))
+    return keep[:n], stats
+
+
+def select_by_mask(data: torch.Tensor, n: int, has_color: bool, keep: torch.Tensor, want_index: bool = True):
+    """Ordered compaction by a uint8 mask: (planes [P, n], count int64[1], source indices int64 [n] | None)."""
+    dev = data.device
+    ctx = ctx_for(dev)
+    out = torch.empty((data.shape[0], max(n, 1)), dtype=data.dtype, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    index = torch.empty(max(n, 1), dtype=torch.int64, device=dev) if want_index else None
+    nb = ctx.lib.rv_filter_workspace_bytes(n)
+    ws = workspace(nb, dev)
+    ctx.check(ctx.lib.rv_select_by_mask(ctx.handle, ptr(data), pstride(data), n, _RV_DT[data.dtype], int(has_color), ptr(keep),
+                                        ptr(out), pstride(out), ptr(count), ptr(index), ptr(ws), ws.numel(), stream_ptr(dev)))
+    return out, count, index
+
+
 def median_depth_window(depth_u16: torch.Tensor, uv: torch.Tensor, window: int) -> torch.Tensor:
     dev = depth_u16.device
     ctx = ctx_for(dev)

@@ -308,6 +308,8 @@ struct FilterArgs {
   int total_tiles, has_color;
   double z_min, z_max, r2_thresh, amin[3], amax[3];
   int use_zclip, use_radius, use_aabb;
+  const uint8_t *keep;   // optional per-point mask (rv_select_by_mask)
+  long long *index_out;  // optional: source index of every kept point
 };
 
 template <typename T>
@@ -343,6 +345,7 @@ __global__ void __launch_bounds__(kThreads) k_filter_cloud(const FilterArgs a) {
       const long long i = i0 + j * 32;
       const double X = (double)x[j], Y = (double)y[j], Z = (double)z[j];
       bool ok = i < a.n;
+      if (a.keep) ok = ok && a.keep[ok ? i : 0] != 0;
       if (a.use_zclip) ok = ok && (Z >= a.z_min) && (Z <= a.z_max);
       if (a.use_radius) ok = ok && (((X * X + Y * Y) + Z * Z) < a.r2_thresh);
       if (a.use_aabb)
@@ -384,6 +387,7 @@ __global__ void __launch_bounds__(kThreads) k_filter_cloud(const FilterArgs a) {
           out[4 * a.out_stride + pos] = in[4 * a.in_stride + i];
           out[5 * a.out_stride + pos] = in[5 * a.in_stride + i];
         }
+        if (a.index_out) a.index_out[pos] = i;
       }
     }
   }
@@ -656,6 +660,50 @@ int rv_filter_cloud(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int6
   a.use_zclip = p->use_zclip ? 1 : 0;
   a.use_radius = p->use_radius ? 1 : 0;
   a.use_aabb = p->use_aabb ? 1 : 0;
+  RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, need, st));
+  if (dtype == RV_F32) {
+    auto k = k_filter_cloud<float>;
+    k<<<rv_persistent_grid(ctx, k, kThreads, 0, tiles), kThreads, 0, st>>>(a);
+  } else {
+    auto k = k_filter_cloud<double>;
+    k<<<rv_persistent_grid(ctx, k, kThreads, 0, tiles), kThreads, 0, st>>>(a);
+  }
+  RV_LAUNCHED(ctx);
+  return RV_OK;
+}
+
+int rv_select_by_mask(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int dtype, int has_color,
+                      const uint8_t *d_keep, void *d_out, int64_t out_plane_stride, int64_t *d_count, int64_t *d_index,
+                      void *d_ws, size_t ws_bytes, rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
+  if (!d_keep || !d_count) RV_FAIL(ctx, RV_EINVAL, "rv_select_by_mask: null mask/count");
+  if (n < 0 || in_plane_stride < n) RV_FAIL(ctx, RV_EINVAL, "rv_select_by_mask: bad n / stride");
+  if (dtype != RV_F32 && dtype != RV_F64) RV_FAIL(ctx, RV_EINVAL, "rv_select_by_mask: bad dtype");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    RV_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+    return RV_OK;
+  }
+  if (!d_in || !d_out) RV_FAIL(ctx, RV_EINVAL, "rv_select_by_mask: null cloud pointer");
+  const size_t need = rv_filter_workspace_bytes(n);
+  if (!d_ws || ws_bytes < need) RV_FAIL(ctx, RV_EWORKSPACE, "rv_select_by_mask: workspace %zu < %zu", ws_bytes, need);
+  const long long tiles = (n + kTile - 1) / kTile;
+  if (tiles > 0x7fffffffll) RV_FAIL(ctx, RV_EINVAL, "rv_select_by_mask: cloud too large");
+  FilterArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = d_in;
+  a.out = d_out;
+  a.in_stride = in_plane_stride;
+  a.out_stride = out_plane_stride;
+  a.n = n;
+  a.count = reinterpret_cast<unsigned long long *>(d_count);
+  a.ticket = reinterpret_cast<unsigned int *>(d_ws);
+  a.status = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(d_ws) + 128);
+  a.total_tiles = (int)tiles;
+  a.has_color = has_color ? 1 : 0;
+  a.keep = d_keep;
+  a.index_out = reinterpret_cast<long long *>(d_index);
   RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, need, st));
   if (dtype == RV_F32) {
     auto k = k_filter_cloud<float>;

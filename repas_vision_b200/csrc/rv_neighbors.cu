@@ -1,0 +1,403 @@
+// rv_neighbors.cu -- SURVEY 8f-4: neighbourhood queries on a hash grid; statistical outlier removal.
+//
+// Replaces pcd.remove_statistical_outlier(nb_neighbors=20, std_ratio=2.0)
+// (femto_bolt_code/scripts/create_masked_ply.py:168-170).  Semantics restated from Open3D 0.19
+// PointCloud::RemoveStatisticalOutliers (the wheel is not in the reference checkout: parity unpinned):
+//   for every point the k nearest neighbours of the cloud INCLUDING the point itself (KDTreeFlann::SearchKNN), squared
+//   distances in float64, ascending; avg[i] = sum(sqrt(d2)) / found;
+//   cloud_mean = (sum of the avg > 0, in index order) / n;  sq_sum = sum over avg > 0 of (avg - cloud_mean)^2;
+//   std_dev = sqrt(sq_sum / (n - 1));  keep i  <=>  avg[i] > 0 && avg[i] < cloud_mean + std_ratio * std_dev.
+//
+// The exact k-nearest search runs on a uniform hash grid instead of a KD-tree:
+//   k_knn_setup    cell size from the bounding box and the point count (about two point spacings of a surface-like cloud)
+//   k_knn_cells    cell key of every point -> open-addressing table of 8-byte keys; the rank inside the cell comes back
+//                  from the per-cell counter
+//   k_knn_alloc    every used cell gets a range of the cell-sorted arrays (one cursor update per warp of table slots)
+//   k_knn_scatter  points into cell order
+//   k_knn_query    one thread per point: shells of cells at Chebyshev distance 0, 1, 2, ... around the point's cell, a sorted
+//                  list of the k smallest squared distances; the search stops once the k-th distance is within the cube
+//                  already visited (any unvisited point is at least r * cell away), so the result is exact
+//   k_sor_stats    the two sums in INDEX ORDER like std::accumulate (one thread adds, the CTA stages chunks in shared memory):
+//                  the threshold, and with it the kept set, is bit-identical to the sequential reference
+//   k_sor_mask     the keep mask; rv_select_by_mask (rv_deproject.cu) then compacts the cloud in order.
+#include "rv_common.cuh"
+
+namespace {
+
+constexpr int kMaxK = 64;
+
+struct KnnParams {  // written by k_knn_setup, read by the later kernels
+  double bounds[6];
+  double origin[3];
+  double cell, rcell;
+  int grid[3];
+  int rmax;
+  unsigned int cursor;  // allocation cursor of the cell-sorted arrays
+  int pad;
+};
+
+struct KnnArgs {
+  const void *in;
+  long long stride, n;
+  KnnParams *prm;
+  unsigned long long *keys;  // [cap] 0 = empty, else packed cell + 1
+  unsigned int *cnt;         // [cap] points in the cell
+  unsigned int *start;       // [cap] first slot of the cell in the sorted arrays
+  unsigned int cap;
+  unsigned int *slot_of;  // [n]
+  unsigned int *rank_of;  // [n]
+  double *sx, *sy, *sz;   // [n] cell-sorted coordinates
+  unsigned int *sidx;     // [n] original index of each sorted point
+  int k;
+  double *mean_out;  // [n], original order
+};
+
+__device__ __forceinline__ unsigned long long cell_hash(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return k;
+}
+__device__ __forceinline__ unsigned long long cell_key(int ix, int iy, int iz) {
+  return (((unsigned long long)ix << 42) | ((unsigned long long)iy << 21) | (unsigned long long)iz) + 1ull;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_knn_bounds(const T *__restrict__ in, long long stride_in, long long n, double *bounds) {
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  double lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double v = (double)in[a * stride_in + i];
+      lo[a] = v < lo[a] ? v : lo[a];
+      hi[a] = v > hi[a] ? v : hi[a];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double l = __shfl_xor_sync(0xffffffffu, lo[a], o), h = __shfl_xor_sync(0xffffffffu, hi[a], o);
+      lo[a] = l < lo[a] ? l : lo[a];
+      hi[a] = h > hi[a] ? h : hi[a];
+    }
+    if ((threadIdx.x & 31) == 0) {
+      rv_atomic_min_f64(bounds + a, lo[a]);
+      rv_atomic_max_f64(bounds + 3 + a, hi[a]);
+    }
+  }
+}
+
+__global__ void k_knn_init(KnnParams *p) {
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  if (threadIdx.x < 3) p->bounds[threadIdx.x] = inf;
+  else if (threadIdx.x < 6) p->bounds[threadIdx.x] = -inf;
+  if (threadIdx.x == 0) p->cursor = 0;
+}
+
+__global__ void k_knn_setup(KnnParams *p, long long n) {
+  double e[3] = {p->bounds[3] - p->bounds[0], p->bounds[4] - p->bounds[1], p->bounds[5] - p->bounds[2]};
+  double a = e[0], b = e[1], c = e[2];  // sort descending
+  if (a < b) { const double t = a; a = b; b = t; }
+  if (b < c) { const double t = b; b = c; c = t; }
+  if (a < b) { const double t = a; a = b; b = t; }
+  // two spacings of a surface-like cloud spread over the two largest extents; a line or a single point degenerate gracefully
+  double s = 2.0 * sqrt(a * b / (double)n);
+  if (!(s > 0.0)) s = a > 0.0 ? 4.0 * a / (double)n : 1.0;
+  const double smin = a / 1048576.0;  // at most 2^20 cells per axis: 21-bit cell indices
+  if (s < smin) s = smin;
+  p->cell = s;
+  p->rcell = 1.0 / s;
+  int rmax = 1;
+  for (int d = 0; d < 3; ++d) {
+    p->origin[d] = p->bounds[d];
+    int g = (int)floor(e[d] / s) + 1;
+    if (g < 1) g = 1;
+    p->grid[d] = g;
+    rmax = g > rmax ? g : rmax;
+  }
+  p->rmax = rmax;
+}
+
+__device__ __forceinline__ void cell_of(const KnnParams *p, double x, double y, double z, int &ix, int &iy, int &iz) {
+  ix = (int)floor((x - p->origin[0]) * p->rcell);
+  iy = (int)floor((y - p->origin[1]) * p->rcell);
+  iz = (int)floor((z - p->origin[2]) * p->rcell);
+  ix = ix < 0 ? 0 : (ix >= p->grid[0] ? p->grid[0] - 1 : ix);
+  iy = iy < 0 ? 0 : (iy >= p->grid[1] ? p->grid[1] - 1 : iy);
+  iz = iz < 0 ? 0 : (iz >= p->grid[2] ? p->grid[2] - 1 : iz);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_knn_cells(const KnnArgs a) {
+  const T *in = reinterpret_cast<const T *>(a.in);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    int ix, iy, iz;
+    cell_of(a.prm, (double)in[i], (double)in[a.stride + i], (double)in[2 * a.stride + i], ix, iy, iz);
+    const unsigned long long key = cell_key(ix, iy, iz);
+    unsigned int h = __umulhi((unsigned int)(cell_hash(key) >> 32), a.cap);
+    for (;;) {
+      const unsigned long long cur = atomicCAS(a.keys + h, 0ull, key);
+      if (cur == 0 || cur == key) break;
+      if (++h == a.cap) h = 0;
+    }
+    a.slot_of[i] = h;
+    a.rank_of[i] = atomicAdd(a.cnt + h, 1u);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_knn_alloc(const KnnArgs a) {
+  const int lane = threadIdx.x & 31;
+  const unsigned int stride = gridDim.x * blockDim.x;
+  for (unsigned int h = blockIdx.x * blockDim.x + threadIdx.x; h < a.cap; h += stride) {  // cap % 32 == 0: whole warps
+    const unsigned int c = a.cnt[h];
+    unsigned int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned int base = 0;
+    if (lane == 0 && total) base = atomicAdd(&a.prm->cursor, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    a.start[h] = base + incl - c;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_knn_scatter(const KnnArgs a) {
+  const T *in = reinterpret_cast<const T *>(a.in);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    const unsigned int pos = a.start[a.slot_of[i]] + a.rank_of[i];
+    a.sx[pos] = (double)in[i];
+    a.sy[pos] = (double)in[a.stride + i];
+    a.sz[pos] = (double)in[2 * a.stride + i];
+    a.sidx[pos] = (unsigned int)i;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_knn_query(const KnnArgs a) {
+  const KnnParams *p = a.prm;
+  const int k = a.k;
+  const double cell = p->cell;
+  const int gx = p->grid[0], gy = p->grid[1], gz = p->grid[2], rmax = p->rmax;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < a.n; q += stride) {
+    const double x = a.sx[q], y = a.sy[q], z = a.sz[q];
+    int cx, cy, cz;
+    cell_of(p, x, y, z, cx, cy, cz);
+    double best[kMaxK];  // ascending squared distances
+    int m = 0;
+    for (int r = 0; r <= rmax; ++r) {
+      // shell of cells at Chebyshev distance exactly r
+      for (int dz = -r; dz <= r; ++dz) {
+        const int iz = cz + dz;
+        if (iz < 0 || iz >= gz) continue;
+        for (int dy = -r; dy <= r; ++dy) {
+          const int iy = cy + dy;
+          if (iy < 0 || iy >= gy) continue;
+          const bool face = (dz == -r || dz == r || dy == -r || dy == r);
+          const int step = (face || r == 0) ? 1 : 2 * r;  // inside the shell only dx = -r and dx = +r remain
+          for (int dx = -r; dx <= r; dx += step) {
+            const int ix = cx + dx;
+            if (ix < 0 || ix >= gx) continue;
+            const unsigned long long key = cell_key(ix, iy, iz);
+            unsigned int h = __umulhi((unsigned int)(cell_hash(key) >> 32), a.cap);
+            unsigned long long cur;
+            while ((cur = a.keys[h]) != key && cur != 0) {
+              if (++h == a.cap) h = 0;
+            }
+            if (cur == 0) continue;  // no point in that cell
+            const unsigned int s0 = a.start[h], s1 = s0 + a.cnt[h];
+            for (unsigned int j = s0; j < s1; ++j) {
+              const double ex = a.sx[j] - x, ey = a.sy[j] - y, ez = a.sz[j] - z;
+              const double d2 = (ex * ex + ey * ey) + ez * ez;
+              if (m < k || d2 < best[m - 1]) {  // sorted insertion
+                int t = m < k ? m : k - 1;
+                while (t > 0 && best[t - 1] > d2) {
+                  best[t] = best[t - 1];
+                  --t;
+                }
+                best[t] = d2;
+                if (m < k) ++m;
+              }
+            }
+          }
+        }
+      }
+      // every point not yet visited lies outside the cube of (2r+1)^3 cells around the query's cell: at least r * cell away
+      const double reach = (double)r * cell * (1.0 - 1e-9);  // (cell assignment rounds: stay a hair inside the bound)
+      if (m == k && best[k - 1] <= reach * reach) break;
+    }
+    double sum = 0.0;
+    for (int j = 0; j < m; ++j) sum += sqrt(best[j]);
+    a.mean_out[a.sidx[q]] = m > 0 ? sum / (double)m : -1.0;
+  }
+}
+
+// sequential sums in index order (std::accumulate / std::inner_product of the reference), staged through shared memory
+__global__ void __launch_bounds__(1024) k_sor_stats(const double *__restrict__ avg, long long n, double std_ratio, double *stats) {
+  __shared__ double s_buf[4096];
+  __shared__ double s_mean;
+  double acc = 0.0;
+  long long valid = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    const double mean = pass ? s_mean : 0.0;
+    acc = 0.0;
+    for (long long c0 = 0; c0 < n; c0 += 4096) {
+      const int len = (int)((n - c0) < 4096 ? (n - c0) : 4096);
+      for (int i = threadIdx.x; i < len; i += blockDim.x) s_buf[i] = avg[c0 + i];
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        if (pass == 0) {
+          for (int i = 0; i < len; ++i) {
+            const double v = s_buf[i];
+            if (v > 0) acc = acc + v;
+            if (v >= 0) ++valid;  // every point with at least one neighbour (itself): dist.size() > 0
+          }
+        } else {
+          for (int i = 0; i < len; ++i) {
+            const double v = s_buf[i];
+            if (v > 0) acc = acc + (v - mean) * (v - mean);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0 && pass == 0) s_mean = valid > 0 ? acc / (double)valid : 0.0;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double mean = s_mean;
+    const double sd = sqrt(acc / (double)(valid - 1));  // Bessel's correction, as the reference
+    stats[0] = mean;
+    stats[1] = sd;
+    stats[2] = mean + std_ratio * sd;
+    stats[3] = (double)valid;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_sor_mask(const double *__restrict__ avg, long long n, const double *__restrict__ stats,
+                                                  uint8_t *__restrict__ keep) {
+  const double thr = stats[2];
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double v = avg[i];
+    keep[i] = (v > 0 && v < thr) ? 1 : 0;
+  }
+}
+
+unsigned long long knn_capacity(long long n) {
+  unsigned long long c = ((unsigned long long)n * 3ull / 2ull + 31ull) & ~31ull;
+  return c < 1024 ? 1024 : c;
+}
+size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int grid_for(const rv_ctx *ctx, long long n, int per_sm = 8, int block = 256) {
+  long long blocks = (n + block - 1) / block;
+  const long long cap = (long long)ctx->sm_count * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t rv_knn_workspace_bytes(int64_t n) {
+  if (n < 0) n = 0;
+  const size_t cap = (size_t)knn_capacity(n);
+  return 256 + up256(cap * 8) + 2 * up256(cap * 4) + 2 * up256((size_t)n * 4) + 3 * up256((size_t)n * 8) + up256((size_t)n * 4);
+}
+
+int rv_knn_mean_distance(rv_ctx *ctx, const void *d_xyz, int64_t plane_stride, int64_t n, int dtype, int k, double *d_mean,
+                         void *d_ws, size_t ws_bytes, rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
+  if (n < 0 || plane_stride < n) RV_FAIL(ctx, RV_EINVAL, "rv_knn_mean_distance: bad n / stride");
+  if (dtype != RV_F32 && dtype != RV_F64) RV_FAIL(ctx, RV_EINVAL, "rv_knn_mean_distance: bad dtype");
+  if (k < 1 || k > kMaxK) RV_FAIL(ctx, RV_EINVAL, "rv_knn_mean_distance: k must be in [1, %d]", kMaxK);
+  if (n >= 0xa0000000ll) RV_FAIL(ctx, RV_EINVAL, "rv_knn_mean_distance: more than 2.6e9 points");
+  if (n == 0) return RV_OK;
+  if (!d_xyz || !d_mean) RV_FAIL(ctx, RV_EINVAL, "rv_knn_mean_distance: null pointer");
+  const size_t need = rv_knn_workspace_bytes(n);
+  if (!d_ws || ws_bytes < need) RV_FAIL(ctx, RV_EWORKSPACE, "rv_knn_mean_distance: workspace %zu < %zu", ws_bytes, need);
+  if (!rv_aligned(d_ws, 256)) RV_FAIL(ctx, RV_EALIGN, "rv_knn_mean_distance: workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t cap = (size_t)knn_capacity(n);
+  char *w = reinterpret_cast<char *>(d_ws);
+  KnnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = d_xyz;
+  a.stride = plane_stride;
+  a.n = n;
+  a.k = k;
+  a.mean_out = d_mean;
+  a.cap = (unsigned int)cap;
+  a.prm = reinterpret_cast<KnnParams *>(w);
+  w += 256;
+  a.keys = reinterpret_cast<unsigned long long *>(w);
+  w += up256(cap * 8);
+  a.cnt = reinterpret_cast<unsigned int *>(w);
+  w += up256(cap * 4);
+  const size_t clear_bytes = (size_t)(w - reinterpret_cast<char *>(d_ws));  // header, keys, counters
+  a.start = reinterpret_cast<unsigned int *>(w);
+  w += up256(cap * 4);
+  a.slot_of = reinterpret_cast<unsigned int *>(w);
+  w += up256((size_t)n * 4);
+  a.rank_of = reinterpret_cast<unsigned int *>(w);
+  w += up256((size_t)n * 4);
+  a.sx = reinterpret_cast<double *>(w);
+  w += up256((size_t)n * 8);
+  a.sy = reinterpret_cast<double *>(w);
+  w += up256((size_t)n * 8);
+  a.sz = reinterpret_cast<double *>(w);
+  w += up256((size_t)n * 8);
+  a.sidx = reinterpret_cast<unsigned int *>(w);
+  RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, clear_bytes, st));
+  k_knn_init<<<1, 32, 0, st>>>(a.prm);
+  RV_LAUNCHED(ctx);
+  const int g = grid_for(ctx, n);
+  if (dtype == RV_F32) k_knn_bounds<float><<<g, 256, 0, st>>>(reinterpret_cast<const float *>(d_xyz), plane_stride, n, a.prm->bounds);
+  else k_knn_bounds<double><<<g, 256, 0, st>>>(reinterpret_cast<const double *>(d_xyz), plane_stride, n, a.prm->bounds);
+  RV_LAUNCHED(ctx);
+  k_knn_setup<<<1, 1, 0, st>>>(a.prm, n);
+  RV_LAUNCHED(ctx);
+  if (dtype == RV_F32) k_knn_cells<float><<<g, 256, 0, st>>>(a);
+  else k_knn_cells<double><<<g, 256, 0, st>>>(a);
+  RV_LAUNCHED(ctx);
+  k_knn_alloc<<<grid_for(ctx, (long long)cap), 256, 0, st>>>(a);
+  RV_LAUNCHED(ctx);
+  if (dtype == RV_F32) k_knn_scatter<float><<<g, 256, 0, st>>>(a);
+  else k_knn_scatter<double><<<g, 256, 0, st>>>(a);
+  RV_LAUNCHED(ctx);
+  k_knn_query<<<grid_for(ctx, n, 16, 128), 128, 0, st>>>(a);
+  RV_LAUNCHED(ctx);
+  return RV_OK;
+}
+
+int rv_statistical_outlier_mask(rv_ctx *ctx, const double *d_mean, int64_t n, double std_ratio, uint8_t *d_keep,
+                                double *d_stats, rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
+  if (n < 0) RV_FAIL(ctx, RV_EINVAL, "rv_statistical_outlier_mask: bad n");
+  if (!(std_ratio > 0.0)) RV_FAIL(ctx, RV_EINVAL, "rv_statistical_outlier_mask: std_ratio must be positive");
+  if (n == 0) return RV_OK;
+  if (!d_mean || !d_keep || !d_stats) RV_FAIL(ctx, RV_EINVAL, "rv_statistical_outlier_mask: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  k_sor_stats<<<1, 1024, 0, st>>>(d_mean, n, std_ratio, d_stats);
+  RV_LAUNCHED(ctx);
+  k_sor_mask<<<grid_for(ctx, n), 256, 0, st>>>(d_mean, n, d_stats, d_keep);
+  RV_LAUNCHED(ctx);
+  return RV_OK;
+}
+
+}  // extern "C"

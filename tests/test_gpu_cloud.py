@@ -191,6 +191,81 @@ def test_voxel_grid_full_size_properties(rv):
         assert m == uniq.numel() and torch.equal(got[order], uniq) and torch.equal(cnt[order], ucnt)
 
 
+def test_statistical_outlier_removal_matches_oracle(rv, O, rs720):
+    """create_masked_ply.py:163-170: voxel_down_sample then remove_statistical_outlier(20, 2.0).  The mean neighbour
+    distances equal the brute-force oracle bit for bit, and so do the threshold and the kept index list."""
+    from repas_vision_b200 import _ops
+    color, depth = load_frame(CANOPY_TS[1])
+    pc = rv.create_masked_pointcloud(color, depth.astype(np.float32) * np.float32(0.001), np.full(depth.shape, 255, np.uint8),
+                                     rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"], max_distance=1.0)
+    down = pc.voxel_down_sample(0.005)
+    P = down.points
+    assert 2000 < len(P) < 60000
+    avg = _ops.knn_mean_distance(down._data, len(down), 20).cpu().numpy()
+    ref_avg = O.knn_mean_distance(P, 20)
+    assert np.array_equal(avg, ref_avg)
+    ref_ind, mean, std, thr = O.statistical_outlier_indices(ref_avg, 2.0)
+    keep, stats = _ops.statistical_outlier_mask(torch_from(avg), 2.0)
+    assert stats.cpu().numpy().tolist() == [mean, std, thr, float(len(P))]
+    kept, ind = down.remove_statistical_outlier(nb_neighbors=20, std_ratio=2.0)
+    assert ind == ref_ind.tolist() and 0 < len(ind) < len(P)
+    assert np.array_equal(kept.points, P[ref_ind]) and np.array_equal(kept.colors, down.colors[ref_ind])
+    # random clouds: clusters, duplicates, an isolated far point, fewer points than neighbours, float32 storage
+    rng = np.random.default_rng(5)
+    Q = np.concatenate([rng.normal(size=(1500, 3)) * 0.05, rng.normal(size=(800, 3)) * 0.3 + 1.0, rng.random((200, 3)) * 4.0,
+                        np.repeat(rng.random((5, 3)), 30, axis=0), [[50.0, -20.0, 3.0]]])
+    for k, ratio, dt in ((20, 2.0, "f64"), (1, 0.5, "f64"), (7, 1.0, "f32"), (64, 3.0, "f64")):
+        pcq = rv.PointCloud.from_arrays(Q, None, dtype=dt)
+        Qs = pcq.points
+        got = _ops.knn_mean_distance(pcq._data, len(pcq), k).cpu().numpy()
+        want = O.knn_mean_distance(Qs, k)
+        assert np.array_equal(got, want), (k, dt, np.abs(got - want).max())
+        _, ind = pcq.remove_statistical_outlier(k, ratio)
+        assert ind == O.statistical_outlier_indices(want, ratio)[0].tolist()
+    few = rv.PointCloud.from_arrays(Q[:7], None)
+    assert np.array_equal(_ops.knn_mean_distance(few._data, 7, 20).cpu().numpy(), O.knn_mean_distance(Q[:7], 20))
+    assert rv.PointCloud.from_arrays(Q[:0], None).remove_statistical_outlier()[1] == []
+    with pytest.raises(RuntimeError):
+        pcq.remove_statistical_outlier(0, 2.0)
+
+
+def torch_from(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_statistical_outlier_removal_full_size_properties(rv):
+    """A regular 1200 x 1000 lattice (1.2 M points, spacing h): the 7 nearest neighbours of an interior point are itself,
+    four at h and two at sqrt(2) h -- a known answer at scale -- and a few raised points are exactly the ones removed."""
+    import torch
+    from repas_vision_b200 import _ops
+    h = 0.002
+    ny, nx = 1000, 1200
+    yy, xx = torch.meshgrid(torch.arange(ny, device="cuda", dtype=torch.float64), torch.arange(nx, device="cuda", dtype=torch.float64),
+                            indexing="ij")
+    z = torch.zeros(ny * nx, device="cuda", dtype=torch.float64)
+    lifted = torch.tensor([5 * nx + 7, 500 * nx + 600, 998 * nx + 1100], device="cuda")
+    z[lifted] = 0.05
+    data = torch.stack([xx.reshape(-1) * h, yy.reshape(-1) * h, z]).contiguous()
+    n = ny * nx
+    avg = _ops.knn_mean_distance(data, n, 7)
+    row, col = 300, 300
+    want = (0.0 + 4 * h + 2 * (2.0 ** 0.5) * h) / 7.0
+    got = float(avg[row * nx + col])
+    assert abs(got - want) <= 1e-12
+    keep, stats = _ops.statistical_outlier_mask(avg, 6.0)
+    dropped = set(torch.nonzero(keep == 0).reshape(-1).cpu().tolist())
+    # the spread of the lattice is tiny, so the threshold sits just above the interior value: out go the lifted points,
+    # the lattice points that lost them as neighbours, and the four corners (three of their neighbours are further away)
+    corners = {0, nx - 1, (ny - 1) * nx, ny * nx - 1}
+    near = {int(i) + dy * nx + dx for i in lifted.cpu().tolist() for dy in (-1, 0, 1) for dx in (-1, 0, 1)}
+    assert set(lifted.cpu().tolist()) <= dropped and corners <= dropped and dropped <= (corners | near)
+    out, count, index = _ops.select_by_mask(data, n, False, keep)
+    m = n - len(dropped)
+    assert int(count.item()) == m
+    assert torch.equal(out[:, :m], data[:, keep.bool()]) and torch.equal(index[:m], torch.nonzero(keep).reshape(-1))
+
+
 def test_pose_from_corners_feeds_fusion(rv, golden):
     """final_view.py:171-225 on exactly projected corners: same winning order and pose as the reference produced."""
     K = np.array(golden["solvepnp_K"])

@@ -120,3 +120,20 @@ def test_final_view_median_and_pixel_to_3d(golden, rs720):
         assert z == rec["z"]
         x, y, zz = O.deproject_pixel_to_point(rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"], (float(u), float(v)), z)
         assert np.allclose([x, y, zz], rec["p"], rtol=1e-15, atol=1e-15)
+
+
+def test_statistical_outlier_oracle_against_independent_kdtree():
+    """Open3D is absent (parity unpinned), so the brute-force restatement of RemoveStatisticalOutliers is cross-checked
+    against an independent formulation: scipy's cKDTree for the k nearest neighbours, numpy reductions for the statistics."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(3)
+    P = np.concatenate([rng.normal(size=(1200, 3)) * 0.1, rng.random((60, 3)) * 3.0 - 1.5])
+    avg = O.knn_mean_distance(P, 20)
+    d, _ = cKDTree(P).query(P, k=20)
+    assert d[:, 0].max() == 0.0  # the point itself is its own first neighbour, as in KDTreeFlann::SearchKNN
+    assert np.allclose(avg, d.mean(axis=1), rtol=1e-12, atol=0)
+    ind, mean, std, thr = O.statistical_outlier_indices(avg, 2.0)
+    assert np.isclose(mean, avg.mean(), rtol=1e-12) and np.isclose(std, avg.std(ddof=1), rtol=1e-12)
+    assert np.array_equal(ind, np.nonzero(avg < avg.mean() + 2.0 * avg.std(ddof=1))[0])
+    assert 0 < len(P) - len(ind) < 100  # the sparse clutter goes, the cluster stays
+    assert (ind < 1200).mean() > 0.97

@@ -120,6 +120,13 @@ def main():
     line("fuse_views: 4 views -> tag frame -> merge -> 5 mm voxel grid (one int64 read back)", ms, N * 24 * 2 + N * 24, N, "points",
          {"points": N, "views_per_s": 4.0 / (ms * 1e-3)})
 
+    # ---- create_masked_ply.py:163-170 on the fused cloud: 5 mm voxel grid, then remove_statistical_outlier(20, 2.0)
+    down = rv.fuse_views(clouds, cam_T, 0.005)
+    ms = timed(lambda: down.remove_statistical_outlier(20, 2.0), max(3, a.reps // 4), flush)
+    kept, _ = down.remove_statistical_outlier(20, 2.0)
+    line("remove_statistical_outlier(20, 2.0) on the 5 mm fused cloud (index list read back)", ms, len(down) * 24 + len(kept) * 24,
+         len(down), "points", {"points": len(down), "kept": len(kept)})
+
     ms = timed(lambda: _ops.pack_ply_records(merged, total, True, "unit", "f32"), a.reps, flush)
     line("PLY records float xyz + uchar rgb", ms, total * 24 + total * 15, total, "points")
 
