@@ -10,6 +10,7 @@
 //
 // The exact k-nearest search runs on a uniform hash grid instead of a KD-tree:
 //   k_knn_setup    cell size from the bounding box and the point count (about two point spacings of a surface-like cloud)
+//   k_knn_refine   more than 16 points per used cell (a far outlier inflated the box): shrink the cells and rebuild, up to 3x
 //   k_knn_cells    cell key of every point -> open-addressing table of 8-byte keys; the rank inside the cell comes back
 //                  from the per-cell counter
 //   k_knn_alloc    every used cell gets a range of the cell-sorted arrays (one cursor update per warp of table slots)
@@ -32,9 +33,13 @@ struct KnnParams {  // written by k_knn_setup, read by the later kernels
   double cell, rcell;
   int grid[3];
   int rmax;
-  unsigned int cursor;  // allocation cursor of the cell-sorted arrays
+  unsigned int cursor;    // allocation cursor of the cell-sorted arrays
+  unsigned int occupied;  // cells in use
+  int redo;               // 1: (re)build the cell table with the current cell size
   int pad;
 };
+constexpr int kRefineRounds = 3;       // the cell size is re-derived from the measured occupancy at most this many times
+constexpr double kMaxOccupancy = 16.0; // points per used cell above which the grid is rebuilt finer
 
 struct KnnArgs {
   const void *in;
@@ -96,20 +101,19 @@ __global__ void k_knn_init(KnnParams *p) {
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
   if (threadIdx.x < 3) p->bounds[threadIdx.x] = inf;
   else if (threadIdx.x < 6) p->bounds[threadIdx.x] = -inf;
-  if (threadIdx.x == 0) p->cursor = 0;
+  if (threadIdx.x == 0) {
+    p->cursor = 0;
+    p->occupied = 0;
+    p->redo = 1;
+  }
 }
 
-__global__ void k_knn_setup(KnnParams *p, long long n) {
-  double e[3] = {p->bounds[3] - p->bounds[0], p->bounds[4] - p->bounds[1], p->bounds[5] - p->bounds[2]};
-  double a = e[0], b = e[1], c = e[2];  // sort descending
-  if (a < b) { const double t = a; a = b; b = t; }
-  if (b < c) { const double t = b; b = c; c = t; }
-  if (a < b) { const double t = a; a = b; b = t; }
-  // two spacings of a surface-like cloud spread over the two largest extents; a line or a single point degenerate gracefully
-  double s = 2.0 * sqrt(a * b / (double)n);
-  if (!(s > 0.0)) s = a > 0.0 ? 4.0 * a / (double)n : 1.0;
-  const double smin = a / 1048576.0;  // at most 2^20 cells per axis: 21-bit cell indices
+__device__ void knn_set_cell(KnnParams *p, double s) {
+  const double e[3] = {p->bounds[3] - p->bounds[0], p->bounds[4] - p->bounds[1], p->bounds[5] - p->bounds[2]};
+  const double emax = fmax(e[0], fmax(e[1], e[2]));
+  const double smin = emax / 1048576.0;  // at most 2^20 cells per axis: 21-bit cell indices
   if (s < smin) s = smin;
+  if (!(s > 0.0)) s = 1.0;
   p->cell = s;
   p->rcell = 1.0 / s;
   int rmax = 1;
@@ -123,6 +127,43 @@ __global__ void k_knn_setup(KnnParams *p, long long n) {
   p->rmax = rmax;
 }
 
+__global__ void k_knn_setup(KnnParams *p, long long n) {
+  double e[3] = {p->bounds[3] - p->bounds[0], p->bounds[4] - p->bounds[1], p->bounds[5] - p->bounds[2]};
+  double a = e[0], b = e[1], c = e[2];  // sort descending
+  if (a < b) { const double t = a; a = b; b = t; }
+  if (b < c) { const double t = b; b = c; c = t; }
+  if (a < b) { const double t = a; a = b; b = t; }
+  // two spacings of a surface-like cloud spread over the two largest extents; a line or a single point degenerate gracefully
+  double s = 2.0 * sqrt(a * b / (double)n);
+  if (!(s > 0.0)) s = a > 0.0 ? 4.0 * a / (double)n : 1.0;
+  knn_set_cell(p, s);
+}
+
+// A far outlier inflates the bounding box and with it the first cell size: when the table shows more than kMaxOccupancy
+// points per used cell, shrink the cells (occupancy of a surface goes with the square of the cell size) and rebuild.
+__global__ void k_knn_refine(KnnParams *p, long long n, int last) {
+  const double occ = p->occupied ? (double)n / (double)p->occupied : 0.0;
+  const double e0 = p->bounds[3] - p->bounds[0], e1 = p->bounds[4] - p->bounds[1], e2 = p->bounds[5] - p->bounds[2];
+  const double emax = fmax(e0, fmax(e1, e2));
+  const bool can_shrink = p->cell > emax / 1048576.0 * 1.5;
+  if (p->redo && !last && occ > kMaxOccupancy && can_shrink) {
+    knn_set_cell(p, p->cell * sqrt(4.0 / occ));
+    p->occupied = 0;
+    p->redo = 1;
+  } else {
+    p->redo = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_knn_clear(const KnnParams *p, unsigned long long *keys, unsigned int *cnt, unsigned int cap) {
+  if (!p->redo) return;
+  const unsigned int stride = gridDim.x * blockDim.x;
+  for (unsigned int h = blockIdx.x * blockDim.x + threadIdx.x; h < cap; h += stride) {
+    keys[h] = 0ull;
+    cnt[h] = 0u;
+  }
+}
+
 __device__ __forceinline__ void cell_of(const KnnParams *p, double x, double y, double z, int &ix, int &iy, int &iz) {
   ix = (int)floor((x - p->origin[0]) * p->rcell);
   iy = (int)floor((y - p->origin[1]) * p->rcell);
@@ -134,6 +175,7 @@ __device__ __forceinline__ void cell_of(const KnnParams *p, double x, double y, 
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_knn_cells(const KnnArgs a) {
+  if (!a.prm->redo) return;  // the table of the previous round stands
   const T *in = reinterpret_cast<const T *>(a.in);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
@@ -143,6 +185,7 @@ __global__ void __launch_bounds__(256) k_knn_cells(const KnnArgs a) {
     unsigned int h = __umulhi((unsigned int)(cell_hash(key) >> 32), a.cap);
     for (;;) {
       const unsigned long long cur = atomicCAS(a.keys + h, 0ull, key);
+      if (cur == 0) atomicAdd(&a.prm->occupied, 1u);
       if (cur == 0 || cur == key) break;
       if (++h == a.cap) h = 0;
     }
@@ -195,7 +238,18 @@ __global__ void __launch_bounds__(128) k_knn_query(const KnnArgs a) {
     cell_of(p, x, y, z, cx, cy, cz);
     double best[kMaxK];  // ascending squared distances
     int m = 0;
+    // an isolated point would walk ever larger empty shells (~24 r^2 cells each): once the shells have cost about as much as
+    // looking at every point, it does exactly that instead
+    const long long shell_budget = a.n / 2 + 4096;
+    long long visited = 0;
+    bool brute = false;
     for (int r = 0; r <= rmax; ++r) {
+      const long long side = 2ll * r + 1;
+      visited += r == 0 ? 1 : side * side * side - (side - 2) * (side - 2) * (side - 2);
+      if (visited > shell_budget) {
+        brute = true;
+        break;
+      }
       // shell of cells at Chebyshev distance exactly r
       for (int dz = -r; dz <= r; ++dz) {
         const int iz = cz + dz;
@@ -235,6 +289,22 @@ __global__ void __launch_bounds__(128) k_knn_query(const KnnArgs a) {
       // every point not yet visited lies outside the cube of (2r+1)^3 cells around the query's cell: at least r * cell away
       const double reach = (double)r * cell * (1.0 - 1e-9);  // (cell assignment rounds: stay a hair inside the bound)
       if (m == k && best[k - 1] <= reach * reach) break;
+    }
+    if (brute) {
+      m = 0;
+      for (long long j = 0; j < a.n; ++j) {
+        const double ex = a.sx[j] - x, ey = a.sy[j] - y, ez = a.sz[j] - z;
+        const double d2 = (ex * ex + ey * ey) + ez * ez;
+        if (m < k || d2 < best[m - 1]) {
+          int t = m < k ? m : k - 1;
+          while (t > 0 && best[t - 1] > d2) {
+            best[t] = best[t - 1];
+            --t;
+          }
+          best[t] = d2;
+          if (m < k) ++m;
+        }
+      }
     }
     double sum = 0.0;
     for (int j = 0; j < m; ++j) sum += sqrt(best[j]);
@@ -371,9 +441,17 @@ int rv_knn_mean_distance(rv_ctx *ctx, const void *d_xyz, int64_t plane_stride, i
   RV_LAUNCHED(ctx);
   k_knn_setup<<<1, 1, 0, st>>>(a.prm, n);
   RV_LAUNCHED(ctx);
-  if (dtype == RV_F32) k_knn_cells<float><<<g, 256, 0, st>>>(a);
-  else k_knn_cells<double><<<g, 256, 0, st>>>(a);
-  RV_LAUNCHED(ctx);
+  for (int round = 0; round <= kRefineRounds; ++round) {
+    if (round > 0) {
+      k_knn_clear<<<grid_for(ctx, (long long)cap), 256, 0, st>>>(a.prm, a.keys, a.cnt, a.cap);
+      RV_LAUNCHED(ctx);
+    }
+    if (dtype == RV_F32) k_knn_cells<float><<<g, 256, 0, st>>>(a);
+    else k_knn_cells<double><<<g, 256, 0, st>>>(a);
+    RV_LAUNCHED(ctx);
+    k_knn_refine<<<1, 1, 0, st>>>(a.prm, n, round == kRefineRounds);
+    RV_LAUNCHED(ctx);
+  }
   k_knn_alloc<<<grid_for(ctx, (long long)cap), 256, 0, st>>>(a);
   RV_LAUNCHED(ctx);
   if (dtype == RV_F32) k_knn_scatter<float><<<g, 256, 0, st>>>(a);

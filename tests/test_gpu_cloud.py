@@ -222,6 +222,11 @@ def test_statistical_outlier_removal_matches_oracle(rv, O, rs720):
         assert np.array_equal(got, want), (k, dt, np.abs(got - want).max())
         _, ind = pcq.remove_statistical_outlier(k, ratio)
         assert ind == O.statistical_outlier_indices(want, ratio)[0].tolist()
+    # a far outlier inflates the bounding box a thousandfold: the grid is rebuilt finer and the answer stays exact
+    S = np.concatenate([np.stack([rng.random(12000) * 0.6, rng.random(12000) * 0.4, rng.normal(size=12000) * 0.002], 1),
+                        [[900.0, 700.0, -300.0]]])
+    pcs = rv.PointCloud.from_arrays(S, None)
+    assert np.array_equal(_ops.knn_mean_distance(pcs._data, len(pcs), 20).cpu().numpy(), O.knn_mean_distance(S, 20))
     few = rv.PointCloud.from_arrays(Q[:7], None)
     assert np.array_equal(_ops.knn_mean_distance(few._data, 7, 20).cpu().numpy(), O.knn_mean_distance(Q[:7], 20))
     assert rv.PointCloud.from_arrays(Q[:0], None).remove_statistical_outlier()[1] == []
