@@ -268,7 +268,10 @@ int rv_unpack_ply_records(rv_ctx *ctx, const uint8_t *d_records, int64_t n, int 
  * neighbours of point i INCLUDING itself (float64), cloud_mean / std_dev over the avg > 0 summed in index order with
  * Bessel's correction, keep i <=> 0 < avg[i] < cloud_mean + std_ratio * std_dev.
  *  rv_knn_mean_distance         exact k-nearest search on a hash grid (1 <= k <= 64); d_mean [n] float64
- *  rv_statistical_outlier_mask  d_keep [n] uint8; d_stats 4 doubles: cloud_mean, std_dev, threshold, points counted
+ *  rv_statistical_outlier_mask  d_keep [n] uint8; d_stats 520 doubles of scratch whose first four are the results:
+ *                               cloud_mean, std_dev, threshold, points counted (parallel sums; redone in index order
+ *                               only when a point sits within rounding distance of the threshold, so d_keep always
+ *                               equals the sequential definition)
  *  rv_select_by_mask            ordered compaction of the cloud by a uint8 mask; d_index (NULL or [n] int64) receives the
  *                               source index of every kept point (Open3D's `ind`); workspace rv_filter_workspace_bytes(n) */
 size_t rv_knn_workspace_bytes(int64_t n);

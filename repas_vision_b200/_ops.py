@@ -297,10 +297,10 @@ def statistical_outlier_mask(mean: torch.Tensor, std_ratio: float):
     ctx = ctx_for(dev)
     n = int(mean.numel())
     keep = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
-    stats = torch.zeros(4, dtype=torch.float64, device=dev)
+    stats = torch.zeros(520, dtype=torch.float64, device=dev)  # 4 results + flag + 2 x 256 block sums
     ctx.check(ctx.lib.rv_statistical_outlier_mask(ctx.handle, ptr(mean), n, float(std_ratio), ptr(keep), ptr(stats),
                                                   stream_ptr(dev)))
-    return keep[:n], stats
+    return keep[:n], stats[:4]
 
 
 def select_by_mask(data: torch.Tensor, n: int, has_color: bool, keep: torch.Tensor, want_index: bool = True):

@@ -163,17 +163,18 @@ class PointCloud:
     def remove_statistical_outlier(self, nb_neighbors: int = 20, std_ratio: float = 2.0, print_progress: bool = False):
         """Open3D PointCloud.remove_statistical_outlier (create_masked_ply.py:169): drops the points whose mean distance
         to their nb_neighbors nearest neighbours (themselves included) is not below cloud mean + std_ratio * std dev.
-        Returns (cloud, ind) like Open3D: the kept points in order and their indices in this cloud."""
+        Returns (cloud, ind) like Open3D: the kept points in order and their indices in this cloud (an int64 numpy
+        array where Open3D hands back an IntVector; both index, iterate and feed select_by_index alike)."""
         if int(nb_neighbors) < 1 or not (float(std_ratio) > 0.0):
             raise RuntimeError("[Open3D-compatible] Illegal input parameters, the number of neighbors and standard "
                                "deviation ratio must be positive.")
         if self._n == 0:
-            return PointCloud(None, 0, self._has_color, device=self.device), []
+            return PointCloud(None, 0, self._has_color, device=self.device), np.zeros(0, np.int64)
         mean = _ops.knn_mean_distance(self._data, self._n, int(nb_neighbors))
         keep, _ = _ops.statistical_outlier_mask(mean, float(std_ratio))
         out, count, index = _ops.select_by_mask(self._data, self._n, self._has_color, keep)
         m = int(count.item())
-        return PointCloud(out, m, self._has_color), index[:m].cpu().numpy().tolist()
+        return PointCloud(out, m, self._has_color), index[:m].cpu().numpy()
 
     def select_by_index(self, indices, invert: bool = False) -> "PointCloud":
         idx = torch.as_tensor(np.asarray(indices), dtype=torch.int64, device=self.device)

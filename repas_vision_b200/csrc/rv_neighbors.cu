@@ -18,8 +18,9 @@
 //   k_knn_query    one thread per point: shells of cells at Chebyshev distance 0, 1, 2, ... around the point's cell, a sorted
 //                  list of the k smallest squared distances; the search stops once the k-th distance is within the cube
 //                  already visited (any unvisited point is at least r * cell away), so the result is exact
-//   k_sor_stats    the two sums in INDEX ORDER like std::accumulate (one thread adds, the CTA stages chunks in shared memory):
-//                  the threshold, and with it the kept set, is bit-identical to the sequential reference
+//   k_sor_partial / k_sor_finish / k_sor_band / k_sor_stats   cloud mean, standard deviation and threshold: parallel sums,
+//                  redone in INDEX ORDER like std::accumulate only when a point lies within rounding distance of the
+//                  threshold, so the kept set always equals the sequential reference's
 //   k_sor_mask     the keep mask; rv_select_by_mask (rv_deproject.cu) then compacts the cloud in order.
 #include "rv_common.cuh"
 
@@ -312,8 +313,71 @@ __global__ void __launch_bounds__(128) k_knn_query(const KnnArgs a) {
   }
 }
 
-// sequential sums in index order (std::accumulate / std::inner_product of the reference), staged through shared memory
-__global__ void __launch_bounds__(1024) k_sor_stats(const double *__restrict__ avg, long long n, double std_ratio, double *stats) {
+// ---- statistics.  The reference sums in index order (std::accumulate / std::inner_product); a parallel sum differs from
+// that in the last bits, which could flip a point sitting exactly at the threshold.  So: deterministic parallel sums first
+// (k_sor_partial / k_sor_finish), then k_sor_band counts the points within the worst-case rounding gap of the threshold
+// (16 n 2^-53 relative); only if there is one does k_sor_stats redo the sums sequentially.  The kept set is identical to
+// the sequential definition either way.
+constexpr int kSorBlocks = 256;
+
+template <int PASS>
+__global__ void __launch_bounds__(256) k_sor_partial(const double *__restrict__ avg, long long n, const double *__restrict__ stats,
+                                                     double *__restrict__ partial) {
+  __shared__ double s_red[2][8];
+  const double mean = PASS ? stats[0] : 0.0;
+  double acc = 0.0, cnt = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double v = avg[i];
+    if (v > 0) acc += PASS ? (v - mean) * (v - mean) : v;
+    if (v >= 0) cnt += 1.0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) s_red[0][threadIdx.x >> 5] = acc, s_red[1][threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    acc = cnt = 0.0;
+    for (int w = 0; w < 8; ++w) acc += s_red[0][w], cnt += s_red[1][w];
+    partial[blockIdx.x] = acc;
+    partial[kSorBlocks + blockIdx.x] = cnt;
+  }
+}
+
+template <int PASS>
+__global__ void k_sor_finish(const double *__restrict__ partial, int blocks, double std_ratio, double *stats, int *band) {
+  double acc = 0.0, cnt = 0.0;
+  for (int b = 0; b < blocks; ++b) acc += partial[b], cnt += partial[kSorBlocks + b];
+  if (PASS == 0) {
+    stats[0] = cnt > 0 ? acc / cnt : 0.0;
+    stats[3] = cnt;
+    *band = 0;
+  } else {
+    const double sd = sqrt(acc / (cnt - 1.0));  // Bessel's correction, as the reference
+    stats[1] = sd;
+    stats[2] = stats[0] + std_ratio * sd;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_sor_band(const double *__restrict__ avg, long long n, const double *__restrict__ stats, int *band) {
+  const double thr = stats[2];
+  const double gap = fabs(thr) * (16.0 * (double)n * 1.1102230246251565e-16);
+  bool hit = false;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double v = avg[i];
+    if (v > 0 && fabs(v - thr) <= gap) hit = true;
+  }
+  if (__any_sync(0xffffffffu, hit) && (threadIdx.x & 31) == 0) atomicOr(band, 1);
+}
+
+// sequential sums in index order, staged through shared memory; runs only when k_sor_band found a point in the gap
+__global__ void __launch_bounds__(1024) k_sor_stats(const double *__restrict__ avg, long long n, double std_ratio, double *stats,
+                                                     const int *band) {
+  if (*band == 0) return;
   __shared__ double s_buf[4096];
   __shared__ double s_mean;
   double acc = 0.0;
@@ -471,7 +535,20 @@ int rv_statistical_outlier_mask(rv_ctx *ctx, const double *d_mean, int64_t n, do
   if (n == 0) return RV_OK;
   if (!d_mean || !d_keep || !d_stats) RV_FAIL(ctx, RV_EINVAL, "rv_statistical_outlier_mask: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  k_sor_stats<<<1, 1024, 0, st>>>(d_mean, n, std_ratio, d_stats);
+  double *partial = d_stats + 8;                          // [2 * kSorBlocks] block sums and counts
+  int *band = reinterpret_cast<int *>(d_stats + 4);       // points inside the rounding gap of the threshold?
+  const int blocks = grid_for(ctx, n, 1) < kSorBlocks ? grid_for(ctx, n, 1) : kSorBlocks;
+  k_sor_partial<0><<<blocks, 256, 0, st>>>(d_mean, n, d_stats, partial);
+  RV_LAUNCHED(ctx);
+  k_sor_finish<0><<<1, 1, 0, st>>>(partial, blocks, std_ratio, d_stats, band);
+  RV_LAUNCHED(ctx);
+  k_sor_partial<1><<<blocks, 256, 0, st>>>(d_mean, n, d_stats, partial);
+  RV_LAUNCHED(ctx);
+  k_sor_finish<1><<<1, 1, 0, st>>>(partial, blocks, std_ratio, d_stats, band);
+  RV_LAUNCHED(ctx);
+  k_sor_band<<<grid_for(ctx, n), 256, 0, st>>>(d_mean, n, d_stats, band);
+  RV_LAUNCHED(ctx);
+  k_sor_stats<<<1, 1024, 0, st>>>(d_mean, n, std_ratio, d_stats, band);
   RV_LAUNCHED(ctx);
   k_sor_mask<<<grid_for(ctx, n), 256, 0, st>>>(d_mean, n, d_stats, d_keep);
   RV_LAUNCHED(ctx);

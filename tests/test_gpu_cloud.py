@@ -206,9 +206,9 @@ def test_statistical_outlier_removal_matches_oracle(rv, O, rs720):
     assert np.array_equal(avg, ref_avg)
     ref_ind, mean, std, thr = O.statistical_outlier_indices(ref_avg, 2.0)
     keep, stats = _ops.statistical_outlier_mask(torch_from(avg), 2.0)
-    assert stats.cpu().numpy().tolist() == [mean, std, thr, float(len(P))]
+    assert np.allclose(stats.cpu().numpy(), [mean, std, thr, float(len(P))], rtol=1e-12, atol=0)  # parallel sums; the list below is exact
     kept, ind = down.remove_statistical_outlier(nb_neighbors=20, std_ratio=2.0)
-    assert ind == ref_ind.tolist() and 0 < len(ind) < len(P)
+    assert np.array_equal(ind, ref_ind) and 0 < len(ind) < len(P)
     assert np.array_equal(kept.points, P[ref_ind]) and np.array_equal(kept.colors, down.colors[ref_ind])
     # random clouds: clusters, duplicates, an isolated far point, fewer points than neighbours, float32 storage
     rng = np.random.default_rng(5)
@@ -221,15 +221,25 @@ def test_statistical_outlier_removal_matches_oracle(rv, O, rs720):
         want = O.knn_mean_distance(Qs, k)
         assert np.array_equal(got, want), (k, dt, np.abs(got - want).max())
         _, ind = pcq.remove_statistical_outlier(k, ratio)
-        assert ind == O.statistical_outlier_indices(want, ratio)[0].tolist()
+        assert np.array_equal(ind, O.statistical_outlier_indices(want, ratio)[0])
     # a far outlier inflates the bounding box a thousandfold: the grid is rebuilt finer and the answer stays exact
     S = np.concatenate([np.stack([rng.random(12000) * 0.6, rng.random(12000) * 0.4, rng.normal(size=12000) * 0.002], 1),
                         [[900.0, 700.0, -300.0]]])
     pcs = rv.PointCloud.from_arrays(S, None)
     assert np.array_equal(_ops.knn_mean_distance(pcs._data, len(pcs), 20).cpu().numpy(), O.knn_mean_distance(S, 20))
+    # a point within rounding distance of the threshold: the statistics are redone in index order and the decision is the
+    # sequential reference's
+    av = rng.random(50000) * 0.01 + 0.002
+    for _ in range(6):
+        av[1234] = O.statistical_outlier_indices(av, 1.5)[3]
+    ind_ref, mean, std, thr = O.statistical_outlier_indices(av, 1.5)
+    assert abs(av[1234] - thr) <= 1e-12 * thr
+    keep, stats = _ops.statistical_outlier_mask(torch_from(av), 1.5)
+    assert np.array_equal(np.nonzero(keep.cpu().numpy())[0], ind_ref)
+    assert stats.cpu().numpy().tolist() == [mean, std, thr, 50000.0]  # this time from the sequential pass: bit-identical
     few = rv.PointCloud.from_arrays(Q[:7], None)
     assert np.array_equal(_ops.knn_mean_distance(few._data, 7, 20).cpu().numpy(), O.knn_mean_distance(Q[:7], 20))
-    assert rv.PointCloud.from_arrays(Q[:0], None).remove_statistical_outlier()[1] == []
+    assert len(rv.PointCloud.from_arrays(Q[:0], None).remove_statistical_outlier()[1]) == 0
     with pytest.raises(RuntimeError):
         pcq.remove_statistical_outlier(0, 2.0)
 
