@@ -442,15 +442,87 @@ def run_b200(a):
                "sample": f"{n_frames} synthetic 720p frames (same generator) x 2 passes, median of 3, through oracle_np "
                          f"depth_to_meters -> create_masked_pointcloud -> ||p||<1.0 m, one worker process per core"}
 
+    # the other rows of the hot path (a6 registration, a11 + a12 fusion) with the CPU oracle timed beside them on a
+    # bounded sample; tools/bench_kernels.py has the full per-kernel table
+    rows = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        rows = other_rows(rv, _ops, dev, gen)
+
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(a, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(gpu_launches), "clocks": clocks, "valid_points_per_step_rank0": valid_per_step,
+            "gpu_launches": int(gpu_launches), "clocks": clocks, "valid_points_per_step_rank0": valid_per_step, "rows": rows,
         }))
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_rows(rv, _ops, dev, gen):
+    """Registration (BASELINE configs[2]) and four-pose fusion (configs[3]): GPU time by CUDA events next to the C oracle on
+    one host core (registration: 2 frames; voxel grid: the same merged cloud).  Reported, not part of `value`."""
+    import numpy as np
+    import torch
+    from oracle import oracle_c, oracle_np as O
+    oracle_c.build()
+
+    def gpu_ms(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    out = []
+    B = 64
+    d720, bgr = synth_chunk(B, gen, dev)
+    depth = d720[:, 120:600, 320:960].contiguous()
+    dcam = rv.Camera(504.3227233886719, 504.2591247558594, 320.16888427734375, 345.57403564453125 - 48.0, 640, 480)
+    ccam = rv.Camera(748.8987426757812, 748.3513793945312, 639.8699951171875, 361.9516906738281, 1280, 720)
+    ang = np.deg2rad(6.0)
+    R = np.array([[1, 0, 0], [0, np.cos(ang), -np.sin(ang)], [0, np.sin(ang), np.cos(ang)]])
+    t = np.array([0.032, -0.002, 0.004])
+    ms = gpu_ms(lambda: rv.register_depth_to_color(depth, dcam, ccam, R, t))
+    host = depth[:2].cpu().numpy()
+    t0 = time.perf_counter()
+    for f in host:
+        oracle_c.register_depth_to_color(f, dcam.as_dict(), ccam.as_dict(), R.T.reshape(9), t)
+    cpu_s = (time.perf_counter() - t0) / len(host)
+    out.append({"row": "a6 registration 640x480 -> 1280x720", "gpu_frames_per_s": B / (ms * 1e-3), "batch": B,
+                "cpu_frames_per_s": 1.0 / cpu_s, "cpu": "oracle.c register_depth_to_color, 1 core, 2 frames"})
+
+    cam = rv.Camera(FX, FY, CX, CY, W, H)
+    batch = rv.deproject_batch(d720[:4].contiguous(), bgr[:4].contiguous(), cam, max_distance=2.5, dtype="f32")
+    clouds = [batch.frame(i) for i in range(4)]
+    poses = []
+    for i in range(4):
+        an = np.deg2rad(90.0 * i)
+        T = np.eye(4)
+        T[:3, :3] = [[np.cos(an), 0, np.sin(an)], [0, 1, 0], [-np.sin(an), 0, np.cos(an)]]
+        T[:3, 3] = [0.02 * i, -0.01, 0.8]
+        poses.append(T)
+    ms = gpu_ms(lambda: rv.fuse_views(clouds, poses, 0.005))
+    n = sum(len(c) for c in clouds)
+    merged, total, _ = _ops.transform_merge([(c._data, c._n) for c in clouds], [rv.world_from_camera(T) for T in poses], True)
+    hp = merged[:3, :total].t().contiguous().cpu().numpy().astype(np.float64)
+    hc = merged[3:, :total].t().contiguous().cpu().numpy().astype(np.float64)
+    t0 = time.perf_counter()
+    parts = [O.transform(c.points, rv.world_from_camera(T)) for c, T in zip(clouds, poses)]
+    t_tr = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    oracle_c.voxel_down_sample(hp, hc, 0.005)
+    t_vx = time.perf_counter() - t0
+    del parts
+    out.append({"row": "a11 + a12 four-pose fusion: transform, merge, 5 mm voxel grid", "points": n, "gpu_ms": ms,
+                "cpu_ms": (t_tr + t_vx) * 1e3, "cpu": "oracle_np.transform + oracle.c voxel_down_sample, 1 core"})
+    return out
 
 
 def main():
