@@ -273,8 +273,20 @@ int rv_unpack_ply_records(rv_ctx *ctx, const uint8_t *d_records, int64_t n, int 
  *                               only when a point sits within rounding distance of the threshold, so d_keep always
  *                               equals the sequential definition)
  *  rv_select_by_mask            ordered compaction of the cloud by a uint8 mask; d_index (NULL or [n] int64) receives the
- *                               source index of every kept point (Open3D's `ind`); workspace rv_filter_workspace_bytes(n) */
+ *                               source index of every kept point (Open3D's `ind`); workspace rv_filter_workspace_bytes(n)
+ *  rv_estimate_normals          pcd.estimate_normals(KDTreeSearchParamHybrid(radius, max_nn)) (create_masked_ply.py:173) and,
+ *                               with camera_location != NULL, pcd.orient_normals_towards_camera_location (:174): per point the
+ *                               up to max_nn nearest neighbours closer than radius, covariance from the cumulants in
+ *                               neighbour order, unit eigenvector of the smallest eigenvalue (Open3D's non-iterative
+ *                               FastEigen3x3), (0,0,1) with fewer than three neighbours; d_normals three float64 planes;
+ *                               workspace rv_knn_workspace_bytes(n)
+ *  rv_orient_normals            the stand-alone orient_normals_towards_camera_location */
 size_t rv_knn_workspace_bytes(int64_t n);
+int rv_orient_normals(rv_ctx *ctx, const void *d_xyz, int64_t plane_stride, int64_t n, int dtype, double *d_normals,
+                      int64_t normal_stride, const double *camera_location, rv_stream stream);
+int rv_estimate_normals(rv_ctx *ctx, const void *d_xyz, int64_t plane_stride, int64_t n, int dtype, double radius, int max_nn,
+                        const double *camera_location, double *d_normals, int64_t normal_stride, void *d_ws, size_t ws_bytes,
+                        rv_stream stream);
 int rv_knn_mean_distance(rv_ctx *ctx, const void *d_xyz, int64_t plane_stride, int64_t n, int dtype, int k, double *d_mean,
                          void *d_ws, size_t ws_bytes, rv_stream stream);
 int rv_statistical_outlier_mask(rv_ctx *ctx, const double *d_mean, int64_t n, double std_ratio, uint8_t *d_keep,

@@ -465,6 +465,42 @@ def remove_statistical_outlier(points, nb_neighbors=20, std_ratio=2.0):
     return ind, avg
 
 
+def estimate_normals(points, radius, max_nn, camera_location=None, chunk=512):
+    """Open3D 0.19 PointCloud::EstimateNormals with KDTreeSearchParamHybrid(radius, max_nn) (create_masked_ply.py:173):
+    neighbours = the max_nn nearest (the point itself included) with squared distance < radius^2; fewer than three -> (0,0,1);
+    covariance from the cumulants (utility::ComputeCovariance); normal = unit eigenvector of the smallest eigenvalue.  Open3D
+    gets it from a closed-form 3x3 solver, this restatement from numpy.linalg.eigh: same line, sign arbitrary until
+    orient_normals_towards_camera_location (:174) turns it towards camera_location."""
+    P = np.asarray(points, dtype=np.float64)
+    n = P.shape[0]
+    kk = min(int(max_nn), n)
+    N = np.zeros((n, 3))
+    r2 = float(radius) * float(radius)
+    for i0 in range(0, n, chunk):
+        q = P[i0:i0 + chunk]
+        dx = q[:, None, 0] - P[None, :, 0]
+        dy = q[:, None, 1] - P[None, :, 1]
+        dz = q[:, None, 2] - P[None, :, 2]
+        d2 = (dx * dx + dy * dy) + dz * dz
+        idx = np.argsort(d2, axis=1, kind="stable")[:, :kk]
+        dd = np.take_along_axis(d2, idx, axis=1)
+        for r in range(q.shape[0]):
+            sel = idx[r][dd[r] < r2]
+            if sel.size < 3:
+                N[i0 + r] = (0.0, 0.0, 1.0)
+                continue
+            nb = P[sel]
+            mu = nb.mean(axis=0)
+            C = (nb[:, :, None] * nb[:, None, :]).mean(axis=0) - mu[:, None] * mu[None, :]
+            w, v = np.linalg.eigh(C)
+            N[i0 + r] = v[:, 0]
+    if camera_location is not None:
+        ref = np.asarray(camera_location, dtype=np.float64)[None, :] - P
+        flip = (N * ref).sum(axis=1) < 0
+        N[flip] *= -1.0
+    return N
+
+
 # ----------------------------------------------------------------------- PLY read
 def read_ply_minimal(path):
     """Independent minimal PLY vertex reader (binary LE / ascii) used to check the

@@ -74,6 +74,9 @@ SIGNATURES = {
                                         C.c_int, c_vp]),
     "rv_knn_workspace_bytes": (C.c_size_t, [c_i64]),
     "rv_knn_mean_distance": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, C.c_int, c_vp, c_vp, C.c_size_t, c_vp]),
+    "rv_estimate_normals": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_f64, C.c_int, C.POINTER(c_f64), c_vp, c_i64, c_vp,
+                                      C.c_size_t, c_vp]),
+    "rv_orient_normals": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_i64, C.POINTER(c_f64), c_vp]),
     "rv_statistical_outlier_mask": (C.c_int, [c_vp, c_vp, c_i64, c_f64, c_vp, c_vp, c_vp]),
     "rv_select_by_mask": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, C.c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp,
                                     C.c_size_t, c_vp]),

@@ -291,6 +291,26 @@ def knn_mean_distance(data: torch.Tensor, n: int, k: int) -> torch.Tensor:
     return out[:n]
 
 
+def estimate_normals(data: torch.Tensor, n: int, radius: float, max_nn: int, camera_location=None) -> torch.Tensor:
+    """float64 [3, n] unit normals (hybrid radius / k-nearest neighbourhoods), turned towards camera_location when given."""
+    dev = data.device
+    ctx = ctx_for(dev)
+    out = torch.empty((3, max(n, 1)), dtype=torch.float64, device=dev)
+    ws = workspace(ctx.lib.rv_knn_workspace_bytes(n), dev)
+    cam = None if camera_location is None else (C.c_double * 3)(*[float(v) for v in np.asarray(camera_location).reshape(3)])
+    ctx.check(ctx.lib.rv_estimate_normals(ctx.handle, ptr(data), pstride(data), n, _RV_DT[data.dtype], float(radius), int(max_nn),
+                                          cam, ptr(out), pstride(out), ptr(ws), ws.numel(), stream_ptr(dev)))
+    return out
+
+
+def orient_normals(data: torch.Tensor, n: int, normals: torch.Tensor, camera_location) -> None:
+    dev = data.device
+    ctx = ctx_for(dev)
+    cam = (C.c_double * 3)(*[float(v) for v in np.asarray(camera_location, dtype=np.float64).reshape(3)])
+    ctx.check(ctx.lib.rv_orient_normals(ctx.handle, ptr(data), pstride(data), n, _RV_DT[data.dtype], ptr(normals), pstride(normals),
+                                        cam, stream_ptr(dev)))
+
+
 def statistical_outlier_mask(mean: torch.Tensor, std_ratio: float):
     """(keep uint8 [n], stats float64 [4] = cloud mean, std dev, threshold, points counted)."""
     dev = mean.device

@@ -41,6 +41,13 @@ def _is_torch_cuda(a) -> bool:
     return isinstance(a, torch.Tensor) and a.is_cuda
 
 
+class KDTreeSearchParamHybrid:
+    """o3d.geometry.KDTreeSearchParamHybrid(radius, max_nn): up to max_nn nearest neighbours closer than radius."""
+
+    def __init__(self, radius: float, max_nn: int):
+        self.radius, self.max_nn = float(radius), int(max_nn)
+
+
 class PointCloud:
     """Coloured cloud held on the GPU as structure-of-arrays planes x,y,z[,r,g,b].
 
@@ -55,6 +62,7 @@ class PointCloud:
             data = torch.empty((6 if has_color else 3, 1), dtype=torch.float64, device=dev)
             n = 0
         self._data = data
+        self._normals = None  # float64 [3, n] once estimate_normals ran; dropped by anything that changes the points
         self._n = int(n)
         self._has_color = bool(has_color) and data.shape[0] >= 6
 
@@ -134,6 +142,7 @@ class PointCloud:
         if self._n:
             out, total, _ = _ops.transform_merge([(self._data, self._n)], [T], self._has_color)
             self._data = out
+            self._normals = None
         return self
 
     def transformed(self, T) -> "PointCloud":
@@ -159,6 +168,31 @@ class PointCloud:
         if return_keys:
             return pc, r["keys"][:, :m].t().cpu().numpy(), r["counts"][:m].cpu().numpy()
         return pc
+
+    # ---- normals (create_masked_ply.py:172-174)
+    def has_normals(self) -> bool:
+        return self._normals is not None and self._n > 0
+
+    @property
+    def normals(self) -> np.ndarray:
+        return self._normals[:, :self._n].t().cpu().numpy() if self._normals is not None else np.zeros((0, 3))
+
+    def estimate_normals(self, search_param=None, fast_normal_computation: bool = True) -> "PointCloud":
+        """Open3D PointCloud.estimate_normals with a KDTreeSearchParamHybrid(radius, max_nn) neighbourhood (the only form
+        the reference uses; Open3D's default is KNN 30, given here as radius = inf).  In place, returns self."""
+        sp = search_param if search_param is not None else KDTreeSearchParamHybrid(radius=float("inf"), max_nn=30)
+        if self._n:
+            radius = sp.radius if np.isfinite(sp.radius) else 1e300
+            self._normals = _ops.estimate_normals(self._data, self._n, radius, sp.max_nn)
+        return self
+
+    def orient_normals_towards_camera_location(self, camera_location=(0.0, 0.0, 0.0)) -> "PointCloud":
+        """Flip every normal that points away from camera_location (in place)."""
+        if self._normals is None:
+            raise RuntimeError("[Open3D-compatible] No normals in the PointCloud. Call estimate_normals() first.")
+        if self._n:
+            _ops.orient_normals(self._data, self._n, self._normals, camera_location)
+        return self
 
     def remove_statistical_outlier(self, nb_neighbors: int = 20, std_ratio: float = 2.0, print_progress: bool = False):
         """Open3D PointCloud.remove_statistical_outlier (create_masked_ply.py:169): drops the points whose mean distance

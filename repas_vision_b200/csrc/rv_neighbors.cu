@@ -55,7 +55,13 @@ struct KnnArgs {
   double *sx, *sy, *sz;   // [n] cell-sorted coordinates
   unsigned int *sidx;     // [n] original index of each sorted point
   int k;
-  double *mean_out;  // [n], original order
+  double *mean_out;  // [n], original order (rv_knn_mean_distance)
+  // rv_estimate_normals
+  double radius2;      // neighbours must be closer than this (squared)
+  double camera[3];    // orient_normals_towards_camera_location
+  int orient;
+  double *normal_out;  // [3][normal_stride], original order
+  long long normal_stride;
 };
 
 __device__ __forceinline__ unsigned long long cell_hash(unsigned long long k) {
@@ -227,6 +233,118 @@ __global__ void __launch_bounds__(256) k_knn_scatter(const KnnArgs a) {
   }
 }
 
+// ---- 3x3 symmetric eigen solver of Open3D's fast normal computation (FastEigen3x3: Eberly, "A Robust Eigensolver for 3x3
+// Symmetric Matrices", non-iterative): the unit eigenvector of the smallest eigenvalue, zero for a zero matrix
+struct V3 {
+  double x, y, z;
+};
+__device__ __forceinline__ V3 v3(double x, double y, double z) { return V3{x, y, z}; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ double dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ V3 scale(V3 a, double s) { return v3(a.x * s, a.y * s, a.z * s); }
+
+// A = [a00 a01 a02; a01 a11 a12; a02 a12 a22]
+__device__ V3 eigenvector0(const double *A, double ev) {
+  const V3 r0 = v3(A[0] - ev, A[1], A[2]), r1 = v3(A[1], A[3] - ev, A[4]), r2 = v3(A[2], A[4], A[5] - ev);
+  const V3 c01 = cross(r0, r1), c02 = cross(r0, r2), c12 = cross(r1, r2);
+  const double d0 = dot(c01, c01), d1 = dot(c02, c02), d2 = dot(c12, c12);
+  double dmax = d0;
+  int imax = 0;
+  if (d1 > dmax) dmax = d1, imax = 1;
+  if (d2 > dmax) imax = 2;
+  if (imax == 0) return scale(c01, 1.0 / sqrt(d0));
+  if (imax == 1) return scale(c02, 1.0 / sqrt(d1));
+  return scale(c12, 1.0 / sqrt(d2));
+}
+__device__ V3 sym_mul(const double *A, V3 v) {
+  return v3((A[0] * v.x + A[1] * v.y) + A[2] * v.z, (A[1] * v.x + A[3] * v.y) + A[4] * v.z, (A[2] * v.x + A[4] * v.y) + A[5] * v.z);
+}
+__device__ V3 eigenvector1(const double *A, V3 e0, double ev1) {
+  V3 U;
+  if (fabs(e0.x) > fabs(e0.y)) {
+    const double inv = 1.0 / sqrt(e0.x * e0.x + e0.z * e0.z);
+    U = v3(-e0.z * inv, 0.0, e0.x * inv);
+  } else {
+    const double inv = 1.0 / sqrt(e0.y * e0.y + e0.z * e0.z);
+    U = v3(0.0, e0.z * inv, -e0.y * inv);
+  }
+  const V3 V = cross(e0, U);
+  const V3 AU = sym_mul(A, U), AV = sym_mul(A, V);
+  double m00 = dot(U, AU) - ev1, m01 = dot(U, AV), m11 = dot(V, AV) - ev1;
+  const double a00 = fabs(m00), a01 = fabs(m01), a11 = fabs(m11);
+  if (a00 >= a11) {
+    if (fmax(a00, a01) > 0) {
+      if (a00 >= a01) {
+        m01 /= m00;
+        m00 = 1.0 / sqrt(1.0 + m01 * m01);
+        m01 *= m00;
+      } else {
+        m00 /= m01;
+        m01 = 1.0 / sqrt(1.0 + m00 * m00);
+        m00 *= m01;
+      }
+      return v3(m01 * U.x - m00 * V.x, m01 * U.y - m00 * V.y, m01 * U.z - m00 * V.z);
+    }
+    return U;
+  }
+  if (fmax(a11, a01) > 0) {
+    if (a11 >= a01) {
+      m01 /= m11;
+      m11 = 1.0 / sqrt(1.0 + m01 * m01);
+      m01 *= m11;
+    } else {
+      m11 /= m01;
+      m01 = 1.0 / sqrt(1.0 + m11 * m11);
+      m11 *= m01;
+    }
+    return v3(m11 * U.x - m01 * V.x, m11 * U.y - m01 * V.y, m11 * U.z - m01 * V.z);
+  }
+  return U;
+}
+__device__ V3 smallest_eigenvector(const double *C) {
+  double A[6];
+  double mx = C[0];
+  for (int i = 1; i < 6; ++i) mx = C[i] > mx ? C[i] : mx;  // A.maxCoeff() of the reference (largest entry, not largest magnitude)
+  if (mx == 0) return v3(0, 0, 0);
+  for (int i = 0; i < 6; ++i) A[i] = C[i] / mx;
+  const double norm = (A[1] * A[1] + A[2] * A[2]) + A[4] * A[4];
+  if (norm > 0) {
+    const double q = ((A[0] + A[3]) + A[5]) / 3.0;
+    const double b00 = A[0] - q, b11 = A[3] - q, b22 = A[5] - q;
+    const double p = sqrt((((b00 * b00 + b11 * b11) + b22 * b22) + norm * 2.0) / 6.0);
+    const double c00 = b11 * b22 - A[4] * A[4];
+    const double c01 = A[1] * b22 - A[4] * A[2];
+    const double c02 = A[1] * A[4] - b11 * A[2];
+    const double det = ((b00 * c00 - A[1] * c01) + A[2] * c02) / (p * p * p);
+    double half_det = det * 0.5;
+    half_det = fmin(fmax(half_det, -1.0), 1.0);
+    const double angle = acos(half_det) / 3.0;
+    const double two_thirds_pi = 2.09439510239319549;
+    const double beta2 = cos(angle) * 2.0;
+    const double beta0 = cos(angle + two_thirds_pi) * 2.0;
+    const double beta1 = -(beta0 + beta2);
+    const double e0 = q + p * beta0, e1 = q + p * beta1, e2 = q + p * beta2;
+    if (half_det >= 0) {
+      const V3 v2 = eigenvector0(A, e2);
+      if (e2 < e0 && e2 < e1) return v2;
+      const V3 v1 = eigenvector1(A, v2, e1);
+      if (e1 < e0 && e1 < e2) return v1;
+      return cross(v1, v2);
+    }
+    const V3 v0 = eigenvector0(A, e0);
+    if (e0 < e1 && e0 < e2) return v0;
+    const V3 v1 = eigenvector1(A, v0, e1);
+    if (e1 < e0 && e1 < e2) return v1;
+    return cross(v0, v1);
+  }
+  if (C[0] < C[3] && C[0] < C[5]) return v3(1, 0, 0);
+  if (C[3] < C[0] && C[3] < C[5]) return v3(0, 1, 0);
+  return v3(0, 0, 1);
+}
+
+// kNormals = false: mean distance to the k nearest (rv_knn_mean_distance); true: normal from the covariance of the up to k
+// nearest neighbours closer than the radius (KDTreeSearchParamHybrid), optionally turned towards the camera
+template <bool kNormals>
 __global__ void __launch_bounds__(128) k_knn_query(const KnnArgs a) {
   const KnnParams *p = a.prm;
   const int k = a.k;
@@ -237,8 +355,22 @@ __global__ void __launch_bounds__(128) k_knn_query(const KnnArgs a) {
     const double x = a.sx[q], y = a.sy[q], z = a.sz[q];
     int cx, cy, cz;
     cell_of(p, x, y, z, cx, cy, cz);
-    double best[kMaxK];  // ascending squared distances
+    double best[kMaxK];          // ascending squared distances
+    unsigned int bidx[kNormals ? kMaxK : 1];  // their positions in the sorted arrays
     int m = 0;
+    auto offer = [&](double d2, unsigned int j) {
+      if (m < k || d2 < best[m - 1]) {  // sorted insertion
+        int t = m < k ? m : k - 1;
+        while (t > 0 && best[t - 1] > d2) {
+          best[t] = best[t - 1];
+          if (kNormals) bidx[t] = bidx[t - 1];
+          --t;
+        }
+        best[t] = d2;
+        if (kNormals) bidx[t] = j;
+        if (m < k) ++m;
+      }
+    };
     // an isolated point would walk ever larger empty shells (~24 r^2 cells each): once the shells have cost about as much as
     // looking at every point, it does exactly that instead
     const long long shell_budget = a.n / 2 + 4096;
@@ -273,16 +405,7 @@ __global__ void __launch_bounds__(128) k_knn_query(const KnnArgs a) {
             const unsigned int s0 = a.start[h], s1 = s0 + a.cnt[h];
             for (unsigned int j = s0; j < s1; ++j) {
               const double ex = a.sx[j] - x, ey = a.sy[j] - y, ez = a.sz[j] - z;
-              const double d2 = (ex * ex + ey * ey) + ez * ez;
-              if (m < k || d2 < best[m - 1]) {  // sorted insertion
-                int t = m < k ? m : k - 1;
-                while (t > 0 && best[t - 1] > d2) {
-                  best[t] = best[t - 1];
-                  --t;
-                }
-                best[t] = d2;
-                if (m < k) ++m;
-              }
+              offer((ex * ex + ey * ey) + ez * ez, j);
             }
           }
         }
@@ -290,26 +413,53 @@ __global__ void __launch_bounds__(128) k_knn_query(const KnnArgs a) {
       // every point not yet visited lies outside the cube of (2r+1)^3 cells around the query's cell: at least r * cell away
       const double reach = (double)r * cell * (1.0 - 1e-9);  // (cell assignment rounds: stay a hair inside the bound)
       if (m == k && best[k - 1] <= reach * reach) break;
+      if (kNormals && reach * reach >= a.radius2) break;  // everything within the radius has been seen
     }
     if (brute) {
       m = 0;
       for (long long j = 0; j < a.n; ++j) {
         const double ex = a.sx[j] - x, ey = a.sy[j] - y, ez = a.sz[j] - z;
-        const double d2 = (ex * ex + ey * ey) + ez * ez;
-        if (m < k || d2 < best[m - 1]) {
-          int t = m < k ? m : k - 1;
-          while (t > 0 && best[t - 1] > d2) {
-            best[t] = best[t - 1];
-            --t;
-          }
-          best[t] = d2;
-          if (m < k) ++m;
-        }
+        offer((ex * ex + ey * ey) + ez * ez, (unsigned int)j);
       }
     }
-    double sum = 0.0;
-    for (int j = 0; j < m; ++j) sum += sqrt(best[j]);
-    a.mean_out[a.sidx[q]] = m > 0 ? sum / (double)m : -1.0;
+    const unsigned int self = a.sidx[q];
+    if (!kNormals) {
+      double sum = 0.0;
+      for (int j = 0; j < m; ++j) sum += sqrt(best[j]);
+      a.mean_out[self] = m > 0 ? sum / (double)m : -1.0;
+    } else {
+      // KDTreeFlann::SearchHybrid: the k nearest, then only those with d2 < radius^2 (lower_bound on the sorted distances)
+      int kk = 0;
+      while (kk < m && best[kk] < a.radius2) ++kk;
+      V3 nrm = v3(0, 0, 1);
+      if (kk >= 3) {
+        // utility::ComputeCovariance: cumulants in neighbour order, divided by the count
+        double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < kk; ++j) {
+          const double px = a.sx[bidx[j]], py = a.sy[bidx[j]], pz = a.sz[bidx[j]];
+          c[0] += px, c[1] += py, c[2] += pz;
+          c[3] += px * px, c[4] += px * py, c[5] += px * pz;
+          c[6] += py * py, c[7] += py * pz, c[8] += pz * pz;
+        }
+        for (int i = 0; i < 9; ++i) c[i] /= (double)kk;
+        double C[6];
+        C[0] = c[3] - c[0] * c[0];
+        C[1] = c[4] - c[0] * c[1];
+        C[2] = c[5] - c[0] * c[2];
+        C[3] = c[6] - c[1] * c[1];
+        C[4] = c[7] - c[1] * c[2];
+        C[5] = c[8] - c[2] * c[2];
+        nrm = smallest_eigenvector(C);
+        if (dot(nrm, nrm) == 0.0) nrm = v3(0, 0, 1);
+      }
+      if (a.orient) {  // orient_normals_towards_camera_location
+        const V3 ref = v3(a.camera[0] - x, a.camera[1] - y, a.camera[2] - z);
+        if (dot(nrm, ref) < 0.0) nrm = scale(nrm, -1.0);
+      }
+      a.normal_out[self] = nrm.x;
+      a.normal_out[a.normal_stride + self] = nrm.y;
+      a.normal_out[2 * a.normal_stride + self] = nrm.z;
+    }
   }
 }
 
@@ -428,6 +578,27 @@ __global__ void __launch_bounds__(256) k_sor_mask(const double *__restrict__ avg
   }
 }
 
+// orient_normals_towards_camera_location: a zero normal becomes the unit direction to the camera ((0,0,1) at the camera),
+// any other is flipped when it points away
+template <typename T>
+__global__ void __launch_bounds__(256) k_orient_normals(const T *__restrict__ xyz, long long stride, long long n,
+                                                        double *__restrict__ nrm, long long nstride, double cx, double cy, double cz) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    const V3 ref = v3(cx - (double)xyz[i], cy - (double)xyz[stride + i], cz - (double)xyz[2 * stride + i]);
+    V3 v = v3(nrm[i], nrm[nstride + i], nrm[2 * nstride + i]);
+    if (dot(v, v) == 0.0) {
+      const double l = sqrt(dot(ref, ref));
+      v = l == 0.0 ? v3(0, 0, 1) : scale(ref, 1.0 / l);
+    } else if (dot(v, ref) < 0.0) {
+      v = scale(v, -1.0);
+    } else {
+      continue;
+    }
+    nrm[i] = v.x, nrm[nstride + i] = v.y, nrm[2 * nstride + i] = v.z;
+  }
+}
+
 unsigned long long knn_capacity(long long n) {
   unsigned long long c = ((unsigned long long)n * 3ull / 2ull + 31ull) & ~31ull;
   return c < 1024 ? 1024 : c;
@@ -452,29 +623,25 @@ size_t rv_knn_workspace_bytes(int64_t n) {
   return 256 + up256(cap * 8) + 2 * up256(cap * 4) + 2 * up256((size_t)n * 4) + 3 * up256((size_t)n * 8) + up256((size_t)n * 4);
 }
 
-int rv_knn_mean_distance(rv_ctx *ctx, const void *d_xyz, int64_t plane_stride, int64_t n, int dtype, int k, double *d_mean,
-                         void *d_ws, size_t ws_bytes, rv_stream stream) {
-  if (!ctx) return RV_EINVAL;
-  RvDeviceGuard dev_guard(ctx);
-  if (n < 0 || plane_stride < n) RV_FAIL(ctx, RV_EINVAL, "rv_knn_mean_distance: bad n / stride");
-  if (dtype != RV_F32 && dtype != RV_F64) RV_FAIL(ctx, RV_EINVAL, "rv_knn_mean_distance: bad dtype");
-  if (k < 1 || k > kMaxK) RV_FAIL(ctx, RV_EINVAL, "rv_knn_mean_distance: k must be in [1, %d]", kMaxK);
-  if (n >= 0xa0000000ll) RV_FAIL(ctx, RV_EINVAL, "rv_knn_mean_distance: more than 2.6e9 points");
+// validation, workspace layout and the grid build shared by the two query entry points
+static int knn_prepare(rv_ctx *ctx, const char *who, const void *d_xyz, int64_t plane_stride, int64_t n, int dtype, int k,
+                       void *d_ws, size_t ws_bytes, cudaStream_t st, KnnArgs &a) {
+  if (n < 0 || plane_stride < n) RV_FAIL(ctx, RV_EINVAL, "%s: bad n / stride", who);
+  if (dtype != RV_F32 && dtype != RV_F64) RV_FAIL(ctx, RV_EINVAL, "%s: bad dtype", who);
+  if (k < 1 || k > kMaxK) RV_FAIL(ctx, RV_EINVAL, "%s: the neighbour count must be in [1, %d]", who, kMaxK);
+  if (n >= 0xa0000000ll) RV_FAIL(ctx, RV_EINVAL, "%s: more than 2.6e9 points", who);
   if (n == 0) return RV_OK;
-  if (!d_xyz || !d_mean) RV_FAIL(ctx, RV_EINVAL, "rv_knn_mean_distance: null pointer");
+  if (!d_xyz) RV_FAIL(ctx, RV_EINVAL, "%s: null pointer", who);
   const size_t need = rv_knn_workspace_bytes(n);
-  if (!d_ws || ws_bytes < need) RV_FAIL(ctx, RV_EWORKSPACE, "rv_knn_mean_distance: workspace %zu < %zu", ws_bytes, need);
-  if (!rv_aligned(d_ws, 256)) RV_FAIL(ctx, RV_EALIGN, "rv_knn_mean_distance: workspace must be 256-byte aligned");
-  cudaStream_t st = (cudaStream_t)stream;
+  if (!d_ws || ws_bytes < need) RV_FAIL(ctx, RV_EWORKSPACE, "%s: workspace %zu < %zu", who, ws_bytes, need);
+  if (!rv_aligned(d_ws, 256)) RV_FAIL(ctx, RV_EALIGN, "%s: workspace must be 256-byte aligned", who);
   const size_t cap = (size_t)knn_capacity(n);
   char *w = reinterpret_cast<char *>(d_ws);
-  KnnArgs a;
   memset(&a, 0, sizeof(a));
   a.in = d_xyz;
   a.stride = plane_stride;
   a.n = n;
   a.k = k;
-  a.mean_out = d_mean;
   a.cap = (unsigned int)cap;
   a.prm = reinterpret_cast<KnnParams *>(w);
   w += 256;
@@ -521,7 +688,59 @@ int rv_knn_mean_distance(rv_ctx *ctx, const void *d_xyz, int64_t plane_stride, i
   if (dtype == RV_F32) k_knn_scatter<float><<<g, 256, 0, st>>>(a);
   else k_knn_scatter<double><<<g, 256, 0, st>>>(a);
   RV_LAUNCHED(ctx);
-  k_knn_query<<<grid_for(ctx, n, 16, 128), 128, 0, st>>>(a);
+  return RV_OK;
+}
+
+int rv_knn_mean_distance(rv_ctx *ctx, const void *d_xyz, int64_t plane_stride, int64_t n, int dtype, int k, double *d_mean,
+                         void *d_ws, size_t ws_bytes, rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
+  if (n > 0 && !d_mean) RV_FAIL(ctx, RV_EINVAL, "rv_knn_mean_distance: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  KnnArgs a;
+  const int rc = knn_prepare(ctx, "rv_knn_mean_distance", d_xyz, plane_stride, n, dtype, k, d_ws, ws_bytes, st, a);
+  if (rc != RV_OK || n == 0) return rc;
+  a.mean_out = d_mean;
+  k_knn_query<false><<<grid_for(ctx, n, 16, 128), 128, 0, st>>>(a);
+  RV_LAUNCHED(ctx);
+  return RV_OK;
+}
+
+int rv_estimate_normals(rv_ctx *ctx, const void *d_xyz, int64_t plane_stride, int64_t n, int dtype, double radius, int max_nn,
+                        const double *camera_location, double *d_normals, int64_t normal_stride, void *d_ws, size_t ws_bytes,
+                        rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
+  if (!(radius > 0.0)) RV_FAIL(ctx, RV_EINVAL, "rv_estimate_normals: radius must be positive");
+  if (n > 0 && (!d_normals || normal_stride < n)) RV_FAIL(ctx, RV_EINVAL, "rv_estimate_normals: bad normal buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  KnnArgs a;
+  const int rc = knn_prepare(ctx, "rv_estimate_normals", d_xyz, plane_stride, n, dtype, max_nn, d_ws, ws_bytes, st, a);
+  if (rc != RV_OK || n == 0) return rc;
+  a.radius2 = radius * radius;
+  a.orient = camera_location ? 1 : 0;
+  for (int i = 0; i < 3; ++i) a.camera[i] = camera_location ? camera_location[i] : 0.0;
+  a.normal_out = d_normals;
+  a.normal_stride = normal_stride;
+  k_knn_query<true><<<grid_for(ctx, n, 16, 128), 128, 0, st>>>(a);
+  RV_LAUNCHED(ctx);
+  return RV_OK;
+}
+
+int rv_orient_normals(rv_ctx *ctx, const void *d_xyz, int64_t plane_stride, int64_t n, int dtype, double *d_normals,
+                      int64_t normal_stride, const double *camera_location, rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
+  if (n < 0 || plane_stride < n || normal_stride < n || !camera_location) RV_FAIL(ctx, RV_EINVAL, "rv_orient_normals: bad arguments");
+  if (dtype != RV_F32 && dtype != RV_F64) RV_FAIL(ctx, RV_EINVAL, "rv_orient_normals: bad dtype");
+  if (n == 0) return RV_OK;
+  if (!d_xyz || !d_normals) RV_FAIL(ctx, RV_EINVAL, "rv_orient_normals: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const double cx = camera_location[0], cy = camera_location[1], cz = camera_location[2];
+  if (dtype == RV_F32)
+    k_orient_normals<float><<<grid_for(ctx, n), 256, 0, st>>>(reinterpret_cast<const float *>(d_xyz), plane_stride, n, d_normals, normal_stride, cx, cy, cz);
+  else
+    k_orient_normals<double><<<grid_for(ctx, n), 256, 0, st>>>(reinterpret_cast<const double *>(d_xyz), plane_stride, n, d_normals, normal_stride, cx, cy, cz);
   RV_LAUNCHED(ctx);
   return RV_OK;
 }

@@ -25,9 +25,11 @@ _NP_T = {"float": "<f4", "float32": "<f4", "double": "<f8", "float64": "<f8", "u
          "int": "<i4", "int32": "<i4", "uint": "<u4", "uint32": "<u4"}
 
 
-def ply_header(n: int, has_color: bool, coord: str = "double", ascii_: bool = False) -> bytes:
+def ply_header(n: int, has_color: bool, coord: str = "double", ascii_: bool = False, has_normals: bool = False) -> bytes:
     lines = ["ply", "format ascii 1.0" if ascii_ else "format binary_little_endian 1.0", "comment Created by Open3D",
              f"element vertex {n}", f"property {coord} x", f"property {coord} y", f"property {coord} z"]
+    if has_normals:  # Open3D's order: x y z nx ny nz red green blue
+        lines += [f"property {coord} nx", f"property {coord} ny", f"property {coord} nz"]
     if has_color:
         lines += ["property uchar red", "property uchar green", "property uchar blue"]
     lines.append("end_header")
@@ -52,14 +54,20 @@ def write_point_cloud(filename, pointcloud: PointCloud, write_ascii: bool = Fals
     filename = os.fspath(filename)
     n = len(pointcloud)
     rec = cloud_to_ply_records(pointcloud, coord)
+    normals = pointcloud.has_normals()
+    if normals and n:  # splice the normals between the coordinates and the colours of every record
+        cw = 8 if coord == "double" else 4
+        nb = np.ascontiguousarray(pointcloud.normals.astype("<f8" if cw == 8 else "<f4")).view(np.uint8).reshape(n, 3 * cw)
+        rec = np.ascontiguousarray(np.concatenate([rec[:, :3 * cw], nb, rec[:, 3 * cw:]], axis=1))
     with open(filename, "wb") as f:
-        f.write(ply_header(n, pointcloud._has_color, coord, write_ascii))
+        f.write(ply_header(n, pointcloud._has_color, coord, write_ascii, normals and n > 0))
         if not write_ascii:
             f.write(rec.tobytes())
         else:
             cw = 8 if coord == "double" else 4
-            xyz = np.ascontiguousarray(rec[:, :3 * cw]).view("<f8" if cw == 8 else "<f4").reshape(n, 3)
-            rgb = rec[:, 3 * cw:3 * cw + 3] if pointcloud._has_color else None
+            nv = 6 if (normals and n) else 3
+            xyz = np.ascontiguousarray(rec[:, :nv * cw]).view("<f8" if cw == 8 else "<f4").reshape(n, nv)
+            rgb = rec[:, nv * cw:nv * cw + 3] if pointcloud._has_color else None
             fmt = "%.10f" if cw == 8 else "%.9g"
             for i in range(n):
                 row = " ".join(fmt % v for v in xyz[i])
@@ -113,7 +121,8 @@ def read_ply_vertices(filename):
 
 def _binary_vertex_layout(filename):
     """For a binary little-endian PLY whose first element is `vertex` with float/double x, y, z (same type) and, if
-    present, uchar red/green/blue: (data offset, n, record bytes, xyz offsets, 'f32'|'f64', rgb offsets or None).
+    present, uchar red/green/blue: (data offset, n, record bytes, xyz offsets, 'f32'|'f64', rgb offsets or None,
+    nx/ny/nz offsets or None).
     Anything else returns None and takes the host reader."""
     with open(filename, "rb") as f:
         head = f.read(1 << 16)
@@ -155,7 +164,10 @@ def _binary_vertex_layout(filename):
         if any(types[k].str != "|u1" for k in ("red", "green", "blue")):
             return None
         rgb = [offsets["red"], offsets["green"], offsets["blue"]]
-    return end, n, off, [offsets[k] for k in "xyz"], "f32" if ct == {"<f4"} else "f64", rgb
+    nrm = None
+    if all(k in offsets for k in ("nx", "ny", "nz")) and {types[k].str for k in ("nx", "ny", "nz")} == ct:
+        nrm = [offsets["nx"], offsets["ny"], offsets["nz"]]
+    return end, n, off, [offsets[k] for k in "xyz"], "f32" if ct == {"<f4"} else "f64", rgb, nrm
 
 
 def read_point_cloud(filename, device=None, dtype: str = "f64") -> PointCloud:
@@ -169,13 +181,17 @@ def read_point_cloud(filename, device=None, dtype: str = "f64") -> PointCloud:
     layout = _binary_vertex_layout(filename)
     if layout is not None and layout[1] > 0:
         import torch
-        start, n, rec, xyz_off, cdt, rgb_off = layout
+        start, n, rec, xyz_off, cdt, rgb_off, nrm_off = layout
         raw = np.fromfile(filename, dtype=np.uint8, count=n * rec, offset=start)
         if raw.size != n * rec:
             raise RuntimeError(f"PLY file is truncated: {filename}")
         dev = _ops.require_cuda(device)
-        planes = _ops.unpack_ply_records(torch.from_numpy(raw).to(dev), n, rec, xyz_off, cdt, rgb_off, dtype)
-        return PointCloud(planes, n, rgb_off is not None)
+        records = torch.from_numpy(raw).to(dev)
+        planes = _ops.unpack_ply_records(records, n, rec, xyz_off, cdt, rgb_off, dtype)
+        pc = PointCloud(planes, n, rgb_off is not None)
+        if nrm_off is not None:  # the same unpacker, pointed at nx ny nz
+            pc._normals = _ops.unpack_ply_records(records, n, rec, nrm_off, cdt, None, "f64")
+        return pc
     _, arr = read_ply_vertices(filename)
     names = arr.dtype.names or ()
     if not all(k in names for k in ("x", "y", "z")):

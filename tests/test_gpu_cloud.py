@@ -281,6 +281,53 @@ def test_statistical_outlier_removal_full_size_properties(rv):
     assert torch.equal(out[:, :m], data[:, keep.bool()]) and torch.equal(index[:m], torch.nonzero(keep).reshape(-1))
 
 
+def test_normals_match_oracle_and_ply_carries_them(rv, O, rs720, tmp_path):
+    """create_masked_ply.py:163-177 in full: voxel grid, outlier removal, estimate_normals(Hybrid(0.02, 30)), orientation
+    towards the camera, PLY with normals.  The neighbourhoods are exact; the eigenvector comes from a closed-form solver on
+    the GPU and from eigh in the oracle, so normals are compared as directions (1e-7) where the two smaller eigenvalues are
+    separated, and everywhere for unit length and orientation."""
+    color, depth = load_frame(CANOPY_TS[2])
+    pc = rv.create_masked_pointcloud(color, depth.astype(np.float32) * np.float32(0.001), np.full(depth.shape, 255, np.uint8),
+                                     rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"], max_distance=1.0)
+    down = pc.voxel_down_sample(0.005)
+    down, _ = down.remove_statistical_outlier(20, 2.0)
+    P = down.points
+    assert 2000 < len(P) < 60000
+    down.estimate_normals(search_param=rv.KDTreeSearchParamHybrid(radius=0.02, max_nn=30))
+    assert down.has_normals()
+    down.orient_normals_towards_camera_location(camera_location=np.array([0.0, 0.0, 0.0]))
+    N = down.normals
+    ref = O.estimate_normals(P, 0.02, 30, camera_location=(0.0, 0.0, 0.0))
+    assert np.abs(np.linalg.norm(N, axis=1) - 1.0).max() < 1e-12
+    assert ((N * (0.0 - P)).sum(axis=1) >= 0).all()
+    cosang = np.abs((N * ref).sum(axis=1))
+    assert np.median(cosang) > 1 - 1e-12
+    assert (cosang > 1 - 1e-7).mean() > 0.995  # the rest: near-degenerate neighbourhoods (two close eigenvalues)
+    same = (N * ref).sum(axis=1) > 0
+    assert same[cosang > 1 - 1e-7].all()
+    # a tilted plane: every interior normal is the plane normal; isolated points get (0, 0, 1) turned to the camera
+    g = np.stack(np.meshgrid(np.arange(60) * 0.004, np.arange(50) * 0.004, indexing="ij"), -1).reshape(-1, 2)
+    nrm = np.array([0.3, -0.2, 1.0]) / np.linalg.norm([0.3, -0.2, 1.0])
+    plane = np.stack([g[:, 0], g[:, 1], 0.7 - (nrm[0] * g[:, 0] + nrm[1] * g[:, 1]) / nrm[2]], 1)
+    pts = np.concatenate([plane, [[5.0, 5.0, 5.0], [-4.0, 2.0, 9.0]]])
+    pp = rv.PointCloud.from_arrays(pts, None)
+    pp.estimate_normals(rv.KDTreeSearchParamHybrid(0.02, 30)).orient_normals_towards_camera_location((0.0, 0.0, 0.0))
+    Np = pp.normals
+    assert np.abs(np.abs(Np[:3000] @ nrm) - 1.0).max() < 1e-9 and (Np[:3000] @ nrm < 0).all()  # towards the camera: -n
+    assert np.array_equal(Np[3000:], [[0.0, 0.0, -1.0], [0.0, 0.0, -1.0]])
+    with pytest.raises(RuntimeError):
+        rv.PointCloud.from_arrays(pts, None).orient_normals_towards_camera_location()
+    # PLY: x y z nx ny nz red green blue, read back by the independent reader and by the device decoder
+    path = tmp_path / "with_normals.ply"
+    rv.write_point_cloud(str(path), down)
+    header, arr = O.read_ply_minimal(str(path))
+    assert [l.split()[-1] for l in header if l.startswith("property")] == ["x", "y", "z", "nx", "ny", "nz", "red", "green", "blue"]
+    assert np.array_equal(np.stack([arr["nx"], arr["ny"], arr["nz"]], 1), N)
+    back = rv.read_point_cloud(str(path))
+    assert back.has_normals() and np.array_equal(back.normals, N) and np.array_equal(back.points, P)
+    assert np.array_equal(back.colors, np.floor(down.colors * 255.0 + 0.5) / 255.0)  # std::round: halves go up
+
+
 def test_pose_from_corners_feeds_fusion(rv, golden):
     """final_view.py:171-225 on exactly projected corners: same winning order and pose as the reference produced."""
     K = np.array(golden["solvepnp_K"])

@@ -220,12 +220,12 @@ def test_binary_ply_layout_parser(tmp_path):
     head = ("ply\nformat binary_little_endian 1.0\ncomment x\nelement vertex 2\nproperty double x\nproperty double y\n"
             "property double z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n").encode()
     p.write_bytes(head + bytes(2 * 27))
-    assert ply._binary_vertex_layout(str(p)) == (len(head), 2, 27, [0, 8, 16], "f64", [24, 25, 26])
+    assert ply._binary_vertex_layout(str(p)) == (len(head), 2, 27, [0, 8, 16], "f64", [24, 25, 26], None)
     q = tmp_path / "b.ply"
     head = ("ply\nformat binary_little_endian 1.0\nelement vertex 1\nproperty uchar blue\nproperty float z\nproperty float nx\n"
             "property float x\nproperty float y\nelement face 0\nproperty list uchar int vertex_indices\nend_header\n").encode()
     q.write_bytes(head + bytes(17))
-    assert ply._binary_vertex_layout(str(q)) == (len(head), 1, 17, [9, 13, 1], "f32", None)  # no red/green: no colours
+    assert ply._binary_vertex_layout(str(q)) == (len(head), 1, 17, [9, 13, 1], "f32", None, None)  # no red/green, no ny/nz
     for bad in ("format ascii 1.0\nelement vertex 1\nproperty float x\nproperty float y\nproperty float z\n",
                 "format binary_little_endian 1.0\nelement vertex 1\nproperty float x\nproperty double y\nproperty float z\n",
                 "format binary_little_endian 1.0\nelement face 1\nproperty list uchar int vertex_indices\nelement vertex 1\n"

@@ -127,6 +127,11 @@ def main():
     line("remove_statistical_outlier(20, 2.0) on the 5 mm fused cloud (index list read back)", ms, len(down) * 24 + len(kept) * 24,
          len(down), "points", {"points": len(down), "kept": len(kept)})
 
+    ms = timed(lambda: kept.estimate_normals(rv.KDTreeSearchParamHybrid(0.02, 30)).orient_normals_towards_camera_location(),
+               max(3, a.reps // 4), flush)
+    line("estimate_normals(Hybrid(0.02, 30)) + orientation on that cloud", ms, len(kept) * 24 + len(kept) * 24, len(kept), "points",
+         {"points": len(kept)})
+
     ms = timed(lambda: _ops.pack_ply_records(merged, total, True, "unit", "f32"), a.reps, flush)
     line("PLY records float xyz + uchar rgb", ms, total * 24 + total * 15, total, "points")
 
