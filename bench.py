@@ -316,6 +316,7 @@ def run_b200(a):
 
     import repas_vision_b200 as rv
     from repas_vision_b200 import _ops, shard
+    numa = shard.bind_to_gpu_numa_node(local) if world > 1 else {}  # pinned staging buffers local to each GPU's PCIe root
 
     cam = rv.Camera(FX, FY, CX, CY, W, H)
     frames, chunk = a.frames, min(a.chunk, a.frames)
@@ -427,7 +428,7 @@ def run_b200(a):
         e_ms = shard.max_over_ranks(e_ms_local, dev)
         e_frames = shard.sum_over_ranks(ef * a.steps, dev)
         e2e = {"value": e_frames / (e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": ef * P * 5,
-               "d2h_bytes_per_step": int(d2h), "frames_per_step_per_gpu": ef,
+               "d2h_bytes_per_step": int(d2h), "frames_per_step_per_gpu": ef, "numa": numa,
                "api": "repas_vision_b200.pipeline.HostPipeline.run(depth_u16[B,H,W], bgr[B,H,W,3]) -> host float32 xyz+rgb + counts"}
         del hd, hc, pipe, res
 

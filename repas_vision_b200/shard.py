@@ -11,6 +11,39 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin this process to the CPU cores of the NUMA node the GPU hangs off, BEFORE it allocates pinned host buffers, so
+    that the staging memory of the host-buffer pipeline is local to the GPU's PCIe root (first-touch placement).  One
+    process per GPU makes this a per-rank call.  Best effort: returns {} and changes nothing when /sys does not tell."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id  # "0000:1B:00.0" (torch >= 2.5)
+    except Exception:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            bus = bus[-12:]
+        except Exception:
+            return {}
+    try:
+        node = int(open(f"/sys/bus/pci/devices/{str(bus).lower()}/numa_node").read().strip())
+        if node < 0:
+            return {}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return {}
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        return {}
+
+
 def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous block partition; the first `total % world` ranks get one extra unit."""
     if world <= 0 or not (0 <= rank < world) or total < 0:
