@@ -21,12 +21,41 @@ from . import _ops
 from .calibration import Camera
 
 
+class _PinnedPool:
+    """Pinned host blocks for the results, recycled when a result is dropped.  Page-locking memory costs milliseconds per
+    hundred megabytes, far more than the copy it serves, so blocks are rounded up to powers of two and reused."""
+
+    def __init__(self, max_bytes: int = 8 << 30):
+        self.free: dict[int, list[torch.Tensor]] = {}
+        self.max_bytes, self.held = int(max_bytes), 0
+
+    def take(self, elements: int) -> torch.Tensor:
+        cap = 1 << max(16, int(elements - 1).bit_length())
+        blocks = self.free.get(cap)
+        if blocks:
+            self.held -= cap * 4
+            return blocks.pop()
+        return torch.empty(cap, dtype=torch.float32, pin_memory=True)
+
+    def give(self, block: torch.Tensor) -> None:
+        cap = block.numel()
+        if self.held + cap * 4 <= self.max_bytes:
+            self.free.setdefault(cap, []).append(block)
+            self.held += cap * 4
+
+
 class HostCloudChunk:
     """Clouds of `frames` consecutive frames on the host: planes [6 or 3, total] float32 (pinned), offsets [frames+1]."""
 
-    def __init__(self, first_frame: int, frames: int, planes: torch.Tensor, offsets: np.ndarray):
+    def __init__(self, first_frame: int, frames: int, planes: torch.Tensor, offsets: np.ndarray, block=None, pool=None):
         self.first_frame, self.frames = first_frame, frames
         self._planes, self.offsets = planes, offsets
+        self._block, self._pool = block, pool
+
+    def __del__(self):
+        if self._pool is not None and self._block is not None:
+            self._pool.give(self._block)
+            self._block = None
 
     @property
     def planes(self) -> np.ndarray:
@@ -81,6 +110,7 @@ class HostPipeline:
         self.d_mask = [torch.empty((C, H, W), dtype=torch.uint8, device=d) for _ in range(self.slots)] if use_mask else None
         self.d_out = [torch.empty((self.planes, C * self.P), dtype=torch.float32, device=d) for _ in range(self.slots)]
         self.h_off = [torch.empty(C + 1, dtype=torch.int64, pin_memory=True) for _ in range(self.slots)]
+        self.pool = _PinnedPool()
         self.s_in, self.s_k, self.s_out = (torch.cuda.Stream(d) for _ in range(3))
         self.ev_in = [torch.cuda.Event() for _ in range(self.slots)]
         self.ev_k = [torch.cuda.Event() for _ in range(self.slots)]
@@ -152,14 +182,15 @@ class HostPipeline:
             self.ev_k[s].synchronize()
             offsets = self.h_off[s][:n + 1].numpy().copy()
             total = int(offsets[-1])
-            host = torch.empty((self.planes, max(total, 1)), dtype=torch.float32, pin_memory=True)
+            block = self.pool.take(self.planes * max(total, 1))
+            host = block[:self.planes * max(total, 1)].view(self.planes, max(total, 1))
             with torch.cuda.stream(self.s_out):
                 if total:
                     for p in range(self.planes):
                         host[p, :total].copy_(self.d_out[s][p, :total], non_blocking=True)
                 self.ev_out[s].record(self.s_out)
             d2h += total * 4 * self.planes + (n + 1) * 8
-            chunks[i] = HostCloudChunk(f0, n, host[:, :total], offsets)
+            chunks[i] = HostCloudChunk(f0, n, host[:, :total], offsets, block, self.pool)
 
         for i in range(n_chunks + 1):
             if i < n_chunks:
