@@ -35,11 +35,14 @@ struct DeprojArgs {
   unsigned int d_cand;  // uint16 depths in [1, d_cand) can still be inside the sphere; 65536 when there is no radius mask
 };
 
-// fast path (rv_deproject_tma.cu): RV_K1_CW compute warps per CTA, 256 pixels each per tile
+// fast path (rv_deproject_tma.cu): RV_K1_CW compute warps per CTA, 32 * RV_K1_ITERS pixels each per tile
 #ifndef RV_K1_CW
 #define RV_K1_CW 8
 #endif
-constexpr int kFastTilePx = RV_K1_CW * 256;
+#ifndef RV_K1_ITERS
+#define RV_K1_ITERS 8  // 32-pixel groups per warp and tile
+#endif
+constexpr int kFastTilePx = RV_K1_CW * 32 * RV_K1_ITERS;
 constexpr int kGenericTilePx = 2048;
 constexpr int kMinTilePx = kFastTilePx < kGenericTilePx ? kFastTilePx : kGenericTilePx;  // sizes the workspace
 

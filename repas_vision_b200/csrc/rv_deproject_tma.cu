@@ -36,7 +36,7 @@ namespace {
 constexpr int kCW = RV_K1_CW;            // compute warps
 constexpr int kCT = kCW * 32;           // compute threads
 constexpr int kThreadsT = kCT + 32;     // + producer warp
-constexpr int kItersT = 8;
+constexpr int kItersT = RV_K1_ITERS;
 constexpr int kWarpPx = 32 * kItersT;   // 256 pixels per warp per tile
 constexpr int kTileT = kCT * kItersT;   // 2048 pixels
 #ifndef RV_K1_STAGES
@@ -156,7 +156,10 @@ struct Layout {
   static constexpr int kSmem = kRingBytes + kCW * kWarpStage;
   // resident CTAs per SM the shared memory allows (227 KB usable, ~1.5 KB static + reserved per CTA)
   static constexpr int kOccSmem = (227 * 1024) / (kSmem + 1536);
-  static constexpr int kOccCap = 32 / kCW;  // 32 compute warps per SM: 4 CTAs of 8 warps (or 8 CTAs of 4)
+#ifndef RV_K1_WARPS_PER_SM
+#define RV_K1_WARPS_PER_SM 32
+#endif
+  static constexpr int kOccCap = RV_K1_WARPS_PER_SM / kCW;  // 32 compute warps per SM: 4 CTAs of 8 warps (or 8 CTAs of 4)
   static constexpr int kOcc = kOccSmem > kOccCap ? kOccCap : kOccSmem;
 };
 
