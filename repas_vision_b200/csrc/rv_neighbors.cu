@@ -9,8 +9,9 @@
 //   std_dev = sqrt(sq_sum / (n - 1));  keep i  <=>  avg[i] > 0 && avg[i] < cloud_mean + std_ratio * std_dev.
 //
 // The exact k-nearest search runs on a uniform hash grid instead of a KD-tree:
-//   k_knn_setup    cell size from the bounding box and the point count (about two point spacings of a surface-like cloud)
-//   k_knn_refine   more than 16 points per used cell (a far outlier inflated the box): shrink the cells and rebuild, up to 3x
+//   k_knn_setup    cell size from the bounding box, the point count and k: large enough that the 27 cells around a point
+//                  normally hold its k nearest neighbours, no larger than a search radius
+//   k_knn_refine   four times the expected points per used cell (a far outlier inflated the box): shrink the cells and rebuild, up to 3x
 //   k_knn_cells    cell key of every point -> open-addressing table of 8-byte keys; the rank inside the cell comes back
 //                  from the per-cell counter
 //   k_knn_alloc    every used cell gets a range of the cell-sorted arrays (one cursor update per warp of table slots)
@@ -38,9 +39,10 @@ struct KnnParams {  // written by k_knn_setup, read by the later kernels
   unsigned int occupied;  // cells in use
   int redo;               // 1: (re)build the cell table with the current cell size
   int pad;
+  double expect;          // points per used cell the chosen cell size should give on a surface
 };
 constexpr int kRefineRounds = 3;       // the cell size is re-derived from the measured occupancy at most this many times
-constexpr double kMaxOccupancy = 16.0; // points per used cell above which the grid is rebuilt finer
+constexpr double kMaxOccupancy = 4.0;  // measured / expected points per used cell above which the grid is rebuilt finer
 
 struct KnnArgs {
   const void *in;
@@ -134,15 +136,23 @@ __device__ void knn_set_cell(KnnParams *p, double s) {
   p->rmax = rmax;
 }
 
-__global__ void k_knn_setup(KnnParams *p, long long n) {
+__global__ void k_knn_setup(KnnParams *p, long long n, int k, double radius) {
   double e[3] = {p->bounds[3] - p->bounds[0], p->bounds[4] - p->bounds[1], p->bounds[5] - p->bounds[2]};
   double a = e[0], b = e[1], c = e[2];  // sort descending
   if (a < b) { const double t = a; a = b; b = t; }
   if (b < c) { const double t = b; b = c; c = t; }
   if (a < b) { const double t = a; a = b; b = t; }
-  // two spacings of a surface-like cloud spread over the two largest extents; a line or a single point degenerate gracefully
-  double s = 2.0 * sqrt(a * b / (double)n);
+  // spacing of a surface-like cloud spread over the two largest extents; the cell is made just large enough that the k
+  // nearest neighbours (a disc of ~sqrt(k / pi) spacings) are normally complete after the 27 cells around the query, and no
+  // larger than a search radius; a line or a single point degenerate gracefully
+  const double spacing = sqrt(a * b / (double)n);
+  double f = 1.2 * sqrt((double)k / 3.141592653589793);
+  if (f < 2.0) f = 2.0;
+  double s = f * spacing;
+  if (radius > 0.0 && radius < s) s = radius > 2.0 * spacing ? radius : 2.0 * spacing;
   if (!(s > 0.0)) s = a > 0.0 ? 4.0 * a / (double)n : 1.0;
+  p->expect = spacing > 0.0 ? (s / spacing) * (s / spacing) : 4.0;
+  if (!(p->expect >= 4.0)) p->expect = 4.0;
   knn_set_cell(p, s);
 }
 
@@ -150,11 +160,12 @@ __global__ void k_knn_setup(KnnParams *p, long long n) {
 // points per used cell, shrink the cells (occupancy of a surface goes with the square of the cell size) and rebuild.
 __global__ void k_knn_refine(KnnParams *p, long long n, int last) {
   const double occ = p->occupied ? (double)n / (double)p->occupied : 0.0;
+  const double expect = p->expect;  // points per cell the setup aimed for (cell / spacing, squared)
   const double e0 = p->bounds[3] - p->bounds[0], e1 = p->bounds[4] - p->bounds[1], e2 = p->bounds[5] - p->bounds[2];
   const double emax = fmax(e0, fmax(e1, e2));
   const bool can_shrink = p->cell > emax / 1048576.0 * 1.5;
-  if (p->redo && !last && occ > kMaxOccupancy && can_shrink) {
-    knn_set_cell(p, p->cell * sqrt(4.0 / occ));
+  if (p->redo && !last && occ > kMaxOccupancy * expect && can_shrink) {
+    knn_set_cell(p, p->cell * sqrt(expect / occ));
     p->occupied = 0;
     p->redo = 1;
   } else {
@@ -625,7 +636,7 @@ size_t rv_knn_workspace_bytes(int64_t n) {
 
 // validation, workspace layout and the grid build shared by the two query entry points
 static int knn_prepare(rv_ctx *ctx, const char *who, const void *d_xyz, int64_t plane_stride, int64_t n, int dtype, int k,
-                       void *d_ws, size_t ws_bytes, cudaStream_t st, KnnArgs &a) {
+                       double radius, void *d_ws, size_t ws_bytes, cudaStream_t st, KnnArgs &a) {
   if (n < 0 || plane_stride < n) RV_FAIL(ctx, RV_EINVAL, "%s: bad n / stride", who);
   if (dtype != RV_F32 && dtype != RV_F64) RV_FAIL(ctx, RV_EINVAL, "%s: bad dtype", who);
   if (k < 1 || k > kMaxK) RV_FAIL(ctx, RV_EINVAL, "%s: the neighbour count must be in [1, %d]", who, kMaxK);
@@ -670,7 +681,7 @@ static int knn_prepare(rv_ctx *ctx, const char *who, const void *d_xyz, int64_t 
   if (dtype == RV_F32) k_knn_bounds<float><<<g, 256, 0, st>>>(reinterpret_cast<const float *>(d_xyz), plane_stride, n, a.prm->bounds);
   else k_knn_bounds<double><<<g, 256, 0, st>>>(reinterpret_cast<const double *>(d_xyz), plane_stride, n, a.prm->bounds);
   RV_LAUNCHED(ctx);
-  k_knn_setup<<<1, 1, 0, st>>>(a.prm, n);
+  k_knn_setup<<<1, 1, 0, st>>>(a.prm, n, k, radius);
   RV_LAUNCHED(ctx);
   for (int round = 0; round <= kRefineRounds; ++round) {
     if (round > 0) {
@@ -698,7 +709,7 @@ int rv_knn_mean_distance(rv_ctx *ctx, const void *d_xyz, int64_t plane_stride, i
   if (n > 0 && !d_mean) RV_FAIL(ctx, RV_EINVAL, "rv_knn_mean_distance: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   KnnArgs a;
-  const int rc = knn_prepare(ctx, "rv_knn_mean_distance", d_xyz, plane_stride, n, dtype, k, d_ws, ws_bytes, st, a);
+  const int rc = knn_prepare(ctx, "rv_knn_mean_distance", d_xyz, plane_stride, n, dtype, k, 0.0, d_ws, ws_bytes, st, a);
   if (rc != RV_OK || n == 0) return rc;
   a.mean_out = d_mean;
   k_knn_query<false><<<grid_for(ctx, n, 16, 128), 128, 0, st>>>(a);
@@ -715,7 +726,7 @@ int rv_estimate_normals(rv_ctx *ctx, const void *d_xyz, int64_t plane_stride, in
   if (n > 0 && (!d_normals || normal_stride < n)) RV_FAIL(ctx, RV_EINVAL, "rv_estimate_normals: bad normal buffer");
   cudaStream_t st = (cudaStream_t)stream;
   KnnArgs a;
-  const int rc = knn_prepare(ctx, "rv_estimate_normals", d_xyz, plane_stride, n, dtype, max_nn, d_ws, ws_bytes, st, a);
+  const int rc = knn_prepare(ctx, "rv_estimate_normals", d_xyz, plane_stride, n, dtype, max_nn, radius, d_ws, ws_bytes, st, a);
   if (rc != RV_OK || n == 0) return rc;
   a.radius2 = radius * radius;
   a.orient = camera_location ? 1 : 0;
