@@ -348,10 +348,11 @@ def median_depth_window(depth_u16: torch.Tensor, uv: torch.Tensor, window: int) 
     return out[:n]
 
 
-def nv12_to_bgr(nv12: torch.Tensor, H: int, W: int) -> torch.Tensor:
+def nv12_to_bgr(nv12: torch.Tensor, H: int, W: int, out: torch.Tensor | None = None) -> torch.Tensor:
     dev = nv12.device
     ctx = ctx_for(dev)
     B = nv12.shape[0]
-    out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
+    if out is None:
+        out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
     ctx.check(ctx.lib.rv_nv12_to_bgr(ctx.handle, ptr(nv12), B, H, W, ptr(out), stream_ptr(dev)))
     return out

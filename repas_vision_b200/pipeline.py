@@ -94,7 +94,15 @@ class HostBatchResult:
 class HostPipeline:
     def __init__(self, camera: Camera, height: int, width: int, *, max_distance=None, z_clip=None, aabb=None,
                  unit_rule: str = "mul_f32", depth_scale=None, use_mask: bool = False, invert_mask: bool = False,
-                 with_color: bool = True, chunk_frames: int = 32, slots: int = 3, device=None):
+                 with_color: bool = True, color_format: str = "bgr", chunk_frames: int = 32, slots: int = 3, device=None):
+        """color_format "nv12": the colour frames arrive as the camera delivers them ([B, H*3/2, W] uint8, the capture
+        script's preferred format, better_three_capture.py:101-106,159) and are decoded on the GPU; the frame then crosses
+        PCIe at 3.5 instead of 5 bytes per pixel."""
+        if color_format not in ("bgr", "nv12"):
+            raise ValueError("color_format must be 'bgr' or 'nv12'")
+        if color_format == "nv12" and (int(height) % 2 or int(width) % 2):
+            raise ValueError("NV12 needs even image sides")
+        self.color_format = color_format
         self.dev = _ops.require_cuda(device)
         self.cam, self.H, self.W = camera, int(height), int(width)
         self.P = self.H * self.W
@@ -107,6 +115,8 @@ class HostPipeline:
         C, H, W = self.C, self.H, self.W
         self.d_depth = [torch.empty((C, H, W), dtype=torch.uint16, device=d) for _ in range(self.slots)]
         self.d_bgr = [torch.empty((C, H, W, 3), dtype=torch.uint8, device=d) for _ in range(self.slots)] if with_color else None
+        self.d_nv12 = ([torch.empty((C, H * 3 // 2, W), dtype=torch.uint8, device=d) for _ in range(self.slots)]
+                       if with_color and color_format == "nv12" else None)
         self.d_mask = [torch.empty((C, H, W), dtype=torch.uint8, device=d) for _ in range(self.slots)] if use_mask else None
         self.d_out = [torch.empty((self.planes, C * self.P), dtype=torch.float32, device=d) for _ in range(self.slots)]
         self.h_off = [torch.empty(C + 1, dtype=torch.int64, pin_memory=True) for _ in range(self.slots)]
@@ -135,7 +145,8 @@ class HostPipeline:
             if bgr is None:
                 raise RuntimeError("this pipeline was built with_color=True: bgr is required")
             hc = self._host_tensor(bgr, torch.uint8)
-            if tuple(hc.shape) != (B, self.H, self.W, 3):
+            want = (B, self.H, self.W, 3) if self.color_format == "bgr" else (B, self.H * 3 // 2, self.W)
+            if tuple(hc.shape) != want:
                 raise RuntimeError(f"Color/depth size mismatch: color {tuple(hc.shape)}, depth {tuple(hd.shape)}")
         hm = None
         if self.use_mask:
@@ -159,7 +170,10 @@ class HostPipeline:
                 self.s_in.wait_event(self.ev_k[s])  # the kernel that last read this input slot
                 self.d_depth[s][:n].copy_(hd[f0:f1], non_blocking=True)
                 h2d += n * self.P * 2
-                if hc is not None:
+                if hc is not None and self.d_nv12 is not None:
+                    self.d_nv12[s][:n].copy_(hc[f0:f1], non_blocking=True)
+                    h2d += n * self.P * 3 // 2
+                elif hc is not None:
                     self.d_bgr[s][:n].copy_(hc[f0:f1], non_blocking=True)
                     h2d += n * self.P * 3
                 if hm is not None:
@@ -169,6 +183,8 @@ class HostPipeline:
             with torch.cuda.stream(self.s_k):
                 self.s_k.wait_event(self.ev_in[s])
                 self.s_k.wait_event(self.ev_out[s])  # the D2H that last read this output slot
+                if self.d_nv12 is not None:
+                    _ops.nv12_to_bgr(self.d_nv12[s][:n], self.H, self.W, out=self.d_bgr[s][:n])
                 r = _ops.deproject(self.d_depth[s][:n], None if hc is None else self.d_bgr[s][:n],
                                    None if hm is None else self.d_mask[s][:n], self.cam, out=self.d_out[s], **self.kw)
                 self.h_off[s][:n + 1].copy_(r["counts"], non_blocking=True)

@@ -450,12 +450,13 @@ def test_median_depth_windows_and_canopy_known_answers(rv, golden, rs720):
 def test_nv12_to_bgr_matches_opencv(rv):
     import cv2
     rng = np.random.default_rng(2)
-    H, W = 72, 128
-    nv12 = rng.integers(0, 256, (3, H * 3 // 2, W), dtype=np.uint8)
-    got = rv.nv12_to_bgr(nv12, H, W)
-    for b in range(3):
-        ref = cv2.cvtColor(nv12[b], cv2.COLOR_YUV2BGR_NV12)
-        assert np.array_equal(got[b], ref)
+    # 16-byte-wide kernel (W % 16 == 0: one partial strip, five full strips, a 48-pixel tail strip) and the byte kernel
+    for H, W in ((72, 128), (720, 1280), (36, 304), (50, 70)):
+        nv12 = rng.integers(0, 256, (3, H * 3 // 2, W), dtype=np.uint8)
+        got = rv.nv12_to_bgr(nv12, H, W)
+        for b in range(3):
+            ref = cv2.cvtColor(nv12[b], cv2.COLOR_YUV2BGR_NV12)
+            assert np.array_equal(got[b], ref), (H, W, b)
 
 
 def test_exact_division_helper_against_numpy(rv):

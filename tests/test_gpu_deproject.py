@@ -307,5 +307,16 @@ def test_packed_mode_and_host_pipeline(rv, O, rs720, kernel):
             xyz, rgb = res.frame(b)
             assert np.array_equal(xyz.T, refs[b]["points"]) and np.array_equal(rgb.T, refs[b]["colors"])
         assert np.array_equal(res.points(2), refs[2]["points"].astype(np.float64))
+        # NV12 colour frames (the capture script's preferred format): decoded on the GPU, same clouds as feeding the BGR
+        # image cv2 makes of them
+        import cv2
+        rng = np.random.default_rng(7)
+        nv12 = rng.integers(0, 256, (B, H * 3 // 2, W), dtype=np.uint8)
+        bgr_cv = np.stack([cv2.cvtColor(f, cv2.COLOR_YUV2BGR_NV12) for f in nv12])
+        a = HostPipeline(cam, H, W, max_distance=1.3, chunk_frames=4, color_format="nv12").run(depth, nv12)
+        b2 = pipe.run(depth, bgr_cv)
+        assert a.h2d_bytes == B * H * W * 7 // 2 and np.array_equal(a.counts, b2.counts)
+        for fb in range(B):
+            assert np.array_equal(a.frame(fb)[0], b2.frame(fb)[0]) and np.array_equal(a.frame(fb)[1], b2.frame(fb)[1])
         res2 = pipe.run(torch.from_numpy(depth).pin_memory(), torch.from_numpy(bgr).pin_memory())  # pinned inputs, reuse
         assert np.array_equal(res2.counts, res.counts) and np.array_equal(res2.frame(B - 1)[0], res.frame(B - 1)[0])
