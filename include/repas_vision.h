@@ -82,7 +82,7 @@ enum RvDepthKind { RV_DEPTH_U16 = 0, RV_DEPTH_F32_METERS = 1 };
 /* ---- output modes of the deprojection kernel ------------------------------ */
 enum RvDeprojectMode {
   RV_MODE_COMPACT_ORDERED = 0,   /* row-major order of valid pixels, == numpy `[valid]` (create_masked_ply.py:89-100) */
-  RV_MODE_COMPACT_UNORDERED = 1, /* tiles land in arrival order; order inside a 2048-pixel tile is kept              */
+  RV_MODE_COMPACT_UNORDERED = 1, /* any order of tiles (generic kernel: arrival order; TMA kernel: row-major like ORDERED)    */
   RV_MODE_DENSE_ZERO = 2,        /* one record per pixel, zeros where invalid (rs.pointcloud / Orbbec RGB_POINT)     */
   RV_MODE_DENSE_NAN = 3,         /* one record per pixel, NaN xyz where invalid (Open3D project_valid_depth_only=False) */
   RV_MODE_COMPACT_PACKED = 4     /* COMPACT_ORDERED with the frames of the batch back to back: frame b occupies
@@ -96,8 +96,8 @@ enum RvColorScale {
 };
 
 /* which K1 kernel runs: AUTO picks the TMA-fed pipeline when H*W % 16 == 0, W >= 32, the inputs are 16-byte
- * aligned, there is no ray table and the mode is not COMPACT_UNORDERED; otherwise the generic kernel.  Both
- * produce identical bytes (tests/test_gpu_deproject.py runs every case through both). */
+ * aligned; otherwise the generic kernel.  Both produce identical bytes (tests/test_gpu_deproject.py runs every case
+ * through both); a COMPACT_UNORDERED request on the TMA path gets the ordered result, which satisfies it. */
 enum RvKernelSelect { RV_KERNEL_AUTO = 0, RV_KERNEL_GENERIC = 1, RV_KERNEL_TMA = 2 };
 
 typedef struct RvDeprojectParams {

@@ -505,7 +505,6 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
   if (dense && frame_stride < P) RV_FAIL(ctx, RV_ECAPACITY, "rv_deproject_mask: dense mode needs frame_stride >= H*W");
   if (d_ray_table && !rv_aligned(d_ray_table, 16)) RV_FAIL(ctx, RV_EALIGN, "rv_deproject_mask: ray table alignment");
   const size_t need = rv_deproject_workspace_bytes(B, H, W);
-  const bool ordered = p->mode == RV_MODE_COMPACT_ORDERED || packed;
   // every mode takes the workspace: the ordered modes keep their prefix chains in it and the TMA pipeline hands
   // out tiles through its ticket counter
   if (!d_ws || ws_bytes < need) RV_FAIL(ctx, RV_EWORKSPACE, "rv_deproject_mask: workspace %zu < %zu", ws_bytes, need);
@@ -586,8 +585,11 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
   const bool fast_ok = rv_deproject_fast_eligible(a, p->mode);
   if (p->kernel_select == RV_KERNEL_TMA && !fast_ok)
     RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: RV_KERNEL_TMA requested but the inputs are not eligible "
-                            "(H*W %% 16 == 0, W >= 32, 16-byte aligned inputs, not COMPACT_UNORDERED)");
+                            "(H*W %% 16 == 0, W >= 32, 16-byte aligned inputs)");
   const bool use_fast = fast_ok && p->kernel_select != RV_KERNEL_GENERIC;
+  // COMPACT_UNORDERED asks for less than COMPACT_ORDERED delivers: on the fast path it simply gets the ordered kernel
+  const int mode = (use_fast && p->mode == RV_MODE_COMPACT_UNORDERED) ? RV_MODE_COMPACT_ORDERED : p->mode;
+  const bool ordered = mode == RV_MODE_COMPACT_ORDERED || packed;
   const int tile_px = use_fast ? kFastTilePx : kTile;
   a.tiles_per_frame = (int)((P + tile_px - 1) / tile_px);
   a.total_tiles = a.tiles_per_frame * B;
@@ -599,7 +601,7 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
     RV_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (size_t)B * sizeof(int64_t), st));
   }
   if (use_fast) {
-    RV_CUDA(ctx, rv_deproject_fast_launch(ctx, a, p->mode, p->out_dtype, p->depth_kind, st));
+    RV_CUDA(ctx, rv_deproject_fast_launch(ctx, a, mode, p->out_dtype, p->depth_kind, st));
   } else if (p->out_dtype == RV_F32) {
     if (p->depth_kind == RV_DEPTH_U16)
       launch_mode<float, RV_DEPTH_U16>(ctx, a, p->mode, st);

@@ -26,8 +26,8 @@
 //    the decision equals the float64 predicate of the oracle bit for bit (exact float64 re-evaluation
 //    inside a 2^-20 band around the sphere).
 //
-// Eligibility (checked by rv_deproject_fast_eligible): H*W % 16 == 0, W >= 32, 16-byte aligned inputs,
-// mode != COMPACT_UNORDERED.  Everything else runs k_deproject.
+// Eligibility (checked by rv_deproject_fast_eligible): H*W % 16 == 0, W >= 32, 16-byte aligned inputs (a COMPACT_UNORDERED
+// request is served by the ordered variant).  Everything else runs k_deproject.
 #include "rv_common.cuh"
 #include "rv_deproject_args.cuh"
 
@@ -628,7 +628,7 @@ cudaError_t launch_tma(const rv_ctx *ctx, const DeprojArgs &a, int mode, cudaStr
 }  // namespace
 
 bool rv_deproject_fast_eligible(const DeprojArgs &a, int mode) {
-  if (mode == RV_MODE_COMPACT_UNORDERED) return false;
+  (void)mode;
   if (a.W < 32 || (a.P % 16) != 0) return false;
   if (!rv_aligned(a.depth, 16) || (a.bgr && !rv_aligned(a.bgr, 16)) || (a.mask && !rv_aligned(a.mask, 16))) return false;
   return true;

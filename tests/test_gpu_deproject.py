@@ -142,7 +142,8 @@ def test_synthetic_frames_all_predicates(rv, O, rs720, shape, kernel, case, dtyp
         assert np.abs(got.astype(np.float64) - ref64["points"][sel]).max(initial=0.0) <= XYZ_TOL_M
 
 
-@pytest.mark.parametrize("mode,kernel", [("compact_unordered", "auto"), ("dense_zero", "tma"), ("dense_zero", "generic"),
+@pytest.mark.parametrize("mode,kernel", [("compact_unordered", "auto"), ("compact_unordered", "generic"), ("compact_unordered", "tma"),
+                                         ("dense_zero", "tma"), ("dense_zero", "generic"),
                                          ("dense_nan", "tma"), ("dense_nan", "generic")])
 def test_other_output_modes(rv, O, rs720, mode, kernel):
     import torch
