@@ -114,6 +114,19 @@ def main():
         ms = timed(lambda: _ops.voxel_downsample(merged, total, True, vs, bounds=bounds), a.reps, flush)
         line(f"K4 voxel_down_sample {vs * 1000:.0f} mm f32", ms, total * 24 + m * 24, total, "points", {"points": total, "voxels": m})
 
+    # ---- a8 / a9 on an existing cloud (distance_masking_on_ply.py:12-19, view_point_cloud.py:109-116): ordered compaction of a
+    # 32 M-point float32 cloud (768 MB in): ||p|| < 1 keeps about a third, the z-clip about half
+    nb = 32 * 1024 * 1024
+    big = (torch.rand((6, nb), generator=gen, device=dev, dtype=torch.float32) * 2.0 - 0.5)
+    big[2] = torch.rand(nb, generator=gen, device=dev) * 1.2
+    for name, kw in (("a8 distance mask ||p|| < 1 m", dict(r_max=1.0)), ("a9 z-clip 0.15 .. 0.8 m", dict(z_clip=(0.15, 0.8)))):
+        o_, cnt_ = _ops.filter_cloud(big, nb, True, **kw)
+        keptf = float(cnt_.item()) / nb
+        del o_
+        ms = timed(lambda: _ops.filter_cloud(big, nb, True, **kw), max(3, a.reps // 4), flush)
+        line(f"{name} on a 32 M-point cloud (ordered compaction)", ms, nb * 24 * (1 + keptf), nb, "points", {"kept": keptf})
+    del big
+
     # ---- BASELINE configs[3] as one call: transform 4 views into the tag frame, merge, 5 mm voxel grid (device-resident)
     cam_T = [np.linalg.inv(np.asarray(p).reshape(4, 4)) for p in poses]
     ms = timed(lambda: rv.fuse_views(clouds, cam_T, 0.005), a.reps, flush)
