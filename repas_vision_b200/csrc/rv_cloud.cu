@@ -73,11 +73,12 @@ __device__ __forceinline__ void block_bounds_commit(double lo[3], double hi[3], 
 template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256) k_transform(const __grid_constant__ XformArgs args) {
   const XformView &a = args.view[blockIdx.y];
-  const InT *in = reinterpret_cast<const InT *>(a.in);
-  OutT *out = reinterpret_cast<OutT *>(args.out) + a.out_offset;
+  const InT *__restrict__ in = reinterpret_cast<const InT *>(a.in);  // the merged cloud never overlaps a view
+  OutT *__restrict__ out = reinterpret_cast<OutT *>(args.out) + a.out_offset;
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
   double lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
   const long long stride = (long long)gridDim.x * blockDim.x;
+#pragma unroll 4
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
     const double x = (double)in[i], y = (double)in[a.in_stride + i], z = (double)in[2 * a.in_stride + i];
     const double *T = a.T;
@@ -418,31 +419,52 @@ unsigned long long vox_capacity(long long n) {  // 1.5 slots per point, a multip
 }
 
 // --------------------------------------------------------------------- PLY records
+// every warp gathers the 32 records of a step in shared memory and writes them out as 16-byte pieces (32 records are
+// 480 or 864 bytes: a multiple of 16); byte-wise stores of 15-byte records reach the L2 as partial-sector writes and ran at
+// an eighth of the bandwidth
 template <typename InT, typename CoordT>
 __global__ void __launch_bounds__(256) k_pack_ply(const InT *__restrict__ in, long long stride_in, long long n,
                                                   int has_color, int color_255, uint8_t *__restrict__ rec) {
   constexpr int kRec = 3 * (int)sizeof(CoordT) + 3;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    uint8_t buf[kRec];
-    CoordT xyz[3] = {(CoordT)in[i], (CoordT)in[stride_in + i], (CoordT)in[2 * stride_in + i]};
-    memcpy(buf, xyz, sizeof(xyz));
+  __shared__ __align__(16) uint8_t s_rec[8][32 * kRec];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool wide = (reinterpret_cast<uintptr_t>(rec) & 15) == 0;
+  const long long warps = (long long)gridDim.x * 8;
+  const long long groups = (n + 31) >> 5;
+  for (long long g = (long long)blockIdx.x * 8 + warp; g < groups; g += warps) {
+    const long long i = g * 32 + lane;
+    uint8_t *buf = &s_rec[warp][lane * kRec];
+    if (i < n) {
+      CoordT xyz[3] = {(CoordT)in[i], (CoordT)in[stride_in + i], (CoordT)in[2 * stride_in + i]};
+      uint8_t raw[3 * sizeof(CoordT)];
+      memcpy(raw, xyz, sizeof(xyz));
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      double v = has_color ? (double)in[(3 + c) * stride_in + i] : 0.0;
-      if (!color_255) {
-        // Open3D: (uint8_t) round(min(1, max(0, c)) * 255)
-        v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
-        v = round(v * 255.0);
-      } else {
-        v = v < 0.0 ? 0.0 : (v > 255.0 ? 255.0 : v);
-        v = round(v);
+      for (int k = 0; k < (int)sizeof(xyz); ++k) buf[k] = raw[k];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double v = has_color ? (double)in[(3 + c) * stride_in + i] : 0.0;
+        if (!color_255) {
+          // Open3D: (uint8_t) round(min(1, max(0, c)) * 255)
+          v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+          v = round(v * 255.0);
+        } else {
+          v = v < 0.0 ? 0.0 : (v > 255.0 ? 255.0 : v);
+          v = round(v);
+        }
+        buf[sizeof(xyz) + c] = (uint8_t)v;
       }
-      buf[sizeof(xyz) + c] = (uint8_t)v;
     }
-    uint8_t *dst = rec + i * kRec;
-#pragma unroll
-    for (int k = 0; k < kRec; ++k) dst[k] = buf[k];
+    __syncwarp();
+    const long long left = n - g * 32;
+    const int bytes = (int)(left < 32 ? left : 32) * kRec;
+    uint8_t *dst = rec + g * 32 * kRec;
+    if (wide && bytes == 32 * kRec) {
+      for (int k = lane; k < 32 * kRec / 16; k += 32)
+        reinterpret_cast<uint4 *>(dst)[k] = reinterpret_cast<const uint4 *>(s_rec[warp])[k];
+    } else {
+      for (int k = lane; k < bytes; k += 32) dst[k] = s_rec[warp][k];
+    }
+    __syncwarp();
   }
 }
 
@@ -656,7 +678,7 @@ int rv_pack_ply_records(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, 
   if (n == 0) return RV_OK;
   if (!d_in || !d_records) RV_FAIL(ctx, RV_EINVAL, "rv_pack_ply_records: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  const int g = grid_for(ctx, n);
+  const int g = grid_for(ctx, n);  // 8 warps per CTA, 32 records per warp and step
   const int c255 = color_scale == RV_COLOR_255;
   if (in_dtype == RV_F32 && coord_dtype == RV_F32)
     k_pack_ply<float, float><<<g, 256, 0, st>>>(reinterpret_cast<const float *>(d_in), in_plane_stride, n, has_color, c255, d_records);
