@@ -295,6 +295,32 @@ int rv_select_by_mask(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, in
                       const uint8_t *d_keep, void *d_out, int64_t out_plane_stride, int64_t *d_count, int64_t *d_index,
                       void *d_ws, size_t ws_bytes, rv_stream stream);
 
+/* ---- next, SURVEY 8f-4: ICP correspondence search ------------------------------------
+ * replaces the per-iteration work of o3d.pipelines.registration.registration_icp(source, target, max_dist, init,
+ * TransformationEstimationPointToPlane(), ICPConvergenceCriteria(...)) (mpa_icp_export.py:187-197, 6dof_icp_export.py:134-144,
+ * mpa_icp.py:159, icp_cad_model.py:90-94,271-275); semantics of Open3D 0.19 Registration.cpp
+ * GetRegistrationResultAndCorrespondences + TransformationEstimationPointToPlane / PointToPoint::ComputeTransformation:
+ *  rv_nn_index_build   hash-grid index of the target cloud (the KD-tree of the reference), built once per registration;
+ *                      workspace rv_knn_workspace_bytes(n), which then IS the index
+ *  rv_nn_search        d_nearest[i] = index of the target point nearest to query i with squared distance strictly below
+ *                      max_distance^2 (KDTreeFlann::SearchHybrid(p, max_distance, 1)), -1 without one; equal distances
+ *                      go to the lower index
+ *  rv_icp_sums         d_sums (rv_icp_sums_bytes() bytes; the first 32 doubles are the result, summed per block in a
+ *                      fixed order): [0] correspondences, [1] sum of squared distances;
+ *                      point_to_plane: [2] sum r^2, [3..8] J^T r, [9..29] upper triangle of J^T J (row-major), with
+ *                      r = (s - t) . n_t and J = [s x n_t, n_t];
+ *                      point-to-point: [2] sum |s|^2, [3..5] sum s, [6..8] sum t, [9..17] sum t_a s_b (a row-major)
+ * The 6x6 solve / Umeyama step and the convergence test stay on the host (repas_vision_b200/registration.py). */
+int rv_nn_index_build(rv_ctx *ctx, const void *d_xyz, int64_t plane_stride, int64_t n, int dtype, double max_distance,
+                      void *d_ws, size_t ws_bytes, rv_stream stream);
+int rv_nn_search(rv_ctx *ctx, const void *d_index_ws, size_t ws_bytes, int64_t n_indexed, const void *d_query_xyz,
+                 int64_t query_stride, int64_t n_query, int dtype, double max_distance, int32_t *d_nearest, rv_stream stream);
+size_t rv_icp_sums_bytes(void);
+int rv_icp_sums(rv_ctx *ctx, int point_to_plane, const void *d_source_xyz, int64_t source_stride, int64_t n_source,
+                int source_dtype, const void *d_target_xyz, int64_t target_stride, int64_t n_target, int target_dtype,
+                const double *d_target_normals, int64_t normal_stride, const int32_t *d_nearest, double *d_sums,
+                rv_stream stream);
+
 /* ---- a2 (next): windowed median depth ------------------------------
  * replaces get_depth_at_pixel (canopy_return.py:279-317) and median_depth
  * (final_view.py:132-141): median of the non-zero raw depths in a win x win

@@ -501,6 +501,118 @@ def estimate_normals(points, radius, max_nn, camera_location=None, chunk=512):
     return N
 
 
+# ----------------------------------------------------------------------- ICP
+def nearest_correspondences(source, target, max_distance, chunk=256):
+    """Open3D 0.19 GetRegistrationResultAndCorrespondences (pipelines/registration/Registration.cpp), as
+    registration_icp uses it (mpa_icp_export.py:187): per source point KDTreeFlann::SearchHybrid(point, max_distance, 1) =
+    the nearest target point if its squared distance is < max_distance^2.  Returns (nearest int32 [n], -1 = unmatched;
+    fitness; inlier_rmse).  Equal distances go to the lower target index (the KD-tree's choice is unspecified)."""
+    S = np.asarray(source, dtype=np.float64)
+    T = np.asarray(target, dtype=np.float64)
+    n = S.shape[0]
+    near = np.full(n, -1, np.int32)
+    if n == 0 or T.shape[0] == 0 or not (max_distance > 0.0):
+        return near, 0.0, 0.0
+    r2 = float(max_distance) * float(max_distance)
+    err2 = 0.0
+    for i0 in range(0, n, chunk):
+        q = S[i0:i0 + chunk]
+        dx = T[None, :, 0] - q[:, None, 0]
+        dy = T[None, :, 1] - q[:, None, 1]
+        dz = T[None, :, 2] - q[:, None, 2]
+        d2 = (dx * dx + dy * dy) + dz * dz
+        j = np.argmin(d2, axis=1)  # first minimum = lowest index
+        best = d2[np.arange(q.shape[0]), j]
+        ok = best < r2
+        near[i0:i0 + chunk][ok] = j[ok]
+        err2 += float(best[ok].sum())
+    m = int((near >= 0).sum())
+    if m == 0:
+        return near, 0.0, 0.0
+    return near, m / float(n), float(np.sqrt(err2 / m))
+
+
+def vector6d_to_matrix4d(x):
+    """utility::TransformVector6dToMatrix4d: AngleAxis(x2, Z) * AngleAxis(x1, Y) * AngleAxis(x0, X), translation x[3:6]."""
+    a, b, c = x[0], x[1], x[2]
+    Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    Rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+    T = np.eye(4)
+    T[:3, :3] = Rz @ Ry @ Rx
+    T[:3, 3] = x[3:6]
+    return T
+
+
+def point_to_plane_update(source, target, target_normals, near):
+    """TransformationEstimationPointToPlane::ComputeTransformation: r = (s - t) . n_t, J = [s x n_t, n_t],
+    x = solve(J^T J, -J^T r) (utility::SolveJacobianSystemAndObtainExtrinsicMatrix), identity without correspondences."""
+    sel = np.nonzero(near >= 0)[0]
+    if sel.size == 0:
+        return np.eye(4)
+    s = np.asarray(source, dtype=np.float64)[sel]
+    t = np.asarray(target, dtype=np.float64)[near[sel]]
+    nt = np.asarray(target_normals, dtype=np.float64)[near[sel]]
+    r = ((s - t) * nt).sum(axis=1)
+    J = np.concatenate([np.cross(s, nt), nt], axis=1)
+    JTJ = J.T @ J
+    JTr = J.T @ r
+    x = np.linalg.solve(JTJ, -JTr)
+    return vector6d_to_matrix4d(x)
+
+
+def point_to_point_update(source, target, near, with_scaling=False):
+    """TransformationEstimationPointToPoint::ComputeTransformation = Eigen::umeyama(source, target, with_scaling)."""
+    sel = np.nonzero(near >= 0)[0]
+    if sel.size == 0:
+        return np.eye(4)
+    s = np.asarray(source, dtype=np.float64)[sel]
+    t = np.asarray(target, dtype=np.float64)[near[sel]]
+    ms, mt = s.mean(axis=0), t.mean(axis=0)
+    sd, td = s - ms, t - mt
+    sigma = td.T @ sd / sel.size
+    U, d, Vt = np.linalg.svd(sigma)
+    S = np.ones(3)
+    if np.linalg.det(U) * np.linalg.det(Vt) < 0:
+        S[2] = -1.0
+    R = U @ np.diag(S) @ Vt
+    T = np.eye(4)
+    if with_scaling:
+        c = float(d @ S) / float((sd * sd).sum() / sel.size)
+        T[:3, :3] = c * R
+        T[:3, 3] = mt - c * (R @ ms)
+    else:
+        T[:3, :3] = R
+        T[:3, 3] = mt - R @ ms
+    return T
+
+
+def registration_icp(source, target, max_distance, init=None, target_normals=None, point_to_plane=True, with_scaling=False,
+                     relative_fitness=1e-6, relative_rmse=1e-6, max_iteration=30):
+    """Open3D 0.19 RegistrationICP: transform the source by init, match, then repeat {estimate the update from the matches,
+    compose it on the left, transform the working copy by the update, match again} until both fitness and inlier_rmse
+    change by less than the criteria or max_iteration is reached.  Returns (transformation, fitness, inlier_rmse, nearest,
+    iterations run)."""
+    T = np.eye(4) if init is None else np.array(init, dtype=np.float64)
+    pcd = np.asarray(source, dtype=np.float64)
+    if not np.array_equal(T, np.eye(4)):
+        pcd = transform(pcd, T)
+    near, fit, rmse = nearest_correspondences(pcd, target, max_distance)
+    it = 0
+    for it in range(1, max_iteration + 1):
+        if point_to_plane:
+            upd = point_to_plane_update(pcd, target, target_normals, near)
+        else:
+            upd = point_to_point_update(pcd, target, near, with_scaling)
+        T = upd @ T
+        pcd = transform(pcd, upd)
+        prev = (fit, rmse)
+        near, fit, rmse = nearest_correspondences(pcd, target, max_distance)
+        if abs(prev[0] - fit) < relative_fitness and abs(prev[1] - rmse) < relative_rmse:
+            break
+    return T, fit, rmse, near, it
+
+
 # ----------------------------------------------------------------------- PLY read
 def read_ply_minimal(path):
     """Independent minimal PLY vertex reader (binary LE / ascii) used to check the

@@ -12,6 +12,9 @@ from .cloud import (CloudBatch, KDTreeSearchParamHybrid, PointCloud, create_from
                     deproject_batch, deproject_pixel_to_point, fuse_views, get_depth_at_pixel, median_depth_windows,
                     merge, nv12_to_bgr, register_depth_to_color)
 from .ply import read_point_cloud, write_point_cloud
+from . import registration
+from .registration import (ICPConvergenceCriteria, RegistrationResult, TransformationEstimationPointToPlane,
+                           TransformationEstimationPointToPoint, evaluate_registration, registration_icp)
 from .pose import (invert_rigid, pose_from_tag_corners, solve_pnp_with_best_obj_order, to_4x4, world_from_camera)
 
 __version__ = "0.1.0"

@@ -80,6 +80,11 @@ SIGNATURES = {
     "rv_statistical_outlier_mask": (C.c_int, [c_vp, c_vp, c_i64, c_f64, c_vp, c_vp, c_vp]),
     "rv_select_by_mask": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, C.c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp,
                                     C.c_size_t, c_vp]),
+    "rv_nn_index_build": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_f64, c_vp, C.c_size_t, c_vp]),
+    "rv_nn_search": (C.c_int, [c_vp, c_vp, C.c_size_t, c_i64, c_vp, c_i64, c_i64, C.c_int, c_f64, c_vp, c_vp]),
+    "rv_icp_sums_bytes": (C.c_size_t, []),
+    "rv_icp_sums": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, c_i64, C.c_int, c_vp, c_i64, c_i64, C.c_int, c_vp, c_i64, c_vp, c_vp,
+                              c_vp]),
     "rv_median_depth_window": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_vp, c_i64, C.c_int, c_vp, c_vp]),
     "rv_nv12_to_bgr": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
 }

@@ -311,6 +311,48 @@ def orient_normals(data: torch.Tensor, n: int, normals: torch.Tensor, camera_loc
                                         cam, stream_ptr(dev)))
 
 
+def nn_index_build(data: torch.Tensor, n: int, max_distance: float) -> torch.Tensor:
+    """Hash-grid index over the first n points of `data` (the reference's KDTreeFlann(target)); returns the workspace that
+    holds it."""
+    dev = data.device
+    ctx = ctx_for(dev)
+    ws = workspace(ctx.lib.rv_knn_workspace_bytes(n), dev)
+    ctx.check(ctx.lib.rv_nn_index_build(ctx.handle, ptr(data), pstride(data), n, _RV_DT[data.dtype], float(max_distance), ptr(ws),
+                                        ws.numel(), stream_ptr(dev)))
+    return ws
+
+
+def nn_search(index_ws: torch.Tensor, n_indexed: int, query: torch.Tensor, n_query: int, max_distance: float,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    """int32 [n_query]: nearest indexed point closer than max_distance, -1 without one."""
+    dev = query.device
+    ctx = ctx_for(dev)
+    if out is None:
+        out = torch.empty(max(n_query, 1), dtype=torch.int32, device=dev)
+    ctx.check(ctx.lib.rv_nn_search(ctx.handle, ptr(index_ws), index_ws.numel(), n_indexed, ptr(query), pstride(query), n_query,
+                                   _RV_DT[query.dtype], float(max_distance), ptr(out), stream_ptr(dev)))
+    return out
+
+
+def icp_scratch(dev: torch.device) -> torch.Tensor:
+    return torch.empty(int(ctx_for(dev).lib.rv_icp_sums_bytes()) // 8, dtype=torch.float64, device=dev)
+
+
+def icp_sums(source: torch.Tensor, n_source: int, target: torch.Tensor, n_target: int, target_normals, nearest: torch.Tensor,
+             point_to_plane: bool, scratch: torch.Tensor | None = None) -> torch.Tensor:
+    """float64 [32] sums of one ICP estimation step over the correspondences (see include/repas_vision.h); a view of
+    `scratch` (rv_icp_sums_bytes() bytes)."""
+    dev = source.device
+    ctx = ctx_for(dev)
+    if scratch is None:
+        scratch = icp_scratch(dev)
+    ctx.check(ctx.lib.rv_icp_sums(ctx.handle, int(bool(point_to_plane)), ptr(source), pstride(source), n_source,
+                                  _RV_DT[source.dtype], ptr(target), pstride(target), n_target, _RV_DT[target.dtype],
+                                  ptr(target_normals), 0 if target_normals is None else pstride(target_normals), ptr(nearest),
+                                  ptr(scratch), stream_ptr(dev)))
+    return scratch[:32]
+
+
 def statistical_outlier_mask(mean: torch.Tensor, std_ratio: float):
     """(keep uint8 [n], stats float64 [4] = cloud mean, std dev, threshold, points counted)."""
     dev = mean.device

@@ -62,7 +62,7 @@ class PointCloud:
             data = torch.empty((6 if has_color else 3, 1), dtype=torch.float64, device=dev)
             n = 0
         self._data = data
-        self._normals = None  # float64 [3, n] once estimate_normals ran; dropped by anything that changes the points
+        self._normals = None  # float64 [3, n] once estimate_normals ran; rotated by transform, dropped by anything that reorders the points
         self._n = int(n)
         self._has_color = bool(has_color) and data.shape[0] >= 6
 
@@ -142,7 +142,10 @@ class PointCloud:
         if self._n:
             out, total, _ = _ops.transform_merge([(self._data, self._n)], [T], self._has_color)
             self._data = out
-            self._normals = None
+            if self._normals is not None:  # Open3D TransformNormals: n' = (T [n,0])[:3], the upper-left 3x3 only
+                R = np.eye(4)
+                R[:3, :3] = T[:3, :3]
+                self._normals = _ops.transform_merge([(self._normals, self._n)], [R], False)[0]
         return self
 
     def transformed(self, T) -> "PointCloud":

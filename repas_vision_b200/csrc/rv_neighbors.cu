@@ -610,6 +610,171 @@ __global__ void __launch_bounds__(256) k_orient_normals(const T *__restrict__ xy
   }
 }
 
+// ---- ICP correspondence search: for every query point the nearest point of the indexed cloud closer than the
+// correspondence distance (KDTreeFlann::SearchHybrid(point, max_distance, 1): squared distance strictly below
+// max_distance^2), -1 without one.  Same shell walk as k_knn_query with k = 1; the query may lie outside the indexed
+// cloud's box (its cell is clamped, which only makes the "everything unvisited is at least r cells away" bound more
+// conservative).  Equal distances go to the lower point index, so the result does not depend on the cell order.
+template <typename T>
+__global__ void __launch_bounds__(128) k_nn_search(const KnnArgs a, const T *__restrict__ q_xyz, long long q_stride, long long nq,
+                                                   double radius2, int *__restrict__ corr) {
+  const KnnParams *p = a.prm;
+  const double cell = p->cell;
+  const int gx = p->grid[0], gy = p->grid[1], gz = p->grid[2], rmax = p->rmax;
+  const long long shell_budget = a.n / 2 + 4096;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+    const double x = (double)q_xyz[q], y = (double)q_xyz[q_stride + q], z = (double)q_xyz[2 * q_stride + q];
+    if (!(isfinite(x) && isfinite(y) && isfinite(z))) {
+      corr[q] = -1;
+      continue;
+    }
+    int cx, cy, cz;
+    cell_of(p, x, y, z, cx, cy, cz);
+    double best = radius2;
+    unsigned int bidx = 0xffffffffu;  // original index of the best point so far
+    auto offer = [&](double d2, unsigned int j) {
+      if (d2 < best) {
+        best = d2;
+        bidx = a.sidx[j];
+      } else if (d2 == best && bidx != 0xffffffffu) {
+        const unsigned int o = a.sidx[j];
+        if (o < bidx) bidx = o;
+      }
+    };
+    long long visited = 0;
+    bool brute = false;
+    for (int r = 0; r <= rmax; ++r) {
+      const long long side = 2ll * r + 1;
+      visited += r == 0 ? 1 : side * side * side - (side - 2) * (side - 2) * (side - 2);
+      if (visited > shell_budget) {
+        brute = true;
+        break;
+      }
+      for (int dz = -r; dz <= r; ++dz) {
+        const int iz = cz + dz;
+        if (iz < 0 || iz >= gz) continue;
+        for (int dy = -r; dy <= r; ++dy) {
+          const int iy = cy + dy;
+          if (iy < 0 || iy >= gy) continue;
+          const bool face = (dz == -r || dz == r || dy == -r || dy == r);
+          const int step = (face || r == 0) ? 1 : 2 * r;
+          for (int dx = -r; dx <= r; dx += step) {
+            const int ix = cx + dx;
+            if (ix < 0 || ix >= gx) continue;
+            const unsigned long long key = cell_key(ix, iy, iz);
+            unsigned int h = __umulhi((unsigned int)(cell_hash(key) >> 32), a.cap);
+            unsigned long long cur;
+            while ((cur = a.keys[h]) != key && cur != 0) {
+              if (++h == a.cap) h = 0;
+            }
+            if (cur == 0) continue;
+            const unsigned int s0 = a.start[h], s1 = s0 + a.cnt[h];
+            for (unsigned int j = s0; j < s1; ++j) {
+              const double ex = a.sx[j] - x, ey = a.sy[j] - y, ez = a.sz[j] - z;
+              offer((ex * ex + ey * ey) + ez * ez, j);
+            }
+          }
+        }
+      }
+      const double reach = (double)r * cell * (1.0 - 1e-9);
+      if (bidx != 0xffffffffu && best <= reach * reach) break;
+      if (reach * reach >= radius2) break;  // nothing closer than the correspondence distance is left
+    }
+    if (brute) {
+      best = radius2;
+      bidx = 0xffffffffu;
+      for (long long j = 0; j < a.n; ++j) {
+        const double ex = a.sx[j] - x, ey = a.sy[j] - y, ez = a.sz[j] - z;
+        offer((ex * ex + ey * ey) + ez * ez, (unsigned int)j);
+      }
+    }
+    corr[q] = bidx == 0xffffffffu ? -1 : (int)bidx;
+  }
+}
+
+// Sums over the correspondences that one ICP step needs, per block in a fixed order (deterministic), 32 doubles each:
+//   both modes  [0] correspondences  [1] sum of squared distances (fitness / inlier_rmse)
+//   kPlane      TransformationEstimationPointToPlane: r = (s - t) . n_t, J = [s x n_t, n_t];  [2] sum r^2,
+//               [3..8] J^T r, [9..29] upper triangle of J^T J, row-major
+//   !kPlane     TransformationEstimationPointToPoint (Eigen::umeyama): [2] sum |s|^2, [3..5] sum s, [6..8] sum t,
+//               [9..17] sum t_a s_b
+constexpr int kIcpSums = 32;
+constexpr int kIcpMaxBlocks = 1024;
+
+template <typename TS, typename TT, bool kPlane>
+__global__ void __launch_bounds__(256) k_icp_sums(const TS *__restrict__ src, long long s_stride, long long n,
+                                                  const TT *__restrict__ tgt, long long t_stride,
+                                                  const double *__restrict__ nrm, long long n_stride,
+                                                  const int *__restrict__ corr, double *__restrict__ partial) {
+  constexpr int kUsed = kPlane ? 30 : 18;
+  __shared__ double s_red[8][kIcpSums];
+  double acc[kUsed];
+#pragma unroll
+  for (int i = 0; i < kUsed; ++i) acc[i] = 0.0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int j = corr[i];
+    if (j < 0) continue;
+    const double sx = (double)src[i], sy = (double)src[s_stride + i], sz = (double)src[2 * s_stride + i];
+    const double tx = (double)tgt[j], ty = (double)tgt[t_stride + j], tz = (double)tgt[2 * t_stride + j];
+    const double ex = tx - sx, ey = ty - sy, ez = tz - sz;
+    acc[0] += 1.0;
+    acc[1] += (ex * ex + ey * ey) + ez * ez;
+    if (kPlane) {
+      const double nx = nrm[j], ny = nrm[n_stride + j], nz = nrm[2 * n_stride + j];
+      const double r = ((sx - tx) * nx + (sy - ty) * ny) + (sz - tz) * nz;
+      const double J[6] = {sy * nz - sz * ny, sz * nx - sx * nz, sx * ny - sy * nx, nx, ny, nz};
+      acc[2] += r * r;
+      int t = 9;
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        acc[3 + u] += J[u] * r;
+#pragma unroll
+        for (int v = u; v < 6; ++v) acc[t++] += J[u] * J[v];
+      }
+    } else {
+      acc[2] += (sx * sx + sy * sy) + sz * sz;
+      acc[3] += sx, acc[4] += sy, acc[5] += sz;
+      acc[6] += tx, acc[7] += ty, acc[8] += tz;
+      acc[9] += tx * sx, acc[10] += tx * sy, acc[11] += tx * sz;
+      acc[12] += ty * sx, acc[13] += ty * sy, acc[14] += ty * sz;
+      acc[15] += tz * sx, acc[16] += tz * sy, acc[17] += tz * sz;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kUsed; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int i = 0; i < kUsed; ++i) s_red[threadIdx.x >> 5][i] = acc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < kIcpSums) {
+    double v = 0.0;
+    if (threadIdx.x < kUsed)
+      for (int w = 0; w < 8; ++w) v += s_red[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * kIcpSums + threadIdx.x] = v;
+  }
+}
+
+__global__ void k_icp_finish(const double *__restrict__ partial, int blocks, double *__restrict__ sums) {
+  double v = 0.0;
+  for (int b = 0; b < blocks; ++b) v += partial[(size_t)b * kIcpSums + threadIdx.x];
+  sums[threadIdx.x] = v;
+}
+
+template <typename TS, typename TT>
+static void icp_sums_launch(int plane, int blocks, cudaStream_t st, const void *src, int64_t ss, int64_t n, const void *tgt, int64_t ts,
+                            const double *nrm, int64_t ns, const int32_t *corr, double *partial) {
+  if (plane)
+    k_icp_sums<TS, TT, true><<<blocks, 256, 0, st>>>(reinterpret_cast<const TS *>(src), ss, n, reinterpret_cast<const TT *>(tgt), ts, nrm, ns, corr, partial);
+  else
+    k_icp_sums<TS, TT, false><<<blocks, 256, 0, st>>>(reinterpret_cast<const TS *>(src), ss, n, reinterpret_cast<const TT *>(tgt), ts, nrm, ns, corr, partial);
+}
+
 unsigned long long knn_capacity(long long n) {
   unsigned long long c = ((unsigned long long)n * 3ull / 2ull + 31ull) & ~31ull;
   return c < 1024 ? 1024 : c;
@@ -634,18 +799,8 @@ size_t rv_knn_workspace_bytes(int64_t n) {
   return 256 + up256(cap * 8) + 2 * up256(cap * 4) + 2 * up256((size_t)n * 4) + 3 * up256((size_t)n * 8) + up256((size_t)n * 4);
 }
 
-// validation, workspace layout and the grid build shared by the two query entry points
-static int knn_prepare(rv_ctx *ctx, const char *who, const void *d_xyz, int64_t plane_stride, int64_t n, int dtype, int k,
-                       double radius, void *d_ws, size_t ws_bytes, cudaStream_t st, KnnArgs &a) {
-  if (n < 0 || plane_stride < n) RV_FAIL(ctx, RV_EINVAL, "%s: bad n / stride", who);
-  if (dtype != RV_F32 && dtype != RV_F64) RV_FAIL(ctx, RV_EINVAL, "%s: bad dtype", who);
-  if (k < 1 || k > kMaxK) RV_FAIL(ctx, RV_EINVAL, "%s: the neighbour count must be in [1, %d]", who, kMaxK);
-  if (n >= 0xa0000000ll) RV_FAIL(ctx, RV_EINVAL, "%s: more than 2.6e9 points", who);
-  if (n == 0) return RV_OK;
-  if (!d_xyz) RV_FAIL(ctx, RV_EINVAL, "%s: null pointer", who);
-  const size_t need = rv_knn_workspace_bytes(n);
-  if (!d_ws || ws_bytes < need) RV_FAIL(ctx, RV_EWORKSPACE, "%s: workspace %zu < %zu", who, ws_bytes, need);
-  if (!rv_aligned(d_ws, 256)) RV_FAIL(ctx, RV_EALIGN, "%s: workspace must be 256-byte aligned", who);
+// the fixed carve-up of a workspace of rv_knn_workspace_bytes(n); returns the bytes that must be zero before a build
+static size_t knn_layout(void *d_ws, const void *d_xyz, int64_t plane_stride, int64_t n, int k, KnnArgs &a) {
   const size_t cap = (size_t)knn_capacity(n);
   char *w = reinterpret_cast<char *>(d_ws);
   memset(&a, 0, sizeof(a));
@@ -660,7 +815,7 @@ static int knn_prepare(rv_ctx *ctx, const char *who, const void *d_xyz, int64_t 
   w += up256(cap * 8);
   a.cnt = reinterpret_cast<unsigned int *>(w);
   w += up256(cap * 4);
-  const size_t clear_bytes = (size_t)(w - reinterpret_cast<char *>(d_ws));  // header, keys, counters
+  const size_t clear_bytes = (size_t)(w - reinterpret_cast<char *>(d_ws));
   a.start = reinterpret_cast<unsigned int *>(w);
   w += up256(cap * 4);
   a.slot_of = reinterpret_cast<unsigned int *>(w);
@@ -674,6 +829,23 @@ static int knn_prepare(rv_ctx *ctx, const char *who, const void *d_xyz, int64_t 
   a.sz = reinterpret_cast<double *>(w);
   w += up256((size_t)n * 8);
   a.sidx = reinterpret_cast<unsigned int *>(w);
+  return clear_bytes;
+}
+
+// validation, workspace layout and the grid build shared by the query entry points
+static int knn_prepare(rv_ctx *ctx, const char *who, const void *d_xyz, int64_t plane_stride, int64_t n, int dtype, int k,
+                       double radius, void *d_ws, size_t ws_bytes, cudaStream_t st, KnnArgs &a) {
+  if (n < 0 || plane_stride < n) RV_FAIL(ctx, RV_EINVAL, "%s: bad n / stride", who);
+  if (dtype != RV_F32 && dtype != RV_F64) RV_FAIL(ctx, RV_EINVAL, "%s: bad dtype", who);
+  if (k < 1 || k > kMaxK) RV_FAIL(ctx, RV_EINVAL, "%s: the neighbour count must be in [1, %d]", who, kMaxK);
+  if (n >= 0xa0000000ll) RV_FAIL(ctx, RV_EINVAL, "%s: more than 2.6e9 points", who);
+  if (n == 0) return RV_OK;
+  if (!d_xyz) RV_FAIL(ctx, RV_EINVAL, "%s: null pointer", who);
+  const size_t need = rv_knn_workspace_bytes(n);
+  if (!d_ws || ws_bytes < need) RV_FAIL(ctx, RV_EWORKSPACE, "%s: workspace %zu < %zu", who, ws_bytes, need);
+  if (!rv_aligned(d_ws, 256)) RV_FAIL(ctx, RV_EALIGN, "%s: workspace must be 256-byte aligned", who);
+  const size_t clear_bytes = knn_layout(d_ws, d_xyz, plane_stride, n, k, a);  // header, keys, counters
+  const size_t cap = a.cap;
   RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, clear_bytes, st));
   k_knn_init<<<1, 32, 0, st>>>(a.prm);
   RV_LAUNCHED(ctx);
@@ -781,6 +953,82 @@ int rv_statistical_outlier_mask(rv_ctx *ctx, const double *d_mean, int64_t n, do
   k_sor_stats<<<1, 1024, 0, st>>>(d_mean, n, std_ratio, d_stats, band);
   RV_LAUNCHED(ctx);
   k_sor_mask<<<grid_for(ctx, n), 256, 0, st>>>(d_mean, n, d_stats, d_keep);
+  RV_LAUNCHED(ctx);
+  return RV_OK;
+}
+
+// ---- ICP correspondence search: index of the target cloud (built once per registration_icp call), nearest-point queries,
+// and the sums of one estimation step
+
+int rv_nn_index_build(rv_ctx *ctx, const void *d_xyz, int64_t plane_stride, int64_t n, int dtype, double max_distance,
+                      void *d_ws, size_t ws_bytes, rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
+  if (!(max_distance > 0.0)) RV_FAIL(ctx, RV_EINVAL, "rv_nn_index_build: max_distance must be positive");
+  KnnArgs a;
+  return knn_prepare(ctx, "rv_nn_index_build", d_xyz, plane_stride, n, dtype, 1, max_distance, d_ws, ws_bytes, (cudaStream_t)stream, a);
+}
+
+int rv_nn_search(rv_ctx *ctx, const void *d_index_ws, size_t ws_bytes, int64_t n_indexed, const void *d_query_xyz,
+                 int64_t query_stride, int64_t n_query, int dtype, double max_distance, int32_t *d_nearest, rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
+  if (n_query < 0 || query_stride < n_query || n_indexed < 0) RV_FAIL(ctx, RV_EINVAL, "rv_nn_search: bad n / stride");
+  if (dtype != RV_F32 && dtype != RV_F64) RV_FAIL(ctx, RV_EINVAL, "rv_nn_search: bad dtype");
+  if (!(max_distance > 0.0)) RV_FAIL(ctx, RV_EINVAL, "rv_nn_search: max_distance must be positive");
+  if (n_query == 0) return RV_OK;
+  if (!d_query_xyz || !d_nearest) RV_FAIL(ctx, RV_EINVAL, "rv_nn_search: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_indexed == 0) {  // nothing to match: every query is unmatched
+    RV_CUDA(ctx, cudaMemsetAsync(d_nearest, 0xff, (size_t)n_query * sizeof(int32_t), st));
+    return RV_OK;
+  }
+  if (!d_index_ws || ws_bytes < rv_knn_workspace_bytes(n_indexed)) RV_FAIL(ctx, RV_EWORKSPACE, "rv_nn_search: index workspace too small");
+  if (!rv_aligned(d_index_ws, 256)) RV_FAIL(ctx, RV_EALIGN, "rv_nn_search: workspace must be 256-byte aligned");
+  KnnArgs a;
+  knn_layout(const_cast<void *>(d_index_ws), nullptr, 0, n_indexed, 1, a);
+  const double r2 = max_distance * max_distance;
+  if (dtype == RV_F32)
+    k_nn_search<float><<<grid_for(ctx, n_query, 16, 128), 128, 0, st>>>(a, reinterpret_cast<const float *>(d_query_xyz), query_stride, n_query, r2, d_nearest);
+  else
+    k_nn_search<double><<<grid_for(ctx, n_query, 16, 128), 128, 0, st>>>(a, reinterpret_cast<const double *>(d_query_xyz), query_stride, n_query, r2, d_nearest);
+  RV_LAUNCHED(ctx);
+  return RV_OK;
+}
+
+size_t rv_icp_sums_bytes(void) { return (size_t)(1 + kIcpMaxBlocks) * kIcpSums * sizeof(double); }
+
+int rv_icp_sums(rv_ctx *ctx, int point_to_plane, const void *d_source_xyz, int64_t source_stride, int64_t n_source, int source_dtype,
+                const void *d_target_xyz, int64_t target_stride, int64_t n_target, int target_dtype, const double *d_target_normals,
+                int64_t normal_stride, const int32_t *d_nearest, double *d_sums, rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
+  if (n_source < 0 || source_stride < n_source || n_target < 0 || target_stride < n_target) RV_FAIL(ctx, RV_EINVAL, "rv_icp_sums: bad n / stride");
+  if ((source_dtype != RV_F32 && source_dtype != RV_F64) || (target_dtype != RV_F32 && target_dtype != RV_F64))
+    RV_FAIL(ctx, RV_EINVAL, "rv_icp_sums: bad dtype");
+  if (!d_sums) RV_FAIL(ctx, RV_EINVAL, "rv_icp_sums: null pointer");
+  if (point_to_plane && n_target > 0 && (!d_target_normals || normal_stride < n_target))
+    RV_FAIL(ctx, RV_EINVAL, "rv_icp_sums: point-to-plane needs the target normals");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_source == 0 || n_target == 0) {
+    RV_CUDA(ctx, cudaMemsetAsync(d_sums, 0, kIcpSums * sizeof(double), st));
+    return RV_OK;
+  }
+  if (!d_source_xyz || !d_target_xyz || !d_nearest) RV_FAIL(ctx, RV_EINVAL, "rv_icp_sums: null pointer");
+  int blocks = grid_for(ctx, n_source, 4);
+  if (blocks > kIcpMaxBlocks) blocks = kIcpMaxBlocks;
+  double *partial = d_sums + kIcpSums;
+  const int pl = point_to_plane ? 1 : 0;
+  if (source_dtype == RV_F32 && target_dtype == RV_F32)
+    icp_sums_launch<float, float>(pl, blocks, st, d_source_xyz, source_stride, n_source, d_target_xyz, target_stride, d_target_normals, normal_stride, d_nearest, partial);
+  else if (source_dtype == RV_F32)
+    icp_sums_launch<float, double>(pl, blocks, st, d_source_xyz, source_stride, n_source, d_target_xyz, target_stride, d_target_normals, normal_stride, d_nearest, partial);
+  else if (target_dtype == RV_F32)
+    icp_sums_launch<double, float>(pl, blocks, st, d_source_xyz, source_stride, n_source, d_target_xyz, target_stride, d_target_normals, normal_stride, d_nearest, partial);
+  else
+    icp_sums_launch<double, double>(pl, blocks, st, d_source_xyz, source_stride, n_source, d_target_xyz, target_stride, d_target_normals, normal_stride, d_nearest, partial);
+  RV_LAUNCHED(ctx);
+  k_icp_finish<<<1, kIcpSums, 0, st>>>(partial, blocks, d_sums);
   RV_LAUNCHED(ctx);
   return RV_OK;
 }

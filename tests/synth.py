@@ -48,3 +48,12 @@ def synth_batch(b, h, w, seed0=0):
     d = np.stack([synth_depth(h, w, seed0 + i) for i in range(b)])
     c = np.stack([synth_color(h, w, seed0 + i) for i in range(b)])
     return d, c
+
+
+def bumpy_surface(rng, n, noise=0.0):
+    """A curved, non-symmetric surface patch (what a depth camera sees of an object): constrains all six degrees of freedom."""
+    u = rng.uniform(-0.15, 0.15, n)
+    v = rng.uniform(-0.10, 0.10, n)
+    z = 0.6 + 0.35 * u * u - 0.5 * u * v + 0.04 * np.sin(25.0 * u) * np.cos(18.0 * v) + 0.6 * v * v * v
+    P = np.stack([u, v, z], axis=1)
+    return P + rng.normal(size=P.shape) * noise if noise else P

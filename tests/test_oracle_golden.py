@@ -9,6 +9,7 @@ import pytest
 
 from conftest import CAL, CANOPY_TS, FRAMES, blob_mask, load_frame, sha
 from oracle import oracle_c, oracle_np as O
+from synth import bumpy_surface
 
 
 def test_canopy_known_answers(golden, rs720):
@@ -137,3 +138,35 @@ def test_statistical_outlier_oracle_against_independent_kdtree():
     assert np.array_equal(ind, np.nonzero(avg < avg.mean() + 2.0 * avg.std(ddof=1))[0])
     assert 0 < len(P) - len(ind) < 100  # the sparse clutter goes, the cluster stays
     assert (ind < 1200).mean() > 0.97
+
+
+def test_icp_oracle_against_independent_kdtree_and_ground_truth():
+    """Open3D is absent (parity unpinned): the restatement of GetRegistrationResultAndCorrespondences is cross-checked against
+    scipy's cKDTree, and the whole RegistrationICP loop (point-to-plane and point-to-point) must walk a displaced copy of a
+    surface back onto it, i.e. return the inverse of the displacement."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(11)
+    tgt = bumpy_surface(rng, 4000)
+    src = bumpy_surface(rng, 1500)
+    x = np.array([0.02, -0.015, 0.03, 0.004, -0.003, 0.005])
+    D = O.vector6d_to_matrix4d(x)
+    assert np.allclose(D[:3, :3] @ D[:3, :3].T, np.eye(3), atol=1e-15) and np.isclose(np.linalg.det(D[:3, :3]), 1.0)
+    moved = O.transform(src, D)
+    near, fit, rmse = O.nearest_correspondences(moved, tgt, 0.01)
+    d, j = cKDTree(tgt).query(moved, k=1)
+    ok = d * d < 0.01 * 0.01
+    assert np.array_equal(near >= 0, ok) and np.array_equal(near[ok], j[ok].astype(np.int32))
+    assert np.isclose(fit, ok.mean(), rtol=0, atol=0) and np.isclose(rmse, np.sqrt((d[ok] ** 2).mean()), rtol=1e-12)
+    # a point exactly max_distance away is NOT a correspondence (d2 < r2, strict)
+    n2, f2, _ = O.nearest_correspondences(np.array([[0.0, 0.0, 0.5]]), np.array([[0.0, 0.0, 0.0]]), 0.5)
+    assert n2[0] == -1 and f2 == 0.0
+    # normals of the analytic surface are not needed exactly: estimate them like the scripts do
+    N = O.estimate_normals(tgt, 0.02, 30, camera_location=(0.0, 0.0, 0.0))
+    T, fit, rmse, near, it = O.registration_icp(moved, tgt, 0.02, target_normals=N, point_to_plane=True, max_iteration=50)
+    assert it < 50 and fit > 0.95
+    assert np.allclose(T @ D, np.eye(4), atol=2e-3)
+    T2, fit2, rmse2, _, it2 = O.registration_icp(moved, tgt, 0.02, point_to_plane=False, max_iteration=200)
+    assert fit2 > 0.95 and np.allclose(T2 @ D, np.eye(4), atol=6e-3)
+    # with an initial guess the loop starts from it: the exact inverse leaves nothing to do
+    T3, fit3, rmse3, _, it3 = O.registration_icp(moved, tgt, 0.02, init=np.linalg.inv(D), target_normals=N, max_iteration=30)
+    assert it3 <= 3 and np.allclose(T3 @ D, np.eye(4), atol=1e-3)

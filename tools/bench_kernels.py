@@ -145,6 +145,22 @@ def main():
     line("estimate_normals(Hybrid(0.02, 30)) + orientation on that cloud", ms, len(kept) * 24 + len(kept) * 24, len(kept), "points",
          {"points": len(kept)})
 
+    # ---- refine_with_icp (mpa_icp_export.py:166-208): point-to-plane ICP of a displaced half of that cloud onto it
+    icp_T = np.eye(4)
+    icp_T[:3, :3] = rv.registration.vector6d_to_matrix4d([0.01, -0.008, 0.012, 0, 0, 0])[:3, :3]
+    icp_T[:3, 3] = (0.003, -0.002, 0.004)
+    icp_src = kept.select_by_index(np.arange(0, len(kept), 2)).transform(icp_T)
+    crit = rv.ICPConvergenceCriteria(max_iteration=30, relative_fitness=1e-6, relative_rmse=1e-6)
+    run_icp = lambda: rv.registration_icp(icp_src, kept, 0.02, np.eye(4), rv.TransformationEstimationPointToPlane(), crit)  # noqa: E731
+    reg = run_icp()
+    ms = timed(run_icp, max(3, a.reps // 4), flush)
+    line("registration_icp point-to-plane, max_dist 0.02, half of that cloud onto it (host solve per iteration)", ms,
+         (reg.iterations + 1) * (len(icp_src) * (24 + 4 + 48) + len(icp_src) * 48), len(icp_src) * (reg.iterations + 1), "matches",
+         {"source_points": len(icp_src), "target_points": len(kept), "iterations": reg.iterations, "fitness": reg.fitness,
+          "inlier_rmse": reg.inlier_rmse, "ms_per_iteration": ms / (reg.iterations + 1),
+          "residual_rotation_translation": [float(np.abs((reg.transformation @ icp_T)[:3, :3] - np.eye(3)).max()),
+                                            float(np.abs((reg.transformation @ icp_T)[:3, 3]).max())]})
+
     ms = timed(lambda: _ops.pack_ply_records(merged, total, True, "unit", "f32"), a.reps, flush)
     line("PLY records float xyz + uchar rgb", ms, total * 24 + total * 15, total, "points")
 
