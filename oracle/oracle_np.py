@@ -21,6 +21,8 @@ checkout):
 * voxel_down_sample ...... Open3D 0.19 PointCloud::VoxelDownSample (SURVEY Appendix B.1),
                            call sites mpa_icp_export.py:44,174, create_masked_ply.py:164
 * create_from_rgbd_image . Open3D 0.19
+* outliers, normals, ICP . Open3D 0.19 RemoveStatisticalOutliers / EstimateNormals / RegistrationICP,
+                           call sites create_masked_ply.py:168-174, mpa_icp_export.py:166-208
 * registration ........... librealsense 2.56 align z16->other (SURVEY Appendix B.3);
                            loops live in oracle/oracle.c, a slow independent
                            numpy formulation lives here for cross-checking.
@@ -29,7 +31,7 @@ Pinning status (see DESIGN.md "Oracle"):
 * deprojection + depth units: PINNED by the reference's four canopy_y goldens and
   by golden vectors generated from the reference's own functions
   (tests/golden/make_golden.py);
-* voxel_down_sample, transform, registration, Open3D/SDK clouds: PARITY UNPINNED --
+* voxel_down_sample, transform, outlier removal, normals, ICP, registration, Open3D/SDK clouds: PARITY UNPINNED --
   the arithmetic lives in wheels that are not in the reference checkout
   (open3d==0.19.0, pyrealsense2==2.56.5.9235, pyorbbecsdk) and the reference
   stores no expected outputs for them.  Their published algorithms are restated
