@@ -523,6 +523,42 @@ def other_rows(rv, _ops, dev, gen):
     del parts
     out.append({"row": "a11 + a12 four-pose fusion: transform, merge, 5 mm voxel grid", "points": n, "gpu_ms": ms,
                 "cpu_ms": (t_tr + t_vx) * 1e3, "cpu": "oracle_np.transform + oracle.c voxel_down_sample, 1 core"})
+
+    # 8f-4 on the fused cloud (create_masked_ply.py:168-174, mpa_icp_export.py:166-208): GPU on the whole cloud, the CPU side
+    # (KD-tree formulations of the oracle, one core) on a contiguous slab of it, both as points per second
+    down = rv.fuse_views(clouds, poses, 0.005)
+    ms_sor = gpu_ms(lambda: down.remove_statistical_outlier(20, 2.0), 3)
+    kept, _ = down.remove_statistical_outlier(20, 2.0)
+    ms_nrm = gpu_ms(lambda: kept.estimate_normals(rv.KDTreeSearchParamHybrid(0.02, 30)), 3)
+    D = rv.registration.vector6d_to_matrix4d([0.01, -0.008, 0.012, 0.003, -0.002, 0.004])
+    src = kept.select_by_index(np.arange(0, len(kept), 2)).transform(D)
+    crit = rv.ICPConvergenceCriteria(max_iteration=30)
+    icp = lambda: rv.registration_icp(src, kept, 0.02, np.eye(4), rv.TransformationEstimationPointToPlane(), crit)  # noqa: E731
+    reg = icp()
+    ms_icp = gpu_ms(icp, 3)
+    P = kept.points
+    slab = P[np.argsort(P[:, 0], kind="stable")[:min(len(P), 100000)]]
+    t0 = time.perf_counter()
+    avg = O.knn_mean_distance_kdtree(slab, 20)
+    O.statistical_outlier_indices(avg, 2.0)
+    t_sor = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    Ns = O.estimate_normals_kdtree(slab, 0.02, 30)
+    t_nrm = time.perf_counter() - t0
+    moved = O.transform(slab[::2], D)
+    t0 = time.perf_counter()
+    near, _, _ = O.nearest_correspondences_kdtree(moved, slab, 0.02)
+    O.point_to_plane_update(moved, slab, Ns, near)
+    t_icp = time.perf_counter() - t0
+    cpu = "oracle_np KD-tree formulation (scipy cKDTree), 1 core, %d-point slab" % len(slab)
+    out.append({"row": "8f-4 remove_statistical_outlier(20, 2.0)", "points": len(down), "gpu_ms": ms_sor,
+                "gpu_points_per_s": len(down) / (ms_sor * 1e-3), "cpu_points_per_s": len(slab) / t_sor, "cpu": cpu})
+    out.append({"row": "8f-4 estimate_normals(Hybrid(0.02, 30))", "points": len(kept), "gpu_ms": ms_nrm,
+                "gpu_points_per_s": len(kept) / (ms_nrm * 1e-3), "cpu_points_per_s": len(slab) / t_nrm, "cpu": cpu})
+    out.append({"row": "8f-4 registration_icp point-to-plane, per iteration (match + estimate + transform)",
+                "source_points": len(src), "target_points": len(kept), "iterations": reg.iterations, "fitness": reg.fitness,
+                "gpu_ms": ms_icp, "gpu_matches_per_s": len(src) * (reg.iterations + 1) / (ms_icp * 1e-3),
+                "cpu_matches_per_s": len(moved) / t_icp, "cpu": cpu + " (one iteration, tree build included)"})
     return out
 
 

@@ -615,6 +615,48 @@ def registration_icp(source, target, max_distance, init=None, target_normals=Non
     return T, fit, rmse, near, it
 
 
+# ---- the same three neighbourhood operations on a KD-tree (scipy's cKDTree in the role of Open3D's KDTreeFlann): an
+# independent formulation used to cross-check the brute-force restatements above and, being O(n log n) like the
+# reference, as the timed CPU side of bench.py's rows for them
+def knn_mean_distance_kdtree(points, k):
+    from scipy.spatial import cKDTree
+    P = np.asarray(points, dtype=np.float64)
+    d, _ = cKDTree(P).query(P, k=min(int(k), len(P)))
+    return d.reshape(len(P), -1).mean(axis=1)
+
+
+def estimate_normals_kdtree(points, radius, max_nn, camera_location=None):
+    from scipy.spatial import cKDTree
+    P = np.asarray(points, dtype=np.float64)
+    n = len(P)
+    kk = min(int(max_nn), n)
+    d, idx = cKDTree(P).query(P, k=kk)
+    d, idx = d.reshape(n, kk), idx.reshape(n, kk)
+    ok = d * d < float(radius) * float(radius)
+    cnt = ok.sum(axis=1)
+    nb = P[idx] * ok[:, :, None]
+    c1 = nb.sum(axis=1) / np.maximum(cnt, 1)[:, None]
+    c2 = np.einsum("nki,nkj->nij", nb, nb) / np.maximum(cnt, 1)[:, None, None]
+    C = c2 - c1[:, :, None] * c1[:, None, :]
+    _, v = np.linalg.eigh(C)
+    N = v[:, :, 0].copy()
+    N[cnt < 3] = (0.0, 0.0, 1.0)
+    if camera_location is not None:
+        ref = np.asarray(camera_location, dtype=np.float64)[None, :] - P
+        N[(N * ref).sum(axis=1) < 0] *= -1.0
+    return N
+
+
+def nearest_correspondences_kdtree(source, target, max_distance):
+    from scipy.spatial import cKDTree
+    S = np.asarray(source, dtype=np.float64)
+    d, j = cKDTree(np.asarray(target, dtype=np.float64)).query(S, k=1)
+    ok = d * d < float(max_distance) * float(max_distance)
+    near = np.where(ok, j, -1).astype(np.int32)
+    m = int(ok.sum())
+    return near, (m / float(len(S)) if len(S) else 0.0), (float(np.sqrt((d[ok] ** 2).sum() / m)) if m else 0.0)
+
+
 # ----------------------------------------------------------------------- PLY read
 def read_ply_minimal(path):
     """Independent minimal PLY vertex reader (binary LE / ascii) used to check the

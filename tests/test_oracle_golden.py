@@ -170,3 +170,18 @@ def test_icp_oracle_against_independent_kdtree_and_ground_truth():
     # with an initial guess the loop starts from it: the exact inverse leaves nothing to do
     T3, fit3, rmse3, _, it3 = O.registration_icp(moved, tgt, 0.02, init=np.linalg.inv(D), target_normals=N, max_iteration=30)
     assert it3 <= 3 and np.allclose(T3 @ D, np.eye(4), atol=1e-3)
+
+
+def test_kdtree_formulations_agree_with_the_brute_force_restatements():
+    """bench.py times the KD-tree formulations as the CPU side of the 8f-4 rows; they must say the same as the restatements
+    the GPU is checked against."""
+    rng = np.random.default_rng(8)
+    P = bumpy_surface(rng, 3000, noise=0.0005)
+    assert np.allclose(O.knn_mean_distance_kdtree(P, 20), O.knn_mean_distance(P, 20), rtol=1e-12, atol=0)
+    a = O.estimate_normals(P, 0.02, 30, camera_location=(0, 0, 0))
+    b = O.estimate_normals_kdtree(P, 0.02, 30, camera_location=(0, 0, 0))
+    assert np.median(np.abs((a * b).sum(axis=1))) > 1 - 1e-12 and ((a * b).sum(axis=1) > 0.999).mean() > 0.99
+    Q = bumpy_surface(rng, 800, noise=0.002)
+    n1, f1, r1 = O.nearest_correspondences(Q, P, 0.004)
+    n2, f2, r2 = O.nearest_correspondences_kdtree(Q, P, 0.004)
+    assert np.array_equal(n1, n2) and f1 == f2 and np.isclose(r1, r2, rtol=1e-12)
