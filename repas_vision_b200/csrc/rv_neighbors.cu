@@ -355,31 +355,43 @@ __device__ V3 smallest_eigenvector(const double *C) {
 
 // kNormals = false: mean distance to the k nearest (rv_knn_mean_distance); true: normal from the covariance of the up to k
 // nearest neighbours closer than the radius (KDTreeSearchParamHybrid), optionally turned towards the camera
+constexpr int kQueryThreads = 128;
+
 template <bool kNormals>
-__global__ void __launch_bounds__(128) k_knn_query(const KnnArgs a) {
+__global__ void __launch_bounds__(kQueryThreads) k_knn_query(const KnnArgs a) {
+  // the sorted candidate lists live in shared memory, [rank][thread]: as per-thread arrays they were local memory, 150 MB of
+  // it in flight, and the kernel waited on that (long-scoreboard stalls, 127 MB of DRAM writes for a 6 MB result)
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  double *s_best = reinterpret_cast<double *>(s_raw);                                                  // ascending squared distances
+  unsigned int *s_bidx = reinterpret_cast<unsigned int *>(s_best + (size_t)a.k * kQueryThreads);        // their sorted positions
+  const int tid = threadIdx.x;
+#define BEST(t) s_best[(t) * kQueryThreads + tid]
+#define BIDX(t) s_bidx[(t) * kQueryThreads + tid]
   const KnnParams *p = a.prm;
   const int k = a.k;
   const double cell = p->cell;
   const int gx = p->grid[0], gy = p->grid[1], gz = p->grid[2], rmax = p->rmax;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < a.n; q += stride) {
+  const long long q = (long long)blockIdx.x * kQueryThreads + tid;  // one point per thread, small CTAs: the scheduler balances
+  if (q < a.n) {
     const double x = a.sx[q], y = a.sy[q], z = a.sz[q];
     int cx, cy, cz;
     cell_of(p, x, y, z, cx, cy, cz);
-    double best[kMaxK];          // ascending squared distances
-    unsigned int bidx[kNormals ? kMaxK : 1];  // their positions in the sorted arrays
     int m = 0;
+    double kth = 0.0;  // BEST(k - 1) once the list is full
     auto offer = [&](double d2, unsigned int j) {
-      if (m < k || d2 < best[m - 1]) {  // sorted insertion
+      if (m < k || d2 < kth) {  // sorted insertion
         int t = m < k ? m : k - 1;
-        while (t > 0 && best[t - 1] > d2) {
-          best[t] = best[t - 1];
-          if (kNormals) bidx[t] = bidx[t - 1];
+        while (t > 0) {
+          const double prev = BEST(t - 1);
+          if (!(prev > d2)) break;
+          BEST(t) = prev;
+          if (kNormals) BIDX(t) = BIDX(t - 1);
           --t;
         }
-        best[t] = d2;
-        if (kNormals) bidx[t] = j;
+        BEST(t) = d2;
+        if (kNormals) BIDX(t) = j;
         if (m < k) ++m;
+        if (m == k) kth = BEST(k - 1);
       }
     };
     // an isolated point would walk ever larger empty shells (~24 r^2 cells each): once the shells have cost about as much as
@@ -423,7 +435,7 @@ __global__ void __launch_bounds__(128) k_knn_query(const KnnArgs a) {
       }
       // every point not yet visited lies outside the cube of (2r+1)^3 cells around the query's cell: at least r * cell away
       const double reach = (double)r * cell * (1.0 - 1e-9);  // (cell assignment rounds: stay a hair inside the bound)
-      if (m == k && best[k - 1] <= reach * reach) break;
+      if (m == k && kth <= reach * reach) break;
       if (kNormals && reach * reach >= a.radius2) break;  // everything within the radius has been seen
     }
     if (brute) {
@@ -436,18 +448,19 @@ __global__ void __launch_bounds__(128) k_knn_query(const KnnArgs a) {
     const unsigned int self = a.sidx[q];
     if (!kNormals) {
       double sum = 0.0;
-      for (int j = 0; j < m; ++j) sum += sqrt(best[j]);
+      for (int j = 0; j < m; ++j) sum += sqrt(BEST(j));
       a.mean_out[self] = m > 0 ? sum / (double)m : -1.0;
     } else {
       // KDTreeFlann::SearchHybrid: the k nearest, then only those with d2 < radius^2 (lower_bound on the sorted distances)
       int kk = 0;
-      while (kk < m && best[kk] < a.radius2) ++kk;
+      while (kk < m && BEST(kk) < a.radius2) ++kk;
       V3 nrm = v3(0, 0, 1);
       if (kk >= 3) {
         // utility::ComputeCovariance: cumulants in neighbour order, divided by the count
         double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         for (int j = 0; j < kk; ++j) {
-          const double px = a.sx[bidx[j]], py = a.sy[bidx[j]], pz = a.sz[bidx[j]];
+          const unsigned int bj = BIDX(j);
+          const double px = a.sx[bj], py = a.sy[bj], pz = a.sz[bj];
           c[0] += px, c[1] += py, c[2] += pz;
           c[3] += px * px, c[4] += px * py, c[5] += px * pz;
           c[6] += py * py, c[7] += py * pz, c[8] += pz * pz;
@@ -472,6 +485,8 @@ __global__ void __launch_bounds__(128) k_knn_query(const KnnArgs a) {
       a.normal_out[2 * a.normal_stride + self] = nrm.z;
     }
   }
+#undef BEST
+#undef BIDX
 }
 
 // ---- statistics.  The reference sums in index order (std::accumulate / std::inner_product); a parallel sum differs from
@@ -775,6 +790,18 @@ static void icp_sums_launch(int plane, int blocks, cudaStream_t st, const void *
     k_icp_sums<TS, TT, false><<<blocks, 256, 0, st>>>(reinterpret_cast<const TS *>(src), ss, n, reinterpret_cast<const TT *>(tgt), ts, nrm, ns, corr, partial);
 }
 
+template <bool kNormals>
+cudaError_t knn_query_launch(const KnnArgs &a, cudaStream_t st) {
+  const size_t smem = (size_t)a.k * kQueryThreads * (kNormals ? 12 : 8);  // at most 96 KB (k = 64 with indices)
+  if (smem > 48 * 1024) {  // opt in per launch: the attribute belongs to the current device's copy of the function
+    const cudaError_t e = cudaFuncSetAttribute(k_knn_query<kNormals>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const long long blocks = (a.n + kQueryThreads - 1) / kQueryThreads;
+  k_knn_query<kNormals><<<(unsigned int)blocks, kQueryThreads, smem, st>>>(a);
+  return cudaSuccess;
+}
+
 unsigned long long knn_capacity(long long n) {
   unsigned long long c = ((unsigned long long)n * 3ull / 2ull + 31ull) & ~31ull;
   return c < 1024 ? 1024 : c;
@@ -884,7 +911,7 @@ int rv_knn_mean_distance(rv_ctx *ctx, const void *d_xyz, int64_t plane_stride, i
   const int rc = knn_prepare(ctx, "rv_knn_mean_distance", d_xyz, plane_stride, n, dtype, k, 0.0, d_ws, ws_bytes, st, a);
   if (rc != RV_OK || n == 0) return rc;
   a.mean_out = d_mean;
-  k_knn_query<false><<<grid_for(ctx, n, 16, 128), 128, 0, st>>>(a);
+  RV_CUDA(ctx, knn_query_launch<false>(a, st));
   RV_LAUNCHED(ctx);
   return RV_OK;
 }
@@ -905,7 +932,7 @@ int rv_estimate_normals(rv_ctx *ctx, const void *d_xyz, int64_t plane_stride, in
   for (int i = 0; i < 3; ++i) a.camera[i] = camera_location ? camera_location[i] : 0.0;
   a.normal_out = d_normals;
   a.normal_stride = normal_stride;
-  k_knn_query<true><<<grid_for(ctx, n, 16, 128), 128, 0, st>>>(a);
+  RV_CUDA(ctx, knn_query_launch<true>(a, st));
   RV_LAUNCHED(ctx);
   return RV_OK;
 }

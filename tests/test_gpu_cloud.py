@@ -472,3 +472,23 @@ def test_exact_division_helper_against_numpy(rv):
             pc = rv.create_masked_pointcloud(col, allv, None, fx, fy, 511.3, 31.7, unit_rule=rule)
             ref = O.deproject_mask(allv, col, None, fx=fx, fy=fy, cx=511.3, cy=31.7, unit_rule=rule, out_dtype="f64")
             assert np.array_equal(pc.points, ref["points"]) and np.array_equal(pc.colors, ref["colors"])
+
+
+@pytest.mark.parametrize("max_nn,radius", [(64, 0.05), (50, 0.012), (3, 1.0)])
+def test_normals_neighbourhood_sizes(rv, O, max_nn, radius):
+    """icp_cad_model.py:267 asks for max_nn=50; 64 is the largest list the kernel holds (96 KB of shared memory per CTA)."""
+    from synth import bumpy_surface
+    rng = np.random.default_rng(13)
+    P = bumpy_surface(rng, 4000)
+    pc = rv.PointCloud.from_arrays(P, None)
+    pc.estimate_normals(rv.KDTreeSearchParamHybrid(radius, max_nn)).orient_normals_towards_camera_location()
+    N = pc.normals
+    ref = O.estimate_normals(P, radius, max_nn, camera_location=(0.0, 0.0, 0.0))
+    assert np.allclose(np.linalg.norm(N, axis=1), 1.0, atol=1e-12)
+    dots = (N * ref).sum(axis=1)
+    if max_nn > 3:
+        assert np.median(dots) > 1 - 1e-12 and (dots > 0.999).mean() > 0.99
+    else:  # three neighbours: a degenerate covariance (rank <= 2), the normal of the triangle they span
+        assert (np.abs(dots) > 0.999).mean() > 0.95
+    with pytest.raises(Exception):
+        pc.estimate_normals(rv.KDTreeSearchParamHybrid(0.02, 65))
