@@ -379,6 +379,8 @@ __global__ void __launch_bounds__(kQueryThreads) k_knn_query(const KnnArgs a) {
     int m = 0;
     double kth = 0.0;  // BEST(k - 1) once the list is full
     auto offer = [&](double d2, unsigned int j) {
+      // hybrid search = the k nearest among the points closer than the radius: the others need not enter the list
+      if (kNormals && !(d2 < a.radius2)) return;
       if (m < k || d2 < kth) {  // sorted insertion
         int t = m < k ? m : k - 1;
         while (t > 0) {
@@ -525,8 +527,14 @@ __global__ void __launch_bounds__(256) k_sor_partial(const double *__restrict__ 
 
 template <int PASS>
 __global__ void k_sor_finish(const double *__restrict__ partial, int blocks, double std_ratio, double *stats, int *band) {
-  double acc = 0.0, cnt = 0.0;
-  for (int b = 0; b < blocks; ++b) acc += partial[b], cnt += partial[kSorBlocks + b];
+  double acc = 0.0, cnt = 0.0;  // one warp: lanes stride over the block sums, fixed shuffle tree
+  for (int b = threadIdx.x; b < blocks; b += 32) acc += partial[b], cnt += partial[kSorBlocks + b];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (threadIdx.x != 0) return;
   if (PASS == 0) {
     stats[0] = cnt > 0 ? acc / cnt : 0.0;
     stats[3] = cnt;
@@ -637,12 +645,12 @@ __global__ void __launch_bounds__(128) k_nn_search(const KnnArgs a, const T *__r
   const double cell = p->cell;
   const int gx = p->grid[0], gy = p->grid[1], gz = p->grid[2], rmax = p->rmax;
   const long long shell_budget = a.n / 2 + 4096;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += stride) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one query per thread, small CTAs
+  if (q < nq) {
     const double x = (double)q_xyz[q], y = (double)q_xyz[q_stride + q], z = (double)q_xyz[2 * q_stride + q];
     if (!(isfinite(x) && isfinite(y) && isfinite(z))) {
       corr[q] = -1;
-      continue;
+      return;
     }
     int cx, cy, cz;
     cell_of(p, x, y, z, cx, cy, cz);
@@ -775,10 +783,14 @@ __global__ void __launch_bounds__(256) k_icp_sums(const TS *__restrict__ src, lo
   }
 }
 
-__global__ void k_icp_finish(const double *__restrict__ partial, int blocks, double *__restrict__ sums) {
+// one warp per sum: lane l adds rows l, l + 32, ... in order, then a fixed shuffle tree -- the same bits every run
+__global__ void __launch_bounds__(kIcpSums * 32) k_icp_finish(const double *__restrict__ partial, int blocks, double *__restrict__ sums) {
+  const int col = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double v = 0.0;
-  for (int b = 0; b < blocks; ++b) v += partial[(size_t)b * kIcpSums + threadIdx.x];
-  sums[threadIdx.x] = v;
+  for (int b = lane; b < blocks; b += 32) v += partial[(size_t)b * kIcpSums + col];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) sums[col] = v;
 }
 
 template <typename TS, typename TT>
@@ -969,11 +981,11 @@ int rv_statistical_outlier_mask(rv_ctx *ctx, const double *d_mean, int64_t n, do
   const int blocks = grid_for(ctx, n, 1) < kSorBlocks ? grid_for(ctx, n, 1) : kSorBlocks;
   k_sor_partial<0><<<blocks, 256, 0, st>>>(d_mean, n, d_stats, partial);
   RV_LAUNCHED(ctx);
-  k_sor_finish<0><<<1, 1, 0, st>>>(partial, blocks, std_ratio, d_stats, band);
+  k_sor_finish<0><<<1, 32, 0, st>>>(partial, blocks, std_ratio, d_stats, band);
   RV_LAUNCHED(ctx);
   k_sor_partial<1><<<blocks, 256, 0, st>>>(d_mean, n, d_stats, partial);
   RV_LAUNCHED(ctx);
-  k_sor_finish<1><<<1, 1, 0, st>>>(partial, blocks, std_ratio, d_stats, band);
+  k_sor_finish<1><<<1, 32, 0, st>>>(partial, blocks, std_ratio, d_stats, band);
   RV_LAUNCHED(ctx);
   k_sor_band<<<grid_for(ctx, n), 256, 0, st>>>(d_mean, n, d_stats, band);
   RV_LAUNCHED(ctx);
@@ -1016,9 +1028,9 @@ int rv_nn_search(rv_ctx *ctx, const void *d_index_ws, size_t ws_bytes, int64_t n
   knn_layout(const_cast<void *>(d_index_ws), nullptr, 0, n_indexed, 1, a);
   const double r2 = max_distance * max_distance;
   if (dtype == RV_F32)
-    k_nn_search<float><<<grid_for(ctx, n_query, 16, 128), 128, 0, st>>>(a, reinterpret_cast<const float *>(d_query_xyz), query_stride, n_query, r2, d_nearest);
+    k_nn_search<float><<<(unsigned int)((n_query + 127) / 128), 128, 0, st>>>(a, reinterpret_cast<const float *>(d_query_xyz), query_stride, n_query, r2, d_nearest);
   else
-    k_nn_search<double><<<grid_for(ctx, n_query, 16, 128), 128, 0, st>>>(a, reinterpret_cast<const double *>(d_query_xyz), query_stride, n_query, r2, d_nearest);
+    k_nn_search<double><<<(unsigned int)((n_query + 127) / 128), 128, 0, st>>>(a, reinterpret_cast<const double *>(d_query_xyz), query_stride, n_query, r2, d_nearest);
   RV_LAUNCHED(ctx);
   return RV_OK;
 }
@@ -1055,7 +1067,7 @@ int rv_icp_sums(rv_ctx *ctx, int point_to_plane, const void *d_source_xyz, int64
   else
     icp_sums_launch<double, double>(pl, blocks, st, d_source_xyz, source_stride, n_source, d_target_xyz, target_stride, d_target_normals, normal_stride, d_nearest, partial);
   RV_LAUNCHED(ctx);
-  k_icp_finish<<<1, kIcpSums, 0, st>>>(partial, blocks, d_sums);
+  k_icp_finish<<<1, kIcpSums * 32, 0, st>>>(partial, blocks, d_sums);
   RV_LAUNCHED(ctx);
   return RV_OK;
 }
