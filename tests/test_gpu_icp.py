@@ -201,3 +201,20 @@ def test_transform_carries_normals(rv, O):
     assert np.array_equal(pc.normals, O.transform(N, R))
     assert np.array_equal(pc.points, O.transform(P, T))
     assert np.allclose(np.linalg.norm(pc.normals, axis=1), 1.0, atol=1e-12)
+
+
+def test_registration_icp_float32_clouds(rv, O):
+    """Clouds straight out of the float32 pipeline (deproject_batch(dtype="f32")): the working copy stays float32, so the result
+    follows the float64 oracle to float32 rounding only."""
+    moved, tgt, D = _scene(O, seed=23, n_t=5000, n_s=2000)
+    source = rv.PointCloud.from_arrays(moved.astype(np.float32), None, dtype="f32")
+    target = rv.PointCloud.from_arrays(tgt.astype(np.float32), None, dtype="f32")
+    target.estimate_normals(rv.KDTreeSearchParamHybrid(0.02, 30))
+    reg = rv.registration_icp(source, target, 0.02, np.eye(4), rv.TransformationEstimationPointToPlane(),
+                              rv.ICPConvergenceCriteria(max_iteration=50))
+    T, fit, rmse, _, _ = O.registration_icp(source.points, target.points, 0.02, target_normals=target.normals, max_iteration=50)
+    assert abs(reg.fitness - fit) < 5e-3 and abs(reg.inlier_rmse - rmse) < 1e-5
+    assert np.allclose(reg.transformation, T, atol=2e-4) and np.allclose(reg.transformation @ D, np.eye(4), atol=3e-3)
+    mixed = rv.registration_icp(rv.PointCloud.from_arrays(moved, None), target, 0.02, np.eye(4),
+                                rv.TransformationEstimationPointToPlane(), rv.ICPConvergenceCriteria(max_iteration=50))
+    assert np.allclose(mixed.transformation, T, atol=2e-4)

@@ -154,10 +154,18 @@ def main():
     run_icp = lambda: rv.registration_icp(icp_src, kept, 0.02, np.eye(4), rv.TransformationEstimationPointToPlane(), crit)  # noqa: E731
     reg = run_icp()
     ms = timed(run_icp, max(3, a.reps // 4), flush)
+    # the same loop on 2 k points: launch + read-back + host solve per iteration, the floor under any cloud size
+    tiny_t = kept.select_by_index(np.arange(0, 4000, 2))
+    tiny_t.estimate_normals(rv.KDTreeSearchParamHybrid(0.05, 30))
+    tiny_s = tiny_t.select_by_index(np.arange(0, len(tiny_t), 2)).transform(icp_T)
+    run_tiny = lambda: rv.registration_icp(tiny_s, tiny_t, 0.05, np.eye(4), rv.TransformationEstimationPointToPlane(), crit)  # noqa: E731
+    tiny = run_tiny()
+    ms_tiny = timed(run_tiny, max(3, a.reps // 4), flush)
     line("registration_icp point-to-plane, max_dist 0.02, half of that cloud onto it (host solve per iteration)", ms,
          (reg.iterations + 1) * (len(icp_src) * (24 + 4 + 48) + len(icp_src) * 48), len(icp_src) * (reg.iterations + 1), "matches",
          {"source_points": len(icp_src), "target_points": len(kept), "iterations": reg.iterations, "fitness": reg.fitness,
           "inlier_rmse": reg.inlier_rmse, "ms_per_iteration": ms / (reg.iterations + 1),
+          "ms_per_iteration_on_2k_points": ms_tiny / (tiny.iterations + 1),
           "residual_rotation_translation": [float(np.abs((reg.transformation @ icp_T)[:3, :3] - np.eye(3)).max()),
                                             float(np.abs((reg.transformation @ icp_T)[:3, 3]).max())]})
 
