@@ -447,7 +447,10 @@ def run_b200(a):
     # bounded sample; tools/bench_kernels.py has the full per-kernel table
     rows = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        rows = other_rows(rv, _ops, dev, gen)
+        try:
+            rows = other_rows(rv, _ops, dev, gen)
+        except Exception as e:  # the headline line must still print; the failure is reported in it
+            rows = [{"row": "other rows failed", "error": repr(e)}]
 
     if rank == 0:
         print(json.dumps({
