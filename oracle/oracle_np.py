@@ -440,6 +440,24 @@ def knn_mean_distance(points, k, chunk=512):
     return out
 
 
+def nearest_neighbor_distance(points, chunk=512):
+    """Open3D 0.19 PointCloud::ComputeNearestNeighborDistance (ply_to_stl.py:45,56): sqrt of the second squared distance of
+    SearchKNN(point, 2) -- the nearest OTHER point (0 for a duplicate); zeros for fewer than two points."""
+    P = np.asarray(points, dtype=np.float64)
+    n = P.shape[0]
+    if n < 2:
+        return np.zeros(n)
+    out = np.empty(n)
+    for i0 in range(0, n, chunk):
+        q = P[i0:i0 + chunk]
+        dx = q[:, None, 0] - P[None, :, 0]
+        dy = q[:, None, 1] - P[None, :, 1]
+        dz = q[:, None, 2] - P[None, :, 2]
+        d2 = (dx * dx + dy * dy) + dz * dz
+        out[i0:i0 + chunk] = np.sqrt(np.partition(d2, 1, axis=1)[:, 1])
+    return out
+
+
 def statistical_outlier_indices(avg, std_ratio):
     """Index-ordered sums of PointCloud::RemoveStatisticalOutliers (Open3D 0.19): returns (indices, mean, std, threshold)."""
     avg = np.asarray(avg, np.float64)

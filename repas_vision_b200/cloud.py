@@ -213,6 +213,53 @@ class PointCloud:
         m = int(count.item())
         return PointCloud(out, m, self._has_color), index[:m].cpu().numpy()
 
+    def compute_nearest_neighbor_distance(self) -> np.ndarray:
+        """Open3D PointCloud.compute_nearest_neighbor_distance (ply_to_stl.py:45,56): distance from every point to its
+        nearest other point, i.e. the second entry of SearchKNN(point, 2); zeros for fewer than two points.  Runs as the
+        k = 2 case of the outlier-removal search: mean(0, d) * 2 = d exactly."""
+        if self._n < 2:
+            return np.zeros(self._n)
+        return (_ops.knn_mean_distance(self._data, self._n, 2) * 2.0).cpu().numpy()
+
+    def translate(self, translation, relative: bool = True) -> "PointCloud":
+        """Open3D PointCloud.translate: p += t (relative) or p += t - centre (absolute).  In place, returns self."""
+        t = np.asarray(translation, dtype=np.float64).reshape(3)
+        if not relative:
+            t = t - self.get_center()
+        T = np.eye(4)
+        T[:3, 3] = t
+        normals, self._normals = self._normals, None  # a shift leaves the normals as they are
+        self.transform(T)
+        self._normals = normals
+        return self
+
+    def scale(self, scale: float, center) -> "PointCloud":
+        """Open3D PointCloud.scale (manual_pose_verify.py:293): p = (p - center) * scale + center, in that order (two K3
+        passes so the rounding is the reference's).  In place, returns self."""
+        c = np.asarray(center, dtype=np.float64).reshape(3)
+        normals, self._normals = self._normals, None  # Open3D scales the points only
+        if np.any(c != 0.0):
+            self.translate(-c)
+        T = np.diag([float(scale)] * 3 + [1.0])
+        T[:3, 3] = c
+        self.transform(T)
+        self._normals = normals
+        return self
+
+    def get_center(self) -> np.ndarray:
+        """Mean of the points (zeros for an empty cloud)."""
+        return self.xyz.to(torch.float64).mean(dim=1).cpu().numpy() if self._n else np.zeros(3)
+
+    def paint_uniform_color(self, color) -> "PointCloud":
+        """Open3D PointCloud.paint_uniform_color: every point gets `color` (unit RGB).  In place, returns self."""
+        c = torch.as_tensor(np.asarray(color, dtype=np.float64).reshape(3), device=self.device).to(self._data.dtype)
+        if not (self._has_color and self._data.shape[0] >= 6):
+            data = torch.empty((6, self._data.shape[1]), dtype=self._data.dtype, device=self.device)
+            data[:3] = self._data[:3]
+            self._data, self._has_color = data, True
+        self._data[3:6] = c[:, None]
+        return self
+
     def select_by_index(self, indices, invert: bool = False) -> "PointCloud":
         idx = torch.as_tensor(np.asarray(indices), dtype=torch.int64, device=self.device)
         if invert:

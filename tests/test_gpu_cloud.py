@@ -492,3 +492,33 @@ def test_normals_neighbourhood_sizes(rv, O, max_nn, radius):
         assert (np.abs(dots) > 0.999).mean() > 0.95
     with pytest.raises(Exception):
         pc.estimate_normals(rv.KDTreeSearchParamHybrid(0.02, 65))
+
+
+def test_small_open3d_cloud_methods(rv, O):
+    """compute_nearest_neighbor_distance (ply_to_stl.py:45,56), scale (manual_pose_verify.py:293), translate,
+    paint_uniform_color, get_center: bit-exact against numpy in the reference's operation order."""
+    rng = np.random.default_rng(17)
+    P = np.concatenate([rng.normal(size=(3000, 3)) * 0.2, np.repeat(rng.random((3, 3)), 2, axis=0), [[9.0, 9.0, 9.0]]])
+    C = rng.random(P.shape)
+    pc = rv.PointCloud.from_arrays(P, C)
+    d = pc.compute_nearest_neighbor_distance()
+    assert d.dtype == np.float64 and np.array_equal(d, O.nearest_neighbor_distance(P))
+    assert (d[3000:3006] == 0.0).all() and d[-1] > 10.0
+    assert rv.PointCloud.from_arrays(P[:1], None).compute_nearest_neighbor_distance().tolist() == [0.0]
+    assert np.allclose(pc.get_center(), P.mean(axis=0), rtol=1e-12)
+    c = np.array([0.1, -0.2, 0.3])
+    pc.estimate_normals(rv.KDTreeSearchParamHybrid(0.1, 30))
+    N = pc.normals
+    pc.scale(1000.0, center=(0, 0, 0))
+    assert np.array_equal(pc.points, P * 1000.0) and np.array_equal(pc.normals, N) and np.array_equal(pc.colors, C)
+    pc.scale(0.001, center=c)
+    Q = (P * 1000.0 - c) * 0.001 + c
+    assert np.array_equal(pc.points, Q)
+    pc.translate((1.0, 2.0, -3.0))
+    assert np.array_equal(pc.points, Q + np.array([1.0, 2.0, -3.0])) and np.array_equal(pc.normals, N)
+    pc.translate((0.0, 0.0, 0.0), relative=False)
+    assert np.allclose(pc.get_center(), 0.0, atol=1e-12)
+    pc.paint_uniform_color([0.7, 0.7, 0.7])
+    assert np.array_equal(pc.colors, np.full(P.shape, 0.7))
+    bare = rv.PointCloud.from_arrays(P, None).paint_uniform_color([1.0, 0.0, 0.25])
+    assert bare.has_colors() and np.array_equal(bare.colors, np.tile([1.0, 0.0, 0.25], (len(P), 1))) and np.array_equal(bare.points, P)
