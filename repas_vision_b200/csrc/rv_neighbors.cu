@@ -191,6 +191,16 @@ __device__ __forceinline__ void cell_of(const KnnParams *p, double x, double y, 
   iz = iz < 0 ? 0 : (iz >= p->grid[2] ? p->grid[2] - 1 : iz);
 }
 
+// Squared distance from coordinate q to the slab of cell i along one axis, shrunk by eps (>> the rounding of the cell
+// assignment) so that it never exceeds the true distance to any point filed under that cell: cells whose bound lies beyond
+// the current search bound are skipped without a table probe.
+__device__ __forceinline__ double axis_gap2(double q, double origin, int i, double cell, double eps) {
+  const double lo = origin + (double)i * cell;
+  double g = fmax(lo - q, q - (lo + cell)) - eps;
+  g = g > 0.0 ? g : 0.0;
+  return g * g;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_knn_cells(const KnnArgs a) {
   if (!a.prm->redo) return;  // the table of the previous round stands
@@ -396,6 +406,10 @@ __global__ void __launch_bounds__(kQueryThreads) k_knn_query(const KnnArgs a) {
         if (m == k) kth = BEST(k - 1);
       }
     };
+    // what a candidate must beat: the k-th distance once the list is full, the radius of a hybrid search before that
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    auto bound = [&]() { return m == k ? kth : (kNormals ? a.radius2 : inf); };
+    const double ox = p->origin[0], oy = p->origin[1], oz = p->origin[2], eps = cell * 4e-9;
     // an isolated point would walk ever larger empty shells (~24 r^2 cells each): once the shells have cost about as much as
     // looking at every point, it does exactly that instead
     const long long shell_budget = a.n / 2 + 4096;
@@ -412,14 +426,19 @@ __global__ void __launch_bounds__(kQueryThreads) k_knn_query(const KnnArgs a) {
       for (int dz = -r; dz <= r; ++dz) {
         const int iz = cz + dz;
         if (iz < 0 || iz >= gz) continue;
+        const double lbz = axis_gap2(z, oz, iz, cell, eps);
+        if (lbz > bound()) continue;
         for (int dy = -r; dy <= r; ++dy) {
           const int iy = cy + dy;
           if (iy < 0 || iy >= gy) continue;
+          const double lbzy = lbz + axis_gap2(y, oy, iy, cell, eps);
+          if (lbzy > bound()) continue;
           const bool face = (dz == -r || dz == r || dy == -r || dy == r);
           const int step = (face || r == 0) ? 1 : 2 * r;  // inside the shell only dx = -r and dx = +r remain
           for (int dx = -r; dx <= r; dx += step) {
             const int ix = cx + dx;
             if (ix < 0 || ix >= gx) continue;
+            if (lbzy + axis_gap2(x, ox, ix, cell, eps) > bound()) continue;  // nothing in that cell can enter the list
             const unsigned long long key = cell_key(ix, iy, iz);
             unsigned int h = __umulhi((unsigned int)(cell_hash(key) >> 32), a.cap);
             unsigned long long cur;
@@ -656,6 +675,7 @@ __global__ void __launch_bounds__(128) k_nn_search(const KnnArgs a, const T *__r
     cell_of(p, x, y, z, cx, cy, cz);
     double best = radius2;
     unsigned int bidx = 0xffffffffu;  // original index of the best point so far
+    const double ox = p->origin[0], oy = p->origin[1], oz = p->origin[2], eps = cell * 4e-9;
     auto offer = [&](double d2, unsigned int j) {
       if (d2 < best) {
         best = d2;
@@ -677,14 +697,19 @@ __global__ void __launch_bounds__(128) k_nn_search(const KnnArgs a, const T *__r
       for (int dz = -r; dz <= r; ++dz) {
         const int iz = cz + dz;
         if (iz < 0 || iz >= gz) continue;
+        const double lbz = axis_gap2(z, oz, iz, cell, eps);
+        if (lbz > best) continue;
         for (int dy = -r; dy <= r; ++dy) {
           const int iy = cy + dy;
           if (iy < 0 || iy >= gy) continue;
+          const double lbzy = lbz + axis_gap2(y, oy, iy, cell, eps);
+          if (lbzy > best) continue;
           const bool face = (dz == -r || dz == r || dy == -r || dy == r);
           const int step = (face || r == 0) ? 1 : 2 * r;
           for (int dx = -r; dx <= r; dx += step) {
             const int ix = cx + dx;
             if (ix < 0 || ix >= gx) continue;
+            if (lbzy + axis_gap2(x, ox, ix, cell, eps) > best) continue;  // every point of that cell is farther than the best
             const unsigned long long key = cell_key(ix, iy, iz);
             unsigned int h = __umulhi((unsigned int)(cell_hash(key) >> 32), a.cap);
             unsigned long long cur;
