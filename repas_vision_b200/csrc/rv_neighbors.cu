@@ -19,6 +19,7 @@
 //   k_knn_query    one thread per point: shells of cells at Chebyshev distance 0, 1, 2, ... around the point's cell, a sorted
 //                  list of the k smallest squared distances; the search stops once the k-th distance is within the cube
 //                  already visited (any unvisited point is at least r * cell away), so the result is exact
+//                  (cells whose box is farther than the current bound are skipped without a probe)
 //   k_sor_partial / k_sor_finish / k_sor_band / k_sor_stats   cloud mean, standard deviation and threshold: parallel sums,
 //                  redone in INDEX ORDER like std::accumulate only when a point lies within rounding distance of the
 //                  threshold, so the kept set always equals the sequential reference's
