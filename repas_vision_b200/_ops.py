@@ -231,6 +231,19 @@ def transform_merge(views, Ts, has_color: bool, out_dtype=None, want_bounds=Fals
     return out, total, bounds
 
 
+def transform_xyz_into(src: torch.Tensor, n: int, T, out: torch.Tensor) -> None:
+    """K3 on the coordinate planes only, into a caller-owned buffer of the same dtype (the ICP working copy: no allocation, no
+    colour traffic)."""
+    dev = src.device
+    ctx = ctx_for(dev)
+    ptrs = (C.c_void_p * 1)(src.data_ptr())
+    strides = (C.c_int64 * 1)(pstride(src))
+    ns = (C.c_int64 * 1)(int(n))
+    Tc = (C.c_double * 16)(*np.asarray(T, dtype=np.float64).reshape(-1))
+    ctx.check(ctx.lib.rv_transform_merge(ctx.handle, 1, ptrs, strides, ns, Tc, _RV_DT[src.dtype], 0, ptr(out), pstride(out),
+                                         _RV_DT[out.dtype], None, stream_ptr(dev)))
+
+
 def voxel_downsample(data: torch.Tensor, n: int, has_color: bool, voxel_size: float, *, bounds=None, out_dtype=None,
                      want_keys=False, want_counts=False, out_capacity=None):
     """Returns dict(data [planes, cap], m (int64 tensor[1]), keys [3,cap] int32 | None, counts [cap] | None)."""

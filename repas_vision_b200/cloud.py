@@ -48,6 +48,37 @@ class KDTreeSearchParamHybrid:
         self.radius, self.max_nn = float(radius), int(max_nn)
 
 
+class DeviceIndexList:
+    """The `ind` of remove_statistical_outlier: Open3D hands back an IntVector, the reference script drops it
+    (create_masked_ply.py:169).  It stays on the GPU until somebody looks at it; then it behaves like the int64 numpy array
+    of kept indices (len, indexing, iteration, np.asarray, select_by_index)."""
+
+    def __init__(self, index: torch.Tensor):
+        self.device_tensor = index
+        self._host = None
+
+    def _array(self) -> np.ndarray:
+        if self._host is None:
+            self._host = self.device_tensor.cpu().numpy()
+        return self._host
+
+    def __len__(self):
+        return int(self.device_tensor.numel())
+
+    def __getitem__(self, i):
+        return self._array()[i]
+
+    def __iter__(self):
+        return iter(self._array())
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._array()
+        return a if dtype is None else a.astype(dtype)
+
+    def __repr__(self):
+        return f"DeviceIndexList with {len(self)} indices"
+
+
 class PointCloud:
     """Coloured cloud held on the GPU as structure-of-arrays planes x,y,z[,r,g,b].
 
@@ -200,18 +231,20 @@ class PointCloud:
     def remove_statistical_outlier(self, nb_neighbors: int = 20, std_ratio: float = 2.0, print_progress: bool = False):
         """Open3D PointCloud.remove_statistical_outlier (create_masked_ply.py:169): drops the points whose mean distance
         to their nb_neighbors nearest neighbours (themselves included) is not below cloud mean + std_ratio * std dev.
-        Returns (cloud, ind) like Open3D: the kept points in order and their indices in this cloud (an int64 numpy
-        array where Open3D hands back an IntVector; both index, iterate and feed select_by_index alike)."""
+        Returns (cloud, ind) like Open3D: the kept points in order and their indices in this cloud (a DeviceIndexList
+        where Open3D hands back an IntVector: it indexes, iterates, converts with np.asarray and feeds select_by_index
+        alike, but crosses PCIe only when looked at)."""
         if int(nb_neighbors) < 1 or not (float(std_ratio) > 0.0):
             raise RuntimeError("[Open3D-compatible] Illegal input parameters, the number of neighbors and standard "
                                "deviation ratio must be positive.")
         if self._n == 0:
-            return PointCloud(None, 0, self._has_color, device=self.device), np.zeros(0, np.int64)
+            return (PointCloud(None, 0, self._has_color, device=self.device),
+                    DeviceIndexList(torch.zeros(0, dtype=torch.int64, device=self.device)))
         mean = _ops.knn_mean_distance(self._data, self._n, int(nb_neighbors))
         keep, _ = _ops.statistical_outlier_mask(mean, float(std_ratio))
         out, count, index = _ops.select_by_mask(self._data, self._n, self._has_color, keep)
         m = int(count.item())
-        return PointCloud(out, m, self._has_color), index[:m].cpu().numpy()
+        return PointCloud(out, m, self._has_color), DeviceIndexList(index[:m])
 
     def compute_nearest_neighbor_distance(self) -> np.ndarray:
         """Open3D PointCloud.compute_nearest_neighbor_distance (ply_to_stl.py:45,56): distance from every point to its
@@ -261,7 +294,10 @@ class PointCloud:
         return self
 
     def select_by_index(self, indices, invert: bool = False) -> "PointCloud":
-        idx = torch.as_tensor(np.asarray(indices), dtype=torch.int64, device=self.device)
+        if isinstance(indices, DeviceIndexList):
+            idx = indices.device_tensor.to(self.device)
+        else:
+            idx = torch.as_tensor(np.asarray(indices), dtype=torch.int64, device=self.device)
         if invert:
             keep = torch.ones(self._n, dtype=torch.bool, device=self.device)
             keep[idx] = False

@@ -145,26 +145,37 @@ class RegistrationResult:
 
 
 class _Matcher:
-    """The target side of a registration: its hash-grid index (the reference's KDTreeFlann) and the per-step buffers."""
+    """One registration: the target's hash-grid index (the reference's KDTreeFlann), the working copy of the source
+    coordinates (two buffers, K3 goes from one into the other) and the per-step buffers."""
 
     def __init__(self, source: PointCloud, target: PointCloud, max_distance: float, point_to_plane: bool):
         if source.device != target.device:
             raise ValueError("source and target must live on the same device")
         self.target, self.max_distance, self.plane = target, float(max_distance), bool(point_to_plane)
+        self.n = len(source)
         self.index = _ops.nn_index_build(target._data, len(target), self.max_distance) if len(target) else None
-        self.nearest = torch.empty(max(len(source), 1), dtype=torch.int32, device=source.device)
+        self.cur = source._data  # read-only until the first transform, which writes into a buffer of its own
+        self.spare = [torch.empty((3, max(self.n, 1)), dtype=source._data.dtype, device=source.device) for _ in range(2)]
+        self.nearest = torch.empty(max(self.n, 1), dtype=torch.int32, device=source.device)
         self.scratch = _ops.icp_scratch(source.device)
 
-    def evaluate(self, pcd: PointCloud, transformation: np.ndarray):
+    def transform(self, T: np.ndarray) -> None:
+        """pcd.Transform(T) on the working copy."""
+        if self.n:
+            out = self.spare[0] if self.cur is not self.spare[0] else self.spare[1]
+            _ops.transform_xyz_into(self.cur, self.n, T, out)
+            self.cur = out
+
+    def evaluate(self, transformation: np.ndarray):
         """GetRegistrationResultAndCorrespondences; also returns the sums the estimation step needs."""
         res = RegistrationResult(transformation)
-        n, nt = len(pcd), len(self.target)
+        n, nt = self.n, len(self.target)
         res._n = n
         if n == 0 or nt == 0:
             return res, np.zeros(32)
-        _ops.nn_search(self.index, nt, pcd._data, n, self.max_distance, out=self.nearest)
+        _ops.nn_search(self.index, nt, self.cur, n, self.max_distance, out=self.nearest)
         normals = self.target._normals if self.plane else None
-        s = _ops.icp_sums(pcd._data, n, self.target._data, nt, normals, self.nearest, self.plane, self.scratch).cpu().numpy()
+        s = _ops.icp_sums(self.cur, n, self.target._data, nt, normals, self.nearest, self.plane, self.scratch).cpu().numpy()
         res._nearest = self.nearest
         if s[0] > 0:
             res.fitness = float(s[0]) / float(n)
@@ -178,9 +189,10 @@ def evaluate_registration(source: PointCloud, target: PointCloud, max_correspond
     T = np.eye(4) if transformation is None else np.asarray(transformation, dtype=np.float64)
     if not (float(max_correspondence_distance) > 0.0):
         return RegistrationResult(T)
-    pcd = source if _is_identity(T) else source.transformed(T)
-    m = _Matcher(pcd, target, max_correspondence_distance, False)
-    res, _ = m.evaluate(pcd, T)
+    m = _Matcher(source, target, max_correspondence_distance, False)
+    if not _is_identity(T):
+        m.transform(T)
+    res, _ = m.evaluate(T)
     res._nearest = None if res._nearest is None else res._nearest.clone()
     return res
 
@@ -198,17 +210,16 @@ def registration_icp(source: PointCloud, target: PointCloud, max_correspondence_
     transformation = np.eye(4) if init is None else np.array(init, dtype=np.float64)
     if transformation.shape != (4, 4):
         raise ValueError(f"Expected 4x4 matrix, got shape {transformation.shape}")
-    pcd = PointCloud(source._data, len(source), source._has_color)  # shares the planes until the first transform
+    m = _Matcher(source, target, max_correspondence_distance, est.point_to_plane)
     if not _is_identity(transformation):
-        pcd.transform(transformation)
-    m = _Matcher(pcd, target, max_correspondence_distance, est.point_to_plane)
-    result, sums = m.evaluate(pcd, transformation)
+        m.transform(transformation)
+    result, sums = m.evaluate(transformation)
     for it in range(1, crit.max_iteration + 1):
         update = est.update_from_sums(sums)
         transformation = update @ transformation
-        pcd.transform(update)
+        m.transform(update)
         backup = result
-        result, sums = m.evaluate(pcd, transformation)
+        result, sums = m.evaluate(transformation)
         result.iterations = it
         if (abs(backup.fitness - result.fitness) < crit.relative_fitness
                 and abs(backup.inlier_rmse - result.inlier_rmse) < crit.relative_rmse):

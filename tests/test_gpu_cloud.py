@@ -209,6 +209,8 @@ def test_statistical_outlier_removal_matches_oracle(rv, O, rs720):
     assert np.allclose(stats.cpu().numpy(), [mean, std, thr, float(len(P))], rtol=1e-12, atol=0)  # parallel sums; the list below is exact
     kept, ind = down.remove_statistical_outlier(nb_neighbors=20, std_ratio=2.0)
     assert np.array_equal(ind, ref_ind) and 0 < len(ind) < len(P)
+    assert int(ind[0]) == int(ref_ind[0]) and [int(v) for v in list(ind)[:5]] == ref_ind[:5].tolist()  # array-like, fetched lazily
+    assert np.array_equal(down.select_by_index(ind).points, kept.points) and np.asarray(ind).dtype == np.int64
     assert np.array_equal(kept.points, P[ref_ind]) and np.array_equal(kept.colors, down.colors[ref_ind])
     # random clouds: clusters, duplicates, an isolated far point, fewer points than neighbours, float32 storage
     rng = np.random.default_rng(5)

@@ -137,7 +137,7 @@ def main():
     down = rv.fuse_views(clouds, cam_T, 0.005)
     ms = timed(lambda: down.remove_statistical_outlier(20, 2.0), max(3, a.reps // 4), flush)
     kept, _ = down.remove_statistical_outlier(20, 2.0)
-    line("remove_statistical_outlier(20, 2.0) on the 5 mm fused cloud (index list read back)", ms, len(down) * 24 + len(kept) * 24,
+    line("remove_statistical_outlier(20, 2.0) on the 5 mm fused cloud (index list left on the device)", ms, len(down) * 24 + len(kept) * 24,
          len(down), "points", {"points": len(down), "kept": len(kept)})
 
     ms = timed(lambda: kept.estimate_normals(rv.KDTreeSearchParamHybrid(0.02, 30)).orient_normals_towards_camera_location(),
