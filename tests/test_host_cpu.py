@@ -234,3 +234,42 @@ def test_binary_ply_layout_parser(tmp_path):
         r = tmp_path / "c.ply"
         r.write_bytes(("ply\n" + bad + "end_header\n").encode() + bytes(64))
         assert ply._binary_vertex_layout(str(r)) is None  # the host reader takes these
+
+
+def test_icp_host_steps_match_the_oracle(built):
+    """registration.py keeps the 6x6 solve / Umeyama step and Eigen's isIdentity on the host: fed with the sums the GPU
+    produces (computed here with numpy), they must return the oracle's update."""
+    from oracle import oracle_np as O
+    from repas_vision_b200 import registration as R
+    from synth import bumpy_surface
+    rng = np.random.default_rng(31)
+    tgt = bumpy_surface(rng, 1500)
+    src = O.transform(bumpy_surface(rng, 600), O.vector6d_to_matrix4d(np.array([0.02, 0.01, -0.02, 0.003, 0.002, -0.004])))
+    N = O.estimate_normals(tgt, 0.03, 30, camera_location=(0, 0, 0))
+    near, _, _ = O.nearest_correspondences(src, tgt, 0.02)
+    sel = near >= 0
+    S, T, Nt = src[sel], tgt[near[sel]], N[near[sel]]
+    r = ((S - T) * Nt).sum(axis=1)
+    J = np.concatenate([np.cross(S, Nt), Nt], axis=1)
+    plane = np.zeros(32)
+    plane[0], plane[1], plane[2] = sel.sum(), ((S - T) ** 2).sum(), (r * r).sum()
+    plane[3:9], plane[9:30] = J.T @ r, (J.T @ J)[np.triu_indices(6)]
+    got = R.TransformationEstimationPointToPlane().update_from_sums(plane)
+    assert np.allclose(got, O.point_to_plane_update(src, tgt, N, near), rtol=0, atol=1e-12)
+    point = np.zeros(32)
+    point[0], point[1], point[2] = sel.sum(), plane[1], (S * S).sum()
+    point[3:6], point[6:9], point[9:18] = S.sum(axis=0), T.sum(axis=0), (T.T @ S).reshape(-1)
+    for scaling in (False, True):
+        got = R.TransformationEstimationPointToPoint(scaling).update_from_sums(point)
+        assert np.allclose(got, O.point_to_point_update(src, tgt, near, scaling), rtol=0, atol=1e-10)
+    assert np.array_equal(R.TransformationEstimationPointToPlane().update_from_sums(np.zeros(32)), np.eye(4))
+    assert np.array_equal(R.TransformationEstimationPointToPoint().update_from_sums(np.zeros(32)), np.eye(4))
+    x = np.array([0.3, -0.2, 0.5, 1.0, 2.0, 3.0])
+    assert np.allclose(R.vector6d_to_matrix4d(x), O.vector6d_to_matrix4d(x), rtol=0, atol=1e-16)
+    # Eigen's isIdentity(1e-12): exact identity and rounding noise pass, a micrometre shift does not
+    assert R._is_identity(np.eye(4)) and R._is_identity(np.eye(4) + 1e-14)
+    shifted = np.eye(4)
+    shifted[0, 3] = 1e-6
+    assert not R._is_identity(shifted)
+    c = R.ICPConvergenceCriteria()
+    assert (c.relative_fitness, c.relative_rmse, c.max_iteration) == (1e-6, 1e-6, 30)
