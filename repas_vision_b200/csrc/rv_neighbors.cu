@@ -373,8 +373,8 @@ __global__ void __launch_bounds__(kQueryThreads) k_knn_query(const KnnArgs a) {
   // the sorted candidate lists live in shared memory, [rank][thread]: as per-thread arrays they were local memory, 150 MB of
   // it in flight, and the kernel waited on that (long-scoreboard stalls, 127 MB of DRAM writes for a 6 MB result)
   extern __shared__ __align__(16) unsigned char s_raw[];
-  double *s_best = reinterpret_cast<double *>(s_raw);                                                  // ascending squared distances
-  unsigned int *s_bidx = reinterpret_cast<unsigned int *>(s_best + (size_t)a.k * kQueryThreads);        // their sorted positions
+  double *s_best = reinterpret_cast<double *>(s_raw);              // !kNormals: ascending squared distances
+  unsigned int *s_bidx = reinterpret_cast<unsigned int *>(s_raw);  // kNormals: sorted positions of the neighbours, nearest first
   const int tid = threadIdx.x;
 #define BEST(t) s_best[(t) * kQueryThreads + tid]
 #define BIDX(t) s_bidx[(t) * kQueryThreads + tid]
@@ -389,20 +389,36 @@ __global__ void __launch_bounds__(kQueryThreads) k_knn_query(const KnnArgs a) {
     cell_of(p, x, y, z, cx, cy, cz);
     int m = 0;
     double kth = 0.0;  // BEST(k - 1) once the list is full
+    auto dist2_of = [&](unsigned int j) {
+      const double ex = a.sx[j] - x, ey = a.sy[j] - y, ez = a.sz[j] - z;
+      return (ex * ex + ey * ey) + ez * ez;
+    };
     auto offer = [&](double d2, unsigned int j) {
-      // hybrid search = the k nearest among the points closer than the radius: the others need not enter the list
-      if (kNormals && !(d2 < a.radius2)) return;
-      if (m < k || d2 < kth) {  // sorted insertion
+      if (kNormals) {
+        // hybrid search = the k nearest among the points closer than the radius: the others need not enter the list.  Only
+        // the sorted positions are kept (4 bytes an entry: four times the resident warps of a distance + index list); the
+        // distance of an entry is recomputed when an insertion has to be placed, by bisection.
+        if (!(d2 < a.radius2) || (m == k && !(d2 < kth))) return;
+        const int last = m < k ? m : k - 1;  // a full list drops its last entry
+        int lo = 0, hi = last;
+        while (lo < hi) {  // first entry farther than d2: equal distances stay in arrival order
+          const int mid = (lo + hi) >> 1;
+          if (dist2_of(BIDX(mid)) > d2) hi = mid;
+          else lo = mid + 1;
+        }
+        for (int t = last; t > lo; --t) BIDX(t) = BIDX(t - 1);
+        BIDX(lo) = j;
+        if (m < k) ++m;
+        if (m == k) kth = lo == k - 1 ? d2 : dist2_of(BIDX(k - 1));
+      } else if (m < k || d2 < kth) {  // sorted insertion
         int t = m < k ? m : k - 1;
         while (t > 0) {
           const double prev = BEST(t - 1);
           if (!(prev > d2)) break;
           BEST(t) = prev;
-          if (kNormals) BIDX(t) = BIDX(t - 1);
           --t;
         }
         BEST(t) = d2;
-        if (kNormals) BIDX(t) = j;
         if (m < k) ++m;
         if (m == k) kth = BEST(k - 1);
       }
@@ -473,9 +489,8 @@ __global__ void __launch_bounds__(kQueryThreads) k_knn_query(const KnnArgs a) {
       for (int j = 0; j < m; ++j) sum += sqrt(BEST(j));
       a.mean_out[self] = m > 0 ? sum / (double)m : -1.0;
     } else {
-      // KDTreeFlann::SearchHybrid: the k nearest, then only those with d2 < radius^2 (lower_bound on the sorted distances)
-      int kk = 0;
-      while (kk < m && BEST(kk) < a.radius2) ++kk;
+      // KDTreeFlann::SearchHybrid: the k nearest, then only those with d2 < radius^2 -- the list holds nothing else
+      const int kk = m;
       V3 nrm = v3(0, 0, 1);
       if (kk >= 3) {
         // utility::ComputeCovariance: cumulants in neighbour order, divided by the count
@@ -830,7 +845,7 @@ static void icp_sums_launch(int plane, int blocks, cudaStream_t st, const void *
 
 template <bool kNormals>
 cudaError_t knn_query_launch(const KnnArgs &a, cudaStream_t st) {
-  const size_t smem = (size_t)a.k * kQueryThreads * (kNormals ? 12 : 8);  // at most 96 KB (k = 64 with indices)
+  const size_t smem = (size_t)a.k * kQueryThreads * (kNormals ? 4 : 8);  // at most 64 KB (k = 64 distances)
   if (smem > 48 * 1024) {  // opt in per launch: the attribute belongs to the current device's copy of the function
     const cudaError_t e = cudaFuncSetAttribute(k_knn_query<kNormals>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
