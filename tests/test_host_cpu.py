@@ -273,3 +273,15 @@ def test_icp_host_steps_match_the_oracle(built):
     assert not R._is_identity(shifted)
     c = R.ICPConvergenceCriteria()
     assert (c.relative_fitness, c.relative_rmse, c.max_iteration) == (1e-6, 1e-6, 30)
+
+
+def test_device_index_list_behaves_like_the_index_array(built):
+    """remove_statistical_outlier's `ind` (Open3D: IntVector) is fetched on first use; until then only its length is known."""
+    import torch
+    from repas_vision_b200.cloud import DeviceIndexList
+    ind = DeviceIndexList(torch.tensor([4, 7, 9, 12], dtype=torch.int64))
+    assert len(ind) == 4 and ind._host is None
+    assert np.array_equal(np.asarray(ind), [4, 7, 9, 12]) and np.asarray(ind).dtype == np.int64
+    assert int(ind[1]) == 7 and [int(v) for v in ind] == [4, 7, 9, 12] and np.array_equal(ind[1:3], [7, 9])
+    assert np.asarray(ind, dtype=np.int32).dtype == np.int32
+    assert len(DeviceIndexList(torch.zeros(0, dtype=torch.int64))) == 0
