@@ -567,10 +567,19 @@ def other_rows(rv, _ops, dev, gen):
 
 def main():
     a = parse_args()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_b200(a)
+    # stdout carries the one JSON line and nothing else: libraries that write to file descriptor 1 on their own (NCCL prints
+    # its version line there when NCCL_DEBUG is set) are pointed at stderr, and the line goes out through the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
+    try:
+        if a.impl == "reference":
+            run_reference(a)
+        else:
+            run_b200(a)
+    finally:
+        real_stdout.flush()
 
 
 if __name__ == "__main__":
