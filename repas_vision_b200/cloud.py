@@ -41,6 +41,13 @@ def _is_torch_cuda(a) -> bool:
     return isinstance(a, torch.Tensor) and a.is_cuda
 
 
+def _lex_order(keys: torch.Tensor) -> torch.Tensor:
+    """Permutation that sorts the columns of an integer [3, m] key array lexicographically (three stable sorts)."""
+    order = torch.argsort(keys[2], stable=True)
+    order = order[torch.argsort(keys[1][order], stable=True)]
+    return order[torch.argsort(keys[0][order], stable=True)]
+
+
 class KDTreeSearchParamHybrid:
     """o3d.geometry.KDTreeSearchParamHybrid(radius, max_nn): up to max_nn nearest neighbours closer than radius."""
 
@@ -93,7 +100,8 @@ class PointCloud:
             data = torch.empty((6 if has_color else 3, 1), dtype=torch.float64, device=dev)
             n = 0
         self._data = data
-        self._normals = None  # float64 [3, n] once estimate_normals ran; rotated by transform, dropped by anything that reorders the points
+        self._normals = None  # float64 [3, n] once estimate_normals ran; rotated by transform, averaged by voxel_down_sample,
+        # dropped by the filters and by +
         self._n = int(n)
         self._has_color = bool(has_color) and data.shape[0] >= 6
 
@@ -193,12 +201,27 @@ class PointCloud:
             raise RuntimeError("[Open3D-compatible] voxel_size <= 0.")
         if self._n == 0:
             return (self, np.zeros((0, 3), np.int32), np.zeros(0, np.int32)) if return_keys else self
-        r = _ops.voxel_downsample(self._data, self._n, self._has_color, float(voxel_size), want_keys=return_keys,
+        carry = self._normals is not None
+        r = _ops.voxel_downsample(self._data, self._n, self._has_color, float(voxel_size), want_keys=return_keys or carry,
                                   want_counts=return_keys)
         m = int(r["m"].item())
         if m < 0:
             raise RuntimeError("[Open3D-compatible] voxel_size is too small.")
         pc = PointCloud(r["data"], m, self._has_color)
+        if carry and m:
+            # Open3D averages the normals per voxel as well (not renormalised).  K4 averages whatever sits in the colour
+            # planes, so a second pass runs on xyz + normals; the two outputs list the voxels in different (hash) orders
+            # and are matched through their voxel keys.
+            tmp = torch.empty((6, self._n), dtype=torch.float64, device=self.device)
+            tmp[:3] = self._data[:3, :self._n]
+            tmp[3:] = self._normals[:, :self._n]
+            r2 = _ops.voxel_downsample(tmp, self._n, True, float(voxel_size), want_keys=True)
+            if int(r2["m"].item()) != m:
+                raise RuntimeError("voxel grids of the colour and the normal pass differ")
+            oa, ob = _lex_order(r["keys"][:, :m]), _lex_order(r2["keys"][:, :m])
+            nrm = torch.empty((3, m), dtype=torch.float64, device=self.device)
+            nrm[:, oa] = r2["data"][3:6, :m][:, ob]
+            pc._normals = nrm
         if return_keys:
             return pc, r["keys"][:, :m].t().cpu().numpy(), r["counts"][:m].cpu().numpy()
         return pc

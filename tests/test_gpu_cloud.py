@@ -524,3 +524,28 @@ def test_small_open3d_cloud_methods(rv, O):
     assert np.array_equal(pc.colors, np.full(P.shape, 0.7))
     bare = rv.PointCloud.from_arrays(P, None).paint_uniform_color([1.0, 0.0, 0.25])
     assert bare.has_colors() and np.array_equal(bare.colors, np.tile([1.0, 0.0, 0.25], (len(P), 1))) and np.array_equal(bare.points, P)
+
+
+def test_voxel_down_sample_averages_normals(rv, O):
+    """Open3D's VoxelDownSample averages colours AND normals per voxel (not renormalised)."""
+    from synth import bumpy_surface
+    rng = np.random.default_rng(19)
+    P = bumpy_surface(rng, 20000)
+    C = rng.random(P.shape)
+    for colors, dtype in ((C, "f64"), (None, "f64"), (C, "f32")):
+        pc = rv.PointCloud.from_arrays(P, colors, dtype=dtype)
+        pc.estimate_normals(rv.KDTreeSearchParamHybrid(0.02, 30)).orient_normals_towards_camera_location()
+        Pg, N = pc.points, pc.normals
+        down, keys, counts = pc.voxel_down_sample(0.01, return_keys=True)
+        assert down.has_normals() and len(down.normals) == len(down) and 1000 < len(down) < len(P)
+        rk, cent, col, cnt = O.voxel_down_sample(Pg, pc.colors if colors is not None else None, 0.01)
+        _, _, nrm, _ = O.voxel_down_sample(Pg, N, 0.01)
+        order = np.lexsort(keys.T[::-1])
+        assert np.array_equal(keys[order], rk) and np.array_equal(counts[order], cnt)
+        tol = dict(rtol=1e-12, atol=1e-14) if dtype == "f64" else dict(rtol=CENTROID_RTOL, atol=1e-7)
+        assert np.allclose(down.points[order], cent, **tol)
+        assert np.allclose(down.normals[order], nrm, rtol=1e-12, atol=1e-14)
+        if colors is not None:
+            assert np.allclose(down.colors[order], col, **tol)
+        single = counts[order] == 1
+        assert np.allclose(np.linalg.norm(down.normals[order][single], axis=1), 1.0, atol=1e-12)
