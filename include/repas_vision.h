@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RV_ABI_VERSION 1
+#define RV_ABI_VERSION 2
 
 typedef struct rv_ctx rv_ctx;
 typedef void *rv_stream; /* cudaStream_t */
@@ -91,8 +91,20 @@ enum RvDeprojectMode {
 };
 
 enum RvColorScale {
-  RV_COLOR_UNIT = 0, /* u8 / 255.0 in [0,1]   (create_masked_ply.py:100)             */
-  RV_COLOR_255 = 1   /* raw 0..255 as floats (Orbbec RGB_POINT, better_three_capture.py:235-237) */
+  RV_COLOR_UNIT = 0,   /* u8 / 255.0 in [0,1]   (create_masked_ply.py:100)             */
+  RV_COLOR_255 = 1,    /* raw 0..255 as floats (Orbbec RGB_POINT, better_three_capture.py:235-237) */
+  RV_COLOR_PACKED8 = 2 /* the colour bytes themselves: ONE plane (plane 3) of 32-bit words holding the bytes r,g,b,0 in
+                          memory order (what a PLY `uchar red green blue` record stores, create_masked_ply.py:177), so a
+                          point costs 16 instead of 24 bytes on its way to the host; float32 output only; the host expands
+                          k / 255.0 lazily */
+};
+
+/* layout of the colour image handed to rv_deproject_mask */
+enum RvColorFormat {
+  RV_COLORFMT_BGR8 = 0, /* [B,H,W,3] uint8, cv2 / SDK bgr8 */
+  RV_COLORFMT_NV12 = 1  /* [B,H*3/2,W] uint8 as the camera delivers it (better_three_capture.py:101-106,159): H rows of
+                           luma, H/2 rows of interleaved U,V; converted per kept pixel with the integer arithmetic of
+                           cv2.cvtColor(COLOR_YUV2BGR_NV12), see rv_nv12_to_bgr.  H and W must be even */
 };
 
 /* which K1 kernel runs: AUTO picks the TMA-fed pipeline when H*W % 16 == 0, W >= 32, the inputs are 16-byte
@@ -120,6 +132,8 @@ typedef struct RvDeprojectParams {
   int32_t out_dtype;   /* RvDType of the six output planes */
   int32_t color_scale; /* RvColorScale */
   int32_t kernel_select; /* RvKernelSelect */
+  int32_t color_format;  /* RvColorFormat of d_bgr */
+  int32_t reserved;
 } RvDeprojectParams;
 
 /* ---- context -------------------------------------------------------------- */
@@ -179,10 +193,11 @@ int rv_build_ray_table(rv_ctx *ctx, const RvCam *cam, double *d_table, rv_stream
  * and fuses the cloud predicates of distance_masking_on_ply.py:12-19,
  * view_point_cloud.py:109-116 and april_tag_bg_removal_pl.py:450-455.
  *  d_depth   [B,H,W] uint16 or float32 (params->depth_kind)
- *  d_bgr     [B,H,W,3] uint8, BGR order (cv2 / SDK bgr8); may be NULL (no colour planes written)
+ *  d_bgr     [B,H,W,3] uint8, BGR order (cv2 / SDK bgr8), or [B,H*3/2,W] NV12 when params->color_format says so;
+ *            may be NULL (no colour planes written)
  *  d_mask    [B,H,W] uint8 segmentation mask, or NULL
  *  d_ray_table  [H,W,2] float64 from rv_build_ray_table, required iff cam.model != RV_DIST_NONE
- *  d_out     six planes (x,y,z,r,g,b), plane p of frame b starts at element
+ *  d_out     six planes (x,y,z,r,g,b) -- four (x,y,z,packed rgb) with RV_COLOR_PACKED8 --, plane p of frame b starts at element
  *            p*plane_stride + b*frame_stride; compact modes write counts[b] elements per
  *            plane, dense modes H*W.  frame_stride is the per-frame capacity.
  *  d_valid   [B,H,W] uint8 (1 = kept) or NULL

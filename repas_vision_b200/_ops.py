@@ -78,9 +78,11 @@ def to_device(a, dev: torch.device, dtype=None) -> torch.Tensor:
 def deproject(depth, bgr, mask, cam: Camera, *, depth_kind, unit_rule="mul_f32", unit_scale=None, invert_mask=False,
               depth_trunc=None, z_clip=None, r_max=None, aabb=None, mode="compact_ordered", out_dtype="f32",
               color_scale="unit", want_valid=False, want_src_index=False, frame_capacity=None, out=None,
-              rays=None, kernel="auto"):
-    """depth [B,H,W] (uint16 or float32), bgr [B,H,W,3] uint8 or None, mask [B,H,W] uint8 or None, all on one
-    CUDA device.  Returns dict(data [6 or 3, B*cap], counts [B] int64, cap, valid, src_index)."""
+              rays=None, kernel="auto", color_format="bgr"):
+    """depth [B,H,W] (uint16 or float32), bgr [B,H,W,3] uint8 (or NV12 frames [B,H*3/2,W] with color_format="nv12") or
+    None, mask [B,H,W] uint8 or None, all on one CUDA device.  Returns dict(data [6 or 3, B*cap], counts [B] int64, cap,
+    valid, src_index); with color_scale="packed8" data has four float32 planes, the last one holding the bytes r,g,b,0
+    of every point."""
     dev = depth.device
     ctx = ctx_for(dev)
     B, H, W = depth.shape
@@ -109,8 +111,15 @@ def deproject(depth, bgr, mask, cam: Camera, *, depth_kind, unit_rule="mul_f32",
     p.out_dtype = _lib.RV_F32 if out_dtype == "f32" else _lib.RV_F64
     p.color_scale = _lib.COLOR_SCALES[color_scale]
     p.kernel_select = _lib.KERNELS[kernel]
+    p.color_format = _lib.COLOR_FORMATS[color_format]
+    if bgr is not None:
+        want = (B, H, W, 3) if color_format == "bgr" else (B, H * 3 // 2, W)
+        if tuple(bgr.shape) != want or bgr.dtype != torch.uint8:
+            raise ValueError(f"colour frames must be uint8 {want} for color_format={color_format!r}, got {tuple(bgr.shape)}")
+    if color_scale == "packed8" and out_dtype != "f32":
+        raise ValueError("color_scale='packed8' stores one 32-bit colour word per point: float32 output only")
     cap = int(frame_capacity) if frame_capacity is not None else P
-    planes = 6 if bgr is not None else 3
+    planes = 3 if bgr is None else (4 if color_scale == "packed8" else 6)
     packed = mode == "compact_packed"
     plane_stride = B * cap
     if out is None:

@@ -447,10 +447,11 @@ def create_from_rgbd_image(color, depth, intrinsic, extrinsic=None, *, depth_sca
 class CloudBatch:
     """Result of a batched deprojection: planes [6 or 3, B*cap] with frame b at columns [b*cap, b*cap+counts[b])."""
 
-    def __init__(self, r: dict, B: int, H: int, W: int, has_color: bool, dense: bool):
+    def __init__(self, r: dict, B: int, H: int, W: int, has_color: bool, dense: bool, packed_color: bool = False):
         self.data, self.counts, self.cap = r["data"], r["counts"], r["cap"]
         self.valid, self.src_index = r["valid"], r["src_index"]
         self.B, self.H, self.W, self.has_color, self.dense = B, H, W, has_color, dense
+        self.packed_color = packed_color and has_color  # plane 3 holds the bytes r,g,b,0 (color_scale="packed8")
         self._counts_host = None
 
     def counts_host(self) -> np.ndarray:
@@ -458,10 +459,26 @@ class CloudBatch:
             self._counts_host = self.counts.cpu().numpy()
         return self._counts_host
 
+    def _n(self, b: int) -> int:
+        return min(self.H * self.W if self.dense else int(self.counts_host()[b]), self.cap)
+
     def frame(self, b: int) -> PointCloud:
-        n = self.H * self.W if self.dense else int(self.counts_host()[b])
-        n = min(n, self.cap)
+        if self.packed_color:
+            raise RuntimeError("this batch carries packed 8-bit colours (color_scale='packed8'): use .rgb8(b) / .xyz(b), or "
+                               "deproject with color_scale='unit' for PointCloud frames")
+        n = self._n(b)
         return PointCloud(self.data[:, b * self.cap:b * self.cap + max(n, 1)], n, self.has_color)
+
+    def xyz(self, b: int) -> torch.Tensor:
+        """[3, n] device view of frame b's coordinates."""
+        return self.data[:3, b * self.cap:b * self.cap + self._n(b)]
+
+    def rgb8(self, b: int) -> torch.Tensor:
+        """[n, 3] uint8 device view (r, g, b) of frame b's colours; packed-colour batches only."""
+        if not self.packed_color:
+            raise RuntimeError("rgb8 needs a batch made with color_scale='packed8'")
+        n = self._n(b)
+        return self.data[3, b * self.cap:b * self.cap + n].view(torch.uint8).view(n, 4)[:, :3]
 
     def __len__(self):
         return self.B
@@ -470,9 +487,13 @@ class CloudBatch:
 def deproject_batch(depth, bgr, camera, mask=None, *, unit_rule: str = "mul_f32", depth_scale=None, invert_mask=False,
                     depth_trunc=None, max_distance=None, z_clip=None, aabb=None, mode: str = "compact_ordered",
                     dtype: str = "f32", color_scale: str = "unit", want_valid=False, want_src_index=False,
-                    frame_capacity=None, out=None, kernel: str = "auto") -> CloudBatch:
+                    frame_capacity=None, out=None, kernel: str = "auto", color_format: str = "bgr") -> CloudBatch:
     """Batched form of create_masked_pointcloud: depth [B,H,W] (uint16 raw or float32 metres), bgr [B,H,W,3] uint8,
-    mask [B,H,W] uint8 or None.  One kernel launch for the whole batch."""
+    mask [B,H,W] uint8 or None.  One kernel launch for the whole batch.
+
+    color_format="nv12": `bgr` holds the camera's NV12 frames [B, H*3/2, W] (better_three_capture.py:101-106,159); the
+    kernel converts the kept pixels itself, identical to feeding cv2.cvtColor(..., COLOR_YUV2BGR_NV12) images.
+    color_scale="packed8": colours stay bytes (one r,g,b,0 word per point in a fourth plane) instead of three float planes."""
     cam = _as_camera(camera)
     dev = depth.device if _is_torch_cuda(depth) else _ops.require_cuda()
     d = _ops.to_device(depth, dev)
@@ -485,7 +506,10 @@ def deproject_batch(depth, bgr, camera, mask=None, *, unit_rule: str = "mul_f32"
         d = d.to(torch.float32)
     B, H, W = d.shape
     c = None if bgr is None else _ops.to_device(bgr, dev, torch.uint8)
-    if c is not None and tuple(c.shape) != (B, H, W, 3):
+    if color_format not in ("bgr", "nv12"):
+        raise ValueError("color_format must be 'bgr' or 'nv12'")
+    want = (B, H, W, 3) if color_format == "bgr" else (B, H * 3 // 2, W)
+    if c is not None and (tuple(c.shape) != want or (color_format == "nv12" and (H % 2 or W % 2))):
         raise RuntimeError(f"Color/depth size mismatch: color {tuple(c.shape)}, depth {(B, H, W)}")
     m = None if mask is None else _ops.to_device(mask, dev, torch.uint8)
     if m is not None and tuple(m.shape) != (B, H, W):
@@ -493,8 +517,8 @@ def deproject_batch(depth, bgr, camera, mask=None, *, unit_rule: str = "mul_f32"
     r = _ops.deproject(d, c, m, cam, depth_kind=kind, unit_rule=unit_rule, unit_scale=depth_scale, invert_mask=invert_mask,
                        depth_trunc=depth_trunc, r_max=max_distance, z_clip=z_clip, aabb=aabb, mode=mode, out_dtype=dtype,
                        color_scale=color_scale, want_valid=want_valid, want_src_index=want_src_index,
-                       frame_capacity=frame_capacity, out=out, kernel=kernel)
-    return CloudBatch(r, B, H, W, c is not None, mode.startswith("dense"))
+                       frame_capacity=frame_capacity, out=out, kernel=kernel, color_format=color_format)
+    return CloudBatch(r, B, H, W, c is not None, mode.startswith("dense"), color_scale == "packed8")
 
 
 # --------------------------------------------------------------------------- a6

@@ -98,7 +98,13 @@ __global__ void __launch_bounds__(kThreads) k_deproject(const DeprojArgs a) {
         else
           draw[j] = __float_as_uint(__ldg(reinterpret_cast<const float *>(a.depth) + g));
         if (a.use_mask) mraw[j] = __ldg(a.mask + g);
-        if (a.bgr) {
+        if (a.bgr && a.color_nv12) {
+          // NV12 frame: H rows of luma, then H/2 rows of interleaved U,V (one pair per 2 x 2 pixels)
+          const uint8_t *f = a.bgr + (long long)b * (a.P + (a.P >> 1));
+          const int pv = p / a.W, pu = p - pv * a.W;
+          const uint8_t *uv = f + a.P + (long long)(pv >> 1) * a.W + (pu & ~1);
+          craw[j] = rv_nv12_pixel_bgr(__ldg(f + p), __ldg(uv), __ldg(uv + 1));
+        } else if (a.bgr) {
           const uint8_t *c = a.bgr + 3 * g;
           craw[j] = (uint32_t)__ldg(c) | ((uint32_t)__ldg(c + 1) << 8) | ((uint32_t)__ldg(c + 2) << 16);
         }
@@ -223,7 +229,9 @@ __global__ void __launch_bounds__(kThreads) k_deproject(const DeprojArgs a) {
           o[0] = xs[j];
           o[a.plane_stride] = ys[j];
           o[2 * a.plane_stride] = zs[j];
-          if (a.bgr) {
+          if (a.bgr && a.color_packed) {
+            reinterpret_cast<uint32_t *>(o + 3 * a.plane_stride)[0] = __byte_perm(craw[j], 0u, 0x4012);  // bytes r,g,b,0
+          } else if (a.bgr) {
             o[3 * a.plane_stride] = color_value<OutT>((craw[j] >> 16) & 255u, a.color_255);
             o[4 * a.plane_stride] = color_value<OutT>((craw[j] >> 8) & 255u, a.color_255);
             o[5 * a.plane_stride] = color_value<OutT>(craw[j] & 255u, a.color_255);
@@ -236,7 +244,9 @@ __global__ void __launch_bounds__(kThreads) k_deproject(const DeprojArgs a) {
         o[0] = ok ? xs[j] : bad;
         o[a.plane_stride] = ok ? ys[j] : bad;
         o[2 * a.plane_stride] = ok ? zs[j] : bad;
-        if (a.bgr) {
+        if (a.bgr && a.color_packed) {
+          reinterpret_cast<uint32_t *>(o + 3 * a.plane_stride)[0] = ok ? __byte_perm(craw[j], 0u, 0x4012) : 0u;
+        } else if (a.bgr) {
           o[3 * a.plane_stride] = ok ? color_value<OutT>((craw[j] >> 16) & 255u, a.color_255) : (OutT)0;
           o[4 * a.plane_stride] = ok ? color_value<OutT>((craw[j] >> 8) & 255u, a.color_255) : (OutT)0;
           o[5 * a.plane_stride] = ok ? color_value<OutT>(craw[j] & 255u, a.color_255) : (OutT)0;
@@ -584,6 +594,12 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
       (p->unit_rule < RV_UNIT_MUL_F32 || p->unit_rule > RV_UNIT_DIV_F64 || !(p->unit_scale > 0.0)))
     RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad unit rule / scale");
   if (p->use_seg_mask && !d_mask) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: use_seg_mask set but mask is null");
+  if (p->color_scale < RV_COLOR_UNIT || p->color_scale > RV_COLOR_PACKED8) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad color_scale");
+  if (p->color_scale == RV_COLOR_PACKED8 && p->out_dtype != RV_F32)
+    RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: RV_COLOR_PACKED8 needs float32 output planes (a colour word per point)");
+  if (p->color_format != RV_COLORFMT_BGR8 && p->color_format != RV_COLORFMT_NV12) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad color_format");
+  if (p->color_format == RV_COLORFMT_NV12 && d_bgr && ((H & 1) || (W & 1)))
+    RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: NV12 frames need even H and W");
   if (p->cam.model != RV_DIST_NONE && p->cam.model != RV_DIST_MODIFIED_BROWN_CONRADY && !d_ray_table)
     RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: distorted camera needs a ray table (rv_build_ray_table)");
   if (!(p->cam.fx != 0.0) || !(p->cam.fy != 0.0)) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: fx/fy must be non-zero");
@@ -648,6 +664,8 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
   a.use_radius = p->use_radius ? 1 : 0;
   a.use_aabb = p->use_aabb ? 1 : 0;
   a.color_255 = p->color_scale == RV_COLOR_255;
+  a.color_packed = (d_bgr && p->color_scale == RV_COLOR_PACKED8) ? 1 : 0;
+  a.color_nv12 = (d_bgr && p->color_format == RV_COLORFMT_NV12) ? 1 : 0;
   a.zmin_f = float_at_least(a.z_min);
   a.zmax_f = float_at_most(a.z_max);
   for (int i = 0; i < 3; ++i) {

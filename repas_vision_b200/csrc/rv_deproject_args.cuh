@@ -27,6 +27,8 @@ struct DeprojArgs {
   double amin[3], amax[3];
   int use_mask, invert_mask, use_trunc, use_zclip, use_radius, use_aabb;
   int color_255;
+  int color_packed;  // RV_COLOR_PACKED8: plane 3 holds the bytes r,g,b,0 of every point (float32 output only)
+  int color_nv12;    // `bgr` points at NV12 frames ([H*3/2, W] bytes each)
   // float32 forms of the cloud predicates (exactly equivalent on float32 storage; rv_deproject_tma.cu)
   float zmin_f, zmax_f;        // smallest float >= z_min, largest float <= z_max
   float amin_f[3], amax_f[3];  // same rounding for the box
@@ -45,6 +47,20 @@ struct DeprojArgs {
 constexpr int kFastTilePx = RV_K1_CW * 32 * RV_K1_ITERS;
 constexpr int kGenericTilePx = 2048;
 constexpr int kMinTilePx = kFastTilePx < kGenericTilePx ? kFastTilePx : kGenericTilePx;  // sizes the workspace
+
+// cv2.cvtColor(COLOR_YUV2BGR_NV12): OpenCV's fixed-point ITU-R BT.601 conversion with 20-bit coefficients (the arithmetic
+// rv_misc.cu checks bit for bit against cv2).  Returns the bytes b | g << 8 | r << 16.
+__device__ __forceinline__ uint32_t rv_nv12_pixel_bgr(uint32_t Y, uint32_t U, uint32_t V) {
+  const int u = (int)U - 128, v = (int)V - 128;
+  const int ruv = (1 << 19) + 1673527 * v;
+  const int guv = (1 << 19) - 852492 * v - 409993 * u;
+  const int buv = (1 << 19) + 2116026 * u;
+  const int y = max(0, (int)Y - 16) * 1220542;
+  const uint32_t b = (uint32_t)min(max((y + buv) >> 20, 0), 255);
+  const uint32_t g = (uint32_t)min(max((y + guv) >> 20, 0), 255);
+  const uint32_t r = (uint32_t)min(max((y + ruv) >> 20, 0), 255);
+  return b | (g << 8) | (r << 16);
+}
 
 bool rv_deproject_fast_eligible(const DeprojArgs &a, int mode);
 cudaError_t rv_deproject_fast_launch(const rv_ctx *ctx, const DeprojArgs &a, int mode, int out_dtype, int depth_kind,

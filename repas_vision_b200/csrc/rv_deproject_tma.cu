@@ -24,10 +24,22 @@
 //    decoupled look-back of rv_common.cuh remains as the fallback when the peek finds no prefix yet;
 //  * the radius / z-clip / AABB decisions are taken on float32 values with thresholds rounded so that
 //    the decision equals the float64 predicate of the oracle bit for bit (exact float64 re-evaluation
-//    inside a 2^-20 band around the sphere).
+//    inside a 2^-20 band around the sphere);
+//  * a warp whose 256-pixel run holds no candidate at all (holes, background beyond the distance mask: four
+//    runs out of five on the benchmark workload) finds that out with ONE 16-byte shared-memory load per lane
+//    and six packed 16-bit min/add instructions, posts a zero total and goes straight to the next tile: it
+//    neither computes pixel coordinates nor waits for the other warps.  The run totals are exchanged through
+//    an mbarrier (arrive by everybody, wait only by the warps that have points to place and by warp 0,
+//    which publishes the tile's prefix), not through a CTA barrier;
+//  * colour arrives as BGR8 or as the camera's NV12 frames (luma row + the interleaved chroma rows of the
+//    tile's row segments, fetched by the same bulk copies); NV12 is converted per KEPT pixel with the
+//    integer arithmetic of cv2.cvtColor, so the BGR image never exists in memory
+//    (better_three_capture.py:101-106,159);
+//  * colours leave as k/255 floats (three planes) or, RV_COLOR_PACKED8, as one plane of r,g,b,0 bytes.
 //
-// Eligibility (checked by rv_deproject_fast_eligible): H*W % 16 == 0, W >= 32, 16-byte aligned inputs (a COMPACT_UNORDERED
-// request is served by the ordered variant).  Everything else runs k_deproject.
+// Eligibility (checked by rv_deproject_fast_eligible): H*W % 16 == 0, W >= 32, 16-byte aligned inputs; NV12 frames
+// additionally W % 16 == 0 and W >= 256 (a COMPACT_UNORDERED request is served by the ordered variant).
+// Everything else runs k_deproject.
 #include "rv_common.cuh"
 #include "rv_deproject_args.cuh"
 
@@ -51,16 +63,17 @@ constexpr int kTileT = kCT * kItersT;   // 2048 pixels
 constexpr int kStages = RV_K1_STAGES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+// mbarrier operations on 32-bit shared-window addresses (computed once per thread, outside the tile loop)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
@@ -69,14 +82,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
 }
 // Waiting threads suspend in hardware for up to `hint_ns` and are woken by the completing arrive, instead of
 // burning issue slots on a poll loop (a plain try_wait returned within a few ns here, and 1 + 8 warps per CTA
 // polling cost ~20 % of all issued instructions).
-__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parity, uint32_t hint_ns) {
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
   uint32_t ok;
   asm volatile(
       "{\n"
@@ -85,22 +98,21 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parit
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   while (!mbar_try_wait_hint(bar, parity, 20000u)) {
   }
 }
 // 1-D bulk copy global -> shared, completion reported to an mbarrier in bytes (TMA engine, no tensor map)
-__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }
 
 // n / d for 0 <= n < 2^24 (exact int -> float) with a precomputed float reciprocal and one fix-up; callers fall
 // back to the integer divide above that range
@@ -148,7 +160,8 @@ __device__ __forceinline__ double qnan<double>() {
 template <typename OutT, int DK, bool kGen>
 struct Layout {
   static constexpr int kDepthB = DK == RV_DEPTH_U16 ? 2 : 4;
-  // the segmentation-mask bytes and the source-index column exist only in the run-time-flag variant
+  // colour bytes of a stage: 3 per pixel for BGR8; NV12 uses the first 2 (one luma byte, one byte of its U,V pair).
+  // The segmentation-mask bytes and the source-index column exist only in the run-time-flag variant
   static constexpr int kStageBytes = kTileT * (kDepthB + 3 + (kGen ? 1 : 0));
   // per-warp staging: x, y, z (OutT), packed colour (u32) [, source index inside the tile (u16)]
   static constexpr int kWarpStage = kWarpPx * (3 * (int)sizeof(OutT) + 4 + (kGen ? 2 : 0));
@@ -180,13 +193,18 @@ template <int OFF>
 __device__ __forceinline__ void st_global(unsigned long long addr, double v) {
   asm volatile("st.global.f64 [%0+%1], %2;" ::"l"(addr), "n"(OFF), "d"(v) : "memory");
 }
+__device__ __forceinline__ void st_global_u32(unsigned long long addr, uint32_t v) {
+  asm volatile("st.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
 
 // SPEC selects how much of the predicate set is compiled in:
 //   0  uint16/float depth with the MUL_F32 unit rule, colour, validity only
 //   1  the same plus the radius mask (the canopy / BASELINE configuration)
 //   2  everything, decided by the run-time flags of DeprojArgs
 //   3  as 1 with the DIV_F32 unit rule (f32(d) / 1000: the RealSense canopy scripts)
-template <typename OutT, int DK, int MODE, int SPEC>
+// CF (SPEC != 2 only; the run-time-flag variant reads a.color_packed / a.color_nv12): bit 0 = RV_COLOR_PACKED8 output,
+// bit 1 = NV12 input.
+template <typename OutT, int DK, int MODE, int SPEC, int CF>
 __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)) k_deproject_tma(const DeprojArgs a) {
   constexpr bool kPacked = MODE == RV_MODE_COMPACT_PACKED;
   constexpr bool kOrdered = MODE == RV_MODE_COMPACT_ORDERED || kPacked;
@@ -198,23 +216,28 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
+  __shared__ __align__(8) uint64_t tot_bar[2];                // the warps' run totals of a tile are posted
   __shared__ __align__(8) uint64_t base_bar[8];               // slow path: warp 0 posts the tile base
   __shared__ int4 s_info[kStages];                            // {status index or -1, frame, tile in frame, pixels in tile}
-  __shared__ __align__(16) uint32_t s_tot[2][kCW];            // kept points of the tile's eight warp runs
+  __shared__ __align__(16) uint32_t s_tot[4][kCW];            // kept points of the tile's eight warp runs
   __shared__ __align__(8) unsigned long long s_peek[2];       // predecessor status word seen by warp 0
   __shared__ uint32_t s_base[8];
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar), tot_a = smem_u32(tot_bar),
+                 base_a = smem_u32(base_bar);
 
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kCW);
+      mbar_init(full_a + 8 * s, 1);
+      mbar_init(empty_a + 8 * s, kCW);
     }
+    mbar_init(tot_a, kCW);
+    mbar_init(tot_a + 8, kCW);
 #pragma unroll
-    for (int s = 0; s < 8; ++s) mbar_init(&base_bar[s], 1);
+    for (int s = 0; s < 8; ++s) mbar_init(base_a + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -224,13 +247,17 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
   const int P = a.P;
   const bool has_bgr = kGen ? (a.bgr != nullptr) : true;
   const bool has_mask = kGen ? (a.use_mask != 0) : false;
+  const bool nv12 = kGen ? (a.color_nv12 != 0) : ((CF & 2) != 0);
+  const bool pk8 = kGen ? (a.color_packed != 0) : ((CF & 1) != 0);
   const bool small_idx = a.total_tiles < (1 << 24) && P < (1 << 24);
+  const uint32_t ring_a = smem_u32(smem);
 
   // ============================================================ producer warp
   if (warp == kCW) {
     if (lane == 0) {
       const float rcpB = 1.0f / (float)nB;
       const float rcpT = 1.0f / (float)tpf;
+      const float rcpWp = 1.0f / (float)a.W;
       // tickets are requested one tile ahead so the atomic's round trip hides behind the wait for a free stage
       int ticket = RV_K1_TICKET_AHEAD ? (int)atomicAdd(a.ticket, 1u) : 0;
       int left = 0;  // tickets still unused from the last batch
@@ -238,7 +265,7 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
         const int s = it % kStages;
         int next = 0;
         if (RV_K1_TICKET_AHEAD) next = ticket < a.total_tiles ? (int)atomicAdd(a.ticket, 1u) : ticket;
-        mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
+        mbar_wait(empty_a + 8 * s, ((it / kStages) & 1) ^ 1);
         if (!RV_K1_TICKET_AHEAD) {
           // (packed mode is ONE chain through the batch: consecutive tickets depend on each other, so they are taken singly)
           constexpr int kBatch = kPacked ? 1 : RV_K1_TICKET_BATCH;
@@ -252,7 +279,7 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
         }
         if (ticket >= a.total_tiles) {
           s_info[s] = make_int4(-1, 0, 0, 0);
-          mbar_arrive(&full_bar[s]);
+          mbar_arrive(full_a + 8 * s);
           break;
         }
         int b, t;
@@ -267,14 +294,33 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
         const int npx = min(kTileT, P - px0);
         s_info[s] = make_int4(b * tpf + t, b, t, npx);
         const long long g = (long long)b * P + px0;
-        unsigned char *st = smem + (size_t)s * L::kStageBytes;
+        const uint32_t st = ring_a + (uint32_t)(s * L::kStageBytes);
+        const uint32_t fb = full_a + 8 * s;
         uint32_t bytes = (uint32_t)npx * kDepthB;
-        if (has_bgr) bytes += (uint32_t)npx * 3;
+        if (has_bgr) bytes += (uint32_t)npx * (nv12 ? 2u : 3u);
         if (has_mask) bytes += (uint32_t)npx;
-        mbar_arrive_expect_tx(&full_bar[s], bytes);
-        bulk_load(st, reinterpret_cast<const unsigned char *>(a.depth) + g * kDepthB, (uint32_t)npx * kDepthB, &full_bar[s]);
-        if (has_bgr) bulk_load(st + kTileT * kDepthB, a.bgr + g * 3, (uint32_t)npx * 3, &full_bar[s]);
-        if (kGen && has_mask) bulk_load(st + kTileT * (kDepthB + 3), a.mask + g, (uint32_t)npx, &full_bar[s]);
+        mbar_arrive_expect_tx(fb, bytes);
+        bulk_load(st, reinterpret_cast<const unsigned char *>(a.depth) + g * kDepthB, (uint32_t)npx * kDepthB, fb);
+        if (has_bgr) {
+          if (nv12) {
+            // luma of the tile: one run; chroma: the tile's row segments, each a run of the interleaved U,V row v / 2.
+            // Laid out by pixel index inside the tile, so pixel li finds its pair at (li & ~1), (li | 1).
+            const unsigned char *frame = a.bgr + (long long)b * (P + (P >> 1));
+            bulk_load(st + kTileT * kDepthB, frame + px0, (uint32_t)npx, fb);
+            int v = fast_div(px0, a.W, rcpWp, small_idx);
+            int u = px0 - v * a.W;
+            for (int done = 0; done < npx;) {
+              const int len = min(a.W - u, npx - done);
+              bulk_load(st + kTileT * (kDepthB + 1) + done, frame + P + (long long)(v >> 1) * a.W + u, (uint32_t)len, fb);
+              done += len;
+              u = 0;
+              ++v;
+            }
+          } else {
+            bulk_load(st + kTileT * kDepthB, a.bgr + g * 3, (uint32_t)npx * 3, fb);
+          }
+        }
+        if (kGen && has_mask) bulk_load(st + kTileT * (kDepthB + 3), a.mask + g, (uint32_t)npx, fb);
         if (RV_K1_TICKET_AHEAD) ticket = next;
       }
     }
@@ -296,6 +342,9 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
   const int unit_rule = kGen ? a.unit_rule : (SPEC == 3 ? RV_UNIT_DIV_F32 : RV_UNIT_MUL_F32);
   // raw depths in [1, dcand) are candidates; dcand folds "z alone is already beyond the sphere" into an integer compare
   const uint32_t dcand_m1 = ((kF32 && use_radius && fast_radius) ? a.d_cand : 65536u) - 1u;
+  // the whole-run rejection test needs nothing but the raw depths; the per-pixel validity image (kGen) and the dense
+  // modes have something to write for every pixel, so they walk the groups
+  const bool quick = DK == RV_DEPTH_U16 && kOrdered && !(kGen && a.valid);
 
   // this warp's staging area: room for its whole 256-pixel run
   unsigned char *const wst = smem + L::kRingBytes + (size_t)warp * L::kWarpStage;
@@ -307,10 +356,11 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
 
   unsigned long long peek_nxt = 0;  // warp 0 lane 0: status word of the NEXT tile's predecessor, requested a tile early
   int peek_nxt_tile = -1;
+  const int w0 = warp * kWarpPx;  // each warp owns 256 consecutive pixels of the tile: its kept points are ONE run of the output
 
   for (int it = 0;; ++it) {
     const int s = it % kStages;
-    mbar_wait(&full_bar[s], (it / kStages) & 1);
+    mbar_wait(full_a + 8 * s, (it / kStages) & 1);
     const int4 info = s_info[s];
     const int tile = info.x;  // index into status[]
     if (tile < 0) break;
@@ -318,7 +368,7 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
     const int n_pred = kPacked ? tile : t;
     const int px0 = t * kTileT;
     unsigned char *st = smem + (size_t)s * L::kStageBytes;
-    const uint8_t *s_bgr = st + kTileT * kDepthB;
+    const uint8_t *s_col = st + kTileT * kDepthB;
     const uint8_t *s_msk = st + kTileT * (kDepthB + 3);
 
     // early peek (warp 0, lane 0): the predecessor's status word.  The request for the NEXT tile is issued here as well
@@ -331,19 +381,17 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
       }
       const int sn = (it + 1) % kStages;
       peek_nxt_tile = -1;
-      if (mbar_try_wait(&full_bar[sn], ((it + 1) / kStages) & 1)) {
+      if (mbar_try_wait(full_a + 8 * sn, ((it + 1) / kStages) & 1)) {
         const int4 nx = s_info[sn];
         if (nx.x >= 0 && (kPacked ? nx.x : nx.z) > 0) {
           peek_nxt = rv_ld_relaxed(a.status + nx.x - 1);
           peek_nxt_tile = nx.x;
         }
       }
-      s_peek[it & 1] = peek;  // read by every warp after the tile barrier
+      s_peek[it & 1] = peek;  // read by the warps that drain, after the totals barrier
     }
 
-    // each warp owns 256 consecutive pixels of the tile, so its kept points are ONE contiguous run of the output
-    const int w0 = warp * kWarpPx;
-    // a partial last tile: zero the depth of this warp's own pixels beyond the frame so the loop needs no bounds test
+    // a partial last tile: zero the depth of this warp's own pixels beyond the frame so the loops need no bounds test
     if (npx < kTileT) {
 #pragma unroll
       for (int j = 0; j < kItersT; ++j) {
@@ -356,153 +404,176 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
       __syncwarp();
     }
 
-    const int p0 = px0 + w0 + lane;  // this lane's pixel in group j = 0
-    const int v0 = fast_div(p0, W, rcpW, small_idx);
-    const int u0 = p0 - v0 * W;
-    uint32_t run = 0;  // kept points of this warp so far (warp-uniform)
-#pragma unroll
-    for (int j = 0; j < kItersT; ++j) {
-      const int li = w0 + j * 32 + lane;  // index inside the tile
-      float z32 = 0.0f;
-      double z64 = 0.0;
-      uint32_t draw = 0;
-      bool ok;
-      if (DK == RV_DEPTH_U16) {
-        draw = reinterpret_cast<const uint16_t *>(st)[li];
-        ok = (draw - 1u) < dcand_m1;  // draw != 0 && draw < dcand
-      } else {
-        z32 = reinterpret_cast<const float *>(st)[li];
-        ok = (z32 > 0.0f) && (z32 < inf_f);
-        if (kF32 && use_radius && fast_radius) ok = ok && (z32 * z32 < a.r2_hi_f);
-      }
-      if (kGen && has_mask) {
-        const uint32_t m = s_msk[li];
-        ok = ok && (a.invert_mask ? (m == 0) : (m != 0));
-      }
+    // ---- whole-run rejection: eight raw depths per lane in one load, min over (d - 1) mod 2^16 with packed 16-bit ops
+    bool any_cand = true;
+    if (quick) {
+      const uint4 q = *reinterpret_cast<const uint4 *>(st + 2 * (w0 + 8 * lane));
+      const uint32_t m2 = __vminu2(__vminu2(__vsub2(q.x, 0x00010001u), __vsub2(q.y, 0x00010001u)),
+                                   __vminu2(__vsub2(q.z, 0x00010001u), __vsub2(q.w, 0x00010001u)));
+      any_cand = __any_sync(0xffffffffu, min(m2 & 0xffffu, m2 >> 16) < dcand_m1);
+    }
 
-      OutT xo = (OutT)0, yo = (OutT)0;
-      if (__any_sync(0xffffffffu, ok)) {  // warp-uniform: 32 consecutive holes / far pixels cost no geometry
+    uint32_t run = 0;  // kept points of this warp so far (warp-uniform)
+    if (any_cand) {
+      const int p0 = px0 + w0 + lane;  // this lane's pixel in group j = 0
+      const int v0 = fast_div(p0, W, rcpW, small_idx);
+      const int u0 = p0 - v0 * W;
+#pragma unroll
+      for (int j = 0; j < kItersT; ++j) {
+        const int li = w0 + j * 32 + lane;  // index inside the tile
+        float z32 = 0.0f;
+        double z64 = 0.0;
+        uint32_t draw = 0;
+        bool ok;
         if (DK == RV_DEPTH_U16) {
-          const float df = (float)draw;
-          if (unit_rule == RV_UNIT_MUL_F32) {
-            z32 = df * unit_f;
-          } else if (unit_rule == RV_UNIT_DIV_F32) {
-            z32 = rv_divf(df, unit_f, a.unit_rcp_f);
+          draw = reinterpret_cast<const uint16_t *>(st)[li];
+          ok = (draw - 1u) < dcand_m1;  // draw != 0 && draw < dcand
+        } else {
+          z32 = reinterpret_cast<const float *>(st)[li];
+          ok = (z32 > 0.0f) && (z32 < inf_f);
+          if (kF32 && use_radius && fast_radius) ok = ok && (z32 * z32 < a.r2_hi_f);
+        }
+        if (kGen && has_mask) {
+          const uint32_t m = s_msk[li];
+          ok = ok && (a.invert_mask ? (m == 0) : (m != 0));
+        }
+
+        OutT xo = (OutT)0, yo = (OutT)0;
+        if (__any_sync(0xffffffffu, ok)) {  // warp-uniform: 32 consecutive holes / far pixels cost no geometry
+          if (DK == RV_DEPTH_U16) {
+            const float df = (float)draw;
+            if (unit_rule == RV_UNIT_MUL_F32) {
+              z32 = df * unit_f;
+            } else if (unit_rule == RV_UNIT_DIV_F32) {
+              z32 = rv_divf(df, unit_f, a.unit_rcp_f);
+            } else {
+              z64 = rv_div((double)draw, a.unit_scale, a.unit_rcp);
+              z32 = (float)z64;
+            }
+          }
+          if (kGen && a.use_trunc) ok = ok && !(z32 >= a.trunc_f);
+          int uj = u0 + j * 32, vj = v0;
+          if (wide) {
+            if (uj >= W) {
+              uj -= W;
+              ++vj;
+            }
           } else {
-            z64 = rv_div((double)draw, a.unit_scale, a.unit_rcp);
-            z32 = (float)z64;
+            const int p = p0 + j * 32;
+            vj = fast_div(p, W, rcpW, small_idx);
+            uj = p - vj * W;
           }
-        }
-        if (kGen && a.use_trunc) ok = ok && !(z32 >= a.trunc_f);
-        int uj = u0 + j * 32, vj = v0;
-        if (wide) {
-          if (uj >= W) {
-            uj -= W;
-            ++vj;
+          if (!(DK == RV_DEPTH_U16 && unit_rule == RV_UNIT_DIV_F64)) z64 = (double)z32;
+          double x64, y64;
+          if (kGen && a.rays) {  // distorted camera: the normalised ray of every pixel comes from the (L2-resident) table
+            double2 r = make_double2(0.0, 0.0);
+            if (li < npx) r = __ldg(a.rays + px0 + li);
+            x64 = z64 * r.x;
+            y64 = z64 * r.y;
+          } else {
+            x64 = rv_div(((double)uj - cx) * z64, fx, rfx);
+            y64 = rv_div(((double)vj - cy) * z64, fy, rfy);
           }
-        } else {
-          const int p = p0 + j * 32;
-          vj = fast_div(p, W, rcpW, small_idx);
-          uj = p - vj * W;
-        }
-        if (!(DK == RV_DEPTH_U16 && unit_rule == RV_UNIT_DIV_F64)) z64 = (double)z32;
-        double x64, y64;
-        if (kGen && a.rays) {  // distorted camera: the normalised ray of every pixel comes from the (L2-resident) table
-          double2 r = make_double2(0.0, 0.0);
-          if (li < npx) r = __ldg(a.rays + px0 + li);
-          x64 = z64 * r.x;
-          y64 = z64 * r.y;
-        } else {
-          x64 = rv_div(((double)uj - cx) * z64, fx, rfx);
-          y64 = rv_div(((double)vj - cy) * z64, fy, rfy);
-        }
-        xo = (OutT)x64;
-        yo = (OutT)y64;
-        if (kF32) {
-          // float32 storage: compare the stored floats against thresholds rounded toward the kept side;
-          // identical to the float64 predicate on their exact up-casts
-          const float xf = (float)xo, yf = (float)yo;
-          if (kGen) {
-            if (a.use_zclip) ok = ok && (z32 >= a.zmin_f) && (z32 <= a.zmax_f);
-            if (a.use_aabb)
-              ok = ok && (xf >= a.amin_f[0]) && (xf <= a.amax_f[0]) && (yf >= a.amin_f[1]) && (yf <= a.amax_f[1]) &&
-                   (z32 >= a.amin_f[2]) && (z32 <= a.amax_f[2]);
-          }
-          if (use_radius) {
-            bool in;
-            if (fast_radius) {
-              const float sf = fmaf(z32, z32, fmaf(yf, yf, xf * xf));
-              in = sf <= a.r2_lo_f;
-              if (sf > a.r2_lo_f && sf < a.r2_hi_f) {  // inside the 2^-20 band: the float64 sum decides
+          xo = (OutT)x64;
+          yo = (OutT)y64;
+          if (kF32) {
+            // float32 storage: compare the stored floats against thresholds rounded toward the kept side;
+            // identical to the float64 predicate on their exact up-casts
+            const float xf = (float)xo, yf = (float)yo;
+            if (kGen) {
+              if (a.use_zclip) ok = ok && (z32 >= a.zmin_f) && (z32 <= a.zmax_f);
+              if (a.use_aabb)
+                ok = ok && (xf >= a.amin_f[0]) && (xf <= a.amax_f[0]) && (yf >= a.amin_f[1]) && (yf <= a.amax_f[1]) &&
+                     (z32 >= a.amin_f[2]) && (z32 <= a.amax_f[2]);
+            }
+            if (use_radius) {
+              bool in;
+              if (fast_radius) {
+                const float sf = fmaf(z32, z32, fmaf(yf, yf, xf * xf));
+                in = sf <= a.r2_lo_f;
+                if (sf > a.r2_lo_f && sf < a.r2_hi_f) {  // inside the 2^-20 band: the float64 sum decides
+                  const double X = (double)xf, Y = (double)yf, Z = (double)z32;
+                  in = ((X * X + Y * Y) + Z * Z) < a.r2_thresh;
+                }
+              } else {
                 const double X = (double)xf, Y = (double)yf, Z = (double)z32;
                 in = ((X * X + Y * Y) + Z * Z) < a.r2_thresh;
               }
-            } else {
-              const double X = (double)xf, Y = (double)yf, Z = (double)z32;
-              in = ((X * X + Y * Y) + Z * Z) < a.r2_thresh;
+              ok = ok && in;
             }
-            ok = ok && in;
+          } else {
+            const double X = (double)xo, Y = (double)yo, Z = z64;
+            if (kGen) {
+              if (a.use_zclip) ok = ok && (Z >= a.z_min) && (Z <= a.z_max);
+              if (a.use_aabb)
+                ok = ok && (X >= a.amin[0]) && (X <= a.amax[0]) && (Y >= a.amin[1]) && (Y <= a.amax[1]) && (Z >= a.amin[2]) &&
+                     (Z <= a.amax[2]);
+            }
+            if (use_radius) ok = ok && (((X * X + Y * Y) + Z * Z) < a.r2_thresh);
           }
+          const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+          // ---- stage the kept lanes behind the warp's earlier groups (compact modes)
+          if (kOrdered && ok) {
+            const uint32_t pos = run + __popc(bal & lt);
+            sx[pos] = xo;
+            sy[pos] = yo;
+            sz[pos] = kF32 ? (OutT)z32 : (OutT)z64;
+            if (has_bgr) {
+              if (nv12) {
+                sc[pos] = rv_nv12_pixel_bgr(s_col[li], s_col[kTileT + (li & ~1)], s_col[kTileT + (li | 1)]);
+              } else {
+                const uint8_t *c = s_col + 3 * li;
+                sc[pos] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16);
+              }
+            }
+            if (kGen) si[pos] = (uint16_t)li;
+          }
+          run += __popc(bal);
         } else {
-          const double X = (double)xo, Y = (double)yo, Z = z64;
-          if (kGen) {
-            if (a.use_zclip) ok = ok && (Z >= a.z_min) && (Z <= a.z_max);
-            if (a.use_aabb)
-              ok = ok && (X >= a.amin[0]) && (X <= a.amax[0]) && (Y >= a.amin[1]) && (Y <= a.amax[1]) && (Z >= a.amin[2]) &&
-                   (Z <= a.amax[2]);
+          ok = false;
+        }
+        if (kGen && a.valid && li < npx) a.valid[(long long)b * P + px0 + li] = ok ? 1 : 0;
+        if (!kOrdered) {  // dense modes fill every lane's slot
+          const OutT bad = (MODE == RV_MODE_DENSE_NAN) ? qnan<OutT>() : (OutT)0;
+          const int pos = j * 32 + lane;
+          sx[pos] = ok ? xo : bad;
+          sy[pos] = ok ? yo : bad;
+          sz[pos] = ok ? (kF32 ? (OutT)z32 : (OutT)z64) : bad;
+          uint32_t cpk = 0;
+          if (has_bgr && ok) {
+            if (nv12) {
+              cpk = rv_nv12_pixel_bgr(s_col[li], s_col[kTileT + (li & ~1)], s_col[kTileT + (li | 1)]);
+            } else {
+              const uint8_t *c = s_col + 3 * li;
+              cpk = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16);
+            }
           }
-          if (use_radius) ok = ok && (((X * X + Y * Y) + Z * Z) < a.r2_thresh);
+          sc[pos] = cpk;
+          if (kGen) si[pos] = ok ? (uint16_t)li : (uint16_t)0xffffu;
         }
-        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-        // ---- stage the kept lanes behind the warp's earlier groups (compact modes)
-        if (kOrdered && ok) {
-          const uint32_t pos = run + __popc(bal & lt);
-          sx[pos] = xo;
-          sy[pos] = yo;
-          sz[pos] = kF32 ? (OutT)z32 : (OutT)z64;
-          if (has_bgr) {
-            const uint8_t *c = s_bgr + 3 * li;
-            sc[pos] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16);
-          }
-          if (kGen) si[pos] = (uint16_t)li;
-        }
-        run += __popc(bal);
-      } else {
-        ok = false;
-      }
-      if (kGen && a.valid && li < npx) a.valid[(long long)b * P + px0 + li] = ok ? 1 : 0;
-      if (!kOrdered) {  // dense modes fill every lane's slot
-        const OutT bad = (MODE == RV_MODE_DENSE_NAN) ? qnan<OutT>() : (OutT)0;
-        const int pos = j * 32 + lane;
-        sx[pos] = ok ? xo : bad;
-        sy[pos] = ok ? yo : bad;
-        sz[pos] = ok ? (kF32 ? (OutT)z32 : (OutT)z64) : bad;
-        uint32_t cpk = 0;
-        if (has_bgr && ok) {
-          const uint8_t *c = s_bgr + 3 * li;
-          cpk = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16);
-        }
-        sc[pos] = cpk;
-        if (kGen) si[pos] = ok ? (uint16_t)li : (uint16_t)0xffffu;
       }
     }
     // the input stage is no longer needed: hand it back to the producer before the prefix is resolved
     if (npx < kTileT) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // our zero fill vs the next bulk copy
     __syncwarp();
-    if (lane == 0) {
-      mbar_arrive(&empty_bar[s]);
-      s_tot[it & 1][warp] = run;  // double-buffered: a warp may run one barrier ahead of the readers
-    }
-    compute_bar();
+    if (lane == 0) mbar_arrive(empty_a + 8 * s);
 
-    // ---------------- the eight run totals -> this warp's offset inside the tile and the tile total
-    const uint32_t t8 = lane < kCW ? s_tot[it & 1][lane] : 0u;
-    const uint32_t tile_total = __reduce_add_sync(0xffffffffu, t8);
-    const uint32_t off = __reduce_add_sync(0xffffffffu, lane < warp ? t8 : 0u);
-
-    // ---------------- tile base
-    uint32_t base = 0;
+    uint32_t base = 0, off = 0;
     if (kOrdered) {
+      // ---------------- the eight run totals.  Everybody posts; only the warps that have points to place (and warp 0,
+      // which publishes the tile's prefix) wait for the others.  s_tot is four deep: a warp that posts without waiting can
+      // be two tiles ahead of the slowest reader (the input ring holds it there).
+      if (lane == 0) {
+        s_tot[it & 3][warp] = run;
+        mbar_arrive(tot_a + 8 * (it & 1));
+      }
+      if (run == 0 && warp != 0) continue;  // warp-uniform
+      mbar_wait(tot_a + 8 * (it & 1), (uint32_t)(it >> 1) & 1u);
+      const uint32_t t8 = lane < kCW ? s_tot[it & 3][lane] : 0u;
+      const uint32_t tile_total = __reduce_add_sync(0xffffffffu, t8);
+      off = __reduce_add_sync(0xffffffffu, lane < warp ? t8 : 0u);
+
+      // ---------------- tile base
       bool hit = false;
       if (n_pred > 0) {
         const unsigned long long pk = s_peek[it & 1];
@@ -513,18 +584,18 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
           base = rv_lookback(a.status, tile, n_pred, tile_total);  // publishes the aggregate, then the prefix
           if (lane == 0) {
             s_base[it & 7] = base;
-            mbar_arrive(&base_bar[it & 7]);
+            mbar_arrive(base_a + 8 * (it & 7));
           }
         } else {
           // the predecessor is still in flight in another CTA: sleep until warp 0 has walked the chain
-          mbar_wait(&base_bar[it & 7], (uint32_t)(it >> 3) & 1u);
+          mbar_wait(base_a + 8 * (it & 7), (uint32_t)(it >> 3) & 1u);
           base = s_base[it & 7];
         }
       }
       if (warp == 0 && lane == 0) {
         if (n_pred == 0 || hit) {
           rv_st_relaxed(a.status + tile, RV_ST_PREFIX | (unsigned long long)(base + tile_total));
-          mbar_arrive(&base_bar[it & 7]);  // keep the slot's phase in step with the iteration count
+          mbar_arrive(base_a + 8 * (it & 7));  // keep the slot's phase in step with the iteration count
         }
         if (kPacked) {
           if (t == 0) a.counts[b] = base;
@@ -534,7 +605,7 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
         }
       }
     } else {
-      if (threadIdx.x == 0 && tile_total) atomicAdd(a.counts + b, (unsigned long long)tile_total);
+      if (lane == 0 && run) atomicAdd(a.counts + b, (unsigned long long)run);
     }
 
     // ---------------- drain: the warp's packed run -> its contiguous place in every plane, all lanes busy
@@ -563,7 +634,9 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
             st_global<0>(oz + j * kStep, sz[k]);
             if (has_bgr) {
               const uint32_t c = sc[k];
-              if (kF32 && !kGen) {
+              if (kF32 && pk8) {
+                st_global_u32(orr + j * kStep, __byte_perm(c, 0u, 0x4012));  // b,g,r,0 -> r,g,b,0
+              } else if (kF32 && !kGen) {
                 st_global<0>(orr + j * kStep, (OutT)unit_color_f((float)((c >> 16) & 255u)));
                 st_global<0>(og + j * kStep, (OutT)unit_color_f((float)((c >> 8) & 255u)));
                 st_global<0>(ob + j * kStep, (OutT)unit_color_f((float)(c & 255u)));
@@ -585,7 +658,7 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
   }
 }
 
-// SPEC 0/1 cover the plain configurations; anything else falls to the run-time-flag variant
+// SPEC 0/1/3 cover the plain configurations; anything else falls to the run-time-flag variant
 int pick_spec(const DeprojArgs &a, int depth_kind) {
   const bool plain = a.bgr && !a.rays && !a.use_mask && !a.use_trunc && !a.use_zclip && !a.use_aabb && !a.valid && !a.src_index &&
                      !a.color_255;
@@ -598,20 +671,39 @@ int pick_spec(const DeprojArgs &a, int depth_kind) {
   return 2;
 }
 
+template <typename OutT, int DK, int MODE, int SPEC, int CF>
+cudaError_t launch_one(const rv_ctx *ctx, const DeprojArgs &a, cudaStream_t st) {
+  const size_t smem = (size_t)Layout<OutT, DK, SPEC == 2>::kSmem;
+  auto k = k_deproject_tma<OutT, DK, MODE, SPEC, CF>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int grid = rv_persistent_grid(ctx, k, kThreadsT, smem, a.total_tiles);
+  k<<<grid, kThreadsT, smem, st>>>(a);
+  return cudaSuccess;
+}
+
+// the colour variants (NV12 in, packed bytes out) are compiled for the configurations the host pipeline runs: uint16
+// depth, float32 storage, the compact modes, plain predicates; every other combination takes the run-time-flag variant
+template <typename OutT, int DK, int MODE, int SPEC>
+cudaError_t launch_cf(const rv_ctx *ctx, const DeprojArgs &a, cudaStream_t st) {
+  constexpr bool kHasCf = sizeof(OutT) == 4 && DK == RV_DEPTH_U16 &&
+                          (MODE == RV_MODE_COMPACT_ORDERED || MODE == RV_MODE_COMPACT_PACKED) && SPEC != 2;
+  const int cf = (a.color_packed ? 1 : 0) | (a.color_nv12 ? 2 : 0);
+  if (cf == 0 || SPEC == 2) return launch_one<OutT, DK, MODE, SPEC, 0>(ctx, a, st);
+  if (kHasCf) {
+    if (cf == 1) return launch_one<OutT, DK, MODE, kHasCf ? SPEC : 2, kHasCf ? 1 : 0>(ctx, a, st);
+    if (cf == 2) return launch_one<OutT, DK, MODE, kHasCf ? SPEC : 2, kHasCf ? 2 : 0>(ctx, a, st);
+    return launch_one<OutT, DK, MODE, kHasCf ? SPEC : 2, kHasCf ? 3 : 0>(ctx, a, st);
+  }
+  return launch_one<OutT, DK, MODE, 2, 0>(ctx, a, st);
+}
+
 template <typename OutT, int DK, int MODE>
 cudaError_t launch_spec(const rv_ctx *ctx, const DeprojArgs &a, int spec, cudaStream_t st) {
-#define RV_GO(S)                                                                                           \
-  {                                                                                                        \
-    const size_t smem = (size_t)Layout<OutT, DK, S == 2>::kSmem;                                           \
-    auto k = k_deproject_tma<OutT, DK, MODE, S>;                                                           \
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-    if (e != cudaSuccess) return e;                                                                        \
-    const int grid = rv_persistent_grid(ctx, k, kThreadsT, smem, a.total_tiles);                           \
-    k<<<grid, kThreadsT, smem, st>>>(a);                                                                   \
-  }
-  if (spec == 0) RV_GO(0) else if (spec == 1) RV_GO(1) else if (spec == 3 && DK == RV_DEPTH_U16) RV_GO(3) else RV_GO(2)
-#undef RV_GO
-  return cudaSuccess;
+  if (spec == 0) return launch_cf<OutT, DK, MODE, 0>(ctx, a, st);
+  if (spec == 1) return launch_cf<OutT, DK, MODE, 1>(ctx, a, st);
+  if (spec == 3 && DK == RV_DEPTH_U16) return launch_cf<OutT, DK, MODE, 3>(ctx, a, st);
+  return launch_cf<OutT, DK, MODE, 2>(ctx, a, st);
 }
 
 template <typename OutT, int DK>
@@ -631,6 +723,7 @@ bool rv_deproject_fast_eligible(const DeprojArgs &a, int mode) {
   (void)mode;
   if (a.W < 32 || (a.P % 16) != 0) return false;
   if (!rv_aligned(a.depth, 16) || (a.bgr && !rv_aligned(a.bgr, 16)) || (a.mask && !rv_aligned(a.mask, 16))) return false;
+  if (a.bgr && a.color_nv12 && ((a.W % 16) != 0 || a.W < 256)) return false;  // chroma row segments as 16-byte bulk copies
   return true;
 }
 

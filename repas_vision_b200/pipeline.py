@@ -2,6 +2,7 @@
 
 This is the call a script makes when its frames live in host memory, the batched form of
 
+    color = frame_to_bgr_image(color_frame)                  better_three_capture.py:101-106 (NV12 from the camera)
     raw, depth_m, _ = depth_to_meters(frame)                 better_three_capture.py:118-125
     pcd = create_masked_pointcloud(bgr, depth_m, mask, ...)  create_masked_ply.py:56-107
     keep = np.linalg.norm(points, axis=1) < 1.0              distance_masking_on_ply.py:12-19
@@ -9,8 +10,15 @@ This is the call a script makes when its frames live in host memory, the batched
 Three CUDA streams walk the batch in chunks: H2D of chunk i+1, the fused kernel on chunk i (COMPACT_PACKED: the
 frames of a chunk land back to back, so each plane is ONE contiguous device->host copy), D2H of chunk i-1.
 The only host synchronisation is reading a chunk's B+1 offsets to size its D2H, done one chunk behind the copy
-engine so PCIe stays busy.  PCIe bounds this path (4.6 MB in per 720p frame); the device-resident API
-(`deproject_batch` on CUDA tensors) is the one the HBM roofline applies to.
+engine so PCIe stays busy.  PCIe bounds this path, so the bytes per frame are what counts:
+
+* colour frames may arrive as the camera's NV12 ([B, H*3/2, W] uint8: 1.5 instead of 3 bytes per pixel); the kernel reads
+  them directly (no BGR image is ever written), a 720p frame then crosses PCIe as 3.5 bytes per pixel;
+* colours come back as the bytes they are (colors="u8": one r,g,b,0 word per point, 16 bytes per point with its float32
+  xyz) and are expanded to k / 255.0 on the host only when somebody asks (`HostBatchResult.colors`); colors="float"
+  returns three float32 colour planes (24 bytes per point).
+
+The device-resident API (`deproject_batch` on CUDA tensors) is the one the HBM roofline applies to.
 """
 from __future__ import annotations
 
@@ -22,8 +30,9 @@ from .calibration import Camera
 
 
 class _PinnedPool:
-    """Pinned host blocks for the results, recycled when a result is dropped.  Page-locking memory costs milliseconds per
-    hundred megabytes, far more than the copy it serves, so blocks are rounded up to powers of two and reused."""
+    """Pinned host blocks for the results.  Page-locking memory costs milliseconds per hundred megabytes, far more than the
+    copy it serves, so blocks are rounded up to powers of two and reused -- but only blocks their owner handed back with
+    `HostBatchResult.release()`: arrays given out by a result alias its block, so nothing is recycled behind the caller."""
 
     def __init__(self, max_bytes: int = 8 << 30):
         self.free: dict[int, list[torch.Tensor]] = {}
@@ -45,32 +54,61 @@ class _PinnedPool:
 
 
 class HostCloudChunk:
-    """Clouds of `frames` consecutive frames on the host: planes [6 or 3, total] float32 (pinned), offsets [frames+1]."""
+    """Clouds of `frames` consecutive frames on the host: float32 planes [3, 4 or 6, total] (pinned), offsets [frames+1].
+    Four planes = x, y, z and the packed colour words (bytes r,g,b,0)."""
 
-    def __init__(self, first_frame: int, frames: int, planes: torch.Tensor, offsets: np.ndarray, block=None, pool=None):
+    def __init__(self, first_frame: int, frames: int, planes: torch.Tensor, offsets: np.ndarray, block=None, pool=None,
+                 packed_color: bool = False):
         self.first_frame, self.frames = first_frame, frames
         self._planes, self.offsets = planes, offsets
         self._block, self._pool = block, pool
+        self.packed_color = packed_color
 
-    def __del__(self):
+    @property
+    def total(self) -> int:
+        return int(self.offsets[-1])
+
+    def release(self) -> None:
+        """Hand the pinned block back for reuse.  Every array obtained from this chunk is invalid afterwards."""
         if self._pool is not None and self._block is not None:
             self._pool.give(self._block)
-            self._block = None
+        self._block = self._planes = None
 
     @property
     def planes(self) -> np.ndarray:
+        if self._planes is None:
+            raise RuntimeError("this result was released")
         return self._planes.numpy()
 
     def frame(self, i: int):
-        """(xyz [3,n], rgb [3,n] or None) views of frame `first_frame + i`."""
+        """Views of frame `first_frame + i`: (xyz [3,n] float32, colours).  colours = [n,3] uint8 (r,g,b) for a packed-colour
+        chunk, [3,n] float32 in [0,1] for colors="float", None without colour."""
         a, b = int(self.offsets[i]), int(self.offsets[i + 1])
         pl = self.planes
-        return pl[:3, a:b], (pl[3:6, a:b] if pl.shape[0] >= 6 else None)
+        if pl.shape[0] < 4:
+            return pl[:3, a:b], None
+        if self.packed_color:
+            return pl[:3, a:b], pl[3, a:b].view(np.uint8).reshape(b - a, 4)[:, :3]
+        return pl[:3, a:b], pl[3:6, a:b]
 
 
 class HostBatchResult:
     def __init__(self, chunks, n_frames, d2h_bytes, h2d_bytes):
         self.chunks, self.n_frames, self.d2h_bytes, self.h2d_bytes = chunks, n_frames, d2h_bytes, h2d_bytes
+
+    def release(self) -> None:
+        """Return the pinned result blocks to the pipeline's pool (a loop that runs batch after batch calls this when it is
+        done with a result; otherwise the blocks are simply freed with the result).  Arrays obtained from `frame`, `planes`
+        alias those blocks and must not be used afterwards; `points` / `colors` return copies and stay valid."""
+        for c in self.chunks:
+            c.release()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.release()
+        return False
 
     @property
     def counts(self) -> np.ndarray:
@@ -87,19 +125,28 @@ class HostBatchResult:
         return np.ascontiguousarray(self.frame(b)[0].T, dtype=np.float64)
 
     def colors(self, b: int) -> np.ndarray:
+        """(n,3) float64 in [0,1] like np.asarray(pcd.colors); packed bytes are expanded here as k / 255.0, which is the
+        reference's own float64 statement (create_masked_ply.py:100)."""
         rgb = self.frame(b)[1]
-        return np.zeros((0, 3)) if rgb is None else np.ascontiguousarray(rgb.T, dtype=np.float64)
+        if rgb is None:
+            return np.zeros((0, 3))
+        if rgb.dtype == np.uint8:
+            return rgb.astype(np.float64) / 255.0
+        return np.ascontiguousarray(rgb.T, dtype=np.float64)
 
 
 class HostPipeline:
     def __init__(self, camera: Camera, height: int, width: int, *, max_distance=None, z_clip=None, aabb=None,
                  unit_rule: str = "mul_f32", depth_scale=None, use_mask: bool = False, invert_mask: bool = False,
-                 with_color: bool = True, color_format: str = "bgr", chunk_frames: int = 32, slots: int = 3, device=None):
+                 with_color: bool = True, color_format: str = "bgr", colors: str = "u8", chunk_frames: int = 32,
+                 slots: int = 3, device=None):
         """color_format "nv12": the colour frames arrive as the camera delivers them ([B, H*3/2, W] uint8, the capture
-        script's preferred format, better_three_capture.py:101-106,159) and are decoded on the GPU; the frame then crosses
-        PCIe at 3.5 instead of 5 bytes per pixel."""
+        script's preferred format, better_three_capture.py:101-106,159) and are read by the deprojection kernel itself.
+        colors "u8" (default): colours come back as bytes, 16 bytes per point; "float": three float32 planes in [0,1]."""
         if color_format not in ("bgr", "nv12"):
             raise ValueError("color_format must be 'bgr' or 'nv12'")
+        if colors not in ("u8", "float"):
+            raise ValueError("colors must be 'u8' or 'float'")
         if color_format == "nv12" and (int(height) % 2 or int(width) % 2):
             raise ValueError("NV12 needs even image sides")
         self.color_format = color_format
@@ -107,16 +154,18 @@ class HostPipeline:
         self.cam, self.H, self.W = camera, int(height), int(width)
         self.P = self.H * self.W
         self.C, self.slots = int(chunk_frames), max(2, int(slots))
-        self.kw = dict(depth_kind="u16", unit_rule=unit_rule, unit_scale=depth_scale, invert_mask=invert_mask,
-                       r_max=max_distance, z_clip=z_clip, aabb=aabb, mode="compact_packed", out_dtype="f32")
         self.use_mask, self.with_color = use_mask, with_color
-        self.planes = 6 if with_color else 3
+        self.packed_color = with_color and colors == "u8"
+        self.planes = 3 if not with_color else (4 if self.packed_color else 6)
+        self.kw = dict(depth_kind="u16", unit_rule=unit_rule, unit_scale=depth_scale, invert_mask=invert_mask,
+                       r_max=max_distance, z_clip=z_clip, aabb=aabb, mode="compact_packed", out_dtype="f32",
+                       color_format=color_format, color_scale="packed8" if self.packed_color else "unit")
         d = self.dev
         C, H, W = self.C, self.H, self.W
+        cshape = (C, H, W, 3) if color_format == "bgr" else (C, H * 3 // 2, W)
+        self.color_bytes = 3 * self.P if color_format == "bgr" else self.P * 3 // 2
         self.d_depth = [torch.empty((C, H, W), dtype=torch.uint16, device=d) for _ in range(self.slots)]
-        self.d_bgr = [torch.empty((C, H, W, 3), dtype=torch.uint8, device=d) for _ in range(self.slots)] if with_color else None
-        self.d_nv12 = ([torch.empty((C, H * 3 // 2, W), dtype=torch.uint8, device=d) for _ in range(self.slots)]
-                       if with_color and color_format == "nv12" else None)
+        self.d_color = [torch.empty(cshape, dtype=torch.uint8, device=d) for _ in range(self.slots)] if with_color else None
         self.d_mask = [torch.empty((C, H, W), dtype=torch.uint8, device=d) for _ in range(self.slots)] if use_mask else None
         self.d_out = [torch.empty((self.planes, C * self.P), dtype=torch.float32, device=d) for _ in range(self.slots)]
         self.h_off = [torch.empty(C + 1, dtype=torch.int64, pin_memory=True) for _ in range(self.slots)]
@@ -133,18 +182,16 @@ class HostPipeline:
             raise RuntimeError(f"expected {dtype}, got {t.dtype}")
         return t.contiguous()
 
-    def run(self, depth_u16, bgr=None, mask=None) -> HostBatchResult:
-        """depth_u16 [B,H,W] uint16, bgr [B,H,W,3] uint8, mask [B,H,W] uint8 host arrays (pinned memory copies
-        asynchronously; pageable memory still works, the driver then stages it)."""
+    def _check_inputs(self, depth_u16, color, mask):
         hd = self._host_tensor(depth_u16, torch.uint16)
         B = hd.shape[0]
         if tuple(hd.shape[1:]) != (self.H, self.W):
             raise RuntimeError(f"depth must be [B,{self.H},{self.W}], got {tuple(hd.shape)}")
         hc = None
         if self.with_color:
-            if bgr is None:
-                raise RuntimeError("this pipeline was built with_color=True: bgr is required")
-            hc = self._host_tensor(bgr, torch.uint8)
+            if color is None:
+                raise RuntimeError("this pipeline was built with_color=True: colour frames are required")
+            hc = self._host_tensor(color, torch.uint8)
             want = (B, self.H, self.W, 3) if self.color_format == "bgr" else (B, self.H * 3 // 2, self.W)
             if tuple(hc.shape) != want:
                 raise RuntimeError(f"Color/depth size mismatch: color {tuple(hc.shape)}, depth {tuple(hd.shape)}")
@@ -155,6 +202,13 @@ class HostPipeline:
             hm = self._host_tensor(mask, torch.uint8)
             if tuple(hm.shape) != (B, self.H, self.W):
                 raise RuntimeError(f"Mask/depth size mismatch: mask {tuple(hm.shape)}, depth {tuple(hd.shape)}")
+        return hd, hc, hm, B
+
+    def run(self, depth_u16, bgr=None, mask=None, *, _copy_only_like: HostBatchResult | None = None) -> HostBatchResult:
+        """depth_u16 [B,H,W] uint16, colour frames ([B,H,W,3] BGR or [B,H*3/2,W] NV12) uint8, mask [B,H,W] uint8 host arrays
+        (pinned memory copies asynchronously; pageable memory still works, the driver then stages it)."""
+        hd, hc, hm, B = self._check_inputs(depth_u16, bgr, mask)
+        probe = _copy_only_like
         n_chunks = (B + self.C - 1) // self.C
         chunks, d2h, h2d = [None] * n_chunks, 0, 0
         cur = torch.cuda.current_stream(self.dev)
@@ -170,12 +224,9 @@ class HostPipeline:
                 self.s_in.wait_event(self.ev_k[s])  # the kernel that last read this input slot
                 self.d_depth[s][:n].copy_(hd[f0:f1], non_blocking=True)
                 h2d += n * self.P * 2
-                if hc is not None and self.d_nv12 is not None:
-                    self.d_nv12[s][:n].copy_(hc[f0:f1], non_blocking=True)
-                    h2d += n * self.P * 3 // 2
-                elif hc is not None:
-                    self.d_bgr[s][:n].copy_(hc[f0:f1], non_blocking=True)
-                    h2d += n * self.P * 3
+                if hc is not None:
+                    self.d_color[s][:n].copy_(hc[f0:f1], non_blocking=True)
+                    h2d += n * self.color_bytes
                 if hm is not None:
                     self.d_mask[s][:n].copy_(hm[f0:f1], non_blocking=True)
                     h2d += n * self.P
@@ -183,11 +234,10 @@ class HostPipeline:
             with torch.cuda.stream(self.s_k):
                 self.s_k.wait_event(self.ev_in[s])
                 self.s_k.wait_event(self.ev_out[s])  # the D2H that last read this output slot
-                if self.d_nv12 is not None:
-                    _ops.nv12_to_bgr(self.d_nv12[s][:n], self.H, self.W, out=self.d_bgr[s][:n])
-                r = _ops.deproject(self.d_depth[s][:n], None if hc is None else self.d_bgr[s][:n],
-                                   None if hm is None else self.d_mask[s][:n], self.cam, out=self.d_out[s], **self.kw)
-                self.h_off[s][:n + 1].copy_(r["counts"], non_blocking=True)
+                if probe is None:
+                    r = _ops.deproject(self.d_depth[s][:n], None if hc is None else self.d_color[s][:n],
+                                       None if hm is None else self.d_mask[s][:n], self.cam, out=self.d_out[s], **self.kw)
+                    self.h_off[s][:n + 1].copy_(r["counts"], non_blocking=True)
                 self.ev_k[s].record(self.s_k)
 
         def drain(i):
@@ -196,7 +246,7 @@ class HostPipeline:
             f0, f1 = i * self.C, min(B, (i + 1) * self.C)
             n = f1 - f0
             self.ev_k[s].synchronize()
-            offsets = self.h_off[s][:n + 1].numpy().copy()
+            offsets = self.h_off[s][:n + 1].numpy().copy() if probe is None else probe.chunks[i].offsets
             total = int(offsets[-1])
             block = self.pool.take(self.planes * max(total, 1))
             host = block[:self.planes * max(total, 1)].view(self.planes, max(total, 1))
@@ -206,7 +256,7 @@ class HostPipeline:
                         host[p, :total].copy_(self.d_out[s][p, :total], non_blocking=True)
                 self.ev_out[s].record(self.s_out)
             d2h += total * 4 * self.planes + (n + 1) * 8
-            chunks[i] = HostCloudChunk(f0, n, host[:, :total], offsets, block, self.pool)
+            chunks[i] = HostCloudChunk(f0, n, host[:, :total], offsets, block, self.pool, self.packed_color)
 
         for i in range(n_chunks + 1):
             if i < n_chunks:
@@ -216,3 +266,9 @@ class HostPipeline:
         self.s_out.synchronize()
         cur.wait_stream(self.s_k)
         return HostBatchResult(chunks, B, d2h, h2d)
+
+    def copy_probe(self, depth_u16, bgr=None, mask=None, *, like: HostBatchResult) -> HostBatchResult:
+        """The copy schedule of `run` without the kernel: the same host->device copies into the same slots and device->host
+        copies of exactly the bytes `like` (a finished run on the same inputs) brought back, on the same three streams.
+        What this takes is what the host side and PCIe cost by themselves (bench.py reports it next to the end-to-end rate)."""
+        return self.run(depth_u16, bgr, mask, _copy_only_like=like)

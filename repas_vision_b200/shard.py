@@ -3,7 +3,8 @@
 Frames (and whole fusion problems) share nothing but a few hundred bytes of calibration, so rank g of G
 takes the contiguous block [g*B/G, (g+1)*B/G) of the batch.  torch.distributed is used only
 AFTER the per-frame kernels: an all-gather of per-rank point counts and, for the fusion configuration, a
-variable-length gather of merged voxel clouds to rank 0.  Works on NCCL (GPU) and gloo (CPU tests).
+variable-length gather of merged voxel clouds to rank 0 (counts first, then grouped send / recv).  Works on NCCL
+(GPU; tests/test_gpu_multi.py under torchrun) and gloo (CPU tests).
 """
 from __future__ import annotations
 
@@ -81,8 +82,11 @@ def gather_counts(local_counts: torch.Tensor, total_frames: int | None = None, g
 
 
 def gather_clouds(data: torch.Tensor, n: int, dst: int = 0, group=None):
-    """Variable-length gather of SoA clouds ([planes, >=n] each) to rank `dst`: sizes first, then one padded
-    all-gather.  Returns (merged [planes, sum n], per-rank sizes) on `dst`, (None, sizes) elsewhere."""
+    """Variable-length gather of SoA clouds ([planes, >=n] each) to rank `dst`: one all-gather of the per-rank
+    point counts, then ONE group of point-to-point transfers -- every other rank sends exactly its n points per plane,
+    `dst` receives each straight into that rank's columns of the merged cloud (ncclGroupStart / ncclSend / ncclRecv /
+    ncclGroupEnd on NCCL; nothing is padded and nothing reaches ranks that do not want it).
+    Returns (merged [planes, sum n], per-rank sizes) on `dst`, (None, sizes) elsewhere."""
     rank, world = _world(group)
     planes = data.shape[0]
     if world == 1:
@@ -91,14 +95,24 @@ def gather_clouds(data: torch.Tensor, n: int, dst: int = 0, group=None):
     sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(sizes, torch.tensor([n], dtype=torch.int64, device=dev), group=group)
     sizes = [int(s.item()) for s in sizes]
-    width = max(max(sizes), 1)
-    padded = torch.zeros((planes, width), dtype=data.dtype, device=dev)
-    padded[:, :n] = data[:, :n]
-    parts = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(parts, padded, group=group)
+    if rank == dst:
+        # plane-major per source rank, so that every receive buffer is one contiguous block
+        parts = [torch.empty((planes, m), dtype=data.dtype, device=dev) for m in sizes]
+        parts[dst].copy_(data[:, :n])
+        ops = [dist.P2POp(dist.irecv, parts[r], _global_rank(r, group), group) for r in range(world) if r != dst and sizes[r] > 0]
+    else:
+        mine = data[:, :n].contiguous()
+        ops = [dist.P2POp(dist.isend, mine, _global_rank(dst, group), group)] if n > 0 else []
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
     if rank != dst:
         return None, sizes
-    return torch.cat([p[:, :m] for p, m in zip(parts, sizes)], dim=1), sizes
+    return torch.cat(parts, dim=1), sizes
+
+
+def _global_rank(group_rank: int, group=None) -> int:
+    return group_rank if group is None else dist.get_global_rank(group, group_rank)
 
 
 def max_over_ranks(value: float, device=None, group=None) -> float:

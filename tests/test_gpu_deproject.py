@@ -301,23 +301,111 @@ def test_packed_mode_and_host_pipeline(rv, O, rs720, kernel):
         assert np.array_equal(data[:3, off[b]:off[b + 1]].T, refs[b]["points"])
         assert np.array_equal(data[3:, off[b]:off[b + 1]].T, refs[b]["colors"])
     if kernel == "tma":
-        pipe = HostPipeline(cam, H, W, max_distance=1.3, chunk_frames=3)
+        pipe = HostPipeline(cam, H, W, max_distance=1.3, chunk_frames=3, colors="float")
         res = pipe.run(depth, bgr)
         assert np.array_equal(res.counts, np.diff(off)) and res.h2d_bytes == B * H * W * 5
         for b in range(B):
             xyz, rgb = res.frame(b)
             assert np.array_equal(xyz.T, refs[b]["points"]) and np.array_equal(rgb.T, refs[b]["colors"])
         assert np.array_equal(res.points(2), refs[2]["points"].astype(np.float64))
-        # NV12 colour frames (the capture script's preferred format): decoded on the GPU, same clouds as feeding the BGR
-        # image cv2 makes of them
+        # default colour transport: the bytes themselves, 16 bytes per point; expanded on the host to the reference's float64
+        pipe8 = HostPipeline(cam, H, W, max_distance=1.3, chunk_frames=3)
+        res8 = pipe8.run(depth, bgr)
+        assert res8.d2h_bytes < res.d2h_bytes and np.array_equal(res8.counts, res.counts)
+        for b in range(B):
+            xyz, rgb8 = res8.frame(b)
+            keep = refs[b]["valid"]
+            assert rgb8.dtype == np.uint8 and np.array_equal(rgb8, bgr[b][keep][:, ::-1])
+            assert np.array_equal(xyz.T, refs[b]["points"])
+            assert np.array_equal(res8.colors(b), bgr[b][keep][:, ::-1].astype(np.float64) / 255.0)
+        # NV12 colour frames (the capture script's preferred format) read by the kernel itself: same clouds as feeding the
+        # BGR image cv2 makes of them
         import cv2
         rng = np.random.default_rng(7)
         nv12 = rng.integers(0, 256, (B, H * 3 // 2, W), dtype=np.uint8)
         bgr_cv = np.stack([cv2.cvtColor(f, cv2.COLOR_YUV2BGR_NV12) for f in nv12])
-        a = HostPipeline(cam, H, W, max_distance=1.3, chunk_frames=4, color_format="nv12").run(depth, nv12)
+        a = HostPipeline(cam, H, W, max_distance=1.3, chunk_frames=4, color_format="nv12", colors="float").run(depth, nv12)
         b2 = pipe.run(depth, bgr_cv)
         assert a.h2d_bytes == B * H * W * 7 // 2 and np.array_equal(a.counts, b2.counts)
         for fb in range(B):
             assert np.array_equal(a.frame(fb)[0], b2.frame(fb)[0]) and np.array_equal(a.frame(fb)[1], b2.frame(fb)[1])
+        a8 = HostPipeline(cam, H, W, max_distance=1.3, chunk_frames=4, color_format="nv12").run(depth, nv12)
+        for fb in range(B):
+            assert np.array_equal(a8.frame(fb)[0], b2.frame(fb)[0])
+            assert np.array_equal(a8.colors(fb), b2.colors(fb))
         res2 = pipe.run(torch.from_numpy(depth).pin_memory(), torch.from_numpy(bgr).pin_memory())  # pinned inputs, reuse
         assert np.array_equal(res2.counts, res.counts) and np.array_equal(res2.frame(B - 1)[0], res.frame(B - 1)[0])
+        # results own their pinned memory: a later run must not overwrite arrays handed out earlier (only release() recycles)
+        keep_xyz = res.frame(0)[0]
+        snapshot = keep_xyz.copy()
+        del res
+        for _ in range(3):
+            pipe.run(depth, bgr_cv)
+        assert np.array_equal(keep_xyz, snapshot)
+        res2.release()
+        with pytest.raises(RuntimeError):
+            res2.frame(0)
+        # the copy-only probe replays the schedule of a finished run
+        pr = pipe8.copy_probe(depth, bgr, like=res8)
+        assert pr.h2d_bytes == res8.h2d_bytes and pr.d2h_bytes == res8.d2h_bytes
+
+
+@pytest.mark.parametrize("shape,kernel", [((720, 1280), "tma"), ((720, 1280), "generic"), ((480, 640), "tma"), ((480, 640), "generic"),
+                                          ((36, 48), "auto"), ((38, 54), "auto"), ((2, 2050), "auto")])
+@pytest.mark.parametrize("case", [dict(), dict(r_max=1.0), dict(r_max=1.2, unit_rule="div_f32"),
+                                  dict(z_clip=(0.3, 2.0), mask=True), dict(mode="dense_zero")])
+def test_nv12_frames_and_packed_colours(rv, O, rs720, shape, kernel, case):
+    """Colour as the camera delivers it (NV12, better_three_capture.py:101-106,159) read by K1 itself, and colours kept as
+    bytes on the way out (RV_COLOR_PACKED8): both must give exactly the cloud of the cv2-decoded BGR image / the float
+    colour planes, on both kernels, including partial tiles, rows shorter than a tile and masks."""
+    import cv2
+    import torch
+    H, W = shape
+    B = 2 if H * W > 10000 else 4
+    kw = dict(case)
+    use_mask = kw.pop("mask", False)
+    mode = kw.pop("mode", "compact_ordered")
+    depth, _, allmask = _dataset(B, H, W)
+    rng = np.random.default_rng(1000 + H)
+    nv12 = rng.integers(0, 256, (B, H * 3 // 2, W), dtype=np.uint8)
+    bgr_cv = np.stack([cv2.cvtColor(f, cv2.COLOR_YUV2BGR_NV12) for f in nv12])
+    cam = rv.Camera(rs720["fx"] * W / 1280, rs720["fy"] * H / 720, rs720["cx"] * W / 1280, rs720["cy"] * H / 720, W, H)
+    gk = dict(unit_rule=kw.get("unit_rule", "mul_f32"), max_distance=kw.get("r_max"), z_clip=kw.get("z_clip"), mode=mode,
+              kernel=kernel, want_src_index=True)
+    d = torch.from_numpy(depth).cuda()
+    m = torch.from_numpy(allmask).cuda() if use_mask else None
+    ref = rv.deproject_batch(d, torch.from_numpy(bgr_cv).cuda(), cam, m, **gk)                       # BGR in, float colours
+    got = rv.deproject_batch(d, torch.from_numpy(nv12).cuda(), cam, m, color_format="nv12", **gk)     # NV12 in, float colours
+    pk = rv.deproject_batch(d, torch.from_numpy(nv12).cuda(), cam, m, color_format="nv12", color_scale="packed8", **gk)
+    pk_bgr = rv.deproject_batch(d, torch.from_numpy(bgr_cv).cuda(), cam, m, color_scale="packed8", **gk)
+    counts = ref.counts_host()
+    assert np.array_equal(got.counts_host(), counts) and np.array_equal(pk.counts_host(), counts)
+    assert pk.data.shape[0] == 4 and got.data.shape[0] == 6
+    for b in range(B):
+        o = O.deproject_mask(depth[b], bgr_cv[b], allmask[b] if use_mask else None, fx=cam.fx, fy=cam.fy, cx=cam.cx, cy=cam.cy,
+                             out_dtype="f32", **{k: v for k, v in kw.items()})
+        n = H * W if mode.startswith("dense") else int(counts[b])
+        assert int(counts[b]) == o["points"].shape[0]
+        lo = b * ref.cap
+        assert torch.equal(got.data[:, lo:lo + n], ref.data[:, lo:lo + n])
+        assert torch.equal(pk.data[:3, lo:lo + n], ref.data[:3, lo:lo + n])
+        assert torch.equal(pk.data[3, lo:lo + n], pk_bgr.data[3, lo:lo + n])
+        rgb8 = pk.rgb8(b).cpu().numpy()
+        src = ref.src_index[lo:lo + n].cpu().numpy()
+        flat = bgr_cv[b].reshape(-1, 3)
+        if mode.startswith("dense"):
+            ok = src >= 0
+            assert np.array_equal(ok, o["valid"].reshape(-1))
+            assert np.array_equal(rgb8[ok], flat[ok][:, ::-1]) and not rgb8[~ok].any()
+            assert np.array_equal(pk.data[3, lo:lo + n].view(torch.int32).cpu().numpy()[~ok], np.zeros((~ok).sum(), np.int32))
+        else:
+            assert np.array_equal(src, o["src_index"])
+            assert np.array_equal(rgb8, flat[src][:, ::-1])
+            assert np.array_equal(ref.data[3:, lo:lo + n].t().cpu().numpy(), o["colors"])
+            assert np.array_equal(ref.data[:3, lo:lo + n].t().cpu().numpy(), o["points"])
+        # the fourth byte of every colour word is zero
+        assert not pk.data[3, lo:lo + n].view(torch.uint8).view(-1, 4)[:, 3].any()
+    with pytest.raises(ValueError):
+        rv.deproject_batch(d, torch.from_numpy(nv12).cuda(), cam, color_format="nv12", color_scale="packed8", dtype="f64")
+    with pytest.raises(RuntimeError):
+        pk.frame(0)

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(built):
         assert hasattr(lib, n), f"{n} declared in include/repas_vision.h but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes prototype"
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.rv_abi_version() == 1
+    assert lib.rv_abi_version() == 2
     assert b"sm_100a" in lib.rv_build_info()
     assert lib.rv_sizeof_cam() == ctypes.sizeof(_lib.RvCam)
     assert lib.rv_sizeof_deproject_params() == ctypes.sizeof(_lib.RvDeprojectParams)
