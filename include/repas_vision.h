@@ -216,11 +216,14 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
  * the stand-alone form of the predicates above (distance_masking_on_ply.py,
  * view_point_cloud.py --z-min/--z-max, AABB crop): ordered compaction of an
  * n-point SoA cloud.  Only use_zclip/use_radius/use_aabb and their values are read
- * from params.  d_count: one int64. */
+ * from params.  d_count: one int64.  d_index: NULL or [n] int64, the source index of every kept
+ * point (what select_by_index takes; used to carry normals along).  The kept count is only
+ * known on the device, so out_plane_stride must be >= n (RV_ECAPACITY otherwise); the same
+ * holds for rv_select_by_mask. */
 size_t rv_filter_workspace_bytes(int64_t n);
 int rv_filter_cloud(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int dtype, int has_color,
                     const RvDeprojectParams *params, void *d_out, int64_t out_plane_stride, int64_t *d_count,
-                    void *d_ws, size_t ws_bytes, rv_stream stream);
+                    int64_t *d_index, void *d_ws, size_t ws_bytes, rv_stream stream);
 
 /* ---- a11: 4x4 pose transform + merge ------------------------------------------
  * replaces geometry.transform(T) (final_view_with_cad.py:333,
@@ -234,6 +237,10 @@ int rv_filter_cloud(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int6
  *  d_bounds     6 doubles (min xyz, max xyz) of the merged cloud, or NULL.  Must be
  *               pre-initialised by rv_bounds_init when several calls accumulate. */
 int rv_bounds_init(rv_ctx *ctx, double *d_bounds, rv_stream stream);
+/* get_min_bound / get_max_bound / get_center of a cloud (april_tag_bg_removal_pl.py:425-431 reads the bounds of every
+ * cloud it crops): d_stats receives 9 doubles, min xyz, max xyz, sum xyz (centre = sum / n), all in float64. */
+int rv_cloud_stats(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int dtype, double *d_stats,
+                   rv_stream stream);
 int rv_transform_merge(rv_ctx *ctx, int n_views, const void *const *d_in, const int64_t *in_plane_stride,
                        const int64_t *n, const double *T, int in_dtype, int has_color, void *d_out,
                        int64_t out_plane_stride, int out_dtype, double *d_bounds, rv_stream stream);

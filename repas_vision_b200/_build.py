@@ -36,17 +36,20 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str | None = None, extra: str | None = None, tag: str = "obj") -> str:
+    """out / extra / tag: a variant build (other -D tunables, other output file, its own object directory)."""
+    if out is None and not force and not needs_build():
         return SO_PATH
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "..", "build", "obj")
+    so_path = out or SO_PATH
+    objdir = os.path.join(HERE, "..", "build", tag)
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("RV_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *(extra if extra is not None else os.environ.get("RV_NVCC_EXTRA", "")).split(), "-c",
+               os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
@@ -55,11 +58,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out.decode()}")
-    tmp = SO_PATH + ".tmp"
+    tmp = so_path + ".tmp"
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs]
     subprocess.check_call(link)
-    os.replace(tmp, SO_PATH)
-    return SO_PATH
+    os.replace(tmp, so_path)
+    return so_path
 
 
 if __name__ == "__main__":

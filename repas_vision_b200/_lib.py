@@ -10,7 +10,8 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "librepasvision.so")
+# RV_LIBRARY_PATH: a differently tuned build of the same sources (tools/k1_sweep.sh builds such variants for A/B runs)
+SO_PATH = os.environ.get("RV_LIBRARY_PATH") or os.path.join(HERE, "librepasvision.so")
 
 # enums (mirror include/repas_vision.h)
 RV_OK, RV_EINVAL, RV_ECAPACITY, RV_ECUDA, RV_EALIGN, RV_EWORKSPACE = range(6)
@@ -64,8 +65,9 @@ SIGNATURES = {
                                     C.c_size_t, c_vp]),
     "rv_filter_workspace_bytes": (C.c_size_t, [c_i64]),
     "rv_filter_cloud": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, C.c_int, C.POINTER(RvDeprojectParams), c_vp,
-                                  c_i64, c_vp, c_vp, C.c_size_t, c_vp]),
+                                  c_i64, c_vp, c_vp, c_vp, C.c_size_t, c_vp]),
     "rv_bounds_init": (C.c_int, [c_vp, c_vp, c_vp]),
+    "rv_cloud_stats": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, c_vp, c_vp]),
     "rv_transform_merge": (C.c_int, [c_vp, C.c_int, C.POINTER(c_vp), C.POINTER(c_i64), C.POINTER(c_i64),
                                      C.POINTER(c_f64), C.c_int, C.c_int, c_vp, c_i64, C.c_int, c_vp, c_vp]),
     "rv_voxel_workspace_bytes": (C.c_size_t, [c_i64]),

@@ -191,7 +191,8 @@ def register(depth: torch.Tensor, dcam: Camera, ccam: Camera, R_colmajor, t, dep
 
 
 # --------------------------------------------------------------------- cloud ops
-def filter_cloud(data: torch.Tensor, n: int, has_color: bool, *, z_clip=None, r_max=None, aabb=None):
+def filter_cloud(data: torch.Tensor, n: int, has_color: bool, *, z_clip=None, r_max=None, aabb=None, want_index=False):
+    """Ordered compaction by the cloud predicates: (planes [P, n], count int64[1][, source indices int64 [n]])."""
     dev = data.device
     ctx = ctx_for(dev)
     p = _lib.RvDeprojectParams()
@@ -209,9 +210,28 @@ def filter_cloud(data: torch.Tensor, n: int, has_color: bool, *, z_clip=None, r_
     out = torch.empty((data.shape[0], max(n, 1)), dtype=data.dtype, device=dev)
     count = torch.zeros(1, dtype=torch.int64, device=dev)
     ws = workspace(ctx.lib.rv_filter_workspace_bytes(n), dev)
+    index = torch.empty(max(n, 1), dtype=torch.int64, device=dev) if want_index else None
     ctx.check(ctx.lib.rv_filter_cloud(ctx.handle, ptr(data), pstride(data), n, _RV_DT[data.dtype], int(has_color), C.byref(p),
-                                      ptr(out), out.shape[1], ptr(count), ptr(ws), ws.numel(), stream_ptr(dev)))
-    return out, count
+                                      ptr(out), out.shape[1], ptr(count), ptr(index), ptr(ws), ws.numel(), stream_ptr(dev)))
+    return (out, count, index) if want_index else (out, count)
+
+
+def cloud_stats(data: torch.Tensor, n: int) -> np.ndarray:
+    """float64 [9] on the host: min xyz, max xyz, sum xyz of the first n points (one kernel, one 72-byte read-back)."""
+    dev = data.device
+    ctx = ctx_for(dev)
+    stats = torch.empty(9, dtype=torch.float64, device=dev)
+    ctx.check(ctx.lib.rv_cloud_stats(ctx.handle, ptr(data), pstride(data), n, _RV_DT[data.dtype], ptr(stats), stream_ptr(dev)))
+    return stats.cpu().numpy()
+
+
+def planes_to_host(data: torch.Tensor, first: int, rows: int, n: int) -> np.ndarray:
+    """(n, rows) float64 numpy copy of planes [first, first+rows) of an SoA cloud: one device->host copy per plane (each is
+    contiguous), transpose and widening on the host -- no device kernel."""
+    host = torch.empty((rows, max(n, 1)), dtype=data.dtype)
+    for r in range(rows):
+        host[r, :n].copy_(data[first + r, :n])
+    return np.ascontiguousarray(host[:, :n].numpy().T, dtype=np.float64)
 
 
 def transform_merge(views, Ts, has_color: bool, out_dtype=None, want_bounds=False):

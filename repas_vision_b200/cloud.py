@@ -101,7 +101,7 @@ class PointCloud:
             n = 0
         self._data = data
         self._normals = None  # float64 [3, n] once estimate_normals ran; rotated by transform, averaged by voxel_down_sample,
-        # dropped by the filters and by +
+        # carried through select_by_index, the filters, remove_statistical_outlier and + (Open3D SelectByIndex / operator+=)
         self._n = int(n)
         self._has_color = bool(has_color) and data.shape[0] >= 6
 
@@ -146,13 +146,14 @@ class PointCloud:
 
     @property
     def points(self) -> np.ndarray:
-        return self.xyz.t().to(torch.float64).cpu().numpy()
+        """(N,3) float64 like np.asarray(pcd.points): one device->host copy per plane, transposed on the host."""
+        return _ops.planes_to_host(self._data, 0, 3, self._n)
 
     @property
     def colors(self) -> np.ndarray:
         if not self._has_color:
             return np.zeros((0, 3))
-        return self.rgb.t().to(torch.float64).cpu().numpy()
+        return _ops.planes_to_host(self._data, 3, 3, self._n)
 
     def has_colors(self) -> bool:
         return self._has_color and self._n > 0
@@ -164,10 +165,10 @@ class PointCloud:
         return self._n == 0
 
     def get_min_bound(self) -> np.ndarray:
-        return self.xyz.to(torch.float64).min(dim=1).values.cpu().numpy() if self._n else np.zeros(3)
+        return _ops.cloud_stats(self._data, self._n)[0:3] if self._n else np.zeros(3)
 
     def get_max_bound(self) -> np.ndarray:
-        return self.xyz.to(torch.float64).max(dim=1).values.cpu().numpy() if self._n else np.zeros(3)
+        return _ops.cloud_stats(self._data, self._n)[3:6] if self._n else np.zeros(3)
 
     def __repr__(self):
         return f"PointCloud with {self._n} points."
@@ -188,7 +189,12 @@ class PointCloud:
         return self
 
     def transformed(self, T) -> "PointCloud":
-        return PointCloud(self._data, self._n, self._has_color).transform(T) if self._n else self
+        """A moved copy; this cloud is left as it is (normals are rotated along, as `transform` does)."""
+        if not self._n:
+            return self
+        pc = PointCloud(self._data, self._n, self._has_color)
+        pc._normals = self._normals
+        return pc.transform(T)
 
     def __add__(self, other: "PointCloud") -> "PointCloud":
         return merge([self, other])
@@ -267,7 +273,10 @@ class PointCloud:
         keep, _ = _ops.statistical_outlier_mask(mean, float(std_ratio))
         out, count, index = _ops.select_by_mask(self._data, self._n, self._has_color, keep)
         m = int(count.item())
-        return PointCloud(out, m, self._has_color), DeviceIndexList(index[:m])
+        pc = PointCloud(out, m, self._has_color)
+        if self._normals is not None:
+            pc._normals = self._normals[:, :self._n].index_select(1, index[:m]).contiguous()
+        return pc, DeviceIndexList(index[:m])
 
     def compute_nearest_neighbor_distance(self) -> np.ndarray:
         """Open3D PointCloud.compute_nearest_neighbor_distance (ply_to_stl.py:45,56): distance from every point to its
@@ -304,7 +313,7 @@ class PointCloud:
 
     def get_center(self) -> np.ndarray:
         """Mean of the points (zeros for an empty cloud)."""
-        return self.xyz.to(torch.float64).mean(dim=1).cpu().numpy() if self._n else np.zeros(3)
+        return _ops.cloud_stats(self._data, self._n)[6:9] / self._n if self._n else np.zeros(3)
 
     def paint_uniform_color(self, color) -> "PointCloud":
         """Open3D PointCloud.paint_uniform_color: every point gets `color` (unit RGB).  In place, returns self."""
@@ -325,14 +334,23 @@ class PointCloud:
             keep = torch.ones(self._n, dtype=torch.bool, device=self.device)
             keep[idx] = False
             idx = torch.nonzero(keep).reshape(-1)
-        return PointCloud(self._data[:, :self._n].index_select(1, idx).contiguous(), idx.numel(), self._has_color)
+        pc = PointCloud(self._data[:, :self._n].index_select(1, idx).contiguous(), idx.numel(), self._has_color)
+        if self._normals is not None:
+            pc._normals = self._normals[:, :self._n].index_select(1, idx).contiguous()
+        return pc
 
     # ---- the reference's cloud predicates, fused into one ordered compaction kernel
     def _filtered(self, **kw) -> "PointCloud":
         if self._n == 0:
             return self
-        out, count = _ops.filter_cloud(self._data, self._n, self._has_color, **kw)
-        return PointCloud(out, int(count.item()), self._has_color)
+        if self._normals is None:
+            out, count = _ops.filter_cloud(self._data, self._n, self._has_color, **kw)
+            return PointCloud(out, int(count.item()), self._has_color)
+        out, count, index = _ops.filter_cloud(self._data, self._n, self._has_color, want_index=True, **kw)
+        m = int(count.item())
+        pc = PointCloud(out, m, self._has_color)
+        pc._normals = self._normals[:, :self._n].index_select(1, index[:m]).contiguous()
+        return pc
 
     def select_within_distance(self, max_distance: float = 1.0) -> "PointCloud":
         """keep ||p||_2 < max_distance (strict), float64 on the stored coordinates."""
@@ -358,7 +376,10 @@ def merge(clouds) -> PointCloud:
     eye = np.eye(4)
     views = [(c._data, c._n) for c in clouds]
     out, total, _ = _ops.transform_merge(views, [eye] * len(views), has_color)
-    return PointCloud(out, total, has_color)
+    pc = PointCloud(out, total, has_color)
+    if total and all(c._normals is not None or c._n == 0 for c in clouds):  # Open3D operator+= keeps normals when both sides have them
+        pc._normals = torch.cat([c._normals[:, :c._n] for c in clouds if c._n], dim=1).contiguous()
+    return pc
 
 
 # --------------------------------------------------------------------------- a1/a2
@@ -380,6 +401,37 @@ def depth_to_meters(depth_raw, rule: str = "mul_f32", scale=None):
 
 
 # --------------------------------------------------------------------------- a3
+def _depth_kind(d):
+    """The kernel reads uint16 raw depth or float32 metres.  The reference converts whatever `np.load` returned with
+    `depth_m[valid].astype(np.float64)` (create_masked_ply.py:91): a float64 image whose values are exactly float32 numbers
+    (what depth_to_meters and the capture scripts write) gives the same bits through float32 and is accepted; anything that
+    would be narrowed or reinterpreted (float64 with more precision, float16, other integers) is refused instead of silently
+    producing a different cloud."""
+    if isinstance(d, torch.Tensor):
+        if d.dtype == torch.uint16:
+            return "u16", d
+        if d.dtype == torch.float32:
+            return "f32", d
+        if d.dtype == torch.float64:
+            n = d.to(torch.float32)
+            if bool(((n.to(torch.float64) == d) | (d != d)).all()):
+                return "f32", n
+            raise RuntimeError("depth is float64 with values that are not float32 numbers: pass float32 metres or uint16 raw depth "
+                               "(the kernel would narrow them and the cloud would differ from the reference's)")
+        raise RuntimeError(f"depth dtype {d.dtype} is not supported: pass uint16 raw depth or float32 metres")
+    if d.dtype == np.uint16:
+        return "u16", d
+    if d.dtype == np.float32:
+        return "f32", d
+    if d.dtype == np.float64:
+        n = d.astype(np.float32)
+        if np.array_equal(n.astype(np.float64), d, equal_nan=True):
+            return "f32", n
+        raise RuntimeError("depth is float64 with values that are not float32 numbers: pass float32 metres or uint16 raw depth "
+                           "(the kernel would narrow them and the cloud would differ from the reference's)")
+    raise RuntimeError(f"depth dtype {d.dtype} is not supported: pass uint16 raw depth or float32 metres")
+
+
 def _prep_frame_inputs(rgb, depth, mask, dev):
     """Validate one frame's arrays the way create_masked_ply.py:134-139 does and upload them as [1,...] tensors."""
     d = depth if isinstance(depth, torch.Tensor) else np.asarray(depth)
@@ -394,12 +446,8 @@ def _prep_frame_inputs(rgb, depth, mask, dev):
         m = mask if isinstance(mask, torch.Tensor) else np.asarray(mask)
         if tuple(m.shape) != (H, W):
             raise RuntimeError(f"Mask/depth size mismatch: mask {tuple(m.shape)}, depth {(H, W)}")
-    if isinstance(d, torch.Tensor):
-        kind = "u16" if d.dtype == torch.uint16 else "f32"
-        dt = _ops.to_device(d, dev, None if kind == "u16" else torch.float32)
-    else:
-        kind = "u16" if d.dtype == np.uint16 else "f32"
-        dt = _ops.to_device(d if kind == "u16" else d.astype(np.float32, copy=False), dev)
+    kind, d = _depth_kind(d)
+    dt = _ops.to_device(d, dev)
     ct = None if rgb is None else _ops.to_device(rgb, dev, torch.uint8)
     mt = None if mask is None else _ops.to_device(mask, dev, torch.uint8)
     return (dt[None], None if ct is None else ct[None], None if mt is None else mt[None], kind, H, W)
@@ -496,14 +544,10 @@ def deproject_batch(depth, bgr, camera, mask=None, *, unit_rule: str = "mul_f32"
     color_scale="packed8": colours stay bytes (one r,g,b,0 word per point in a fourth plane) instead of three float planes."""
     cam = _as_camera(camera)
     dev = depth.device if _is_torch_cuda(depth) else _ops.require_cuda()
-    d = _ops.to_device(depth, dev)
+    kind, d = _depth_kind(depth if isinstance(depth, torch.Tensor) else np.asarray(depth))
+    d = _ops.to_device(d, dev)
     if d.dim() != 3:
         raise RuntimeError(f"depth must be [B,H,W], got {tuple(d.shape)}")
-    if d.dtype == torch.uint16:
-        kind = "u16"
-    else:
-        kind = "f32"
-        d = d.to(torch.float32)
     B, H, W = d.shape
     c = None if bgr is None else _ops.to_device(bgr, dev, torch.uint8)
     if color_format not in ("bgr", "nv12"):

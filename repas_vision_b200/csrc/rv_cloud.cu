@@ -137,6 +137,37 @@ __global__ void __launch_bounds__(256) k_bounds(const T *__restrict__ in, long l
   block_bounds_commit(lo, hi, bounds);
 }
 
+// min / max / sum of the coordinates in one pass (get_min_bound, get_max_bound, get_center)
+template <typename T>
+__global__ void __launch_bounds__(256) k_cloud_stats(const T *__restrict__ in, long long stride_in, long long n, double *stats) {
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  double lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf}, sum[3] = {0.0, 0.0, 0.0};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double v = (double)in[a * stride_in + i];
+      lo[a] = v < lo[a] ? v : lo[a];
+      hi[a] = v > hi[a] ? v : hi[a];
+      sum[a] += v;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum[a] += __shfl_xor_sync(0xffffffffu, sum[a], o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(stats + 6 + a, sum[a]);
+  }
+  block_bounds_commit(lo, hi, stats);
+}
+
+__global__ void k_stats_init(double *b) {
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  if (threadIdx.x < 3) b[threadIdx.x] = inf;
+  else if (threadIdx.x < 6) b[threadIdx.x] = -inf;
+  else if (threadIdx.x < 9) b[threadIdx.x] = 0.0;
+}
+
 // --------------------------------------------------------------------- voxel grid
 // Workspace: [header 256 B][per-part counters: 2048 x 8 B][keys: capacity x 8 B][record index: capacity x 4 B][records: n x 64 B][list: n x 4 B]
 //
@@ -517,6 +548,24 @@ int rv_bounds_init(rv_ctx *ctx, double *d_bounds, rv_stream stream) {
   RvDeviceGuard dev_guard(ctx);
   if (!d_bounds) RV_FAIL(ctx, RV_EINVAL, "rv_bounds_init: null pointer");
   k_bounds_init<<<1, 32, 0, (cudaStream_t)stream>>>(d_bounds);
+  RV_LAUNCHED(ctx);
+  return RV_OK;
+}
+
+int rv_cloud_stats(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int dtype, double *d_stats,
+                   rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
+  if (!d_stats || n < 0 || in_plane_stride < n) RV_FAIL(ctx, RV_EINVAL, "rv_cloud_stats: bad n / stride / null output");
+  if (dtype != RV_F32 && dtype != RV_F64) RV_FAIL(ctx, RV_EINVAL, "rv_cloud_stats: bad dtype");
+  if (n > 0 && !d_in) RV_FAIL(ctx, RV_EINVAL, "rv_cloud_stats: null cloud pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  k_stats_init<<<1, 32, 0, st>>>(d_stats);
+  RV_LAUNCHED(ctx);
+  if (n == 0) return RV_OK;
+  const int g = grid_for(ctx, n);
+  if (dtype == RV_F32) k_cloud_stats<float><<<g, 256, 0, st>>>(reinterpret_cast<const float *>(d_in), in_plane_stride, n, d_stats);
+  else k_cloud_stats<double><<<g, 256, 0, st>>>(reinterpret_cast<const double *>(d_in), in_plane_stride, n, d_stats);
   RV_LAUNCHED(ctx);
   return RV_OK;
 }

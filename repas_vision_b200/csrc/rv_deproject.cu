@@ -733,12 +733,14 @@ size_t rv_filter_workspace_bytes(int64_t n) {
 }
 
 int rv_filter_cloud(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int dtype, int has_color,
-                    const RvDeprojectParams *p, void *d_out, int64_t out_plane_stride, int64_t *d_count, void *d_ws,
-                    size_t ws_bytes, rv_stream stream) {
+                    const RvDeprojectParams *p, void *d_out, int64_t out_plane_stride, int64_t *d_count, int64_t *d_index,
+                    void *d_ws, size_t ws_bytes, rv_stream stream) {
   if (!ctx) return RV_EINVAL;
   RvDeviceGuard dev_guard(ctx);
   if (!p || !d_count) RV_FAIL(ctx, RV_EINVAL, "rv_filter_cloud: null params/count");
   if (n < 0 || in_plane_stride < n) RV_FAIL(ctx, RV_EINVAL, "rv_filter_cloud: bad n / stride");
+  // the kept count is only known on the device: every plane must be able to take all n points
+  if (out_plane_stride < n) RV_FAIL(ctx, RV_ECAPACITY, "rv_filter_cloud: out_plane_stride %lld < n %lld", (long long)out_plane_stride, (long long)n);
   if (dtype != RV_F32 && dtype != RV_F64) RV_FAIL(ctx, RV_EINVAL, "rv_filter_cloud: bad dtype");
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) {
@@ -770,6 +772,7 @@ int rv_filter_cloud(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int6
   a.use_zclip = p->use_zclip ? 1 : 0;
   a.use_radius = p->use_radius ? 1 : 0;
   a.use_aabb = p->use_aabb ? 1 : 0;
+  a.index_out = reinterpret_cast<long long *>(d_index);
   if (dtype == RV_F32) filter_launch<float>(ctx, a, st);
   else filter_launch<double>(ctx, a, st);
   RV_LAUNCHED(ctx);
@@ -783,6 +786,7 @@ int rv_select_by_mask(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, in
   RvDeviceGuard dev_guard(ctx);
   if (!d_keep || !d_count) RV_FAIL(ctx, RV_EINVAL, "rv_select_by_mask: null mask/count");
   if (n < 0 || in_plane_stride < n) RV_FAIL(ctx, RV_EINVAL, "rv_select_by_mask: bad n / stride");
+  if (out_plane_stride < n) RV_FAIL(ctx, RV_ECAPACITY, "rv_select_by_mask: out_plane_stride %lld < n %lld", (long long)out_plane_stride, (long long)n);
   if (dtype != RV_F32 && dtype != RV_F64) RV_FAIL(ctx, RV_EINVAL, "rv_select_by_mask: bad dtype");
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) {

@@ -167,8 +167,8 @@ struct Layout {
   static constexpr int kWarpStage = kWarpPx * (3 * (int)sizeof(OutT) + 4 + (kGen ? 2 : 0));
   static constexpr int kRingBytes = kStages * kStageBytes;
   static constexpr int kSmem = kRingBytes + kCW * kWarpStage;
-  // resident CTAs per SM the shared memory allows (227 KB usable, ~1.5 KB static + reserved per CTA)
-  static constexpr int kOccSmem = (227 * 1024) / (kSmem + 1536);
+  // resident CTAs per SM the shared memory allows (227 KB usable, 1.4 KB static + 1 KB reserved per CTA)
+  static constexpr int kOccSmem = (227 * 1024) / (kSmem + 2560);
 #ifndef RV_K1_WARPS_PER_SM
 #define RV_K1_WARPS_PER_SM 32
 #endif

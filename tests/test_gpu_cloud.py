@@ -549,3 +549,70 @@ def test_voxel_down_sample_averages_normals(rv, O):
             assert np.allclose(down.colors[order], col, **tol)
         single = counts[order] == 1
         assert np.allclose(np.linalg.norm(down.normals[order][single], axis=1), 1.0, atol=1e-12)
+
+
+def test_normals_follow_selection_filters_and_merge(rv):
+    """Open3D's SelectByIndex and operator+= carry normals; so do the fused predicates and the outlier filter here.  A target
+    cropped after estimate_normals must still feed point-to-plane ICP (mpa_icp_export.py:166-197)."""
+    rng = np.random.default_rng(41)
+    P = np.concatenate([rng.uniform(-0.4, 0.4, (4000, 2)), rng.normal(0.9, 0.002, (4000, 1))], axis=1)
+    pc = rv.PointCloud.from_arrays(P, rng.random((4000, 3)))
+    pc.estimate_normals(rv.KDTreeSearchParamHybrid(0.1, 20))
+    N = pc.normals
+    idx = np.array([5, 17, 3999, 0, 256])
+    assert np.array_equal(pc.select_by_index(idx).normals, N[idx])
+    inv = pc.select_by_index(idx, invert=True)
+    keep = np.ones(4000, bool)
+    keep[idx] = False
+    assert np.array_equal(inv.normals, N[keep]) and np.array_equal(inv.points, P[keep])
+    near = pc.select_within_distance(0.95)
+    m = np.sqrt((P * P).sum(1)) < 0.95
+    assert near.has_normals() and np.array_equal(near.normals, N[m]) and np.array_equal(near.points, P[m])
+    box = pc.crop_aabb([-0.2, -0.1, 0.0], [0.3, 0.25, 2.0])
+    mb = (P >= [-0.2, -0.1, 0.0]).all(1) & (P <= [0.3, 0.25, 2.0]).all(1)
+    assert np.array_equal(box.normals, N[mb])
+    zc = pc.clip_z(0.899, 0.901)
+    assert np.array_equal(zc.normals, N[(P[:, 2] >= 0.899) & (P[:, 2] <= 0.901)])
+    kept, ind = pc.remove_statistical_outlier(20, 2.0)
+    assert np.array_equal(kept.normals, N[np.asarray(ind)])
+    both = near + box
+    assert both.has_normals() and np.array_equal(both.normals, np.concatenate([N[m], N[mb]]))
+    plain = rv.PointCloud.from_arrays(P[:10], None)
+    assert not (near + plain).has_normals()  # one side without normals: the sum has none (Open3D)
+    T = _rand_pose(rng)
+    moved = pc.transformed(T)
+    assert moved.has_normals() and np.abs(moved.normals - N @ T[:3, :3].T).max() < 1e-12 and np.array_equal(pc.normals, N)
+    # the cropped target is still a valid point-to-plane target
+    src = near.select_by_index(np.arange(0, len(near), 3))
+    reg = rv.registration_icp(src, near, 0.02, np.eye(4), rv.TransformationEstimationPointToPlane(), rv.ICPConvergenceCriteria(max_iteration=3))
+    assert reg.fitness == 1.0
+
+
+def test_bounds_center_and_filter_capacity(rv):
+    import ctypes as C
+    import torch
+    from repas_vision_b200 import _lib, _ops
+    rng = np.random.default_rng(9)
+    for dtype in ("f64", "f32"):
+        P = rng.normal(0.0, 1.0, (50001, 3))
+        pc = rv.PointCloud.from_arrays(P, None, dtype=dtype)
+        Q = pc.points
+        assert np.array_equal(pc.get_min_bound(), Q.min(0)) and np.array_equal(pc.get_max_bound(), Q.max(0))
+        assert np.abs(pc.get_center() - Q.mean(0)).max() < 1e-12
+    empty = rv.PointCloud(None, 0, False)
+    assert np.array_equal(empty.get_min_bound(), np.zeros(3)) and np.array_equal(empty.get_center(), np.zeros(3))
+    # the kept count is only known on the device: an output too small for all n points is refused, not overrun
+    ctx = _lib.context(0)
+    data = torch.zeros((3, 1000), dtype=torch.float32, device="cuda")
+    out = torch.zeros((3, 10), dtype=torch.float32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    keep = torch.ones(1000, dtype=torch.uint8, device="cuda")
+    ws = _ops.workspace(ctx.lib.rv_filter_workspace_bytes(1000), data.device)
+    p = _lib.RvDeprojectParams()
+    p.use_radius, p.r_max = 1, 1.0
+    st = ctx.lib.rv_filter_cloud(ctx.handle, _ops.ptr(data), 1000, 1000, _lib.RV_F32, 0, C.byref(p), _ops.ptr(out), 10, _ops.ptr(cnt),
+                                 None, _ops.ptr(ws), ws.numel(), None)
+    assert st == _lib.RV_ECAPACITY
+    st = ctx.lib.rv_select_by_mask(ctx.handle, _ops.ptr(data), 1000, 1000, _lib.RV_F32, 0, _ops.ptr(keep), _ops.ptr(out), 10,
+                                   _ops.ptr(cnt), None, _ops.ptr(ws), ws.numel(), None)
+    assert st == _lib.RV_ECAPACITY

@@ -332,7 +332,9 @@ def test_packed_mode_and_host_pipeline(rv, O, rs720, kernel):
         a8 = HostPipeline(cam, H, W, max_distance=1.3, chunk_frames=4, color_format="nv12").run(depth, nv12)
         for fb in range(B):
             assert np.array_equal(a8.frame(fb)[0], b2.frame(fb)[0])
-            assert np.array_equal(a8.colors(fb), b2.colors(fb))
+            assert np.array_equal(a8.frame(fb)[1].astype(np.float32) / np.float32(255.0), b2.frame(fb)[1].T)
+            keep = O.deproject_mask(depth[fb], bgr_cv[fb], None, fx=cam.fx, fy=cam.fy, cx=cam.cx, cy=cam.cy, r_max=1.3, out_dtype="f32")["valid"]
+            assert np.array_equal(a8.colors(fb), bgr_cv[fb][keep][:, ::-1].astype(np.float64) / 255.0)
         res2 = pipe.run(torch.from_numpy(depth).pin_memory(), torch.from_numpy(bgr).pin_memory())  # pinned inputs, reuse
         assert np.array_equal(res2.counts, res.counts) and np.array_equal(res2.frame(B - 1)[0], res.frame(B - 1)[0])
         # results own their pinned memory: a later run must not overwrite arrays handed out earlier (only release() recycles)

@@ -285,3 +285,26 @@ def test_device_index_list_behaves_like_the_index_array(built):
     assert int(ind[1]) == 7 and [int(v) for v in ind] == [4, 7, 9, 12] and np.array_equal(ind[1:3], [7, 9])
     assert np.asarray(ind, dtype=np.int32).dtype == np.int32
     assert len(DeviceIndexList(torch.zeros(0, dtype=torch.int64))) == 0
+
+
+def test_depth_dtype_policy():
+    """create_masked_ply.py:91 converts whatever dtype np.load returned to float64; the kernel reads uint16 or float32.  A
+    float64 image of float32 numbers is the same cloud and passes, anything that would be narrowed is refused."""
+    import torch
+    from repas_vision_b200.cloud import _depth_kind
+    u = np.arange(12, dtype=np.uint16).reshape(3, 4)
+    assert _depth_kind(u)[0] == "u16" and _depth_kind(u)[1] is u
+    f = (u.astype(np.float32) * np.float32(0.001))
+    assert _depth_kind(f)[0] == "f32"
+    f64 = f.astype(np.float64)
+    f64[0, 0] = np.nan
+    k, d = _depth_kind(f64)
+    assert k == "f32" and d.dtype == np.float32 and np.array_equal(d.astype(np.float64), f64, equal_nan=True)
+    with pytest.raises(RuntimeError):
+        _depth_kind(u.astype(np.float64) * 0.001)  # float64 products are not float32 numbers
+    for bad in (np.int32, np.float16, np.uint8):
+        with pytest.raises(RuntimeError):
+            _depth_kind(u.astype(bad))
+    assert _depth_kind(torch.from_numpy(f64))[0] == "f32"
+    with pytest.raises(RuntimeError):
+        _depth_kind(torch.from_numpy(u.astype(np.int32)))

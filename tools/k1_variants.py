@@ -1,0 +1,38 @@
+#!/usr/bin/env python3
+"""Builds differently tuned variants of the library for A/B runs of K1 on the GPU box (ring depth, tile size, CTAs per SM).
+    python tools/k1_variants.py            # build/variants/librv_<name>.so
+The GPU side: RV_LIBRARY_PATH=build/variants/librv_<name>.so python bench.py --no-e2e --no-cpu-baseline --no-rows ..."""
+import os
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from repas_vision_b200 import _build  # noqa: E402
+
+VARIANTS = {
+    "s2_i8_c4": "-DRV_K1_STAGES=2 -DRV_K1_ITERS=8 -DRV_K1_WARPS_PER_SM=32",   # shipped in round 1
+    "s3_i8_c3": "-DRV_K1_STAGES=3 -DRV_K1_ITERS=8 -DRV_K1_WARPS_PER_SM=24",
+    "s4_i8_c3": "-DRV_K1_STAGES=4 -DRV_K1_ITERS=8 -DRV_K1_WARPS_PER_SM=24",
+    "s3_i6_c4": "-DRV_K1_STAGES=3 -DRV_K1_ITERS=6 -DRV_K1_WARPS_PER_SM=32",
+    "s4_i4_c4": "-DRV_K1_STAGES=4 -DRV_K1_ITERS=4 -DRV_K1_WARPS_PER_SM=32",
+    "s6_i4_c4": "-DRV_K1_STAGES=6 -DRV_K1_ITERS=4 -DRV_K1_WARPS_PER_SM=32",
+    "s4_i4_c5": "-DRV_K1_STAGES=4 -DRV_K1_ITERS=4 -DRV_K1_WARPS_PER_SM=40",
+}
+
+
+def main():
+    names = sys.argv[1:] or list(VARIANTS)
+    outdir = os.path.join(ROOT, "build", "variants")
+    os.makedirs(outdir, exist_ok=True)
+
+    def one(n):
+        return _build.build(out=os.path.join(outdir, f"librv_{n}.so"), extra=VARIANTS[n], tag="obj_" + n)
+
+    with ThreadPoolExecutor(max_workers=3) as ex:
+        for p in ex.map(one, names):
+            print(p)
+
+
+if __name__ == "__main__":
+    main()
