@@ -216,12 +216,16 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
-  __shared__ __align__(8) uint64_t tot_bar[2];                // the warps' run totals of a tile are posted
+  // Per-tile exchange slots are eight deep (tile it uses slot it & 7): a warp that finds nothing in its run posts its zero
+  // and moves on without waiting, so it can be up to kStages - 1 tiles ahead of the slowest warp of the CTA (the input ring
+  // holds it there: a stage is refilled only after all eight warps released it).  kStages <= 7.
+  __shared__ __align__(8) uint64_t tot_bar[8];                // the warps' run totals of a tile are posted
   __shared__ __align__(8) uint64_t base_bar[8];               // slow path: warp 0 posts the tile base
   __shared__ int4 s_info[kStages];                            // {status index or -1, frame, tile in frame, pixels in tile}
-  __shared__ __align__(16) uint32_t s_tot[4][kCW];            // kept points of the tile's eight warp runs
-  __shared__ __align__(8) unsigned long long s_peek[2];       // predecessor status word seen by warp 0
+  __shared__ __align__(16) uint32_t s_tot[8][kCW];            // kept points of the tile's eight warp runs
+  __shared__ __align__(8) unsigned long long s_peek[8];       // predecessor status word seen by warp 0
   __shared__ uint32_t s_base[8];
+  static_assert(kStages >= 2 && kStages <= 7, "exchange slots are eight deep");
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -234,10 +238,11 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
       mbar_init(full_a + 8 * s, 1);
       mbar_init(empty_a + 8 * s, kCW);
     }
-    mbar_init(tot_a, kCW);
-    mbar_init(tot_a + 8, kCW);
 #pragma unroll
-    for (int s = 0; s < 8; ++s) mbar_init(base_a + 8 * s, 1);
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(tot_a + 8 * s, kCW);
+      mbar_init(base_a + 8 * s, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -388,7 +393,7 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
           peek_nxt_tile = nx.x;
         }
       }
-      s_peek[it & 1] = peek;  // read by the warps that drain, after the totals barrier
+      s_peek[it & 7] = peek;  // read by the warps that drain, after the totals barrier
     }
 
     // a partial last tile: zero the depth of this warp's own pixels beyond the frame so the loops need no bounds test
@@ -553,30 +558,36 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
         }
       }
     }
-    // the input stage is no longer needed: hand it back to the producer before the prefix is resolved
+    // the input stage is no longer needed: hand it back to the producer before the prefix is resolved (the run total is
+    // posted first: the stage release is what lets the other warps, and this one, run ahead)
     if (npx < kTileT) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // our zero fill vs the next bulk copy
     __syncwarp();
-    if (lane == 0) mbar_arrive(empty_a + 8 * s);
+    if (lane == 0) {
+      if (kOrdered) {
+        s_tot[it & 7][warp] = run;
+        mbar_arrive(tot_a + 8 * (it & 7));
+      }
+      mbar_arrive(empty_a + 8 * s);
+    }
 
     uint32_t base = 0, off = 0;
     if (kOrdered) {
       // ---------------- the eight run totals.  Everybody posts; only the warps that have points to place (and warp 0,
-      // which publishes the tile's prefix) wait for the others.  s_tot is four deep: a warp that posts without waiting can
-      // be two tiles ahead of the slowest reader (the input ring holds it there).
-      if (lane == 0) {
-        s_tot[it & 3][warp] = run;
-        mbar_arrive(tot_a + 8 * (it & 1));
-      }
+      // which publishes the tile's prefix) wait for the others.
       if (run == 0 && warp != 0) continue;  // warp-uniform
-      mbar_wait(tot_a + 8 * (it & 1), (uint32_t)(it >> 1) & 1u);
-      const uint32_t t8 = lane < kCW ? s_tot[it & 3][lane] : 0u;
+      mbar_wait(tot_a + 8 * (it & 7), (uint32_t)(it >> 3) & 1u);
+      const uint32_t t8 = lane < kCW ? s_tot[it & 7][lane] : 0u;
       const uint32_t tile_total = __reduce_add_sync(0xffffffffu, t8);
       off = __reduce_add_sync(0xffffffffu, lane < warp ? t8 : 0u);
 
       // ---------------- tile base
       bool hit = false;
+#ifdef RV_K1_NO_CHAIN  // timing experiment only (wrong offsets): what the kernel would cost without the prefix chain
+      if (false) {
+#else
       if (n_pred > 0) {
-        const unsigned long long pk = s_peek[it & 1];
+#endif
+        const unsigned long long pk = s_peek[it & 7];
         hit = (pk >> 62) == 2;
         if (hit) {
           base = (uint32_t)pk;

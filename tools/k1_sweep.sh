@@ -9,7 +9,7 @@ for so in build/variants/librv_*.so; do
 import json
 try:
     d = json.loads(open("gpurun_out/sweep_$n.json").read().strip().splitlines()[-1])
-    print("$n", round(d["value"]), round(d["roofline"]["frac"], 4), round(d["roofline"]["launch_ms"], 4))
+    print("$n", round(d["value"]), round(d["roofline"]["frac"], 4), round(d["roofline"]["launch_ms"], 4), "kept points/step", d["valid_points_per_step_rank0"])
 except Exception as e:
     print("$n", "failed", e)
 PY

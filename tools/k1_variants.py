@@ -18,6 +18,13 @@ VARIANTS = {
     "s4_i4_c4": "-DRV_K1_STAGES=4 -DRV_K1_ITERS=4 -DRV_K1_WARPS_PER_SM=32",
     "s6_i4_c4": "-DRV_K1_STAGES=6 -DRV_K1_ITERS=4 -DRV_K1_WARPS_PER_SM=32",
     "s4_i4_c5": "-DRV_K1_STAGES=4 -DRV_K1_ITERS=4 -DRV_K1_WARPS_PER_SM=40",
+    "s2_i8_c4_tb1": "-DRV_K1_STAGES=2 -DRV_K1_ITERS=8 -DRV_K1_WARPS_PER_SM=32 -DRV_K1_TICKET_BATCH=1",
+    "s2_i8_c4_tb2": "-DRV_K1_STAGES=2 -DRV_K1_ITERS=8 -DRV_K1_WARPS_PER_SM=32 -DRV_K1_TICKET_BATCH=2",
+    "s2_i8_c4_ahead": "-DRV_K1_STAGES=2 -DRV_K1_ITERS=8 -DRV_K1_WARPS_PER_SM=32 -DRV_K1_TICKET_AHEAD=1",
+    # timing experiments without the prefix chain (offsets are wrong): what the chain costs at each ring depth
+    "nochain_s2_i8_c4": "-DRV_K1_NO_CHAIN -DRV_K1_STAGES=2 -DRV_K1_ITERS=8 -DRV_K1_WARPS_PER_SM=32",
+    "nochain_s4_i8_c3": "-DRV_K1_NO_CHAIN -DRV_K1_STAGES=4 -DRV_K1_ITERS=8 -DRV_K1_WARPS_PER_SM=24",
+    "nochain_s6_i4_c4": "-DRV_K1_NO_CHAIN -DRV_K1_STAGES=6 -DRV_K1_ITERS=4 -DRV_K1_WARPS_PER_SM=32",
 }
 
 
