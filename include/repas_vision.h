@@ -257,14 +257,30 @@ int rv_transform_merge(rv_ctx *ctx, int n_views, const void *const *d_in, const 
  *  d_keys       [3, out_capacity] int32 voxel indices, or NULL
  *  d_counts_out [out_capacity] int32 points per voxel, or NULL
  *  d_m          one int64: number of voxels (true number even if > out_capacity)
- *  d_ws         rv_voxel_workspace_bytes(n) bytes, 64-B aligned: 1.5 n eight-byte hash keys (+ 4 B record index each),
- *               one 64-byte record and one list entry per point; only the keys are cleared by the call
- * Each voxel index must fit 21 bits (extent/voxel < 2^21); otherwise d_m is set to -1. */
+ *  d_ws         rv_voxel_workspace_bytes(n) bytes, 64-B aligned: 1.5 n eight-byte hash keys + 4-byte chain heads, one
+ *               8-byte list entry and one 4-byte link per point, one bit per point of run heads, a small pool for voxels
+ *               with very long chains (about 30 bytes per point in all); keys and chain heads are initialised by the call
+ * Each voxel index must fit 21 bits (extent/voxel < 2^21); otherwise d_m is set to -1.  n < 2^31.
+ * Voxels made of at most eight runs of consecutive points (practically all of a 5 mm grid over camera clouds) are summed
+ * point by point in index order in float64: their means equal the sequential Open3D loop bit for bit. */
 size_t rv_voxel_workspace_bytes(int64_t n);
 int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int in_dtype,
                         int has_color, double voxel_size, const double *d_bounds, void *d_out,
                         int64_t out_plane_stride, int out_dtype, int64_t out_capacity, int32_t *d_keys,
                         int32_t *d_counts_out, int64_t *d_m, void *d_ws, size_t ws_bytes, rv_stream stream);
+
+/* ---- a11 + a12 in one call: the four_pose_captures fusion -------------------------
+ * pcd_i.transform(T_i) for every view, `+`, voxel_down_sample(voxel_size) (SURVEY Appendix D.4;
+ * final_view_with_cad.py:333, mpa_icp_export.py:174) without ever writing the merged cloud: the
+ * views are read where they lie, p' = T_v p is rounded to in_dtype exactly as
+ * rv_transform_merge would store it, and the voxel grid (origin = min bound of the merged
+ * cloud - voxel/2) is built from those values.  Same results as rv_transform_merge followed by
+ * rv_voxel_downsample.  Up to 8 views; arguments as in those two calls; workspace
+ * rv_voxel_workspace_bytes(sum of n). */
+int rv_fuse_voxel(rv_ctx *ctx, int n_views, const void *const *d_in, const int64_t *in_plane_stride, const int64_t *n,
+                  const double *T, int in_dtype, int has_color, double voxel_size, void *d_out, int64_t out_plane_stride,
+                  int out_dtype, int64_t out_capacity, int32_t *d_keys, int32_t *d_counts_out, int64_t *d_m, void *d_ws,
+                  size_t ws_bytes, rv_stream stream);
 
 /* ---- a13 (next): PLY vertex records on device -----------------------
  * packs an SoA cloud into the binary little-endian vertex records that

@@ -73,6 +73,8 @@ SIGNATURES = {
     "rv_voxel_workspace_bytes": (C.c_size_t, [c_i64]),
     "rv_voxel_downsample": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, C.c_int, c_f64, c_vp, c_vp, c_i64, C.c_int,
                                       c_i64, c_vp, c_vp, c_vp, c_vp, C.c_size_t, c_vp]),
+    "rv_fuse_voxel": (C.c_int, [c_vp, C.c_int, C.POINTER(c_vp), C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_f64), C.c_int,
+                                C.c_int, c_f64, c_vp, c_i64, C.c_int, c_i64, c_vp, c_vp, c_vp, c_vp, C.c_size_t, c_vp]),
     "rv_pack_ply_records": (C.c_int, [c_vp, c_vp, c_i64, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
     "rv_unpack_ply_records": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, C.POINTER(c_i32), C.c_int, C.POINTER(c_i32), c_vp, c_i64,
                                         C.c_int, c_vp]),

@@ -295,6 +295,34 @@ def voxel_downsample(data: torch.Tensor, n: int, has_color: bool, voxel_size: fl
     return dict(data=out, m=m, keys=keys, counts=cnts, cap=out.shape[1])
 
 
+def fuse_voxel(views, Ts, has_color: bool, voxel_size: float, *, out_dtype=None, want_keys=False, want_counts=False):
+    """K3 + K4 in one call (rv_fuse_voxel): views = list of (data [planes, stride], n), Ts = list of 4x4 moving each view into
+    the common frame.  The merged cloud is never written.  Returns the dict of voxel_downsample."""
+    dev = views[0][0].device
+    ctx = ctx_for(dev)
+    in_dt = views[0][0].dtype
+    if any(v[0].dtype != in_dt for v in views):
+        raise ValueError("all views must share one dtype")
+    out_dt = in_dt if out_dtype is None else _TORCH_DT[out_dtype]
+    nv = len(views)
+    total = int(sum(v[1] for v in views))
+    planes = 6 if has_color else 3
+    out = torch.empty((planes, max(total, 1)), dtype=out_dt, device=dev)
+    keys = torch.empty((3, max(total, 1)), dtype=torch.int32, device=dev) if want_keys else None
+    cnts = torch.empty(max(total, 1), dtype=torch.int32, device=dev) if want_counts else None
+    m = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = workspace(ctx.lib.rv_voxel_workspace_bytes(total), dev)
+    ptrs = (C.c_void_p * nv)(*[v[0].data_ptr() for v in views])
+    strides = (C.c_int64 * nv)(*[pstride(v[0]) for v in views])
+    ns = (C.c_int64 * nv)(*[int(v[1]) for v in views])
+    Tflat = np.ascontiguousarray(np.stack([np.asarray(T, dtype=np.float64).reshape(4, 4) for T in Ts])).reshape(-1)
+    Tc = (C.c_double * (16 * nv))(*Tflat.tolist())
+    ctx.check(ctx.lib.rv_fuse_voxel(ctx.handle, nv, ptrs, strides, ns, Tc, _RV_DT[in_dt], int(has_color), float(voxel_size),
+                                    ptr(out), out.shape[1], _RV_DT[out_dt], total, ptr(keys), ptr(cnts), ptr(m), ptr(ws),
+                                    ws.numel(), stream_ptr(dev)))
+    return dict(data=out, m=m, keys=keys, counts=cnts, cap=out.shape[1])
+
+
 def pack_ply_records(data: torch.Tensor, n: int, has_color: bool, color_scale="unit", coord_dtype="f32") -> torch.Tensor:
     dev = data.device
     ctx = ctx_for(dev)

@@ -635,12 +635,19 @@ def fuse_views(clouds, T_cam_tag_list, voxel_size: float = 0.005, *, return_keys
         raise ValueError("need one pose per cloud")
     has_color = all(c._has_color for c in clouds)
     Ts = [world_from_camera(T) for T in T_cam_tag_list]
-    out, total, bounds = _ops.transform_merge([(c._data, c._n) for c in clouds], Ts, has_color, want_bounds=True)
-    merged = PointCloud(out, total, has_color)
+    if not (float(voxel_size) > 0.0):
+        raise RuntimeError("[Open3D-compatible] voxel_size <= 0.")
+    total = sum(c._n for c in clouds)
     if total == 0:
-        return (merged, np.zeros((0, 3), np.int32), np.zeros(0, np.int32)) if return_keys else merged
-    r = _ops.voxel_downsample(out, total, has_color, float(voxel_size), bounds=bounds, want_keys=return_keys,
-                              want_counts=return_keys)
+        empty = PointCloud(None, 0, has_color, device=clouds[0].device)
+        return (empty, np.zeros((0, 3), np.int32), np.zeros(0, np.int32)) if return_keys else empty
+    if len(clouds) > 8:  # the fused call takes eight views; more go through the merged cloud
+        out, total, bounds = _ops.transform_merge([(c._data, c._n) for c in clouds], Ts, has_color, want_bounds=True)
+        r = _ops.voxel_downsample(out, total, has_color, float(voxel_size), bounds=bounds, want_keys=return_keys,
+                                  want_counts=return_keys)
+    else:
+        r = _ops.fuse_voxel([(c._data, c._n) for c in clouds], Ts, has_color, float(voxel_size), want_keys=return_keys,
+                            want_counts=return_keys)
     m = int(r["m"].item())
     if m < 0:
         raise RuntimeError("[Open3D-compatible] voxel_size is too small.")

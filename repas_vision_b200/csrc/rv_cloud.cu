@@ -121,22 +121,6 @@ __global__ void k_bounds_init(double *b) {
   else if (threadIdx.x < 6) b[threadIdx.x] = -inf;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) k_bounds(const T *__restrict__ in, long long stride_in, long long n, double *bounds) {
-  const double inf = __longlong_as_double(0x7ff0000000000000ll);
-  double lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const double v = (double)in[a * stride_in + i];
-      lo[a] = v < lo[a] ? v : lo[a];
-      hi[a] = v > hi[a] ? v : hi[a];
-    }
-  }
-  block_bounds_commit(lo, hi, bounds);
-}
-
 // min / max / sum of the coordinates in one pass (get_min_bound, get_max_bound, get_center)
 template <typename T>
 __global__ void __launch_bounds__(256) k_cloud_stats(const T *__restrict__ in, long long stride_in, long long n, double *stats) {
@@ -169,49 +153,68 @@ __global__ void k_stats_init(double *b) {
 }
 
 // --------------------------------------------------------------------- voxel grid
-// Workspace: [header 256 B][per-part counters: 2048 x 8 B][keys: capacity x 8 B][record index: capacity x 4 B][records: n x 64 B][list: n x 4 B]
+// Hash grid without per-point records (round 1 wrote a 64-byte record per run of points and read it back twice: 6.1 x the
+// algorithmic DRAM traffic).  Workspace:
+//   [header 256 B][per-part counters 2048 x 8 B][keys: cap x 8 B][chain: cap x 4 B][list: n x 8 B][next: n x 4 B]
+//   [head masks: ceil(n / 32) x 4 B][long-voxel pool: (n / 256 + 1) x 64 B]
+// k_vox_insert  reads the coordinates only (four 32-point groups per warp and step, all loads and then all first-probe
+//               compare-and-swaps issued before anything is consumed).  Points arrive in pixel order, so consecutive points
+//               usually share a voxel: a run of equal keys inside a 32-point group is represented by its first point (the
+//               "head"; the ballot of heads is kept per group, 1 bit per point).  A head claims its key's slot with ONE
+//               compare-and-swap ("creator") or finds it taken ("joiner"); both append (point index, slot) to their part's
+//               stretch of the list (creators from the front, joiners from the back; positions from shared-memory counters:
+//               the cloud is cut into one contiguous part per CTA, no global counter anywhere); a joiner additionally links
+//               itself into the slot's chain with one atomic exchange.
+// k_vox_emit    one thread per creator = per voxel: it gathers the voxel's runs (its own and the chain's), sorts the run heads
+//               by point index when there are at most eight of them, and adds the points one by one in float64 -- for those
+//               voxels exactly the index-order sums of Open3D's loop, so the means are bit-identical to the oracle's.  Points
+//               are re-read from the input (L2-resident: the insert just streamed it) and, for a fusion, re-transformed.
+//               mean = sum / count by the exact-quotient helper.  Part p's voxels go behind those of parts 0..p-1.
+// A voxel whose chain is longer than kVoxLongChain runs (a coarse grid over a big cloud) is finished by k_vox_long instead:
+// every joiner of such a voxel adds its run into a pool record with float64 atomics, k_vox_long_final divides.  Both return at
+// once when no voxel is long.
 //
-// The hash table holds only 8-byte keys (1.5 n slots, any size: the hash is mapped with a multiply-high), so clearing it
-// and probing it touch an eighth of the bytes a table of full records would and the whole table stays in the L2; the record
-// index of each slot lives in a parallel array that is written by the slot's creator and never cleared.  Points arrive in
-// pixel order, so consecutive points usually share a voxel: each warp first folds runs of equal keys with a segmented
-// shuffle reduction, and only the head of a run goes to memory.  A run head
-//   * writes its partial sums to the record with its own point index (plain stores, no allocation counter),
-//   * tries to claim the slot of its key with ONE compare-and-swap: the winner's record becomes the voxel's record
-//     ("creator"); a head that finds the key already there is a "joiner",
-//   * creators and joiners are appended to the two ends of the CTA's own stretch of the list (the cloud is cut into one
-//     contiguous part per CTA), positions from shared-memory counters: no global counter anywhere.
-// k_voxel_merge then adds every joiner's record into its voxel's record with float64 atomics (the kernel boundary is
-// the only ordering the scheme needs: no fences, no spinning on another thread's publication), and k_voxel_emit writes
-// part p's creators behind the creators of parts 0..p-1 (a 2048-entry prefix sum per CTA).
+// The pose transform of a fusion (K3) is fused in: the views are read where they lie, p' = T p is rounded to the cloud's
+// storage type exactly as rv_transform_merge stores it, and the merged cloud is never written.
+constexpr int kVoxViews = 8;
+struct VoxView {
+  const void *in;
+  long long stride, n, first;  // first: index of the view's first point in the merged order
+  double T[16];
+};
 struct VoxHeader {
   double bounds[6];
   int error;  // 1: a voxel index does not fit 21 bits / extent check failed
-  int pad;
+  unsigned int n_long;
 };
 constexpr int kVoxMaxParts = 2048;
 constexpr size_t kVoxHead = 256 + (size_t)kVoxMaxParts * 8;  // header + per-part {creators, joiners}
-struct __align__(64) VoxAcc {
+constexpr unsigned int kVoxNil = 0xffffffffu;
+constexpr unsigned int kVoxLongTag = 0x80000000u;
+constexpr int kVoxLongChain = 256;
+struct __align__(64) VoxLong {
   unsigned long long key;
   unsigned int count;
-  unsigned int pad;
+  unsigned int out;  // output position of the voxel
   double sum[6];
 };
-static_assert(sizeof(VoxAcc) == 64, "record layout");
+static_assert(sizeof(VoxLong) == 64, "pool record layout");
 
 struct VoxArgs {
-  const void *in;
-  long long in_stride, n;
-  int has_color;
+  VoxView view[kVoxViews];
+  int n_views, identity, has_color;
+  long long n;
   double voxel, rvoxel;
   const double *bounds;  // device
   VoxHeader *hdr;
   unsigned long long *keys;  // 0 = empty, else packed(ix,iy,iz) + 1
-  unsigned int *slot_rec;    // record index of the slot's creator (valid where keys[] != 0 once k_voxel_insert is done)
-  VoxAcc *acc;
-  unsigned int *list;  // part p owns list[p * span, ...): creators from its front, joiners from its back (record indices)
-  uint2 *parts;        // per part {creators, joiners}
-  long long span;      // points per part, a multiple of 32
+  unsigned int *chain;       // per slot: list position of the most recent joiner, kVoxNil = none, tag | pool index once long
+  uint2 *list;               // (point index, slot) of every head; part p owns list[p * span, ...)
+  unsigned int *next;        // per list position of a joiner: the joiner linked before it
+  unsigned int *headmask;    // per 32-point group: bit l set = point l starts a run
+  VoxLong *pool;
+  uint2 *parts;  // per part {creators, joiners}
+  long long span;  // points per part, a multiple of 128
   unsigned int cap;
 };
 
@@ -224,9 +227,76 @@ __device__ __forceinline__ unsigned long long vox_hash(unsigned long long k) {
   return k;
 }
 
+// view of merged point i (views are few: a short scan)
+__device__ __forceinline__ int vox_view_of(const VoxArgs &a, long long i) {
+  int v = 0;
+#pragma unroll 1
+  for (int q = 1; q < a.n_views; ++q)
+    if (i >= a.view[q].first) v = q;
+  return v;
+}
+
+// coordinates of merged point i as they are STORED in the cloud's element type T (after the pose transform of its view)
 template <typename T>
-__global__ void __launch_bounds__(256) k_voxel_insert(const VoxArgs a) {
-  const T *in = reinterpret_cast<const T *>(a.in);
+__device__ __forceinline__ void vox_xyz(const VoxArgs &a, long long i, double &x, double &y, double &z) {
+  const int v = a.n_views > 1 ? vox_view_of(a, i) : 0;
+  const VoxView &w = a.view[v];
+  const T *in = reinterpret_cast<const T *>(w.in);
+  const long long k = i - w.first;
+  x = (double)in[k];
+  y = (double)in[w.stride + k];
+  z = (double)in[2 * w.stride + k];
+  if (!a.identity) {  // Open3D Transform, one rounding per operation (k_transform), then the store's rounding
+    const double *M = w.T;
+    const double qx = ((M[0] * x + M[1] * y) + M[2] * z) + M[3];
+    const double qy = ((M[4] * x + M[5] * y) + M[6] * z) + M[7];
+    const double qz = ((M[8] * x + M[9] * y) + M[10] * z) + M[11];
+    const double qw = ((M[12] * x + M[13] * y) + M[14] * z) + M[15];
+    double px = qx, py = qy, pz = qz;
+    if (qw != 1.0) {
+      px = qx / qw;
+      py = qy / qw;
+      pz = qz / qw;
+    }
+    x = (double)(T)px;
+    y = (double)(T)py;
+    z = (double)(T)pz;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void vox_rgb(const VoxArgs &a, long long i, double &r, double &g, double &b) {
+  const int v = a.n_views > 1 ? vox_view_of(a, i) : 0;
+  const VoxView &w = a.view[v];
+  const T *in = reinterpret_cast<const T *>(w.in);
+  const long long k = i - w.first;
+  r = (double)in[3 * w.stride + k];
+  g = (double)in[4 * w.stride + k];
+  b = (double)in[5 * w.stride + k];
+}
+
+// bounds of the (transformed, stored) cloud: the grid's origin is min_bound - voxel / 2
+template <typename T>
+__global__ void __launch_bounds__(256) k_vox_bounds(const VoxArgs a, double *bounds) {
+  const double inf = __longlong_as_double(0x7ff0000000000000ll);
+  double lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    double p[3];
+    vox_xyz<T>(a, i, p[0], p[1], p[2]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      lo[c] = p[c] < lo[c] ? p[c] : lo[c];
+      hi[c] = p[c] > hi[c] ? p[c] : hi[c];
+    }
+  }
+  block_bounds_commit(lo, hi, bounds);
+}
+
+constexpr int kVoxGroups = 4;  // 32-point groups per warp and step
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_vox_insert(const VoxArgs a) {
   const double half = a.voxel * 0.5;
   const double ox = a.bounds[0] - half, oy = a.bounds[1] - half, oz = a.bounds[2] - half;
   {
@@ -240,167 +310,159 @@ __global__ void __launch_bounds__(256) k_voxel_insert(const VoxArgs a) {
       return;
     }
   }
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = rv_lanemask_lt();
   __shared__ unsigned int s_create, s_join;
   if (threadIdx.x == 0) s_create = s_join = 0;
   __syncthreads();
-  const long long p0 = (long long)blockIdx.x * a.span;                  // this CTA's part of the cloud
-  const long long p1 = p0 + a.span < a.n ? p0 + a.span : a.n;           // (empty when p0 >= n)
-  for (long long i = p0 + threadIdx.x; i < p0 + a.span && i - lane < p1; i += blockDim.x) {  // whole warps: full shuffles
-    const bool valid = i < p1;
-    double v[6] = {0, 0, 0, 0, 0, 0};
-    unsigned long long key = 0;  // lanes past the end form one run that is never written
-    if (valid) {
-      v[0] = (double)in[i], v[1] = (double)in[a.in_stride + i], v[2] = (double)in[2 * a.in_stride + i];
-      if (a.has_color) {
-        v[3] = (double)in[3 * a.in_stride + i];
-        v[4] = (double)in[4 * a.in_stride + i];
-        v[5] = (double)in[5 * a.in_stride + i];
-      }
-      // key = floor((p - origin) / voxel), IEEE division via the exact-reciprocal helper
-      const long long ix = (long long)floor(rv_div(v[0] - ox, a.voxel, a.rvoxel));
-      const long long iy = (long long)floor(rv_div(v[1] - oy, a.voxel, a.rvoxel));
-      const long long iz = (long long)floor(rv_div(v[2] - oz, a.voxel, a.rvoxel));
-      key = (((unsigned long long)ix & 0x1fffff) << 42 | ((unsigned long long)iy & 0x1fffff) << 21 | ((unsigned long long)iz & 0x1fffff)) + 1ull;
-    }
-    // ---- fold runs of equal keys inside the warp (segmented reduction towards the first lane of each run)
-    const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
-    const bool head = lane == 0 || key != prev;
-    const uint32_t heads = __ballot_sync(0xffffffffu, head);
-    const uint32_t after = lane == 31 ? 0u : (heads >> (lane + 1));
-    const int run = after ? __ffs(after) : 32 - lane;  // lanes from this one to the end of its run
-    const int ncol = a.has_color ? 6 : 3;
-    const int longest = __reduce_max_sync(0xffffffffu, run);  // steps needed: log2 of the longest run in the warp (often 2-4 points)
-#pragma unroll 1
-    for (int d = 1; d < longest; d <<= 1) {
-      const bool take = d < run;  // lane + d still belongs to this lane's run
+  const long long p0 = (long long)blockIdx.x * a.span;         // this CTA's part of the cloud
+  const long long p1 = p0 + a.span < a.n ? p0 + a.span : a.n;  // (empty when p0 >= n)
+  for (long long w0 = p0 + warp * (32 * kVoxGroups); w0 < p1; w0 += 8 * 32 * kVoxGroups) {
+    // ---- every load of the step first, then the keys
+    double px[kVoxGroups], py[kVoxGroups], pz[kVoxGroups];
+    bool valid[kVoxGroups];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        if (c < ncol) {
-          const double o = __shfl_down_sync(0xffffffffu, v[c], d);
-          if (take) v[c] += o;
-        }
-      }
+    for (int g = 0; g < kVoxGroups; ++g) {
+      const long long i = w0 + 32 * g + lane;
+      valid[g] = i < p1;
+      px[g] = py[g] = pz[g] = 0.0;
+      if (valid[g]) vox_xyz<T>(a, i, px[g], py[g], pz[g]);
     }
-    // ---- one record and one slot probe per run
-    const bool lead = head && valid;
-    bool created = false;
-    if (lead) {
-      VoxAcc *acc = a.acc + i;
-      acc->key = key;
-      acc->count = (unsigned int)run;
+    unsigned long long key[kVoxGroups];
+    uint32_t heads[kVoxGroups];
+    bool lead[kVoxGroups];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) acc->sum[c] = v[c];
-      unsigned int h = __umulhi((unsigned int)(vox_hash(key) >> 32), a.cap);  // uniform over [0, cap)
-      for (;;) {
-        const unsigned long long cur = atomicCAS(a.keys + h, 0ull, key);  // the table is at most two thirds full: usually empty
-        if (cur == 0) {
-          a.slot_rec[h] = (unsigned int)i;  // read by the next kernel
-          created = true;
-          break;
-        }
-        if (cur == key) {
-          acc->pad = h;  // joiner: where its voxel's slot is, so the merge pass does not probe again
-          break;
-        }
-        if (++h == a.cap) h = 0;
+    for (int g = 0; g < kVoxGroups; ++g) {
+      key[g] = 0;  // lanes past the end form one run that is never written
+      if (valid[g]) {
+        // key = floor((p - origin) / voxel), IEEE division via the exact-reciprocal helper
+        const long long ix = (long long)floor(rv_div(px[g] - ox, a.voxel, a.rvoxel));
+        const long long iy = (long long)floor(rv_div(py[g] - oy, a.voxel, a.rvoxel));
+        const long long iz = (long long)floor(rv_div(pz[g] - oz, a.voxel, a.rvoxel));
+        key[g] = (((unsigned long long)ix & 0x1fffff) << 42 | ((unsigned long long)iy & 0x1fffff) << 21 | ((unsigned long long)iz & 0x1fffff)) + 1ull;
+      }
+      // runs of equal keys inside the group: only the first point of a run goes to the table
+      const unsigned long long prev = __shfl_up_sync(0xffffffffu, key[g], 1);
+      const bool head = lane == 0 || key[g] != prev;
+      heads[g] = __ballot_sync(0xffffffffu, head);
+      lead[g] = head && valid[g];
+      if (lane == 0 && valid[g]) a.headmask[(w0 >> 5) + g] = heads[g];
+    }
+    // ---- one slot probe per run: the first compare-and-swap of all groups is in flight before any result is looked at
+    unsigned int h[kVoxGroups];
+    unsigned long long cur[kVoxGroups];
+#pragma unroll
+    for (int g = 0; g < kVoxGroups; ++g) {
+      h[g] = 0;
+      cur[g] = 0;
+      if (lead[g]) {
+        h[g] = __umulhi((unsigned int)(vox_hash(key[g]) >> 32), a.cap);  // uniform over [0, cap)
+        cur[g] = atomicCAS(a.keys + h[g], 0ull, key[g]);                   // the table is at most two thirds full: usually empty
       }
     }
-    // ---- creators to the front of the part's stretch of the list, joiners to its back
-    const uint32_t cb = __ballot_sync(0xffffffffu, created);
-    const uint32_t jb = __ballot_sync(0xffffffffu, lead && !created);
-    unsigned int cbase = 0, jbase = 0;
-    if (lane == 0) {
-      if (cb) cbase = atomicAdd(&s_create, (unsigned int)__popc(cb));
-      if (jb) jbase = atomicAdd(&s_join, (unsigned int)__popc(jb));
+#pragma unroll
+    for (int g = 0; g < kVoxGroups; ++g) {
+      bool created = false;
+      if (lead[g]) {
+        while (cur[g] != 0ull && cur[g] != key[g]) {  // another voxel's slot: linear probing
+          if (++h[g] == a.cap) h[g] = 0;
+          cur[g] = atomicCAS(a.keys + h[g], 0ull, key[g]);
+        }
+        created = cur[g] == 0ull;
+      }
+      // ---- creators to the front of the part's stretch of the list, joiners to its back
+      const uint32_t cb = __ballot_sync(0xffffffffu, created);
+      const uint32_t jb = __ballot_sync(0xffffffffu, lead[g] && !created);
+      unsigned int cbase = 0, jbase = 0;
+      if (lane == 0) {
+        if (cb) cbase = atomicAdd(&s_create, (unsigned int)__popc(cb));
+        if (jb) jbase = atomicAdd(&s_join, (unsigned int)__popc(jb));
+      }
+      cbase = __shfl_sync(0xffffffffu, cbase, 0);
+      jbase = __shfl_sync(0xffffffffu, jbase, 0);
+      const unsigned int i32 = (unsigned int)(w0 + 32 * g + lane);
+      if (created) {
+        a.list[p0 + cbase + __popc(cb & lt)] = make_uint2(i32, h[g]);
+      } else if (lead[g]) {
+        const unsigned int pos = (unsigned int)(p1 - 1 - (long long)(jbase + __popc(jb & lt)));
+        a.list[pos] = make_uint2(i32, h[g]);
+        a.next[pos] = atomicExch(a.chain + h[g], pos);  // link behind whoever joined this voxel before
+      }
     }
-    cbase = __shfl_sync(0xffffffffu, cbase, 0);
-    jbase = __shfl_sync(0xffffffffu, jbase, 0);
-    if (created) a.list[p0 + cbase + __popc(cb & rv_lanemask_lt())] = (unsigned int)i;
-    else if (lead) a.list[p1 - 1 - (long long)(jbase + __popc(jb & rv_lanemask_lt()))] = (unsigned int)i;
   }
   __syncthreads();
   if (threadIdx.x == 0) a.parts[blockIdx.x] = make_uint2(s_create, s_join);
 }
 
-// every joiner's record is added to the record of its voxel's creator; the joiners of all parts are dealt evenly to
-// the threads of the grid (prefix sum of the per-part counts in shared memory, binary search per joiner)
-__global__ void __launch_bounds__(256) k_voxel_merge(const VoxArgs a, int n_parts) {
-  __shared__ unsigned int s_pre[kVoxMaxParts + 1];  // exclusive prefix of the joiner counts
-  __shared__ unsigned int s_warp[8];
-  // block-wide exclusive scan, eight parts per thread
-  unsigned int v[8], sum = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int q = threadIdx.x * 8 + k;
-    v[k] = q < n_parts ? a.parts[q].y : 0u;
-    sum += v[k];
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned int incl = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += up;
-  }
-  if (lane == 31) s_warp[warp] = incl;
-  __syncthreads();
-  unsigned int wbase = 0;
-#pragma unroll
-  for (int w = 0; w < 8; ++w)
-    if (w < warp) wbase += s_warp[w];
-  unsigned int run = wbase + incl - sum;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    s_pre[threadIdx.x * 8 + k] = run;
-    run += v[k];
-  }
-  if (threadIdx.x == 255) s_pre[kVoxMaxParts] = run;
-  __syncthreads();
-  const unsigned int total = s_pre[kVoxMaxParts];
-  const unsigned int stride = gridDim.x * blockDim.x;
-  for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += stride) {
-    int lo = 0, hi = kVoxMaxParts;  // last part whose prefix is <= j
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (s_pre[mid] <= j) lo = mid; else hi = mid;
-    }
-    const long long p0 = (long long)lo * a.span;
-    const long long p1 = p0 + a.span < a.n ? p0 + a.span : a.n;
-    const VoxAcc r = a.acc[a.list[p1 - 1 - (long long)(j - s_pre[lo])]];
-    VoxAcc *acc = a.acc + a.slot_rec[r.pad];
-    atomicAdd(&acc->count, r.count);
-    atomicAdd(&acc->sum[0], r.sum[0]);
-    atomicAdd(&acc->sum[1], r.sum[1]);
-    atomicAdd(&acc->sum[2], r.sum[2]);
-    if (a.has_color) {
-      atomicAdd(&acc->sum[3], r.sum[3]);
-      atomicAdd(&acc->sum[4], r.sum[4]);
-      atomicAdd(&acc->sum[5], r.sum[5]);
-    }
-  }
-}
-
 struct VoxOutArgs {
-  const VoxHeader *hdr;
-  const VoxAcc *acc;
-  const unsigned int *list;
-  const uint2 *parts;
-  long long span;
   void *out;
   long long out_stride, out_capacity;
   int32_t *keys;
   int32_t *counts;
   long long *m;
-  int has_color;
 };
 
-// CTA p writes the voxels part p created, behind those of parts 0..p-1: mean = sum / count (one IEEE division for
-// 1 / count, then the exact-quotient correction of rv_div per component)
+// length of the run that starts at point i: up to the next head of its 32-point group
+__device__ __forceinline__ int vox_run(const VoxArgs &a, unsigned int i) {
+  const uint32_t m = a.headmask[i >> 5];
+  const int l = (int)(i & 31u);
+  const uint32_t after = l == 31 ? 0u : (m >> (l + 1));
+  return after ? __ffs(after) : 32 - l;
+}
+
+struct VoxSum {
+  double s[6];
+  unsigned int count;
+};
+
+// add the points of the run starting at i, one by one (index order inside the run)
+template <typename T>
+__device__ __forceinline__ void vox_add_run(const VoxArgs &a, unsigned int i, VoxSum &acc) {
+  const int run = vox_run(a, i);
+  for (int r = 0; r < run; ++r) {
+    double x, y, z;
+    vox_xyz<T>(a, (long long)i + r, x, y, z);
+    acc.s[0] += x;
+    acc.s[1] += y;
+    acc.s[2] += z;
+    if (a.has_color) {
+      double cr, cg, cb;
+      vox_rgb<T>(a, (long long)i + r, cr, cg, cb);
+      acc.s[3] += cr;
+      acc.s[4] += cg;
+      acc.s[5] += cb;
+    }
+  }
+  acc.count += (unsigned int)run;
+}
+
 template <typename OutT>
-__global__ void __launch_bounds__(256) k_voxel_emit(const VoxOutArgs a) {
-  OutT *out = reinterpret_cast<OutT *>(a.out);
-  __shared__ unsigned long long s_red[2][8];
+__device__ __forceinline__ void vox_store(const VoxOutArgs &o, int has_color, long long pos, const double s[6], unsigned int count,
+                                          unsigned long long key) {
+  if (pos >= o.out_capacity) return;
+  OutT *out = reinterpret_cast<OutT *>(o.out);
+  const double c = (double)count, rc = 1.0 / c;
+  out[pos] = (OutT)rv_div(s[0], c, rc);
+  out[o.out_stride + pos] = (OutT)rv_div(s[1], c, rc);
+  out[2 * o.out_stride + pos] = (OutT)rv_div(s[2], c, rc);
+  if (has_color) {
+    out[3 * o.out_stride + pos] = (OutT)rv_div(s[3], c, rc);
+    out[4 * o.out_stride + pos] = (OutT)rv_div(s[4], c, rc);
+    out[5 * o.out_stride + pos] = (OutT)rv_div(s[5], c, rc);
+  }
+  if (o.keys) {
+    const unsigned long long kk = key - 1ull;
+    o.keys[pos] = (int32_t)((kk >> 42) & 0x1fffff);
+    o.keys[o.out_capacity + pos] = (int32_t)((kk >> 21) & 0x1fffff);
+    o.keys[2 * o.out_capacity + pos] = (int32_t)(kk & 0x1fffff);
+  }
+  if (o.counts) o.counts[pos] = (int32_t)count;
+}
+
+// CTA p finishes the voxels part p created, behind those of parts 0..p-1
+template <typename T, typename OutT>
+__global__ void __launch_bounds__(128) k_vox_emit(const VoxArgs a, const VoxOutArgs o) {
+  __shared__ unsigned long long s_red[2][4];
   unsigned long long before = 0, total = 0;
   for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) {
     const unsigned long long c = a.parts[q].x;
@@ -408,45 +470,156 @@ __global__ void __launch_bounds__(256) k_voxel_emit(const VoxOutArgs a) {
     if (q < (int)blockIdx.x) before += c;
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    before += __shfl_xor_sync(0xffffffffu, before, o);
-    total += __shfl_xor_sync(0xffffffffu, total, o);
+  for (int s = 16; s > 0; s >>= 1) {
+    before += __shfl_xor_sync(0xffffffffu, before, s);
+    total += __shfl_xor_sync(0xffffffffu, total, s);
   }
   if ((threadIdx.x & 31) == 0) s_red[0][threadIdx.x >> 5] = before, s_red[1][threadIdx.x >> 5] = total;
   __syncthreads();
   before = total = 0;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) before += s_red[0][w], total += s_red[1][w];
-  if (blockIdx.x == 0 && threadIdx.x == 0) *a.m = a.hdr->error ? -1ll : (long long)total;
+  for (int w = 0; w < 4; ++w) before += s_red[0][w], total += s_red[1][w];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *o.m = a.hdr->error ? -1ll : (long long)total;
   if (a.hdr->error) return;
   const unsigned int mine = a.parts[blockIdx.x].x;
-  const unsigned int *list = a.list + (long long)blockIdx.x * a.span;
+  const uint2 *list = a.list + (long long)blockIdx.x * a.span;
   for (unsigned int k = threadIdx.x; k < mine; k += blockDim.x) {
-    const long long o = (long long)(before + k);
-    if (o >= a.out_capacity) break;
-    const VoxAcc s = a.acc[list[k]];
-    const double c = (double)s.count, rc = 1.0 / c;
-    out[o] = (OutT)rv_div(s.sum[0], c, rc);
-    out[a.out_stride + o] = (OutT)rv_div(s.sum[1], c, rc);
-    out[2 * a.out_stride + o] = (OutT)rv_div(s.sum[2], c, rc);
-    if (a.has_color) {
-      out[3 * a.out_stride + o] = (OutT)rv_div(s.sum[3], c, rc);
-      out[4 * a.out_stride + o] = (OutT)rv_div(s.sum[4], c, rc);
-      out[5 * a.out_stride + o] = (OutT)rv_div(s.sum[5], c, rc);
+    const long long pos = (long long)(before + k);
+    const uint2 me = list[k];  // (first point, slot)
+    // ---- the voxel's run heads: its creator and up to seven joiners in registers, sorted by point index so that the
+    // points are added in index order (the order of Open3D's loop); whatever a longer chain holds follows in chain order
+    unsigned int idx[8];
+    idx[0] = me.x;
+    unsigned int link = a.chain[me.y];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) {
+      idx[q] = kVoxNil;
+      if (link != kVoxNil) {
+        idx[q] = a.list[link].x;
+        link = a.next[link];
+      }
     }
-    if (a.keys) {
-      const unsigned long long kk = s.key - 1ull;
-      a.keys[o] = (int32_t)((kk >> 42) & 0x1fffff);
-      a.keys[a.out_capacity + o] = (int32_t)((kk >> 21) & 0x1fffff);
-      a.keys[2 * a.out_capacity + o] = (int32_t)(kk & 0x1fffff);
+#define RV_CX(i, j)                                     \
+  {                                                     \
+    const unsigned int lo_ = min(idx[i], idx[j]);       \
+    const unsigned int hi_ = max(idx[i], idx[j]);       \
+    idx[i] = lo_;                                       \
+    idx[j] = hi_;                                       \
+  }
+    if (idx[1] != kVoxNil) {  // 19-comparator network for eight keys (empty entries sort last)
+      RV_CX(0, 1) RV_CX(2, 3) RV_CX(4, 5) RV_CX(6, 7)
+      RV_CX(0, 2) RV_CX(1, 3) RV_CX(4, 6) RV_CX(5, 7)
+      RV_CX(1, 2) RV_CX(5, 6) RV_CX(0, 4) RV_CX(3, 7)
+      RV_CX(1, 5) RV_CX(2, 6)
+      RV_CX(1, 4) RV_CX(3, 6)
+      RV_CX(2, 4) RV_CX(3, 5)
+      RV_CX(3, 4)
     }
-    if (a.counts) a.counts[o] = (int32_t)s.count;
+#undef RV_CX
+    VoxSum acc;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc.s[c] = 0.0;
+    acc.count = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (idx[q] != kVoxNil) vox_add_run<T>(a, idx[q], acc);
+    int hops = 8;
+    while (link != kVoxNil && hops < kVoxLongChain) {
+      vox_add_run<T>(a, a.list[link].x, acc);
+      link = a.next[link];
+      ++hops;
+    }
+    const unsigned long long key = a.keys[me.y];
+    if (link != kVoxNil) {
+      // a very long chain (coarse grid): hand the voxel to the atomic path; everything added so far is dropped
+      const unsigned int q = atomicAdd(&a.hdr->n_long, 1u);
+      VoxLong *rec = a.pool + q;
+      rec->key = key;
+      rec->out = (unsigned int)pos;
+      VoxSum own;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) own.s[c] = 0.0;
+      own.count = 0;
+      vox_add_run<T>(a, me.x, own);
+      rec->count = own.count;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) rec->sum[c] = own.s[c];
+      a.chain[me.y] = kVoxLongTag | q;
+      continue;
+    }
+    vox_store<OutT>(o, a.has_color, pos, acc.s, acc.count, key);
+  }
+}
+
+// every joiner of a long voxel adds its run into the voxel's pool record (float64 atomics); nothing to do without long voxels
+template <typename T>
+__global__ void __launch_bounds__(256) k_vox_long(const VoxArgs a, int n_parts) {
+  if (a.hdr->error || a.hdr->n_long == 0) return;
+  for (int p = blockIdx.x; p < n_parts; p += gridDim.x) {
+    const long long p0 = (long long)p * a.span;
+    const long long p1 = p0 + a.span < a.n ? p0 + a.span : a.n;
+    const unsigned int joiners = a.parts[p].y;
+    for (unsigned int j = threadIdx.x; j < joiners; j += blockDim.x) {
+      const uint2 e = a.list[p1 - 1 - (long long)j];
+      const unsigned int v = a.chain[e.y];
+      if (v == kVoxNil || !(v & kVoxLongTag)) continue;
+      VoxSum s;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) s.s[c] = 0.0;
+      s.count = 0;
+      vox_add_run<T>(a, e.x, s);
+      VoxLong *rec = a.pool + (v & ~kVoxLongTag);
+      atomicAdd(&rec->count, s.count);
+      atomicAdd(&rec->sum[0], s.s[0]);
+      atomicAdd(&rec->sum[1], s.s[1]);
+      atomicAdd(&rec->sum[2], s.s[2]);
+      if (a.has_color) {
+        atomicAdd(&rec->sum[3], s.s[3]);
+        atomicAdd(&rec->sum[4], s.s[4]);
+        atomicAdd(&rec->sum[5], s.s[5]);
+      }
+    }
+  }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) k_vox_long_final(const VoxArgs a, const VoxOutArgs o) {
+  if (a.hdr->error) return;
+  const unsigned int n_long = a.hdr->n_long;
+  for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_long; q += gridDim.x * blockDim.x) {
+    const VoxLong rec = a.pool[q];
+    vox_store<OutT>(o, a.has_color, (long long)rec.out, rec.sum, rec.count, rec.key);
   }
 }
 
 unsigned long long vox_capacity(long long n) {  // 1.5 slots per point, a multiple of 32
   unsigned long long c = ((unsigned long long)n * 3ull / 2ull + 31ull) & ~31ull;
   return c < 1024 ? 1024 : c;
+}
+
+size_t vox_align(size_t b) { return (b + 255) & ~(size_t)255; }
+
+struct VoxLayout {
+  size_t keys, chain, list, next, masks, pool, total;
+};
+VoxLayout vox_layout(long long n) {
+  VoxLayout L;
+  const unsigned long long cap = vox_capacity(n);
+  size_t off = kVoxHead;
+  L.keys = off;
+  off += vox_align((size_t)cap * 8);
+  L.chain = off;
+  off += vox_align((size_t)cap * 4);
+  L.list = off;
+  off += vox_align((size_t)n * 8);
+  L.next = off;
+  off += vox_align((size_t)n * 4);
+  L.masks = off;
+  off += vox_align((size_t)((n + 31) / 32) * 4);
+  L.pool = off;
+  off += vox_align((size_t)(n / kVoxLongChain + 1) * sizeof(VoxLong));
+  L.total = off;
+  return L;
 }
 
 // --------------------------------------------------------------------- PLY records
@@ -624,7 +797,104 @@ int rv_transform_merge(rv_ctx *ctx, int n_views, const void *const *d_in, const 
 
 size_t rv_voxel_workspace_bytes(int64_t n) {
   if (n < 0) n = 0;
-  return kVoxHead + (size_t)vox_capacity(n) * 12 + (size_t)n * sizeof(VoxAcc) + (((size_t)n * 4 + 63) & ~(size_t)63);
+  return vox_layout(n).total;
+}
+
+// shared body of rv_voxel_downsample (one view, no transform) and rv_fuse_voxel (K3 fused in)
+static int vox_run_all(rv_ctx *ctx, const char *who, int n_views, const void *const *d_in, const int64_t *in_plane_stride,
+                       const int64_t *n, const double *T, int in_dtype, int has_color, double voxel_size, const double *d_bounds,
+                       void *d_out, int64_t out_plane_stride, int out_dtype, int64_t out_capacity, int32_t *d_keys,
+                       int32_t *d_counts_out, int64_t *d_m, void *d_ws, size_t ws_bytes, cudaStream_t st) {
+  if (!(voxel_size > 0.0)) RV_FAIL(ctx, RV_EINVAL, "%s: voxel_size <= 0", who);
+  if (n_views < 1 || n_views > kVoxViews || !d_in || !in_plane_stride || !n || !d_m)
+    RV_FAIL(ctx, RV_EINVAL, "%s: 1..%d views and non-null arrays are required", who, kVoxViews);
+  if ((in_dtype != RV_F32 && in_dtype != RV_F64) || (out_dtype != RV_F32 && out_dtype != RV_F64)) RV_FAIL(ctx, RV_EINVAL, "%s: bad dtype", who);
+  if (out_capacity < 0 || out_plane_stride < out_capacity) RV_FAIL(ctx, RV_EINVAL, "%s: bad output capacity", who);
+  VoxArgs a;
+  memset(&a, 0, sizeof(a));
+  long long total = 0;
+  int nv = 0;
+  for (int v = 0; v < n_views; ++v) {
+    if (n[v] < 0 || in_plane_stride[v] < n[v]) RV_FAIL(ctx, RV_EINVAL, "%s: bad n / stride for view %d", who, v);
+    if (n[v] == 0) continue;
+    if (!d_in[v]) RV_FAIL(ctx, RV_EINVAL, "%s: view %d is null", who, v);
+    VoxView &w = a.view[nv++];
+    w.in = d_in[v];
+    w.stride = in_plane_stride[v];
+    w.n = n[v];
+    w.first = total;
+    if (T) memcpy(w.T, T + 16 * v, sizeof(w.T));
+    total += n[v];
+  }
+  if (total >= 0x7fffffffll) RV_FAIL(ctx, RV_EINVAL, "%s: more than 2^31 points", who);  // list positions and the long tag share 32 bits
+  if (total == 0) {
+    RV_CUDA(ctx, cudaMemsetAsync(d_m, 0, sizeof(int64_t), st));
+    return RV_OK;
+  }
+  if (out_capacity > 0 && !d_out) RV_FAIL(ctx, RV_EINVAL, "%s: null output", who);
+  const VoxLayout L = vox_layout(total);
+  if (!d_ws || ws_bytes < L.total) RV_FAIL(ctx, RV_EWORKSPACE, "%s: workspace %zu < %zu", who, ws_bytes, L.total);
+  if (!rv_aligned(d_ws, 64)) RV_FAIL(ctx, RV_EALIGN, "%s: workspace must be 64-byte aligned", who);
+  const unsigned long long cap = vox_capacity(total);
+  char *w = reinterpret_cast<char *>(d_ws);
+  a.n_views = nv;
+  a.identity = T ? 0 : 1;
+  a.has_color = has_color ? 1 : 0;
+  a.n = total;
+  a.voxel = voxel_size;
+  a.rvoxel = 1.0 / voxel_size;
+  a.hdr = reinterpret_cast<VoxHeader *>(w);
+  a.parts = reinterpret_cast<uint2 *>(w + 256);
+  a.keys = reinterpret_cast<unsigned long long *>(w + L.keys);
+  a.chain = reinterpret_cast<unsigned int *>(w + L.chain);
+  a.list = reinterpret_cast<uint2 *>(w + L.list);
+  a.next = reinterpret_cast<unsigned int *>(w + L.next);
+  a.headmask = reinterpret_cast<unsigned int *>(w + L.masks);
+  a.pool = reinterpret_cast<VoxLong *>(w + L.pool);
+  a.cap = (unsigned int)cap;
+  // header, part counters and keys are cleared, the chain heads set to "none"; nothing else needs initialising
+  RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, L.keys + (size_t)cap * 8, st));
+  RV_CUDA(ctx, cudaMemsetAsync(w + L.chain, 0xff, (size_t)cap * 4, st));
+  const double *bounds = d_bounds;
+  if (!bounds) {
+    k_bounds_init<<<1, 32, 0, st>>>(a.hdr->bounds);
+    RV_LAUNCHED(ctx);
+    const int g = grid_for(ctx, total);
+    if (in_dtype == RV_F32) k_vox_bounds<float><<<g, 256, 0, st>>>(a, a.hdr->bounds);
+    else k_vox_bounds<double><<<g, 256, 0, st>>>(a, a.hdr->bounds);
+    RV_LAUNCHED(ctx);
+    bounds = a.hdr->bounds;
+  }
+  a.bounds = bounds;
+  // parts of at least 1024 points, up to 2048 of them: two to three waves of small CTAs keep the tail of the kernel short
+  int parts_n = (int)((total + 1023) / 1024 < kVoxMaxParts ? (total + 1023) / 1024 : kVoxMaxParts);
+  if (parts_n < 1) parts_n = 1;
+  a.span = (((total + parts_n - 1) / parts_n) + 127) & ~127ll;
+  if (in_dtype == RV_F32) k_vox_insert<float><<<parts_n, 256, 0, st>>>(a);
+  else k_vox_insert<double><<<parts_n, 256, 0, st>>>(a);
+  RV_LAUNCHED(ctx);
+  VoxOutArgs o;
+  memset(&o, 0, sizeof(o));
+  o.out = d_out;
+  o.out_stride = out_plane_stride;
+  o.out_capacity = out_capacity;
+  o.keys = d_keys;
+  o.counts = d_counts_out;
+  o.m = reinterpret_cast<long long *>(d_m);
+  if (in_dtype == RV_F32 && out_dtype == RV_F32) k_vox_emit<float, float><<<parts_n, 128, 0, st>>>(a, o);
+  else if (in_dtype == RV_F32) k_vox_emit<float, double><<<parts_n, 128, 0, st>>>(a, o);
+  else if (out_dtype == RV_F32) k_vox_emit<double, float><<<parts_n, 128, 0, st>>>(a, o);
+  else k_vox_emit<double, double><<<parts_n, 128, 0, st>>>(a, o);
+  RV_LAUNCHED(ctx);
+  // voxels with very long chains (none on a fine grid: both kernels then return at once)
+  const int lg = parts_n < ctx->sm_count * 4 ? parts_n : ctx->sm_count * 4;
+  if (in_dtype == RV_F32) k_vox_long<float><<<lg, 256, 0, st>>>(a, parts_n);
+  else k_vox_long<double><<<lg, 256, 0, st>>>(a, parts_n);
+  RV_LAUNCHED(ctx);
+  if (out_dtype == RV_F32) k_vox_long_final<float><<<8, 256, 0, st>>>(a, o);
+  else k_vox_long_final<double><<<8, 256, 0, st>>>(a, o);
+  RV_LAUNCHED(ctx);
+  return RV_OK;
 }
 
 int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int in_dtype, int has_color,
@@ -633,88 +903,23 @@ int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, 
                         size_t ws_bytes, rv_stream stream) {
   if (!ctx) return RV_EINVAL;
   RvDeviceGuard dev_guard(ctx);
-  if (!(voxel_size > 0.0)) RV_FAIL(ctx, RV_EINVAL, "rv_voxel_downsample: voxel_size <= 0");
-  if (n >= 0xa0000000ll) RV_FAIL(ctx, RV_EINVAL, "rv_voxel_downsample: more than 2.6e9 points");  // 1.5 n slots in 32 bits
   if (n < 0 || in_plane_stride < n || !d_m) RV_FAIL(ctx, RV_EINVAL, "rv_voxel_downsample: bad n / stride / m");
-  if ((in_dtype != RV_F32 && in_dtype != RV_F64) || (out_dtype != RV_F32 && out_dtype != RV_F64))
-    RV_FAIL(ctx, RV_EINVAL, "rv_voxel_downsample: bad dtype");
-  if (out_capacity < 0 || out_plane_stride < out_capacity) RV_FAIL(ctx, RV_EINVAL, "rv_voxel_downsample: bad output capacity");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (n == 0) {
-    RV_CUDA(ctx, cudaMemsetAsync(d_m, 0, sizeof(int64_t), st));
-    return RV_OK;
-  }
-  if (!d_in || (out_capacity > 0 && !d_out)) RV_FAIL(ctx, RV_EINVAL, "rv_voxel_downsample: null cloud pointer");
-  const size_t need = rv_voxel_workspace_bytes(n);
-  if (!d_ws || ws_bytes < need) RV_FAIL(ctx, RV_EWORKSPACE, "rv_voxel_downsample: workspace %zu < %zu", ws_bytes, need);
-  if (!rv_aligned(d_ws, 64)) RV_FAIL(ctx, RV_EALIGN, "rv_voxel_downsample: workspace must be 64-byte aligned");
-  const unsigned long long cap = vox_capacity(n);
-  VoxHeader *hdr = reinterpret_cast<VoxHeader *>(d_ws);
-  uint2 *parts = reinterpret_cast<uint2 *>(reinterpret_cast<char *>(d_ws) + 256);
-  char *w = reinterpret_cast<char *>(d_ws) + kVoxHead;
-  unsigned long long *keys = reinterpret_cast<unsigned long long *>(w);
-  unsigned int *slot_rec = reinterpret_cast<unsigned int *>(w + cap * 8);
-  VoxAcc *acc = reinterpret_cast<VoxAcc *>(w + cap * 12);  // cap % 32 == 0: 64-byte aligned
-  unsigned int *list = reinterpret_cast<unsigned int *>(acc + n);
-  RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, kVoxHead + cap * 8, st));  // header, counters, keys; everything else is written, not cleared
-  const double *bounds = d_bounds;
-  if (!bounds) {
-    k_bounds_init<<<1, 32, 0, st>>>(hdr->bounds);
-    RV_LAUNCHED(ctx);
-    const int g = grid_for(ctx, n);
-    if (in_dtype == RV_F32) k_bounds<float><<<g, 256, 0, st>>>(reinterpret_cast<const float *>(d_in), in_plane_stride, n, hdr->bounds);
-    else k_bounds<double><<<g, 256, 0, st>>>(reinterpret_cast<const double *>(d_in), in_plane_stride, n, hdr->bounds);
-    RV_LAUNCHED(ctx);
-    bounds = hdr->bounds;
-  }
-  VoxArgs a;
-  memset(&a, 0, sizeof(a));
-  a.in = d_in;
-  a.in_stride = in_plane_stride;
-  a.n = n;
-  a.has_color = has_color ? 1 : 0;
-  a.voxel = voxel_size;
-  a.rvoxel = 1.0 / voxel_size;
-  a.bounds = bounds;
-  a.hdr = hdr;
-  a.keys = keys;
-  a.slot_rec = slot_rec;
-  a.acc = acc;
-  a.list = list;
-  a.cap = (unsigned int)cap;
-  int parts_n;
-  {
-    auto kf = k_voxel_insert<float>;
-    auto kd = k_voxel_insert<double>;
-    // parts of at least 1024 points, up to 2048 of them: two to three waves of small CTAs keep the tail of the kernel short
-    parts_n = (int)((n + 1023) / 1024 < kVoxMaxParts ? (n + 1023) / 1024 : kVoxMaxParts);
-    if (parts_n < 1) parts_n = 1;
-    a.span = (((n + parts_n - 1) / parts_n) + 31) & ~31ll;
-    a.parts = parts;
-    if (in_dtype == RV_F32) kf<<<parts_n, 256, 0, st>>>(a);
-    else kd<<<parts_n, 256, 0, st>>>(a);
-  }
-  RV_LAUNCHED(ctx);
-  k_voxel_merge<<<grid_for(ctx, n / 2 + 1, 8), 256, 0, st>>>(a, parts_n);  // joiners < points; grid-stride over the real count
-  RV_LAUNCHED(ctx);
-  VoxOutArgs o;
-  memset(&o, 0, sizeof(o));
-  o.hdr = hdr;
-  o.acc = acc;
-  o.list = list;
-  o.parts = parts;
-  o.span = a.span;
-  o.out = d_out;
-  o.out_stride = out_plane_stride;
-  o.out_capacity = out_capacity;
-  o.keys = d_keys;
-  o.counts = d_counts_out;
-  o.m = reinterpret_cast<long long *>(d_m);
-  o.has_color = has_color ? 1 : 0;
-  if (out_dtype == RV_F32) k_voxel_emit<float><<<parts_n, 256, 0, st>>>(o);
-  else k_voxel_emit<double><<<parts_n, 256, 0, st>>>(o);
-  RV_LAUNCHED(ctx);
-  return RV_OK;
+  if (n > 0 && !d_in) RV_FAIL(ctx, RV_EINVAL, "rv_voxel_downsample: null cloud pointer");
+  const void *views[1] = {d_in};
+  const int64_t strides[1] = {in_plane_stride}, ns[1] = {n};
+  return vox_run_all(ctx, "rv_voxel_downsample", 1, views, strides, ns, nullptr, in_dtype, has_color, voxel_size, d_bounds, d_out,
+                     out_plane_stride, out_dtype, out_capacity, d_keys, d_counts_out, d_m, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int rv_fuse_voxel(rv_ctx *ctx, int n_views, const void *const *d_in, const int64_t *in_plane_stride, const int64_t *n,
+                  const double *T, int in_dtype, int has_color, double voxel_size, void *d_out, int64_t out_plane_stride,
+                  int out_dtype, int64_t out_capacity, int32_t *d_keys, int32_t *d_counts_out, int64_t *d_m, void *d_ws,
+                  size_t ws_bytes, rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
+  if (!T) RV_FAIL(ctx, RV_EINVAL, "rv_fuse_voxel: the poses are required (rv_voxel_downsample takes a cloud as it is)");
+  return vox_run_all(ctx, "rv_fuse_voxel", n_views, d_in, in_plane_stride, n, T, in_dtype, has_color, voxel_size, nullptr, d_out,
+                     out_plane_stride, out_dtype, out_capacity, d_keys, d_counts_out, d_m, d_ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int rv_pack_ply_records(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int in_dtype, int has_color,

@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
   __shared__ __align__(16) uint32_t s_tot[8][kCW];            // kept points of the tile's eight warp runs
   __shared__ __align__(8) unsigned long long s_peek[8];       // predecessor status word seen by warp 0
   __shared__ uint32_t s_base[8];
+  __shared__ uint32_t s_arrived[8];                           // warps that posted their total (running count per slot)
   static_assert(kStages >= 2 && kStages <= 7, "exchange slots are eight deep");
 
   const int lane = threadIdx.x & 31;
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
   const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar), tot_a = smem_u32(tot_bar),
                  base_a = smem_u32(base_bar);
 
+  if (threadIdx.x < 8) s_arrived[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
@@ -562,9 +564,11 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
     // posted first: the stage release is what lets the other warps, and this one, run ahead)
     if (npx < kTileT) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // our zero fill vs the next bulk copy
     __syncwarp();
+    uint32_t arrived = 0;
     if (lane == 0) {
       if (kOrdered) {
         s_tot[it & 7][warp] = run;
+        arrived = atomicAdd(&s_arrived[it & 7], 1u);
         mbar_arrive(tot_a + 8 * (it & 7));
       }
       mbar_arrive(empty_a + 8 * s);
@@ -572,9 +576,10 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
 
     uint32_t base = 0, off = 0;
     if (kOrdered) {
-      // ---------------- the eight run totals.  Everybody posts; only the warps that have points to place (and warp 0,
-      // which publishes the tile's prefix) wait for the others.
-      if (run == 0 && warp != 0) continue;  // warp-uniform
+      // ---------------- the eight run totals.  Everybody posts; only the warps that have points to place wait for the
+      // others, and the warp that posted LAST (it waits for nobody) publishes the tile's prefix for the frame's chain.
+      const bool publisher = (__shfl_sync(0xffffffffu, arrived, 0) & 7u) == 7u;
+      if (run == 0 && !publisher) continue;  // warp-uniform
       mbar_wait(tot_a + 8 * (it & 7), (uint32_t)(it >> 3) & 1u);
       const uint32_t t8 = lane < kCW ? s_tot[it & 7][lane] : 0u;
       const uint32_t tile_total = __reduce_add_sync(0xffffffffu, t8);
@@ -591,19 +596,19 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
         hit = (pk >> 62) == 2;
         if (hit) {
           base = (uint32_t)pk;
-        } else if (warp == 0) {
+        } else if (publisher) {
           base = rv_lookback(a.status, tile, n_pred, tile_total);  // publishes the aggregate, then the prefix
           if (lane == 0) {
             s_base[it & 7] = base;
             mbar_arrive(base_a + 8 * (it & 7));
           }
         } else {
-          // the predecessor is still in flight in another CTA: sleep until warp 0 has walked the chain
+          // the predecessor is still in flight in another CTA: sleep until the publisher has walked the chain
           mbar_wait(base_a + 8 * (it & 7), (uint32_t)(it >> 3) & 1u);
           base = s_base[it & 7];
         }
       }
-      if (warp == 0 && lane == 0) {
+      if (publisher && lane == 0) {
         if (n_pred == 0 || hit) {
           rv_st_relaxed(a.status + tile, RV_ST_PREFIX | (unsigned long long)(base + tile_total));
           mbar_arrive(base_a + 8 * (it & 7));  // keep the slot's phase in step with the iteration count

@@ -616,3 +616,71 @@ def test_bounds_center_and_filter_capacity(rv):
     st = ctx.lib.rv_select_by_mask(ctx.handle, _ops.ptr(data), 1000, 1000, _lib.RV_F32, 0, _ops.ptr(keep), _ops.ptr(out), 10,
                                    _ops.ptr(cnt), None, _ops.ptr(ws), ws.numel(), None)
     assert st == _lib.RV_ECAPACITY
+
+
+def test_voxel_means_are_the_index_order_sums(rv, O):
+    """Open3D adds the points of a voxel in index order in float64.  The grid kernel does the same whenever a voxel is made of
+    at most eight runs of consecutive points: those means are bit-identical to the oracle's, not just within tolerance; the
+    rest (voxels gathered from longer chains) stay within 1e-12."""
+    rng = np.random.default_rng(77)
+    # scan-ordered surface (runs of consecutive points per voxel, several rows per voxel) plus isolated clutter
+    n = 120000
+    u = np.arange(n)
+    P = np.stack([(u % 600) * 0.0011 - 0.33, (u // 600) * 0.0013 - 0.13, 0.8 + 0.0005 * rng.standard_normal(n)], axis=1)
+    clutter = rng.random(n) < 0.1
+    P[clutter] = rng.uniform(-0.4, 0.4, (int(clutter.sum()), 3))
+    C = rng.random((n, 3))
+    for dtype, vox in (("f64", 0.005), ("f32", 0.004)):
+        Pd = P.astype(np.float32) if dtype == "f32" else P
+        Cd = C.astype(np.float32) if dtype == "f32" else C
+        pc = rv.PointCloud.from_arrays(Pd, Cd, dtype=dtype)
+        down, keys, counts = pc.voxel_down_sample(vox, return_keys=True)
+        rk, rc, rcol, rn = O.voxel_down_sample(Pd.astype(np.float64), Cd.astype(np.float64), vox)
+        gk, gc, gcol, gn = _sorted_voxels(keys, down.points, down.colors, counts)
+        assert np.array_equal(gk, rk) and np.array_equal(gn, rn)
+        if dtype == "f32":  # stored means are the float32 roundings of the same float64 quotients
+            rc, rcol = rc.astype(np.float32).astype(np.float64), rcol.astype(np.float32).astype(np.float64)
+        small = rn <= 8  # at most eight points, hence at most eight runs
+        assert small.sum() > 1000
+        assert np.array_equal(gc[small], rc[small]) and np.array_equal(gcol[small], rcol[small])
+        exact = (gc == rc).all(axis=1)
+        assert exact.mean() > 0.9
+        assert np.abs(gc - rc).max() <= 1e-12 if dtype == "f64" else np.abs(gc - rc).max() <= 1e-7
+
+
+def test_voxel_grid_long_chains_and_fused_equals_unfused(rv, O):
+    """A coarse grid over points in random order: every voxel is a chain of thousands of single-point runs, which takes the
+    atomic path (k_vox_long).  And the fused call (views transformed on the fly, merged cloud never written) gives the voxels
+    of transform + merge + voxel_down_sample."""
+    rng = np.random.default_rng(78)
+    P = rng.uniform(0.0, 1.0, (150000, 3))
+    C = rng.random((150000, 3))
+    pc = rv.PointCloud.from_arrays(P, C)
+    down, keys, counts = pc.voxel_down_sample(0.5, return_keys=True)
+    assert len(down) <= 27 and counts.min() > 256
+    _check_voxels(down, keys, counts, O.voxel_down_sample(P, C, 0.5))
+    gk, gc, gcol, gn = _sorted_voxels(keys, down.points, down.colors, counts)
+    ref = O.voxel_down_sample(P, C, 0.5)
+    assert np.abs(gc - ref[1]).max() <= 1e-12 and np.abs(gcol - ref[2]).max() <= 1e-12
+    # mixed: a few heavy voxels among many light ones
+    Q = np.concatenate([rng.uniform(0.0, 0.004, (3000, 3)), rng.uniform(0.0, 1.0, (40000, 3))])
+    Q = Q[rng.permutation(len(Q))]
+    pq = rv.PointCloud.from_arrays(Q, None)
+    dq, kq, nq = pq.voxel_down_sample(0.005, return_keys=True)
+    _check_voxels(dq, kq, nq, O.voxel_down_sample(Q, None, 0.005))
+    assert nq.max() >= 1000
+    # fused == unfused, float32 and float64 storage, 1..5 views (one of them empty)
+    for dtype in ("f32", "f64"):
+        views, poses = [], []
+        for v in range(5):
+            m = 0 if v == 2 else 20000 + 1000 * v
+            pts = rng.uniform(-0.3, 0.3, (m, 3)) + [0.0, 0.0, 0.9]
+            views.append(rv.PointCloud.from_arrays(pts, rng.random((m, 3)), dtype=dtype))
+            poses.append(_rand_pose(rng, 0.2))
+        fused, fk, fn = rv.fuse_views(views, poses, 0.01, return_keys=True)
+        merged = rv.merge([c.transformed(rv.world_from_camera(T)) for c, T in zip(views, poses)])
+        plain, pk, pn = merged.voxel_down_sample(0.01, return_keys=True)
+        a = _sorted_voxels(fk, fused.points, fused.colors, fn)
+        b = _sorted_voxels(pk, plain.points, plain.colors, pn)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3])
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])  # same values summed in the same order
