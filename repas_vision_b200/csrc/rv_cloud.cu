@@ -156,8 +156,8 @@ __global__ void k_stats_init(double *b) {
 // Hash grid without per-point records (round 1 wrote a 64-byte record per run of points and read it back twice: 6.1 x the
 // algorithmic DRAM traffic).  Workspace:
 //   [header 256 B][per-part counters 2048 x 8 B][keys: cap x 8 B][chain: cap x 4 B][list: n x 8 B][next: n x 4 B]
-//   [head masks: ceil(n / 32) x 4 B][long-voxel pool: (n / 256 + 1) x 64 B]
-// k_vox_insert  reads the coordinates only (four 32-point groups per warp and step, all loads and then all first-probe
+//   [head masks: ceil(n / 32) x 4 B][long-voxel pool: (n / 9 + 1) x 64 B]
+// k_vox_insert  reads the coordinates only (RV_VOX_GROUPS 32-point groups per warp and step, their loads and first-probe
 //               compare-and-swaps issued before anything is consumed).  Points arrive in pixel order, so consecutive points
 //               usually share a voxel: a run of equal keys inside a 32-point group is represented by its first point (the
 //               "head"; the ballot of heads is kept per group, 1 bit per point).  A head claims its key's slot with ONE
@@ -170,9 +170,9 @@ __global__ void k_stats_init(double *b) {
 //               voxels exactly the index-order sums of Open3D's loop, so the means are bit-identical to the oracle's.  Points
 //               are re-read from the input (L2-resident: the insert just streamed it) and, for a fusion, re-transformed.
 //               mean = sum / count by the exact-quotient helper.  Part p's voxels go behind those of parts 0..p-1.
-// A voxel whose chain is longer than kVoxLongChain runs (a coarse grid over a big cloud) is finished by k_vox_long instead:
-// every joiner of such a voxel adds its run into a pool record with float64 atomics, k_vox_long_final divides.  Both return at
-// once when no voxel is long.
+// A voxel made of more than kVoxHeads runs (a coarse grid, or a surface seen at close range) is finished by k_vox_long instead:
+// a thread walking a long chain would serialise the gather, so every joiner of such a voxel adds its run into a pool record
+// with float64 atomics, in parallel, and k_vox_long_final divides.  Both return at once when no voxel is long.
 //
 // The pose transform of a fusion (K3) is fused in: the views are read where they lie, p' = T p is rounded to the cloud's
 // storage type exactly as rv_transform_merge stores it, and the merged cloud is never written.
@@ -191,7 +191,22 @@ constexpr int kVoxMaxParts = 2048;
 constexpr size_t kVoxHead = 256 + (size_t)kVoxMaxParts * 8;  // header + per-part {creators, joiners}
 constexpr unsigned int kVoxNil = 0xffffffffu;
 constexpr unsigned int kVoxLongTag = 0x80000000u;
-constexpr int kVoxLongChain = 256;
+constexpr int kVoxHeads = 8;  // run heads of a voxel that k_vox_emit gathers itself (sorted, summed in index order)
+// Both kernels are chains of dependent L2 round trips, so resident warps are what hides them: measured on the four-view
+// 5 mm fusion cloud (tools/k4_sweep.sh), one group per warp step at six CTAs per SM and 256-thread emit CTAs at eight per SM
+// took 134 us where four groups (69 registers, three CTAs per SM) and 128-thread emit CTAs took 193 us.
+#ifndef RV_VOX_GROUPS
+#define RV_VOX_GROUPS 1
+#endif
+#ifndef RV_VOX_INSERT_OCC
+#define RV_VOX_INSERT_OCC 6
+#endif
+#ifndef RV_VOX_EMIT_THREADS
+#define RV_VOX_EMIT_THREADS 256
+#endif
+#ifndef RV_VOX_EMIT_OCC
+#define RV_VOX_EMIT_OCC 8
+#endif
 struct __align__(64) VoxLong {
   unsigned long long key;
   unsigned int count;
@@ -293,10 +308,10 @@ __global__ void __launch_bounds__(256) k_vox_bounds(const VoxArgs a, double *bou
   block_bounds_commit(lo, hi, bounds);
 }
 
-constexpr int kVoxGroups = 4;  // 32-point groups per warp and step
+constexpr int kVoxGroups = RV_VOX_GROUPS;  // 32-point groups per warp and step
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_vox_insert(const VoxArgs a) {
+__global__ void __launch_bounds__(256, RV_VOX_INSERT_OCC) k_vox_insert(const VoxArgs a) {
   const double half = a.voxel * 0.5;
   const double ox = a.bounds[0] - half, oy = a.bounds[1] - half, oz = a.bounds[2] - half;
   {
@@ -460,9 +475,11 @@ __device__ __forceinline__ void vox_store(const VoxOutArgs &o, int has_color, lo
 }
 
 // CTA p finishes the voxels part p created, behind those of parts 0..p-1
+constexpr int kVoxEmitThreads = RV_VOX_EMIT_THREADS;
+
 template <typename T, typename OutT>
-__global__ void __launch_bounds__(128) k_vox_emit(const VoxArgs a, const VoxOutArgs o) {
-  __shared__ unsigned long long s_red[2][4];
+__global__ void __launch_bounds__(kVoxEmitThreads, RV_VOX_EMIT_OCC) k_vox_emit(const VoxArgs a, const VoxOutArgs o) {
+  __shared__ unsigned long long s_red[2][kVoxEmitThreads / 32];
   unsigned long long before = 0, total = 0;
   for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) {
     const unsigned long long c = a.parts[q].x;
@@ -478,7 +495,7 @@ __global__ void __launch_bounds__(128) k_vox_emit(const VoxArgs a, const VoxOutA
   __syncthreads();
   before = total = 0;
 #pragma unroll
-  for (int w = 0; w < 4; ++w) before += s_red[0][w], total += s_red[1][w];
+  for (int w = 0; w < kVoxEmitThreads / 32; ++w) before += s_red[0][w], total += s_red[1][w];
   if (blockIdx.x == 0 && threadIdx.x == 0) *o.m = a.hdr->error ? -1ll : (long long)total;
   if (a.hdr->error) return;
   const unsigned int mine = a.parts[blockIdx.x].x;
@@ -506,7 +523,7 @@ __global__ void __launch_bounds__(128) k_vox_emit(const VoxArgs a, const VoxOutA
     idx[i] = lo_;                                       \
     idx[j] = hi_;                                       \
   }
-    if (idx[1] != kVoxNil) {  // 19-comparator network for eight keys (empty entries sort last)
+    if (idx[1] != kVoxNil && link == kVoxNil) {  // 19-comparator network for eight keys (empty entries sort last)
       RV_CX(0, 1) RV_CX(2, 3) RV_CX(4, 5) RV_CX(6, 7)
       RV_CX(0, 2) RV_CX(1, 3) RV_CX(4, 6) RV_CX(5, 7)
       RV_CX(1, 2) RV_CX(5, 6) RV_CX(0, 4) RV_CX(3, 7)
@@ -516,23 +533,21 @@ __global__ void __launch_bounds__(128) k_vox_emit(const VoxArgs a, const VoxOutA
       RV_CX(3, 4)
     }
 #undef RV_CX
-    VoxSum acc;
-#pragma unroll
-    for (int c = 0; c < 6; ++c) acc.s[c] = 0.0;
-    acc.count = 0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      if (idx[q] != kVoxNil) vox_add_run<T>(a, idx[q], acc);
-    int hops = 8;
-    while (link != kVoxNil && hops < kVoxLongChain) {
-      vox_add_run<T>(a, a.list[link].x, acc);
-      link = a.next[link];
-      ++hops;
-    }
     const unsigned long long key = a.keys[me.y];
-    if (link != kVoxNil) {
-      // a very long chain (coarse grid): hand the voxel to the atomic path; everything added so far is dropped
-      const unsigned int q = atomicAdd(&a.hdr->n_long, 1u);
+    // pool slots for the long voxels of this warp step: one atomic per warp (a coarse grid makes every voxel long, and
+    // same-address atomics serialise)
+    const bool is_long = link != kVoxNil;
+    const unsigned int active = __activemask();
+    const unsigned int lm = __ballot_sync(active, is_long);
+    unsigned int qbase = 0;
+    if (lm) {
+      const int leader = __ffs(lm) - 1;
+      if ((int)(threadIdx.x & 31) == leader) qbase = atomicAdd(&a.hdr->n_long, (unsigned int)__popc(lm));
+      qbase = __shfl_sync(active, qbase, leader);
+    }
+    if (is_long) {
+      // more than eight runs: hand the voxel to the atomic path (its joiners add themselves in parallel in k_vox_long)
+      const unsigned int q = qbase + __popc(lm & rv_lanemask_lt());
       VoxLong *rec = a.pool + q;
       rec->key = key;
       rec->out = (unsigned int)pos;
@@ -547,6 +562,13 @@ __global__ void __launch_bounds__(128) k_vox_emit(const VoxArgs a, const VoxOutA
       a.chain[me.y] = kVoxLongTag | q;
       continue;
     }
+    VoxSum acc;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) acc.s[c] = 0.0;
+    acc.count = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (idx[q] != kVoxNil) vox_add_run<T>(a, idx[q], acc);
     vox_store<OutT>(o, a.has_color, pos, acc.s, acc.count, key);
   }
 }
@@ -617,7 +639,7 @@ VoxLayout vox_layout(long long n) {
   L.masks = off;
   off += vox_align((size_t)((n + 31) / 32) * 4);
   L.pool = off;
-  off += vox_align((size_t)(n / kVoxLongChain + 1) * sizeof(VoxLong));
+  off += vox_align((size_t)(n / (kVoxHeads + 1) + 1) * sizeof(VoxLong));  // a long voxel has more than kVoxHeads run heads
   L.total = off;
   return L;
 }
@@ -881,10 +903,10 @@ static int vox_run_all(rv_ctx *ctx, const char *who, int n_views, const void *co
   o.keys = d_keys;
   o.counts = d_counts_out;
   o.m = reinterpret_cast<long long *>(d_m);
-  if (in_dtype == RV_F32 && out_dtype == RV_F32) k_vox_emit<float, float><<<parts_n, 128, 0, st>>>(a, o);
-  else if (in_dtype == RV_F32) k_vox_emit<float, double><<<parts_n, 128, 0, st>>>(a, o);
-  else if (out_dtype == RV_F32) k_vox_emit<double, float><<<parts_n, 128, 0, st>>>(a, o);
-  else k_vox_emit<double, double><<<parts_n, 128, 0, st>>>(a, o);
+  if (in_dtype == RV_F32 && out_dtype == RV_F32) k_vox_emit<float, float><<<parts_n, kVoxEmitThreads, 0, st>>>(a, o);
+  else if (in_dtype == RV_F32) k_vox_emit<float, double><<<parts_n, kVoxEmitThreads, 0, st>>>(a, o);
+  else if (out_dtype == RV_F32) k_vox_emit<double, float><<<parts_n, kVoxEmitThreads, 0, st>>>(a, o);
+  else k_vox_emit<double, double><<<parts_n, kVoxEmitThreads, 0, st>>>(a, o);
   RV_LAUNCHED(ctx);
   // voxels with very long chains (none on a fine grid: both kernels then return at once)
   const int lg = parts_n < ctx->sm_count * 4 ? parts_n : ctx->sm_count * 4;

@@ -28,6 +28,20 @@ VARIANTS = {
 }
 
 
+# K4 tunables (tools/k4_sweep.sh): groups per warp step and occupancy of the insert, block size / occupancy of the emit
+VARIANTS.update({
+    "k4_g4_i3_e128x8": "-DRV_VOX_GROUPS=4 -DRV_VOX_INSERT_OCC=3 -DRV_VOX_EMIT_THREADS=128 -DRV_VOX_EMIT_OCC=8",
+    "k4_g2_i5_e128x8": "-DRV_VOX_GROUPS=2 -DRV_VOX_INSERT_OCC=5 -DRV_VOX_EMIT_THREADS=128 -DRV_VOX_EMIT_OCC=8",
+    "k4_g2_i6_e256x6": "-DRV_VOX_GROUPS=2 -DRV_VOX_INSERT_OCC=6 -DRV_VOX_EMIT_THREADS=256 -DRV_VOX_EMIT_OCC=6",
+    "k4_g4_i4_e256x6": "-DRV_VOX_GROUPS=4 -DRV_VOX_INSERT_OCC=4 -DRV_VOX_EMIT_THREADS=256 -DRV_VOX_EMIT_OCC=6",
+    "k4_g1_i6_e256x8": "-DRV_VOX_GROUPS=1 -DRV_VOX_INSERT_OCC=6 -DRV_VOX_EMIT_THREADS=256 -DRV_VOX_EMIT_OCC=8",
+    "k4_g4_i3_e512x3": "-DRV_VOX_GROUPS=4 -DRV_VOX_INSERT_OCC=3 -DRV_VOX_EMIT_THREADS=512 -DRV_VOX_EMIT_OCC=3",
+    "k4_g1_i8_e256x8": "-DRV_VOX_GROUPS=1 -DRV_VOX_INSERT_OCC=8 -DRV_VOX_EMIT_THREADS=256 -DRV_VOX_EMIT_OCC=8",
+    "k4_g1_i6_e256x6": "-DRV_VOX_GROUPS=1 -DRV_VOX_INSERT_OCC=6 -DRV_VOX_EMIT_THREADS=256 -DRV_VOX_EMIT_OCC=6",
+    "k4_g1_i6_e128x12": "-DRV_VOX_GROUPS=1 -DRV_VOX_INSERT_OCC=6 -DRV_VOX_EMIT_THREADS=128 -DRV_VOX_EMIT_OCC=12",
+})
+
+
 def main():
     names = sys.argv[1:] or list(VARIANTS)
     outdir = os.path.join(ROOT, "build", "variants")
