@@ -348,7 +348,9 @@ int rv_select_by_mask(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, in
  *                      point_to_plane: [2] sum r^2, [3..8] J^T r, [9..29] upper triangle of J^T J (row-major), with
  *                      r = (s - t) . n_t and J = [s x n_t, n_t];
  *                      point-to-point: [2] sum |s|^2, [3..5] sum s, [6..8] sum t, [9..17] sum t_a s_b (a row-major)
- * The 6x6 solve / Umeyama step and the convergence test stay on the host (repas_vision_b200/registration.py). */
+ * With these three calls the 6x6 solve / Umeyama step and the convergence test run on the host
+ * (repas_vision_b200/registration.py: the point-to-point estimation and `device_loop=False`); rv_icp_iterate below keeps
+ * the point-to-plane loop on the device. */
 int rv_nn_index_build(rv_ctx *ctx, const void *d_xyz, int64_t plane_stride, int64_t n, int dtype, double max_distance,
                       void *d_ws, size_t ws_bytes, rv_stream stream);
 int rv_nn_search(rv_ctx *ctx, const void *d_index_ws, size_t ws_bytes, int64_t n_indexed, const void *d_query_xyz,
@@ -358,6 +360,24 @@ int rv_icp_sums(rv_ctx *ctx, int point_to_plane, const void *d_source_xyz, int64
                 int source_dtype, const void *d_target_xyz, int64_t target_stride, int64_t n_target, int target_dtype,
                 const double *d_target_normals, int64_t normal_stride, const int32_t *d_nearest, double *d_sums,
                 rv_stream stream);
+
+/* the whole point-to-plane loop on the device: rv_icp_begin writes the state (accumulated transformation = T_init, the
+ * stopping rule's thresholds), rv_icp_iterate queues `steps` iterations -- each: pcd.Transform(update) on the caller's
+ * working copy of the source coordinates IN PLACE, nearest search, sums, then ONE thread's worth of host logic on the
+ * device: fitness / inlier RMSE, |delta fitness| < relative_fitness && |delta rmse| < relative_rmse, the 6 x 6 solve
+ * (elimination with partial pivoting; a vanishing pivot leaves the update at identity) and transformation = update *
+ * transformation -- preceded, when `first` is set, by the evaluation of the initial alignment.  Once the loop has
+ * stopped every queued kernel returns at once, so the host reads the state back once per few iterations instead of
+ * once per iteration.  The state (rv_icp_state_bytes() = 448 bytes): double T[16], update[16], fitness, inlier_rmse,
+ * relative_fitness, relative_rmse, iterations, max_iteration, n_source, evaluated, 8 reserved; then int32 done.
+ * d_nearest holds the correspondences of the last evaluation; d_sums as in rv_icp_sums. */
+size_t rv_icp_state_bytes(void);
+int rv_icp_begin(rv_ctx *ctx, void *d_state, const double *T_init, int max_iteration, double relative_fitness,
+                 double relative_rmse, int64_t n_source, rv_stream stream);
+int rv_icp_iterate(rv_ctx *ctx, void *d_state, int first, int steps, void *d_work_xyz, int64_t work_stride, int64_t n_source,
+                   int work_dtype, const void *d_index_ws, size_t ws_bytes, int64_t n_target, const void *d_target_xyz,
+                   int64_t target_stride, int target_dtype, const double *d_target_normals, int64_t normal_stride,
+                   double max_distance, int32_t *d_nearest, double *d_sums, rv_stream stream);
 
 /* ---- a2 (next): windowed median depth ------------------------------
  * replaces get_depth_at_pixel (canopy_return.py:279-317) and median_depth

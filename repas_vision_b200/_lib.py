@@ -91,6 +91,10 @@ SIGNATURES = {
     "rv_icp_sums_bytes": (C.c_size_t, []),
     "rv_icp_sums": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, c_i64, C.c_int, c_vp, c_i64, c_i64, C.c_int, c_vp, c_i64, c_vp, c_vp,
                               c_vp]),
+    "rv_icp_state_bytes": (C.c_size_t, []),
+    "rv_icp_begin": (C.c_int, [c_vp, c_vp, C.POINTER(c_f64), C.c_int, c_f64, c_f64, c_i64, c_vp]),
+    "rv_icp_iterate": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_vp, c_i64, c_i64, C.c_int, c_vp, C.c_size_t, c_i64, c_vp, c_i64,
+                                 C.c_int, c_vp, c_i64, c_f64, c_vp, c_vp, c_vp]),
     "rv_median_depth_window": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_vp, c_i64, C.c_int, c_vp, c_vp]),
     "rv_nv12_to_bgr": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
 }

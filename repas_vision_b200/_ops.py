@@ -423,6 +423,30 @@ def icp_sums(source: torch.Tensor, n_source: int, target: torch.Tensor, n_target
     return scratch[:32]
 
 
+def icp_state(dev: torch.device) -> torch.Tensor:
+    return torch.zeros(int(ctx_for(dev).lib.rv_icp_state_bytes()) // 8, dtype=torch.float64, device=dev)
+
+
+def icp_begin(state: torch.Tensor, T_init, max_iteration: int, relative_fitness: float, relative_rmse: float, n_source: int) -> None:
+    dev = state.device
+    ctx = ctx_for(dev)
+    Tc = (C.c_double * 16)(*np.asarray(T_init, dtype=np.float64).reshape(-1))
+    ctx.check(ctx.lib.rv_icp_begin(ctx.handle, ptr(state), Tc, int(max_iteration), float(relative_fitness), float(relative_rmse),
+                                   int(n_source), stream_ptr(dev)))
+
+
+def icp_iterate(state: torch.Tensor, first: bool, steps: int, work: torch.Tensor, n_source: int, index_ws: torch.Tensor,
+                target: torch.Tensor, n_target: int, target_normals: torch.Tensor, max_distance: float, nearest: torch.Tensor,
+                scratch: torch.Tensor) -> None:
+    """Queues `steps` point-to-plane iterations (and the initial evaluation when `first`) on the current stream."""
+    dev = work.device
+    ctx = ctx_for(dev)
+    ctx.check(ctx.lib.rv_icp_iterate(ctx.handle, ptr(state), int(bool(first)), int(steps), ptr(work), pstride(work), n_source,
+                                     _RV_DT[work.dtype], ptr(index_ws), index_ws.numel(), n_target, ptr(target), pstride(target),
+                                     _RV_DT[target.dtype], ptr(target_normals), pstride(target_normals), float(max_distance),
+                                     ptr(nearest), ptr(scratch), stream_ptr(dev)))
+
+
 def statistical_outlier_mask(mean: torch.Tensor, std_ratio: float):
     """(keep uint8 [n], stats float64 [4] = cloud mean, std dev, threshold, points counted)."""
     dev = mean.device

@@ -675,7 +675,8 @@ __global__ void __launch_bounds__(256) k_orient_normals(const T *__restrict__ xy
 // conservative).  Equal distances go to the lower point index, so the result does not depend on the cell order.
 template <typename T>
 __global__ void __launch_bounds__(128) k_nn_search(const KnnArgs a, const T *__restrict__ q_xyz, long long q_stride, long long nq,
-                                                   double radius2, int *__restrict__ corr) {
+                                                   double radius2, int *__restrict__ corr, const int *__restrict__ skip) {
+  if (skip && *skip) return;  // device-side ICP loop: the registration has already stopped
   const KnnParams *p = a.prm;
   const double cell = p->cell;
   const int gx = p->grid[0], gy = p->grid[1], gz = p->grid[2], rmax = p->rmax;
@@ -770,7 +771,9 @@ template <typename TS, typename TT, bool kPlane>
 __global__ void __launch_bounds__(256) k_icp_sums(const TS *__restrict__ src, long long s_stride, long long n,
                                                   const TT *__restrict__ tgt, long long t_stride,
                                                   const double *__restrict__ nrm, long long n_stride,
-                                                  const int *__restrict__ corr, double *__restrict__ partial) {
+                                                  const int *__restrict__ corr, double *__restrict__ partial,
+                                                  const int *__restrict__ skip) {
+  if (skip && *skip) return;
   constexpr int kUsed = kPlane ? 30 : 18;
   __shared__ double s_red[8][kIcpSums];
   double acc[kUsed];
@@ -836,11 +839,150 @@ __global__ void __launch_bounds__(kIcpSums * 32) k_icp_finish(const double *__re
 
 template <typename TS, typename TT>
 static void icp_sums_launch(int plane, int blocks, cudaStream_t st, const void *src, int64_t ss, int64_t n, const void *tgt, int64_t ts,
-                            const double *nrm, int64_t ns, const int32_t *corr, double *partial) {
+                            const double *nrm, int64_t ns, const int32_t *corr, double *partial, const int *skip = nullptr) {
   if (plane)
-    k_icp_sums<TS, TT, true><<<blocks, 256, 0, st>>>(reinterpret_cast<const TS *>(src), ss, n, reinterpret_cast<const TT *>(tgt), ts, nrm, ns, corr, partial);
+    k_icp_sums<TS, TT, true><<<blocks, 256, 0, st>>>(reinterpret_cast<const TS *>(src), ss, n, reinterpret_cast<const TT *>(tgt), ts, nrm, ns, corr, partial, skip);
   else
-    k_icp_sums<TS, TT, false><<<blocks, 256, 0, st>>>(reinterpret_cast<const TS *>(src), ss, n, reinterpret_cast<const TT *>(tgt), ts, nrm, ns, corr, partial);
+    k_icp_sums<TS, TT, false><<<blocks, 256, 0, st>>>(reinterpret_cast<const TS *>(src), ss, n, reinterpret_cast<const TT *>(tgt), ts, nrm, ns, corr, partial, skip);
+}
+
+// ---- the ICP loop on the device (point-to-plane): state, in-place update of the working copy, and the step that follows
+// an evaluation -- fitness / inlier RMSE, the reference's stopping rule, the 6 x 6 solve and the pose composition -- so that
+// the host reads back once per few iterations instead of once per iteration (Open3D 0.19 RegistrationICP, restated in
+// repas_vision_b200/registration.py; mpa_icp_export.py:187-197).
+struct IcpState {
+  double T[16];       // accumulated transformation
+  double update[16];  // what the working copy is moved by next
+  double fitness, rmse, rel_fitness, rel_rmse;
+  double iterations, max_iteration, n_source, evaluated;
+  double pad[8];
+  int done;  // converged, or max_iteration estimation steps taken: every later kernel of the queue returns at once
+  int pad2[15];
+};
+static_assert(sizeof(IcpState) == 448, "state layout is read by the host (registration.py)");
+
+__global__ void k_icp_begin(IcpState *s, const __grid_constant__ IcpState init) {
+  if (threadIdx.x == 0) *s = init;
+}
+
+// pcd.Transform(update) on the working copy, in place (every thread owns its point); arithmetic of k_transform
+template <typename T>
+__global__ void __launch_bounds__(256) k_icp_apply(const IcpState *__restrict__ s, T *__restrict__ xyz, long long stride, long long n) {
+  if (s->done) return;
+  double M[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) M[i] = s->update[i];
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    const double x = (double)xyz[i], y = (double)xyz[stride + i], z = (double)xyz[2 * stride + i];
+    const double qx = ((M[0] * x + M[1] * y) + M[2] * z) + M[3];
+    const double qy = ((M[4] * x + M[5] * y) + M[6] * z) + M[7];
+    const double qz = ((M[8] * x + M[9] * y) + M[10] * z) + M[11];
+    const double qw = ((M[12] * x + M[13] * y) + M[14] * z) + M[15];
+    double px = qx, py = qy, pz = qz;
+    if (qw != 1.0) {
+      px = qx / qw;
+      py = qy / qw;
+      pz = qz / qw;
+    }
+    xyz[i] = (T)px;
+    xyz[stride + i] = (T)py;
+    xyz[2 * stride + i] = (T)pz;
+  }
+}
+
+// x = solve(A, b) for the symmetric 6 x 6 system by elimination with partial pivoting; false when a pivot vanishes
+__device__ bool icp_solve6(double A[6][6], double b[6], double x[6]) {
+  for (int c = 0; c < 6; ++c) {
+    int piv = c;
+    double best = fabs(A[c][c]);
+    for (int r = c + 1; r < 6; ++r)
+      if (fabs(A[r][c]) > best) best = fabs(A[r][c]), piv = r;
+    if (!(best > 0.0) || !isfinite(best)) return false;
+    if (piv != c) {
+      for (int k = 0; k < 6; ++k) {
+        const double t = A[c][k];
+        A[c][k] = A[piv][k];
+        A[piv][k] = t;
+      }
+      const double t = b[c];
+      b[c] = b[piv];
+      b[piv] = t;
+    }
+    for (int r = c + 1; r < 6; ++r) {
+      const double f = A[r][c] / A[c][c];
+      for (int k = c; k < 6; ++k) A[r][k] -= f * A[c][k];
+      b[r] -= f * b[c];
+    }
+  }
+  for (int r = 5; r >= 0; --r) {
+    double v = b[r];
+    for (int k = r + 1; k < 6; ++k) v -= A[r][k] * x[k];
+    x[r] = v / A[r][r];
+  }
+  for (int r = 0; r < 6; ++r)
+    if (!isfinite(x[r])) return false;
+  return true;
+}
+
+// finishes an evaluation (sums of the per-block rows in a fixed order, as k_icp_finish) and takes the loop's next decision
+__global__ void __launch_bounds__(kIcpSums * 32) k_icp_finish_step(const double *__restrict__ partial, int blocks, double *__restrict__ sums,
+                                                                   IcpState *__restrict__ s) {
+  if (s->done) return;
+  __shared__ double s_sum[kIcpSums];
+  const int col = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double v = 0.0;
+  for (int b = lane; b < blocks; b += 32) v += partial[(size_t)b * kIcpSums + col];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) {
+    s_sum[col] = v;
+    sums[col] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const double count = s_sum[0];
+  const double fitness = count > 0.0 ? count / s->n_source : 0.0;
+  const double rmse = count > 0.0 ? sqrt(s_sum[1] / count) : 0.0;
+  bool stop = false;
+  if (s->evaluated != 0.0)  // the reference compares with the evaluation before this estimation step
+    stop = fabs(s->fitness - fitness) < s->rel_fitness && fabs(s->rmse - rmse) < s->rel_rmse;
+  s->fitness = fitness;
+  s->rmse = rmse;
+  s->evaluated = 1.0;
+  if (stop || s->iterations >= s->max_iteration) {
+    s->done = 1;
+    return;
+  }
+  // TransformationEstimationPointToPlane::ComputeTransformation: x = solve(J^T J, -J^T r), update = [Rz Ry Rx | t]
+  double U[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  if (count > 0.0) {
+    double A[6][6], b[6], x[6];
+    int t = 9;
+    for (int u = 0; u < 6; ++u) {
+      b[u] = -s_sum[3 + u];
+      for (int w = u; w < 6; ++w) A[u][w] = A[w][u] = s_sum[t++];
+    }
+    if (icp_solve6(A, b, x)) {
+      const double ca = cos(x[0]), sa = sin(x[0]), cb = cos(x[1]), sb = sin(x[1]), cc = cos(x[2]), sc = sin(x[2]);
+      // Rz(c) Ry(b) Rx(a)
+      U[0] = cc * cb, U[1] = cc * sb * sa - sc * ca, U[2] = cc * sb * ca + sc * sa, U[3] = x[3];
+      U[4] = sc * cb, U[5] = sc * sb * sa + cc * ca, U[6] = sc * sb * ca - cc * sa, U[7] = x[4];
+      U[8] = -sb, U[9] = cb * sa, U[10] = cb * ca, U[11] = x[5];
+    }
+  }
+  double N[16];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {
+      double acc = 0.0;
+      for (int k = 0; k < 4; ++k) acc += U[4 * r + k] * s->T[4 * k + c];
+      N[4 * r + c] = acc;
+    }
+  for (int i = 0; i < 16; ++i) {
+    s->T[i] = N[i];
+    s->update[i] = U[i];
+  }
+  s->iterations += 1.0;
 }
 
 template <bool kNormals>
@@ -1069,9 +1211,9 @@ int rv_nn_search(rv_ctx *ctx, const void *d_index_ws, size_t ws_bytes, int64_t n
   knn_layout(const_cast<void *>(d_index_ws), nullptr, 0, n_indexed, 1, a);
   const double r2 = max_distance * max_distance;
   if (dtype == RV_F32)
-    k_nn_search<float><<<(unsigned int)((n_query + 127) / 128), 128, 0, st>>>(a, reinterpret_cast<const float *>(d_query_xyz), query_stride, n_query, r2, d_nearest);
+    k_nn_search<float><<<(unsigned int)((n_query + 127) / 128), 128, 0, st>>>(a, reinterpret_cast<const float *>(d_query_xyz), query_stride, n_query, r2, d_nearest, nullptr);
   else
-    k_nn_search<double><<<(unsigned int)((n_query + 127) / 128), 128, 0, st>>>(a, reinterpret_cast<const double *>(d_query_xyz), query_stride, n_query, r2, d_nearest);
+    k_nn_search<double><<<(unsigned int)((n_query + 127) / 128), 128, 0, st>>>(a, reinterpret_cast<const double *>(d_query_xyz), query_stride, n_query, r2, d_nearest, nullptr);
   RV_LAUNCHED(ctx);
   return RV_OK;
 }
@@ -1110,6 +1252,79 @@ int rv_icp_sums(rv_ctx *ctx, int point_to_plane, const void *d_source_xyz, int64
   RV_LAUNCHED(ctx);
   k_icp_finish<<<1, kIcpSums * 32, 0, st>>>(partial, blocks, d_sums);
   RV_LAUNCHED(ctx);
+  return RV_OK;
+}
+
+size_t rv_icp_state_bytes(void) { return sizeof(IcpState); }
+
+int rv_icp_begin(rv_ctx *ctx, void *d_state, const double *T_init, int max_iteration, double relative_fitness, double relative_rmse,
+                 int64_t n_source, rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
+  if (!d_state || !T_init || max_iteration < 0 || n_source < 0) RV_FAIL(ctx, RV_EINVAL, "rv_icp_begin: bad argument");
+  IcpState init;
+  memset(&init, 0, sizeof(init));
+  for (int i = 0; i < 16; ++i) {
+    init.T[i] = T_init[i];
+    init.update[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  }
+  init.rel_fitness = relative_fitness;
+  init.rel_rmse = relative_rmse;
+  init.max_iteration = (double)max_iteration;
+  init.n_source = (double)n_source;
+  k_icp_begin<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<IcpState *>(d_state), init);
+  RV_LAUNCHED(ctx);
+  return RV_OK;
+}
+
+int rv_icp_iterate(rv_ctx *ctx, void *d_state, int first, int steps, void *d_work_xyz, int64_t work_stride, int64_t n_source,
+                   int work_dtype, const void *d_index_ws, size_t ws_bytes, int64_t n_target, const void *d_target_xyz,
+                   int64_t target_stride, int target_dtype, const double *d_target_normals, int64_t normal_stride,
+                   double max_distance, int32_t *d_nearest, double *d_sums, rv_stream stream) {
+  if (!ctx) return RV_EINVAL;
+  RvDeviceGuard dev_guard(ctx);
+  if (!d_state || steps < 0 || n_source <= 0 || n_target <= 0 || work_stride < n_source || target_stride < n_target)
+    RV_FAIL(ctx, RV_EINVAL, "rv_icp_iterate: bad n / stride / state (empty clouds are the caller's business)");
+  if ((work_dtype != RV_F32 && work_dtype != RV_F64) || (target_dtype != RV_F32 && target_dtype != RV_F64))
+    RV_FAIL(ctx, RV_EINVAL, "rv_icp_iterate: bad dtype");
+  if (!d_work_xyz || !d_target_xyz || !d_nearest || !d_sums || !d_target_normals || normal_stride < n_target)
+    RV_FAIL(ctx, RV_EINVAL, "rv_icp_iterate: null pointer (point-to-plane needs the target normals)");
+  if (!(max_distance > 0.0)) RV_FAIL(ctx, RV_EINVAL, "rv_icp_iterate: max_distance must be positive");
+  if (!d_index_ws || ws_bytes < rv_knn_workspace_bytes(n_target)) RV_FAIL(ctx, RV_EWORKSPACE, "rv_icp_iterate: index workspace too small");
+  if (!rv_aligned(d_index_ws, 256)) RV_FAIL(ctx, RV_EALIGN, "rv_icp_iterate: workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  IcpState *state = reinterpret_cast<IcpState *>(d_state);
+  const int *skip = &state->done;
+  KnnArgs a;
+  knn_layout(const_cast<void *>(d_index_ws), nullptr, 0, n_target, 1, a);
+  const double r2 = max_distance * max_distance;
+  int blocks = grid_for(ctx, n_source, 4);
+  if (blocks > kIcpMaxBlocks) blocks = kIcpMaxBlocks;
+  double *partial = d_sums + kIcpSums;
+  const int ag = grid_for(ctx, n_source);
+  for (int it = first ? 0 : 1; it <= steps; ++it) {
+    if (it > 0) {  // pcd.Transform(update)
+      if (work_dtype == RV_F32) k_icp_apply<float><<<ag, 256, 0, st>>>(state, reinterpret_cast<float *>(d_work_xyz), work_stride, n_source);
+      else k_icp_apply<double><<<ag, 256, 0, st>>>(state, reinterpret_cast<double *>(d_work_xyz), work_stride, n_source);
+      RV_LAUNCHED(ctx);
+    }
+    if (work_dtype == RV_F32)
+      k_nn_search<float><<<(unsigned int)((n_source + 127) / 128), 128, 0, st>>>(a, reinterpret_cast<const float *>(d_work_xyz), work_stride, n_source, r2, d_nearest, skip);
+    else
+      k_nn_search<double><<<(unsigned int)((n_source + 127) / 128), 128, 0, st>>>(a, reinterpret_cast<const double *>(d_work_xyz), work_stride, n_source, r2, d_nearest, skip);
+    RV_LAUNCHED(ctx);
+    if (work_dtype == RV_F32 && target_dtype == RV_F32)
+      icp_sums_launch<float, float>(1, blocks, st, d_work_xyz, work_stride, n_source, d_target_xyz, target_stride, d_target_normals, normal_stride, d_nearest, partial, skip);
+    else if (work_dtype == RV_F32)
+      icp_sums_launch<float, double>(1, blocks, st, d_work_xyz, work_stride, n_source, d_target_xyz, target_stride, d_target_normals, normal_stride, d_nearest, partial, skip);
+    else if (target_dtype == RV_F32)
+      icp_sums_launch<double, float>(1, blocks, st, d_work_xyz, work_stride, n_source, d_target_xyz, target_stride, d_target_normals, normal_stride, d_nearest, partial, skip);
+    else
+      icp_sums_launch<double, double>(1, blocks, st, d_work_xyz, work_stride, n_source, d_target_xyz, target_stride, d_target_normals, normal_stride, d_nearest, partial, skip);
+    RV_LAUNCHED(ctx);
+    k_icp_finish_step<<<1, kIcpSums * 32, 0, st>>>(partial, blocks, d_sums, state);
+    RV_LAUNCHED(ctx);
+  }
   return RV_OK;
 }
 

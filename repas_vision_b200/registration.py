@@ -17,8 +17,11 @@ utility/Eigen.cpp; the wheel is not part of the reference checkout, see DESIGN.m
       update = [Rz(x2) Ry(x1) Rx(x0) | x3..5]
   point-to-point:   Eigen::umeyama(source, target, with_scaling)
 
-Per iteration the GPU runs three kernels (K3 transform, nearest-point search on the target's hash grid, the sums of the
-estimation step) and 32 doubles come back; the 6x6 solve / 3x3 SVD and the stopping rule run here on the host.
+Point-to-plane (what every call site of the reference uses) runs the whole loop on the device: per iteration four kernels
+(move the working copy, nearest-point search on the target's hash grid, the sums of the estimation step, and one that takes
+the loop's decisions: fitness / RMSE, the stopping rule, the 6x6 solve, the pose composition); the host queues a few
+iterations at a time and reads 448 bytes of state back per batch.  Point-to-point (Umeyama's SVD) and
+`device_loop=False` keep the solve and the stopping rule here on the host: three kernels and 32 doubles per iteration.
 """
 from __future__ import annotations
 
@@ -197,9 +200,39 @@ def evaluate_registration(source: PointCloud, target: PointCloud, max_correspond
     return res
 
 
+ICP_STEPS_PER_READBACK = 4  # iterations queued between two looks at the device-side state
+
+
+def _icp_on_device(m: _Matcher, source: PointCloud, transformation: np.ndarray, crit: ICPConvergenceCriteria) -> RegistrationResult:
+    """The point-to-plane loop with its decisions taken on the device (rv_icp_iterate)."""
+    n, nt = m.n, len(m.target)
+    dev = source.device
+    work = m.spare[0]
+    _ops.transform_xyz_into(source._data, n, transformation, work)  # pcd = source transformed by init (a copy, always)
+    state = _ops.icp_state(dev)
+    _ops.icp_begin(state, transformation, crit.max_iteration, crit.relative_fitness, crit.relative_rmse, n)
+    queued, first = 0, True
+    while True:
+        steps = min(ICP_STEPS_PER_READBACK, crit.max_iteration - queued)
+        _ops.icp_iterate(state, first, steps, work, n, m.index, m.target._data, nt, m.target._normals, m.max_distance, m.nearest,
+                         m.scratch)
+        queued += steps
+        first = False
+        host = state.cpu().numpy()
+        done = int(host[48:49].view(np.int32)[0])
+        if done or queued >= crit.max_iteration:
+            break
+    res = RegistrationResult(host[:16].reshape(4, 4).copy())
+    res._n, res._nearest = n, m.nearest
+    res.fitness, res.inlier_rmse, res.iterations = float(host[32]), float(host[33]), int(host[36])
+    return res
+
+
 def registration_icp(source: PointCloud, target: PointCloud, max_correspondence_distance: float, init=None,
-                     estimation_method=None, criteria: ICPConvergenceCriteria | None = None) -> RegistrationResult:
-    """o3d.pipelines.registration.registration_icp (legacy pipeline), same argument order and defaults."""
+                     estimation_method=None, criteria: ICPConvergenceCriteria | None = None, *,
+                     device_loop: bool = True) -> RegistrationResult:
+    """o3d.pipelines.registration.registration_icp (legacy pipeline), same argument order and defaults.  device_loop=False
+    keeps the solve and the stopping rule on the host for point-to-plane as well (one read-back per iteration)."""
     est = estimation_method if estimation_method is not None else TransformationEstimationPointToPoint()
     crit = criteria if criteria is not None else ICPConvergenceCriteria()
     if not (float(max_correspondence_distance) > 0.0):
@@ -211,6 +244,8 @@ def registration_icp(source: PointCloud, target: PointCloud, max_correspondence_
     if transformation.shape != (4, 4):
         raise ValueError(f"Expected 4x4 matrix, got shape {transformation.shape}")
     m = _Matcher(source, target, max_correspondence_distance, est.point_to_plane)
+    if (device_loop and est.point_to_plane and type(est) is TransformationEstimationPointToPlane and m.n > 0 and len(target) > 0):
+        return _icp_on_device(m, source, transformation, crit)
     if not _is_identity(transformation):
         m.transform(transformation)
     result, sums = m.evaluate(transformation)

@@ -218,3 +218,29 @@ def test_registration_icp_float32_clouds(rv, O):
     mixed = rv.registration_icp(rv.PointCloud.from_arrays(moved, None), target, 0.02, np.eye(4),
                                 rv.TransformationEstimationPointToPlane(), rv.ICPConvergenceCriteria(max_iteration=50))
     assert np.allclose(mixed.transformation, T, atol=2e-4)
+
+
+def test_device_loop_equals_host_loop(rv, O):
+    """Point-to-plane ICP with the loop's decisions taken on the device (rv_icp_iterate: stopping rule, 6x6 solve, pose
+    composition) against the same loop with those steps on the host: same number of estimation steps, same correspondences,
+    transformation to rounding, for several caps on the iteration count (0 = evaluate only; caps that fall inside and across
+    the read-back batches) and a non-identity initial alignment."""
+    moved, tgt, D = _scene(O, seed=33)
+    target = rv.PointCloud.from_arrays(tgt, None)
+    target.estimate_normals(search_param=rv.KDTreeSearchParamHybrid(radius=0.02, max_nn=30))
+    est = rv.TransformationEstimationPointToPlane()
+    init = O.vector6d_to_matrix4d(np.array([0.002, 0.001, -0.003, 0.0005, 0.0, -0.0004]))
+    for dtype in ("f64", "f32"):
+        source = rv.PointCloud.from_arrays(moved.astype(np.float32) if dtype == "f32" else moved, None, dtype=dtype)
+        tg = rv.PointCloud.from_arrays(tgt.astype(np.float32) if dtype == "f32" else tgt, None, dtype=dtype)
+        tg._normals = target._normals
+        for cap, T0 in ((0, np.eye(4)), (1, np.eye(4)), (3, init), (4, np.eye(4)), (5, init), (50, np.eye(4)), (50, init)):
+            crit = rv.ICPConvergenceCriteria(max_iteration=cap, relative_fitness=1e-6, relative_rmse=1e-6)
+            a = rv.registration_icp(source, tg, 0.02, T0, est, crit)
+            b = rv.registration_icp(source, tg, 0.02, T0, est, crit, device_loop=False)
+            assert a.iterations == b.iterations and a.iterations <= cap
+            assert a.fitness == b.fitness and np.isclose(a.inlier_rmse, b.inlier_rmse, rtol=1e-9)
+            assert np.allclose(a.transformation, b.transformation, rtol=0, atol=1e-9 if dtype == "f64" else 1e-6)
+            if dtype == "f64":
+                assert np.array_equal(a.correspondence_set, b.correspondence_set)
+        assert a.iterations < 50  # converged by the stopping rule, not by the cap
