@@ -431,6 +431,8 @@ struct VoxSum {
 };
 
 // add the points of the run starting at i, one by one (index order inside the run)
+// (kept inline on purpose: as a called function -- eight calls per voxel instead of eight copies of the loop -- the emit
+// kernel ran 2.6 x slower, 351 vs 134 us on the 5 mm fusion cloud)
 template <typename T>
 __device__ __forceinline__ void vox_add_run(const VoxArgs &a, unsigned int i, VoxSum &acc) {
   const int run = vox_run(a, i);

@@ -114,6 +114,25 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, ui
                : "memory");
 }
 
+// shared-memory loads by 32-bit shared-window address.  The per-warp base addresses are computed once and made opaque to
+// the compiler (it otherwise rebuilds them from the thread index and the CTA's shared window on every tile: ~25 of the ~85
+// instructions a warp spends on a tile that holds nothing for it).  volatile: never moved across the mbarrier waits.
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // n / d for 0 <= n < 2^24 (exact int -> float) with a precomputed float reciprocal and one fix-up; callers fall
 // back to the integer divide above that range
 __device__ __forceinline__ int fast_div(int n, int d, float rcp, bool small) {
@@ -362,14 +381,25 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
   unsigned long long peek_nxt = 0;  // warp 0 lane 0: status word of the NEXT tile's predecessor, requested a tile early
   int peek_nxt_tile = -1;
   const int w0 = warp * kWarpPx;  // each warp owns 256 consecutive pixels of the tile: its kept points are ONE run of the output
+  // this lane's addresses inside stage 0: its eight raw depths of the whole-run test, its pixel of group 0
+  uint32_t q_a = ring_a + 2u * (uint32_t)(w0 + 8 * lane);
+  uint32_t g_a = ring_a + (uint32_t)kDepthB * (uint32_t)(w0 + lane);
+  uint32_t info_a = smem_u32(s_info), full_r = full_a, empty_r = empty_a, tot_r = tot_a;
+#ifndef RV_K1_OPAQUE
+#define RV_K1_OPAQUE 1
+#endif
+#if RV_K1_OPAQUE
+  asm volatile("" : "+r"(q_a), "+r"(g_a), "+r"(info_a), "+r"(full_r), "+r"(empty_r), "+r"(tot_r));
+#endif
 
   for (int it = 0;; ++it) {
     const int s = it % kStages;
-    mbar_wait(full_a + 8 * s, (it / kStages) & 1);
-    const int4 info = s_info[s];
-    const int tile = info.x;  // index into status[]
+    mbar_wait(full_r + 8 * s, (it / kStages) & 1);
+    const uint4 info = lds_v4(info_a + 16 * s);
+    const int tile = (int)info.x;  // index into status[]
     if (tile < 0) break;
-    const int b = info.y, t = info.z, npx = info.w;
+    const int b = (int)info.y, t = (int)info.z, npx = (int)info.w;
+    const uint32_t so = (uint32_t)(s * L::kStageBytes);
     const int n_pred = kPacked ? tile : t;
     const int px0 = t * kTileT;
     unsigned char *st = smem + (size_t)s * L::kStageBytes;
@@ -412,7 +442,7 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
     // ---- whole-run rejection: eight raw depths per lane in one load, min over (d - 1) mod 2^16 with packed 16-bit ops
     bool any_cand = true;
     if (quick) {
-      const uint4 q = *reinterpret_cast<const uint4 *>(st + 2 * (w0 + 8 * lane));
+      const uint4 q = lds_v4(q_a + so);
       const uint32_t m2 = __vminu2(__vminu2(__vsub2(q.x, 0x00010001u), __vsub2(q.y, 0x00010001u)),
                                    __vminu2(__vsub2(q.z, 0x00010001u), __vsub2(q.w, 0x00010001u)));
       any_cand = __any_sync(0xffffffffu, min(m2 & 0xffffu, m2 >> 16) < dcand_m1);
@@ -431,10 +461,10 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
         uint32_t draw = 0;
         bool ok;
         if (DK == RV_DEPTH_U16) {
-          draw = reinterpret_cast<const uint16_t *>(st)[li];
+          draw = lds_u16(g_a + so + (uint32_t)(j * 32 * kDepthB));
           ok = (draw - 1u) < dcand_m1;  // draw != 0 && draw < dcand
         } else {
-          z32 = reinterpret_cast<const float *>(st)[li];
+          z32 = lds_f32(g_a + so + (uint32_t)(j * 32 * kDepthB));
           ok = (z32 > 0.0f) && (z32 < inf_f);
           if (kF32 && use_radius && fast_radius) ok = ok && (z32 * z32 < a.r2_hi_f);
         }
@@ -565,9 +595,9 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
     if (lane == 0) {
       if (kOrdered) {
         s_tot[it & 7][warp] = run;
-        mbar_arrive(tot_a + 8 * (it & 7));
+        mbar_arrive(tot_r + 8 * (it & 7));
       }
-      mbar_arrive(empty_a + 8 * s);
+      mbar_arrive(empty_r + 8 * s);
     }
 
     uint32_t base = 0, off = 0;
@@ -578,7 +608,7 @@ __global__ void __launch_bounds__(kThreadsT, (Layout<OutT, DK, SPEC == 2>::kOcc)
       // tile, and the early peek stays with warp 0 anyway.)
       const bool publisher = warp == 0;
       if (run == 0 && !publisher) continue;  // warp-uniform
-      mbar_wait(tot_a + 8 * (it & 7), (uint32_t)(it >> 3) & 1u);
+      mbar_wait(tot_r + 8 * (it & 7), (uint32_t)(it >> 3) & 1u);
       const uint32_t t8 = lane < kCW ? s_tot[it & 7][lane] : 0u;
       const uint32_t tile_total = __reduce_add_sync(0xffffffffu, t8);
       off = __reduce_add_sync(0xffffffffu, lane < warp ? t8 : 0u);

@@ -1,0 +1,12 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_deproject.py -q -x > gpurun_out/h_pytest_k1.log 2>&1; echo "exit $?" >> gpurun_out/h_pytest_k1.log
+for n in k1_pair1 k1_pair2 k1_pair4 k1_pair1 k1_pair2 k1_pair4; do
+  RV_LIBRARY_PATH=$PWD/build/variants/librv_$n.so timeout 300 python bench.py --no-e2e --no-cpu-baseline --no-rows --steps 10 --warmup 3 --frames 4096 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$n', round(d['value']), round(d['roofline']['frac'], 4), d['valid_points_per_step_rank0'])"
+done > gpurun_out/h_k1_pair.txt 2>&1
+for n in k1_pair1 k1_pair2; do for c in "bgr unit --r-max 0" "nv12 packed8"; do set -- $c; echo -n "$n "; RV_LIBRARY_PATH=$PWD/build/variants/librv_$n.so timeout 300 python tools/k1_probe.py --color $1 --colors $2 $3 $4 | tail -1; done; done > gpurun_out/h_k1_probe.txt 2>&1
+bash tools/k4_sweep.sh > gpurun_out/h_k4_sweep.log 2>&1
+echo done

@@ -28,6 +28,7 @@ VARIANTS = {
 }
 
 
+VARIANTS.update({"k1_opaque1": "-DRV_K1_OPAQUE=1", "k1_opaque0": "-DRV_K1_OPAQUE=0"})
 # K4 tunables (tools/k4_sweep.sh): groups per warp step and occupancy of the insert, block size / occupancy of the emit
 VARIANTS.update({
     "k4_g4_i3_e128x8": "-DRV_VOX_GROUPS=4 -DRV_VOX_INSERT_OCC=3 -DRV_VOX_EMIT_THREADS=128 -DRV_VOX_EMIT_OCC=8",
