@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=8192, help="frames per GPU per step (BASELINE configs[4] batch)")
     ap.add_argument("--chunk", type=int, default=2048, help="frames per kernel launch (resident output ring slot)")
+    ap.add_argument("--ring-slots", type=int, default=2, help="output ring depth (slots of `chunk` frames at dense capacity)")
     ap.add_argument("--e2e-frames", type=int, default=512, help="frames per end-to-end step (pinned host buffers)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0 = auto)")
     ap.add_argument("--mode", default="compact_ordered", choices=["compact_ordered", "compact_unordered", "dense_zero"])
@@ -302,7 +303,7 @@ def workload_config(a, world):
     chunk = min(a.chunk, fpg)
     return {"workload": "BASELINE configs[4]: synthetic 1280x720 RGB-D (u16 depth + BGR8) -> validity + ||p||<1.0 m mask -> "
                         "ordered compacted float32 SoA xyz+rgb cloud",
-            "frames_per_gpu_per_step": fpg, "global_batch": fpg * world, "chunk_frames": chunk,
+            "frames_per_gpu_per_step": fpg, "global_batch": fpg * world, "chunk_frames": chunk, "output_ring_slots": a.ring_slots,
             "resolution": [W, H], "mode": a.mode, "kernel": a.kernel, "r_max_m": R_MAX, "unit_rule": "mul_f32",
             "e2e_workload": f"the same frames through HostPipeline.run: {min(a.e2e_frames, fpg)} frames per GPU per step from pinned "
                             "host memory, u16 depth + NV12 colour in (3.5 B/px, the camera's format), float32 xyz + r,g,b bytes "
@@ -378,7 +379,7 @@ def run_b200(a):
         d, c = synth_chunk(n, gen, dev)
         depth[f0:f0 + n], bgr[f0:f0 + n] = d, c
     del d, c
-    ring = [torch.empty((6, chunk * P), dtype=torch.float32, device=dev) for _ in range(2)]
+    ring = [torch.empty((6, chunk * P), dtype=torch.float32, device=dev) for _ in range(max(1, a.ring_slots))]
     torch.cuda.synchronize()
 
     kw = dict(max_distance=R_MAX, mode=a.mode, dtype="f32", kernel=a.kernel)
@@ -392,7 +393,7 @@ def run_b200(a):
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
                 e0.record()
-            r = rv.deproject_batch(depth[f0:f1], bgr[f0:f1], cam, out=ring[i & 1], **kw)
+            r = rv.deproject_batch(depth[f0:f1], bgr[f0:f1], cam, out=ring[i % len(ring)], **kw)
             if events is not None:
                 e1.record()
                 events.append((e0, e1, f1 - f0))

@@ -259,10 +259,12 @@ int rv_transform_merge(rv_ctx *ctx, int n_views, const void *const *d_in, const 
  *  d_m          one int64: number of voxels (true number even if > out_capacity)
  *  d_ws         rv_voxel_workspace_bytes(n) bytes, 64-B aligned: 1.5 n eight-byte hash keys + 4-byte chain heads, one
  *               8-byte list entry and one 4-byte link per point, one bit per point of run heads, a small pool for voxels
- *               with very long chains (about 30 bytes per point in all); keys and chain heads are initialised by the call
+ *               with very long chains (about 34 bytes per point) and room for a fusion's transformed coordinates (24 bytes
+ *               per point, untouched by this call); keys and chain heads are initialised by the call
  * Each voxel index must fit 21 bits (extent/voxel < 2^21); otherwise d_m is set to -1.  n < 2^31.
  * Voxels made of at most eight runs of consecutive points (practically all of a 5 mm grid over camera clouds) are summed
- * point by point in index order in float64: their means equal the sequential Open3D loop bit for bit. */
+ * point by point in index order in float64: their means equal the sequential Open3D loop bit for bit; voxels of more runs
+ * are summed by float64 atomics (1e-15 relative). */
 size_t rv_voxel_workspace_bytes(int64_t n);
 int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, int64_t n, int in_dtype,
                         int has_color, double voxel_size, const double *d_bounds, void *d_out,
@@ -271,10 +273,12 @@ int rv_voxel_downsample(rv_ctx *ctx, const void *d_in, int64_t in_plane_stride, 
 
 /* ---- a11 + a12 in one call: the four_pose_captures fusion -------------------------
  * pcd_i.transform(T_i) for every view, `+`, voxel_down_sample(voxel_size) (SURVEY Appendix D.4;
- * final_view_with_cad.py:333, mpa_icp_export.py:174) without ever writing the merged cloud: the
- * views are read where they lie, p' = T_v p is rounded to in_dtype exactly as
- * rv_transform_merge would store it, and the voxel grid (origin = min bound of the merged
- * cloud - voxel/2) is built from those values.  Same results as rv_transform_merge followed by
+ * final_view_with_cad.py:333, mpa_icp_export.py:174) without building the merged six-plane cloud:
+ * the views are read where they lie; the pass that finds the merged cloud's bounds stores
+ * p' = T_v p (rounded to in_dtype exactly as rv_transform_merge would store it) in the
+ * workspace, the colours are read from the views when a voxel is summed, and the voxel grid
+ * (origin = min bound of the merged cloud - voxel/2) is built from those values.
+ * Same results as rv_transform_merge followed by
  * rv_voxel_downsample.  Up to 8 views; arguments as in those two calls; workspace
  * rv_voxel_workspace_bytes(sum of n). */
 int rv_fuse_voxel(rv_ctx *ctx, int n_views, const void *const *d_in, const int64_t *in_plane_stride, const int64_t *n,

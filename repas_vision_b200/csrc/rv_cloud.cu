@@ -156,7 +156,7 @@ __global__ void k_stats_init(double *b) {
 // Hash grid without per-point records (round 1 wrote a 64-byte record per run of points and read it back twice: 6.1 x the
 // algorithmic DRAM traffic).  Workspace:
 //   [header 256 B][per-part counters 2048 x 8 B][keys: cap x 8 B][chain: cap x 4 B][list: n x 8 B][next: n x 4 B]
-//   [head masks: ceil(n / 32) x 4 B][long-voxel pool: (n / 9 + 1) x 64 B]
+//   [head masks: ceil(n / 32) x 4 B][long-voxel pool: (n / 9 + 1) x 64 B][fusion only: transformed xyz, n x 24 B]
 // k_vox_insert  reads the coordinates only (RV_VOX_GROUPS 32-point groups per warp and step, their loads and first-probe
 //               compare-and-swaps issued before anything is consumed).  Points arrive in pixel order, so consecutive points
 //               usually share a voxel: a run of equal keys inside a 32-point group is represented by its first point (the
@@ -228,6 +228,8 @@ struct VoxArgs {
   unsigned int *next;        // per list position of a joiner: the joiner linked before it
   unsigned int *headmask;    // per 32-point group: bit l set = point l starts a run
   VoxLong *pool;
+  void *mxyz;    // fusion only: the transformed coordinates (three planes of n, the cloud's element type), written once by the
+                 // bounds pass so that insert and emit read plain values instead of transforming every point again
   uint2 *parts;  // per part {creators, joiners}
   long long span;  // points per part, a multiple of 128
   unsigned int cap;
@@ -253,7 +255,24 @@ __device__ __forceinline__ int vox_view_of(const VoxArgs &a, long long i) {
 
 // coordinates of merged point i as they are STORED in the cloud's element type T (after the pose transform of its view)
 template <typename T>
+__device__ __forceinline__ void vox_xyz_src(const VoxArgs &a, long long i, double &x, double &y, double &z);
+
+// kFused is a compile-time flag: the emit kernel holds eight copies of this read and lost a quarter of its speed (62 -> 84
+// us) when the choice was a run-time branch
+template <typename T, bool kFused>
 __device__ __forceinline__ void vox_xyz(const VoxArgs &a, long long i, double &x, double &y, double &z) {
+  if (kFused) {  // fusion: transformed once by the bounds pass
+    const T *m = reinterpret_cast<const T *>(a.mxyz);
+    x = (double)m[i];
+    y = (double)m[a.n + i];
+    z = (double)m[2 * a.n + i];
+    return;
+  }
+  vox_xyz_src<T>(a, i, x, y, z);
+}
+
+template <typename T>
+__device__ __forceinline__ void vox_xyz_src(const VoxArgs &a, long long i, double &x, double &y, double &z) {
   const int v = a.n_views > 1 ? vox_view_of(a, i) : 0;
   const VoxView &w = a.view[v];
   const T *in = reinterpret_cast<const T *>(w.in);
@@ -296,9 +315,15 @@ __global__ void __launch_bounds__(256) k_vox_bounds(const VoxArgs a, double *bou
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
   double lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
   const long long stride = (long long)gridDim.x * blockDim.x;
+  T *m = reinterpret_cast<T *>(a.mxyz);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
     double p[3];
-    vox_xyz<T>(a, i, p[0], p[1], p[2]);
+    vox_xyz_src<T>(a, i, p[0], p[1], p[2]);
+    if (m) {
+      m[i] = (T)p[0];
+      m[a.n + i] = (T)p[1];
+      m[2 * a.n + i] = (T)p[2];
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       lo[c] = p[c] < lo[c] ? p[c] : lo[c];
@@ -310,7 +335,7 @@ __global__ void __launch_bounds__(256) k_vox_bounds(const VoxArgs a, double *bou
 
 constexpr int kVoxGroups = RV_VOX_GROUPS;  // 32-point groups per warp and step
 
-template <typename T>
+template <typename T, bool kFused>
 __global__ void __launch_bounds__(256, RV_VOX_INSERT_OCC) k_vox_insert(const VoxArgs a) {
   const double half = a.voxel * 0.5;
   const double ox = a.bounds[0] - half, oy = a.bounds[1] - half, oz = a.bounds[2] - half;
@@ -341,7 +366,7 @@ __global__ void __launch_bounds__(256, RV_VOX_INSERT_OCC) k_vox_insert(const Vox
       const long long i = w0 + 32 * g + lane;
       valid[g] = i < p1;
       px[g] = py[g] = pz[g] = 0.0;
-      if (valid[g]) vox_xyz<T>(a, i, px[g], py[g], pz[g]);
+      if (valid[g]) vox_xyz<T, kFused>(a, i, px[g], py[g], pz[g]);
     }
     unsigned long long key[kVoxGroups];
     uint32_t heads[kVoxGroups];
@@ -433,12 +458,12 @@ struct VoxSum {
 // add the points of the run starting at i, one by one (index order inside the run)
 // (kept inline on purpose: as a called function -- eight calls per voxel instead of eight copies of the loop -- the emit
 // kernel ran 2.6 x slower, 351 vs 134 us on the 5 mm fusion cloud)
-template <typename T>
+template <typename T, bool kFused>
 __device__ __forceinline__ void vox_add_run(const VoxArgs &a, unsigned int i, VoxSum &acc) {
   const int run = vox_run(a, i);
   for (int r = 0; r < run; ++r) {
     double x, y, z;
-    vox_xyz<T>(a, (long long)i + r, x, y, z);
+    vox_xyz<T, kFused>(a, (long long)i + r, x, y, z);
     acc.s[0] += x;
     acc.s[1] += y;
     acc.s[2] += z;
@@ -479,7 +504,7 @@ __device__ __forceinline__ void vox_store(const VoxOutArgs &o, int has_color, lo
 // CTA p finishes the voxels part p created, behind those of parts 0..p-1
 constexpr int kVoxEmitThreads = RV_VOX_EMIT_THREADS;
 
-template <typename T, typename OutT>
+template <typename T, typename OutT, bool kFused>
 __global__ void __launch_bounds__(kVoxEmitThreads, RV_VOX_EMIT_OCC) k_vox_emit(const VoxArgs a, const VoxOutArgs o) {
   __shared__ unsigned long long s_red[2][kVoxEmitThreads / 32];
   unsigned long long before = 0, total = 0;
@@ -548,7 +573,9 @@ __global__ void __launch_bounds__(kVoxEmitThreads, RV_VOX_EMIT_OCC) k_vox_emit(c
       qbase = __shfl_sync(active, qbase, leader);
     }
     if (is_long) {
-      // more than eight runs: hand the voxel to the atomic path (its joiners add themselves in parallel in k_vox_long)
+      // more than eight runs: hand the voxel to the atomic path (its joiners add themselves in parallel in k_vox_long).
+      // (Letting the thread gather runs 9..16 itself, so that a fine grid has no long voxel and k_vox_long returns at once
+      // instead of walking the joiners for 10 us, made this kernel 29 us slower: 62 -> 91 us.)
       const unsigned int q = qbase + __popc(lm & rv_lanemask_lt());
       VoxLong *rec = a.pool + q;
       rec->key = key;
@@ -557,7 +584,7 @@ __global__ void __launch_bounds__(kVoxEmitThreads, RV_VOX_EMIT_OCC) k_vox_emit(c
 #pragma unroll
       for (int c = 0; c < 6; ++c) own.s[c] = 0.0;
       own.count = 0;
-      vox_add_run<T>(a, me.x, own);
+      vox_add_run<T, kFused>(a, me.x, own);
       rec->count = own.count;
 #pragma unroll
       for (int c = 0; c < 6; ++c) rec->sum[c] = own.s[c];
@@ -570,13 +597,13 @@ __global__ void __launch_bounds__(kVoxEmitThreads, RV_VOX_EMIT_OCC) k_vox_emit(c
     acc.count = 0;
 #pragma unroll
     for (int q = 0; q < 8; ++q)
-      if (idx[q] != kVoxNil) vox_add_run<T>(a, idx[q], acc);
+      if (idx[q] != kVoxNil) vox_add_run<T, kFused>(a, idx[q], acc);
     vox_store<OutT>(o, a.has_color, pos, acc.s, acc.count, key);
   }
 }
 
 // every joiner of a long voxel adds its run into the voxel's pool record (float64 atomics); nothing to do without long voxels
-template <typename T>
+template <typename T, bool kFused>
 __global__ void __launch_bounds__(256) k_vox_long(const VoxArgs a, int n_parts) {
   if (a.hdr->error || a.hdr->n_long == 0) return;
   for (int p = blockIdx.x; p < n_parts; p += gridDim.x) {
@@ -591,7 +618,7 @@ __global__ void __launch_bounds__(256) k_vox_long(const VoxArgs a, int n_parts) 
 #pragma unroll
       for (int c = 0; c < 6; ++c) s.s[c] = 0.0;
       s.count = 0;
-      vox_add_run<T>(a, e.x, s);
+      vox_add_run<T, kFused>(a, e.x, s);
       VoxLong *rec = a.pool + (v & ~kVoxLongTag);
       atomicAdd(&rec->count, s.count);
       atomicAdd(&rec->sum[0], s.s[0]);
@@ -624,7 +651,7 @@ unsigned long long vox_capacity(long long n) {  // 1.5 slots per point, a multip
 size_t vox_align(size_t b) { return (b + 255) & ~(size_t)255; }
 
 struct VoxLayout {
-  size_t keys, chain, list, next, masks, pool, total;
+  size_t keys, chain, list, next, masks, pool, mxyz, total;
 };
 VoxLayout vox_layout(long long n) {
   VoxLayout L;
@@ -642,6 +669,8 @@ VoxLayout vox_layout(long long n) {
   off += vox_align((size_t)((n + 31) / 32) * 4);
   L.pool = off;
   off += vox_align((size_t)(n / (kVoxHeads + 1) + 1) * sizeof(VoxLong));  // a long voxel has more than kVoxHeads run heads
+  L.mxyz = off;
+  off += vox_align((size_t)n * 24);  // a fusion's transformed coordinates (float64 at most); unused by rv_voxel_downsample
   L.total = off;
   return L;
 }
@@ -875,6 +904,7 @@ static int vox_run_all(rv_ctx *ctx, const char *who, int n_views, const void *co
   a.next = reinterpret_cast<unsigned int *>(w + L.next);
   a.headmask = reinterpret_cast<unsigned int *>(w + L.masks);
   a.pool = reinterpret_cast<VoxLong *>(w + L.pool);
+  a.mxyz = a.identity ? nullptr : (void *)(w + L.mxyz);
   a.cap = (unsigned int)cap;
   // header, part counters and keys are cleared, the chain heads set to "none"; nothing else needs initialising
   RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, L.keys + (size_t)cap * 8, st));
@@ -884,7 +914,7 @@ static int vox_run_all(rv_ctx *ctx, const char *who, int n_views, const void *co
     k_bounds_init<<<1, 32, 0, st>>>(a.hdr->bounds);
     RV_LAUNCHED(ctx);
     const int g = grid_for(ctx, total);
-    if (in_dtype == RV_F32) k_vox_bounds<float><<<g, 256, 0, st>>>(a, a.hdr->bounds);
+    if (in_dtype == RV_F32) k_vox_bounds<float><<<g, 256, 0, st>>>(a, a.hdr->bounds);  // a fusion also stores p' = T p here
     else k_vox_bounds<double><<<g, 256, 0, st>>>(a, a.hdr->bounds);
     RV_LAUNCHED(ctx);
     bounds = a.hdr->bounds;
@@ -894,8 +924,14 @@ static int vox_run_all(rv_ctx *ctx, const char *who, int n_views, const void *co
   int parts_n = (int)((total + 1023) / 1024 < kVoxMaxParts ? (total + 1023) / 1024 : kVoxMaxParts);
   if (parts_n < 1) parts_n = 1;
   a.span = (((total + parts_n - 1) / parts_n) + 127) & ~127ll;
-  if (in_dtype == RV_F32) k_vox_insert<float><<<parts_n, 256, 0, st>>>(a);
-  else k_vox_insert<double><<<parts_n, 256, 0, st>>>(a);
+  const bool fused = a.mxyz != nullptr;
+  if (in_dtype == RV_F32) {
+    if (fused) k_vox_insert<float, true><<<parts_n, 256, 0, st>>>(a);
+    else k_vox_insert<float, false><<<parts_n, 256, 0, st>>>(a);
+  } else {
+    if (fused) k_vox_insert<double, true><<<parts_n, 256, 0, st>>>(a);
+    else k_vox_insert<double, false><<<parts_n, 256, 0, st>>>(a);
+  }
   RV_LAUNCHED(ctx);
   VoxOutArgs o;
   memset(&o, 0, sizeof(o));
@@ -905,15 +941,26 @@ static int vox_run_all(rv_ctx *ctx, const char *who, int n_views, const void *co
   o.keys = d_keys;
   o.counts = d_counts_out;
   o.m = reinterpret_cast<long long *>(d_m);
-  if (in_dtype == RV_F32 && out_dtype == RV_F32) k_vox_emit<float, float><<<parts_n, kVoxEmitThreads, 0, st>>>(a, o);
-  else if (in_dtype == RV_F32) k_vox_emit<float, double><<<parts_n, kVoxEmitThreads, 0, st>>>(a, o);
-  else if (out_dtype == RV_F32) k_vox_emit<double, float><<<parts_n, kVoxEmitThreads, 0, st>>>(a, o);
-  else k_vox_emit<double, double><<<parts_n, kVoxEmitThreads, 0, st>>>(a, o);
+#define RV_EMIT(TI, TO)                                                                        \
+  {                                                                                            \
+    if (fused) k_vox_emit<TI, TO, true><<<parts_n, kVoxEmitThreads, 0, st>>>(a, o);            \
+    else k_vox_emit<TI, TO, false><<<parts_n, kVoxEmitThreads, 0, st>>>(a, o);                 \
+  }
+  if (in_dtype == RV_F32 && out_dtype == RV_F32) RV_EMIT(float, float)
+  else if (in_dtype == RV_F32) RV_EMIT(float, double)
+  else if (out_dtype == RV_F32) RV_EMIT(double, float)
+  else RV_EMIT(double, double)
+#undef RV_EMIT
   RV_LAUNCHED(ctx);
   // voxels with very long chains (none on a fine grid: both kernels then return at once)
   const int lg = parts_n < ctx->sm_count * 4 ? parts_n : ctx->sm_count * 4;
-  if (in_dtype == RV_F32) k_vox_long<float><<<lg, 256, 0, st>>>(a, parts_n);
-  else k_vox_long<double><<<lg, 256, 0, st>>>(a, parts_n);
+  if (in_dtype == RV_F32) {
+    if (fused) k_vox_long<float, true><<<lg, 256, 0, st>>>(a, parts_n);
+    else k_vox_long<float, false><<<lg, 256, 0, st>>>(a, parts_n);
+  } else {
+    if (fused) k_vox_long<double, true><<<lg, 256, 0, st>>>(a, parts_n);
+    else k_vox_long<double, false><<<lg, 256, 0, st>>>(a, parts_n);
+  }
   RV_LAUNCHED(ctx);
   if (out_dtype == RV_F32) k_vox_long_final<float><<<8, 256, 0, st>>>(a, o);
   else k_vox_long_final<double><<<8, 256, 0, st>>>(a, o);

@@ -49,8 +49,9 @@ def test_library_exports_every_declared_symbol(built):
     per_frame = 640 * 480 * 8 + 480 * 20 * 8 + 2048 + 20 * 23 * 256 * 4  # each part is a multiple of 256 B here
     tables = (640 + 480) * 2 * 4  # normalised corner coordinates per column / row, 256-byte multiple here
     assert lib.rv_register_workspace_bytes(64, 480, 640, 720, 1280) == tables + 16 * per_frame
-    # header + part counters, keys, chain heads, list, links, run-head bits, long-voxel pool (each rounded up to 256 B)
-    assert lib.rv_voxel_workspace_bytes(1000) == (256 + 2048 * 8) + 12032 + 6144 + 8192 + 4096 + 256 + 112 * 64
+    # header + part counters, keys, chain heads, list, links, run-head bits, long-voxel pool, a fusion's transformed xyz (each
+    # rounded up to 256 B)
+    assert lib.rv_voxel_workspace_bytes(1000) == (256 + 2048 * 8) + 12032 + 6144 + 8192 + 4096 + 256 + 112 * 64 + 24064
 
 
 def test_shared_object_holds_only_sm100a_code(built):

@@ -209,6 +209,7 @@ def main():
         res = pipe.run(hd.numpy(), hn.numpy())
         torch.cuda.synchronize()
         runs.append(_t.perf_counter() - t0)
+        res.release()
     dt = float(np.median(runs[3:]))
     print(json.dumps({"kernel": "e2e HostPipeline with NV12 colour frames (pinned host in, host clouds out), 512 x 720p",
                       "ms": dt * 1e3, "frames_per_s": ef / dt, "h2d_GBps": ef * H * W * 3.5 / dt / 1e9}))
