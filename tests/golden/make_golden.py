@@ -65,6 +65,7 @@ def _install_stubs():
 def _load(path, name):
     spec = importlib.util.spec_from_file_location(name, path)
     mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod  # dataclasses look their module up while the class body runs
     spec.loader.exec_module(mod)
     return mod
 
@@ -294,6 +295,19 @@ def main():
                               "label": label, "T_cam_tag": T.tolist()})
     G["solvepnp_K"] = K.tolist()
     G["solvepnp_tag_size"] = tag
+
+    # ---- 8. the reference's own statement of a rigid transform of points: transform_point_tag_local_to_camera
+    # (april_tag_bg_removal_pl.py:177-179, `R @ p + t`), what geom.transform(T) does to every point of a cloud
+    # (final_view_with_cad.py:333).  Poses: the 4x4 the reference ships (6dof/20250917_164430.txt) and the solvePnP results above.
+    bgr_mod = _load(os.path.join(REF, "femto_bolt_code/scripts/april_tag_bg_removal_pl.py"), "ref_april_tag_bg_removal_pl")
+    rngt = np.random.default_rng(11)
+    pts = np.concatenate([rngt.uniform(-0.5, 0.5, (96, 3)), rngt.uniform(-3.0, 3.0, (32, 3))])
+    poses = [np.loadtxt(os.path.join(CAL, "20250917_164430.txt"))] + [np.array(g["T_cam_tag"]) for g in G["solvepnp"][:3]]
+    G["rigid_transform"] = {"points": pts.tolist(), "cases": []}
+    for T in poses:
+        R, t = T[:3, :3].copy(), T[:3, 3].copy()
+        out = np.stack([bgr_mod.transform_point_tag_local_to_camera(p, R, t) for p in pts])
+        G["rigid_transform"]["cases"].append({"T": T.tolist(), "out": out.tolist()})
 
     with open(os.path.join(HERE, "reference_golden.json"), "w") as f:
         json.dump(G, f, indent=1)

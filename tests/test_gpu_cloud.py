@@ -684,3 +684,17 @@ def test_voxel_grid_long_chains_and_fused_equals_unfused(rv, O):
         b = _sorted_voxels(pk, plain.points, plain.colors, pn)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3])
         assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])  # same values summed in the same order
+
+
+def test_transform_matches_the_reference_point_form(rv, golden):
+    """K3 against the reference's own `R @ p + t` (april_tag_bg_removal_pl.py:177-179) on the stored golden points and poses
+    (the 4x4 the reference ships and three solvePnP results): float64 to rounding, float32 storage within one ulp."""
+    g = golden["rigid_transform"]
+    P = np.array(g["points"])
+    for c in g["cases"]:
+        T, ref = np.array(c["T"]), np.array(c["out"])
+        got = rv.PointCloud.from_arrays(P, None).transform(T).points
+        assert np.abs(got - ref).max() <= 2e-15
+        got32 = rv.PointCloud.from_arrays(P.astype(np.float32), None, dtype="f32").transform(T).points
+        ref32 = np.stack([T[:3, :3] @ p + T[:3, 3] for p in P.astype(np.float32).astype(np.float64)])
+        assert np.abs(got32 - ref32).max() <= 4e-7  # float32 spacing at |coordinate| <= 4 m

@@ -185,3 +185,17 @@ def test_kdtree_formulations_agree_with_the_brute_force_restatements():
     n1, f1, r1 = O.nearest_correspondences(Q, P, 0.004)
     n2, f2, r2 = O.nearest_correspondences_kdtree(Q, P, 0.004)
     assert np.array_equal(n1, n2) and f1 == f2 and np.isclose(r1, r2, rtol=1e-12)
+
+
+def test_rigid_transform_matches_the_reference_point_form(golden):
+    """`geom.transform(T)` is Open3D's, but the reference states the same map itself for single points:
+    transform_point_tag_local_to_camera = R @ p + t (april_tag_bg_removal_pl.py:177-179).  Its outputs on 128 seeded points
+    under the pose file the reference ships (6dof/20250917_164430.txt) and three solvePnP poses are stored in the goldens;
+    the oracle's Open3D-ordered arithmetic agrees with them to rounding (the matrix product may fuse or reorder: <= 2e-15 m)."""
+    from oracle import oracle_np as O
+    g = golden["rigid_transform"]
+    P = np.array(g["points"])
+    assert len(g["cases"]) == 4
+    for c in g["cases"]:
+        got = O.transform(P, np.array(c["T"]))
+        assert np.abs(got - np.array(c["out"])).max() <= 2e-15
