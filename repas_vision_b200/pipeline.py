@@ -124,6 +124,30 @@ class HostBatchResult:
         """(n,3) float64 like np.asarray(pcd.points)."""
         return np.ascontiguousarray(self.frame(b)[0].T, dtype=np.float64)
 
+    def write_ply(self, b: int, filename) -> bool:
+        """Frame b as the binary PLY the SDK writers of the capture scripts emit (save_point_cloud_to_ply
+        better_three_capture.py:242, points.export_to_ply capture_aligned_all.py:262): `float x y z` + `uchar red green blue`,
+        15 bytes per vertex, readable by o3d.io.read_point_cloud / rv.read_point_cloud.  With byte colours (colors="u8") the
+        record is exactly what came back from the GPU: nothing is rescaled on the way to the file."""
+        import os
+        from .ply import ply_header
+        xyz, rgb = self.frame(b)
+        n = xyz.shape[1]
+        if rgb is None:
+            rec = np.zeros(n, dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4")])
+        else:
+            rec = np.zeros(n, dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("r", "u1"), ("g", "u1"), ("b", "u1")])
+            if rgb.dtype == np.uint8:
+                rec["r"], rec["g"], rec["b"] = rgb[:, 0], rgb[:, 1], rgb[:, 2]
+            else:  # float planes in [0,1]: Open3D's round(clamp(c) * 255)
+                q = np.rint(np.clip(rgb.astype(np.float64), 0.0, 1.0) * 255.0).astype(np.uint8)
+                rec["r"], rec["g"], rec["b"] = q[0], q[1], q[2]
+        rec["x"], rec["y"], rec["z"] = xyz[0], xyz[1], xyz[2]
+        with open(os.fspath(filename), "wb") as f:
+            f.write(ply_header(n, rgb is not None, "float"))
+            f.write(rec.tobytes())
+        return True
+
     def colors(self, b: int) -> np.ndarray:
         """(n,3) float64 in [0,1] like np.asarray(pcd.colors); packed bytes are expanded here as k / 255.0, which is the
         reference's own float64 statement (create_masked_ply.py:100)."""

@@ -256,6 +256,20 @@ def test_full_size_batch_properties(rv, rs720):
     for b in (1, B - 2):
         n = int(counts[b])
         assert torch.equal(a2.data[:, b * a.cap:b * a.cap + n], a.data[:, b * a.cap:b * a.cap + n])
+    # byte colours: the same points, and the bytes are the float colours times 255; NV12 in: counts and coordinates do not
+    # depend on the colour format, every colour byte of a kept point is written
+    pk = rv.deproject_batch(depth, bgr, cam, max_distance=2.0, color_scale="packed8")
+    nv12 = torch.randint(0, 256, (B, H * 3 // 2, W), generator=g, device="cuda", dtype=torch.int32).to(torch.uint8)
+    nv = rv.deproject_batch(depth, nv12, cam, max_distance=2.0, color_format="nv12", color_scale="packed8")
+    assert torch.equal(pk.counts.cpu(), counts) and torch.equal(nv.counts.cpu(), counts)
+    for b in (0, B // 3, B - 1):
+        n = int(counts[b])
+        assert torch.equal(pk.data[:3, b * pk.cap:b * pk.cap + n], a.data[:3, b * a.cap:b * a.cap + n])
+        assert torch.equal(nv.data[:3, b * nv.cap:b * nv.cap + n], a.data[:3, b * a.cap:b * a.cap + n])
+        rgb8 = pk.rgb8(b).to(torch.float32)
+        assert torch.equal(torch.round(a.data[3:, b * a.cap:b * a.cap + n].t() * 255.0), rgb8)
+        idx = a.src_index[b * a.cap:b * a.cap + n].long()
+        assert torch.equal(pk.rgb8(b), bgr[b].view(-1, 3)[idx].flip(1))
 
 
 def test_edge_cases_and_errors(rv, rs720):
@@ -347,6 +361,20 @@ def test_packed_mode_and_host_pipeline(rv, O, rs720, kernel):
         res2.release()
         with pytest.raises(RuntimeError):
             res2.frame(0)
+        # frames -> PLY files (the capture loop's save_point_cloud_to_ply, better_three_capture.py:242): read back by the product's
+        # reader and by the independent minimal reader of the oracle
+        import os
+        import tempfile
+        with tempfile.TemporaryDirectory() as tmp:
+            for res_x in (res8, pipe.run(depth, bgr)):
+                path = os.path.join(tmp, "frame3.ply")
+                assert res_x.write_ply(3, path)
+                back = rv.read_point_cloud(path)
+                assert np.array_equal(back.points, refs[3]["points"].astype(np.float64))
+                assert np.array_equal(back.colors, bgr[3][refs[3]["valid"]][:, ::-1].astype(np.float64) / 255.0)
+                _, arr = O.read_ply_minimal(path)
+                assert np.array_equal(np.stack([arr["x"], arr["y"], arr["z"]], 1), refs[3]["points"])
+                assert np.array_equal(np.stack([arr["red"], arr["green"], arr["blue"]], 1), bgr[3][refs[3]["valid"]][:, ::-1])
         # the copy-only probe replays the schedule of a finished run
         pr = pipe8.copy_probe(depth, bgr, like=res8)
         assert pr.h2d_bytes == res8.h2d_bytes and pr.d2h_bytes == res8.d2h_bytes
