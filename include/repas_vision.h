@@ -99,6 +99,16 @@ enum RvColorScale {
                           k / 255.0 lazily */
 };
 
+/* which arithmetic produces x and y */
+enum RvGeometry {
+  RV_GEOM_REFERENCE_F64 = 0, /* x = (u - cx) * z / fx in float64, multiply then divide, rounded once to the output type:
+                                the reference's numpy statement (create_masked_ply.py:94-95) */
+  RV_GEOM_SDK_F32 = 1        /* x = z * ((u - ppx) / fx) in float32 throughout: rs2_deproject_pixel_to_point as rs.pointcloud
+                                (capture_aligned_all.py:209-216) and Orbbec's PointCloudFilter (better_three_capture.py:235-237)
+                                evaluate it; pinhole cameras (RV_DIST_NONE) only; served by the generic kernel.  Differs from
+                                the reference form by at most one float32 ulp on the captured frames */
+};
+
 /* layout of the colour image handed to rv_deproject_mask */
 enum RvColorFormat {
   RV_COLORFMT_BGR8 = 0, /* [B,H,W,3] uint8, cv2 / SDK bgr8 */
@@ -133,7 +143,7 @@ typedef struct RvDeprojectParams {
   int32_t color_scale; /* RvColorScale */
   int32_t kernel_select; /* RvKernelSelect */
   int32_t color_format;  /* RvColorFormat of d_bgr */
-  int32_t reserved;
+  int32_t geometry;      /* RvGeometry */
 } RvDeprojectParams;
 
 /* ---- context -------------------------------------------------------------- */

@@ -140,8 +140,12 @@ def ray_table(fx, fy, cx, cy, dist, model, width, height):
 
 def deproject_mask(depth, bgr, mask=None, *, fx, fy, cx, cy, depth_kind="u16", unit_rule="mul_f32",
                    unit_scale=None, invert_mask=False, depth_trunc=None, z_clip=None, r_max=None, aabb=None,
-                   out_dtype="f32", color_scale="unit", rays=None):
+                   out_dtype="f32", color_scale="unit", rays=None, geometry="reference"):
     """One frame of the fused kernel's contract (DESIGN.md "K1").
+
+    geometry="sdk_f32": the arithmetic of the SDK clouds instead of the reference's numpy statement -- librealsense
+    rs2_deproject_pixel_to_point as rs.pointcloud / Orbbec's PointCloudFilter evaluate it, all in float32:
+    x = z * ((u - ppx) / fx), y = z * ((v - ppy) / fy) (pinhole cameras only).
 
     Returns dict(valid [H,W] bool, points [N,3], colors [N,3], src_index [N]) in
     row-major order of kept pixels.  The cloud predicates are evaluated in
@@ -166,7 +170,13 @@ def deproject_mask(depth, bgr, mask=None, *, fx, fy, cx, cy, depth_kind="u16", u
     u = np.arange(W, dtype=F64)[None, :]
     v = np.arange(H, dtype=F64)[:, None]
     with np.errstate(all="ignore"):
-        if rays is None:
+        if geometry == "sdk_f32":
+            if rays is not None:
+                raise ValueError("sdk_f32 geometry is restated for pinhole cameras only")
+            uf, vf = np.arange(W, dtype=F32)[None, :], np.arange(H, dtype=F32)[:, None]
+            x64 = (z32 * ((uf - F32(cx)) / F32(fx))).astype(F64)
+            y64 = (z32 * ((vf - F32(cy)) / F32(fy))).astype(F64)
+        elif rays is None:
             x64 = (u - cx) * z64 / fx
             y64 = (v - cy) * z64 / fy
         else:

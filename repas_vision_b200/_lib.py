@@ -22,6 +22,7 @@ DEPTH_KINDS = {"u16": 0, "f32": 1}
 MODES = {"compact_ordered": 0, "compact_unordered": 1, "dense_zero": 2, "dense_nan": 3, "compact_packed": 4}
 COLOR_SCALES = {"unit": 0, "255": 1, "packed8": 2}
 COLOR_FORMATS = {"bgr": 0, "nv12": 1}
+GEOMETRIES = {"reference": 0, "sdk_f32": 1}
 KERNELS = {"auto": 0, "generic": 1, "tma": 2}
 
 c_i32, c_i64, c_f64, c_vp = C.c_int32, C.c_int64, C.c_double, C.c_void_p
@@ -38,7 +39,7 @@ class RvDeprojectParams(C.Structure):
                 ("depth_trunc", c_f64), ("z_min", c_f64), ("z_max", c_f64), ("use_radius", c_i32), ("use_aabb", c_i32),
                 ("r_max", c_f64), ("aabb_min", c_f64 * 3), ("aabb_max", c_f64 * 3), ("mode", c_i32),
                 ("out_dtype", c_i32), ("color_scale", c_i32), ("kernel_select", c_i32), ("color_format", c_i32),
-                ("reserved", c_i32)]
+                ("geometry", c_i32)]
 
 
 # name -> (restype, argtypes); every symbol include/repas_vision.h declares

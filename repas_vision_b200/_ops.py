@@ -78,7 +78,7 @@ def to_device(a, dev: torch.device, dtype=None) -> torch.Tensor:
 def deproject(depth, bgr, mask, cam: Camera, *, depth_kind, unit_rule="mul_f32", unit_scale=None, invert_mask=False,
               depth_trunc=None, z_clip=None, r_max=None, aabb=None, mode="compact_ordered", out_dtype="f32",
               color_scale="unit", want_valid=False, want_src_index=False, frame_capacity=None, out=None,
-              rays=None, kernel="auto", color_format="bgr"):
+              rays=None, kernel="auto", color_format="bgr", geometry="reference"):
     """depth [B,H,W] (uint16 or float32), bgr [B,H,W,3] uint8 (or NV12 frames [B,H*3/2,W] with color_format="nv12") or
     None, mask [B,H,W] uint8 or None, all on one CUDA device.  Returns dict(data [6 or 3, B*cap], counts [B] int64, cap,
     valid, src_index); with color_scale="packed8" data has four float32 planes, the last one holding the bytes r,g,b,0
@@ -112,6 +112,7 @@ def deproject(depth, bgr, mask, cam: Camera, *, depth_kind, unit_rule="mul_f32",
     p.color_scale = _lib.COLOR_SCALES[color_scale]
     p.kernel_select = _lib.KERNELS[kernel]
     p.color_format = _lib.COLOR_FORMATS[color_format]
+    p.geometry = _lib.GEOMETRIES[geometry]
     if bgr is not None:
         want = (B, H, W, 3) if color_format == "bgr" else (B, H * 3 // 2, W)
         if tuple(bgr.shape) != want or bgr.dtype != torch.uint8:

@@ -535,13 +535,17 @@ class CloudBatch:
 def deproject_batch(depth, bgr, camera, mask=None, *, unit_rule: str = "mul_f32", depth_scale=None, invert_mask=False,
                     depth_trunc=None, max_distance=None, z_clip=None, aabb=None, mode: str = "compact_ordered",
                     dtype: str = "f32", color_scale: str = "unit", want_valid=False, want_src_index=False,
-                    frame_capacity=None, out=None, kernel: str = "auto", color_format: str = "bgr") -> CloudBatch:
+                    frame_capacity=None, out=None, kernel: str = "auto", color_format: str = "bgr",
+                    geometry: str = "reference") -> CloudBatch:
     """Batched form of create_masked_pointcloud: depth [B,H,W] (uint16 raw or float32 metres), bgr [B,H,W,3] uint8,
     mask [B,H,W] uint8 or None.  One kernel launch for the whole batch.
 
     color_format="nv12": `bgr` holds the camera's NV12 frames [B, H*3/2, W] (better_three_capture.py:101-106,159); the
     kernel converts the kept pixels itself, identical to feeding cv2.cvtColor(..., COLOR_YUV2BGR_NV12) images.
-    color_scale="packed8": colours stay bytes (one r,g,b,0 word per point in a fourth plane) instead of three float planes."""
+    color_scale="packed8": colours stay bytes (one r,g,b,0 word per point in a fourth plane) instead of three float planes.
+    geometry="sdk_f32": x = z * ((u - ppx) / fx) in float32 like rs.pointcloud / PointCloudFilter (capture_aligned_all.py:209-216,
+    better_three_capture.py:235-237) instead of the reference's float64 numpy form; with mode="dense_zero" and
+    color_scale="255" this is the SDKs' cloud, value for value."""
     cam = _as_camera(camera)
     dev = depth.device if _is_torch_cuda(depth) else _ops.require_cuda()
     kind, d = _depth_kind(depth if isinstance(depth, torch.Tensor) else np.asarray(depth))
@@ -561,7 +565,7 @@ def deproject_batch(depth, bgr, camera, mask=None, *, unit_rule: str = "mul_f32"
     r = _ops.deproject(d, c, m, cam, depth_kind=kind, unit_rule=unit_rule, unit_scale=depth_scale, invert_mask=invert_mask,
                        depth_trunc=depth_trunc, r_max=max_distance, z_clip=z_clip, aabb=aabb, mode=mode, out_dtype=dtype,
                        color_scale=color_scale, want_valid=want_valid, want_src_index=want_src_index,
-                       frame_capacity=frame_capacity, out=out, kernel=kernel, color_format=color_format)
+                       frame_capacity=frame_capacity, out=out, kernel=kernel, color_format=color_format, geometry=geometry)
     return CloudBatch(r, B, H, W, c is not None, mode.startswith("dense"), color_scale == "packed8")
 
 

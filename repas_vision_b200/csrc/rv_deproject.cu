@@ -146,7 +146,10 @@ __global__ void __launch_bounds__(kThreads) k_deproject(const DeprojArgs a) {
       if (a.use_trunc) ok = ok && !(z32 >= a.trunc_f);
 
       double x64, y64;
-      if (a.rays) {
+      if (a.geom_f32) {  // the SDKs' float32 form: z * ((u - ppx) / fx), IEEE division, one rounding per operation
+        x64 = (double)(z32 * rv_divf((float)u - a.cx_f, a.fx_f, a.rfx_f));
+        y64 = (double)(z32 * rv_divf((float)v - a.cy_f, a.fy_f, a.rfy_f));
+      } else if (a.rays) {
         double2 r = make_double2(0.0, 0.0);
         if (p < a.P) r = __ldg(a.rays + p);
         x64 = z64 * r.x;
@@ -598,6 +601,11 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
   if (p->color_scale == RV_COLOR_PACKED8 && p->out_dtype != RV_F32)
     RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: RV_COLOR_PACKED8 needs float32 output planes (a colour word per point)");
   if (p->color_format != RV_COLORFMT_BGR8 && p->color_format != RV_COLORFMT_NV12) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad color_format");
+  if (p->geometry != RV_GEOM_REFERENCE_F64 && p->geometry != RV_GEOM_SDK_F32) RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: bad geometry");
+  if (p->geometry == RV_GEOM_SDK_F32 && p->cam.model != RV_DIST_NONE && p->cam.model != RV_DIST_MODIFIED_BROWN_CONRADY)
+    RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: RV_GEOM_SDK_F32 is restated for pinhole deprojection only");
+  if (p->geometry == RV_GEOM_SDK_F32 && p->kernel_select == RV_KERNEL_TMA)
+    RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: RV_GEOM_SDK_F32 runs on the generic kernel");
   if (p->color_format == RV_COLORFMT_NV12 && d_bgr && ((H & 1) || (W & 1)))
     RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: NV12 frames need even H and W");
   if (p->cam.model != RV_DIST_NONE && p->cam.model != RV_DIST_MODIFIED_BROWN_CONRADY && !d_ray_table)
@@ -666,6 +674,13 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
   a.color_255 = p->color_scale == RV_COLOR_255;
   a.color_packed = (d_bgr && p->color_scale == RV_COLOR_PACKED8) ? 1 : 0;
   a.color_nv12 = (d_bgr && p->color_format == RV_COLORFMT_NV12) ? 1 : 0;
+  a.geom_f32 = p->geometry == RV_GEOM_SDK_F32 ? 1 : 0;
+  a.cx_f = (float)p->cam.cx;
+  a.cy_f = (float)p->cam.cy;
+  a.fx_f = (float)p->cam.fx;
+  a.fy_f = (float)p->cam.fy;
+  a.rfx_f = 1.0f / a.fx_f;
+  a.rfy_f = 1.0f / a.fy_f;
   a.zmin_f = float_at_least(a.z_min);
   a.zmax_f = float_at_most(a.z_max);
   for (int i = 0; i < 3; ++i) {
@@ -695,7 +710,7 @@ int rv_deproject_mask(rv_ctx *ctx, const void *d_depth, const uint8_t *d_bgr, co
   if (p->kernel_select == RV_KERNEL_TMA && !fast_ok)
     RV_FAIL(ctx, RV_EINVAL, "rv_deproject_mask: RV_KERNEL_TMA requested but the inputs are not eligible "
                             "(H*W %% 16 == 0, W >= 32, 16-byte aligned inputs)");
-  const bool use_fast = fast_ok && p->kernel_select != RV_KERNEL_GENERIC;
+  const bool use_fast = fast_ok && p->kernel_select != RV_KERNEL_GENERIC && !a.geom_f32;
   // COMPACT_UNORDERED asks for less than COMPACT_ORDERED delivers: on the fast path it simply gets the ordered kernel
   const int mode = (use_fast && p->mode == RV_MODE_COMPACT_UNORDERED) ? RV_MODE_COMPACT_ORDERED : p->mode;
   const bool ordered = mode == RV_MODE_COMPACT_ORDERED || packed;

@@ -29,6 +29,8 @@ struct DeprojArgs {
   int color_255;
   int color_packed;  // RV_COLOR_PACKED8: plane 3 holds the bytes r,g,b,0 of every point (float32 output only)
   int color_nv12;    // `bgr` points at NV12 frames ([H*3/2, W] bytes each)
+  int geom_f32;      // RV_GEOM_SDK_F32: x = z * ((u - ppx) / fx) in float32 (generic kernel only)
+  float cx_f, cy_f, fx_f, fy_f, rfx_f, rfy_f;
   // float32 forms of the cloud predicates (exactly equivalent on float32 storage; rv_deproject_tma.cu)
   float zmin_f, zmax_f;        // smallest float >= z_min, largest float <= z_max
   float amin_f[3], amax_f[3];  // same rounding for the box

@@ -439,3 +439,46 @@ def test_nv12_frames_and_packed_colours(rv, O, rs720, shape, kernel, case):
         rv.deproject_batch(d, torch.from_numpy(nv12).cuda(), cam, color_format="nv12", color_scale="packed8", dtype="f64")
     with pytest.raises(RuntimeError):
         pk.frame(0)
+
+
+@pytest.mark.parametrize("mode", ["dense_zero", "compact_ordered"])
+def test_sdk_float32_geometry(rv, O, rs720, mode):
+    """the SDK clouds (rs.pointcloud, PointCloudFilter) evaluate z * ((u - ppx) / fx) in float32.
+    geometry="sdk_f32" reproduces that arithmetic value for value (against the oracle's restatement of
+    rs2_deproject_pixel_to_point); it stays within one float32 ulp of the reference's float64-then-round form."""
+    import torch
+    color, depth = load_frame(CANOPY_TS[1])
+    H, W = depth.shape
+    cam = rv.Camera(rs720["fx"], rs720["fy"], rs720["cx"], rs720["cy"], W, H)
+    d = torch.from_numpy(depth[None]).cuda()
+    c = torch.from_numpy(color[None]).cuda()
+    kw = dict(max_distance=3.0, mode=mode, color_scale="255", want_src_index=True)
+    sdk = rv.deproject_batch(d, c, cam, geometry="sdk_f32", **kw)
+    ref = rv.deproject_batch(d, c, cam, **kw)
+    o = O.deproject_mask(depth, color, None, fx=cam.fx, fy=cam.fy, cx=cam.cx, cy=cam.cy, r_max=3.0, out_dtype="f32", color_scale="255",
+                         geometry="sdk_f32")
+    # the oracle's array form equals the scalar restatement of rs2_deproject_pixel_to_point
+    v, u = np.nonzero(o["valid"])
+    z = depth[o["valid"]].astype(np.float32) * np.float32(0.001)
+    X, Y, Z = O._rs_deproject_f32(u.astype(np.float32), v.astype(np.float32), z, dict(fx=cam.fx, fy=cam.fy, cx=cam.cx, cy=cam.cy))
+    assert np.array_equal(o["points"], np.stack([X, Y, Z], 1))
+    n = int(sdk.counts_host()[0])
+    assert n == o["points"].shape[0]
+    if mode == "dense_zero":
+        flat = o["valid"].reshape(-1)
+        got = sdk.data[:, :H * W].cpu().numpy()
+        assert np.array_equal(got[:3][:, flat].T, o["points"]) and np.array_equal(got[3:][:, flat].T, o["colors"])
+        assert not got[:, ~flat].any()
+    else:
+        got = sdk.data[:, :n].cpu().numpy()
+        assert np.array_equal(got[:3].T, o["points"]) and np.array_equal(got[3:].T, o["colors"])
+        assert np.array_equal(sdk.src_index[:n].cpu().numpy(), o["src_index"])
+        # against the reference form on the pixels both keep: at most one unit in the last place
+        a, b = sdk.src_index[:n].cpu().numpy(), ref.src_index[:int(ref.counts_host()[0])].cpu().numpy()
+        both = np.intersect1d(a, b)
+        pa = got[:3].T[np.isin(a, both)]
+        pb = ref.data[:3, :len(b)].cpu().numpy().T[np.isin(b, both)]
+        assert len(both) > 0.99 * n
+        assert (np.abs(pa.astype(np.float64) - pb) <= np.spacing(np.abs(pb)).astype(np.float64)).all()
+    with pytest.raises(RuntimeError):
+        rv.deproject_batch(d, c, cam, geometry="sdk_f32", kernel="tma")
