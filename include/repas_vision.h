@@ -377,10 +377,12 @@ int rv_icp_sums(rv_ctx *ctx, int point_to_plane, const void *d_source_xyz, int64
 
 /* the whole point-to-plane loop on the device: rv_icp_begin writes the state (accumulated transformation = T_init, the
  * stopping rule's thresholds), rv_icp_iterate queues `steps` iterations -- each: pcd.Transform(update) on the caller's
- * working copy of the source coordinates IN PLACE, nearest search, sums, then ONE thread's worth of host logic on the
- * device: fitness / inlier RMSE, |delta fitness| < relative_fitness && |delta rmse| < relative_rmse, the 6 x 6 solve
- * (elimination with partial pivoting; a vanishing pivot leaves the update at identity) and transformation = update *
- * transformation -- preceded, when `first` is set, by the evaluation of the initial alignment.  Once the loop has
+ * working copy of the source coordinates IN PLACE (done by the search kernel on its way in), nearest search (bounded from
+ * the start by the previous evaluation's match, which d_nearest must therefore still hold when `first` is 0; the result
+ * is the same), sums, then ONE thread's worth of host logic on the device: fitness / inlier RMSE, |delta fitness| <
+ * relative_fitness && |delta rmse| < relative_rmse, the 6 x 6 solve (L D L^T in registers; elimination with partial
+ * pivoting when a pivot is not positive, and a vanishing pivot there leaves the update at identity) and transformation =
+ * update * transformation -- preceded, when `first` is set, by the evaluation of the initial alignment.  Once the loop has
  * stopped every queued kernel returns at once, so the host reads the state back once per few iterations instead of
  * once per iteration.  The state (rv_icp_state_bytes() = 448 bytes): double T[16], update[16], fitness, inlier_rmse,
  * relative_fitness, relative_rmse, iterations, max_iteration, n_source, evaluated, 8 reserved; then int32 done.

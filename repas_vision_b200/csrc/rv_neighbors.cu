@@ -42,19 +42,42 @@ struct KnnParams {  // written by k_knn_setup, read by the later kernels
   int pad;
   double expect;          // points per used cell the chosen cell size should give on a surface
 };
+#ifndef RV_NN_CELL_SPACINGS
+#define RV_NN_CELL_SPACINGS 3.0
+#endif
+#ifndef RV_NN_WARM
+#define RV_NN_WARM 1
+#endif
 constexpr int kRefineRounds = 3;       // the cell size is re-derived from the measured occupancy at most this many times
 constexpr double kMaxOccupancy = 4.0;  // measured / expected points per used cell above which the grid is rebuilt finer
+
+struct __align__(16) KnnCell {
+  unsigned long long key;  // 0 = empty, else packed cell + 1
+  unsigned int cnt;        // points in the cell
+  unsigned int start;      // first slot of the cell in the sorted arrays
+};
+
+// the table slot of a cell, or an empty slot when no point lies in it (linear probing)
+__device__ __forceinline__ KnnCell knn_find(const KnnCell *__restrict__ cells, unsigned int cap, unsigned long long key, unsigned int h) {
+  for (;;) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(cells + h));
+    KnnCell c;
+    c.key = ((unsigned long long)raw.y << 32) | raw.x;
+    c.cnt = raw.z;
+    c.start = raw.w;
+    if (c.key == key || c.key == 0) return c;
+    if (++h == cap) h = 0;
+  }
+}
 
 struct KnnArgs {
   const void *in;
   long long stride, n;
   KnnParams *prm;
-  unsigned long long *keys;  // [cap] 0 = empty, else packed cell + 1
-  unsigned int *cnt;         // [cap] points in the cell
-  unsigned int *start;       // [cap] first slot of the cell in the sorted arrays
+  KnnCell *cells;  // [cap] open-addressing table: one 16-byte load answers "which cell, where are its points"
   unsigned int cap;
   unsigned int *slot_of;  // [n]
-  unsigned int *rank_of;  // [n]
+  unsigned int *rank_of;  // [n] rank inside the cell while the table is built, position in the sorted arrays afterwards
   double *sx, *sy, *sz;   // [n] cell-sorted coordinates
   unsigned int *sidx;     // [n] original index of each sorted point
   int k;
@@ -149,6 +172,7 @@ __global__ void k_knn_setup(KnnParams *p, long long n, int k, double radius) {
   const double spacing = sqrt(a * b / (double)n);
   double f = 1.2 * sqrt((double)k / 3.141592653589793);
   if (f < 2.0) f = 2.0;
+  if (k == 1 && radius > 0.0) f = RV_NN_CELL_SPACINGS;  // nearest-point index of ICP: queries sit off the surface
   double s = f * spacing;
   if (radius > 0.0 && radius < s) s = radius > 2.0 * spacing ? radius : 2.0 * spacing;
   if (!(s > 0.0)) s = a > 0.0 ? 4.0 * a / (double)n : 1.0;
@@ -174,12 +198,11 @@ __global__ void k_knn_refine(KnnParams *p, long long n, int last) {
   }
 }
 
-__global__ void __launch_bounds__(256) k_knn_clear(const KnnParams *p, unsigned long long *keys, unsigned int *cnt, unsigned int cap) {
+__global__ void __launch_bounds__(256) k_knn_clear(const KnnParams *p, KnnCell *cells, unsigned int cap) {
   if (!p->redo) return;
   const unsigned int stride = gridDim.x * blockDim.x;
   for (unsigned int h = blockIdx.x * blockDim.x + threadIdx.x; h < cap; h += stride) {
-    keys[h] = 0ull;
-    cnt[h] = 0u;
+    *reinterpret_cast<uint4 *>(cells + h) = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
@@ -213,13 +236,13 @@ __global__ void __launch_bounds__(256) k_knn_cells(const KnnArgs a) {
     const unsigned long long key = cell_key(ix, iy, iz);
     unsigned int h = __umulhi((unsigned int)(cell_hash(key) >> 32), a.cap);
     for (;;) {
-      const unsigned long long cur = atomicCAS(a.keys + h, 0ull, key);
+      const unsigned long long cur = atomicCAS(&a.cells[h].key, 0ull, key);
       if (cur == 0) atomicAdd(&a.prm->occupied, 1u);
       if (cur == 0 || cur == key) break;
       if (++h == a.cap) h = 0;
     }
     a.slot_of[i] = h;
-    a.rank_of[i] = atomicAdd(a.cnt + h, 1u);
+    a.rank_of[i] = atomicAdd(&a.cells[h].cnt, 1u);
   }
 }
 
@@ -227,7 +250,7 @@ __global__ void __launch_bounds__(256) k_knn_alloc(const KnnArgs a) {
   const int lane = threadIdx.x & 31;
   const unsigned int stride = gridDim.x * blockDim.x;
   for (unsigned int h = blockIdx.x * blockDim.x + threadIdx.x; h < a.cap; h += stride) {  // cap % 32 == 0: whole warps
-    const unsigned int c = a.cnt[h];
+    const unsigned int c = a.cells[h].cnt;
     unsigned int incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -238,7 +261,7 @@ __global__ void __launch_bounds__(256) k_knn_alloc(const KnnArgs a) {
     unsigned int base = 0;
     if (lane == 0 && total) base = atomicAdd(&a.prm->cursor, total);
     base = __shfl_sync(0xffffffffu, base, 0);
-    a.start[h] = base + incl - c;
+    a.cells[h].start = base + incl - c;
   }
 }
 
@@ -247,11 +270,12 @@ __global__ void __launch_bounds__(256) k_knn_scatter(const KnnArgs a) {
   const T *in = reinterpret_cast<const T *>(a.in);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-    const unsigned int pos = a.start[a.slot_of[i]] + a.rank_of[i];
+    const unsigned int pos = a.cells[a.slot_of[i]].start + a.rank_of[i];
     a.sx[pos] = (double)in[i];
     a.sy[pos] = (double)in[a.stride + i];
     a.sz[pos] = (double)in[2 * a.stride + i];
     a.sidx[pos] = (unsigned int)i;
+    a.rank_of[i] = pos;  // from here on: where point i sits in the cell-sorted arrays (k_nn_search's warm start)
   }
 }
 
@@ -457,13 +481,9 @@ __global__ void __launch_bounds__(kQueryThreads) k_knn_query(const KnnArgs a) {
             if (ix < 0 || ix >= gx) continue;
             if (lbzy + axis_gap2(x, ox, ix, cell, eps) > bound()) continue;  // nothing in that cell can enter the list
             const unsigned long long key = cell_key(ix, iy, iz);
-            unsigned int h = __umulhi((unsigned int)(cell_hash(key) >> 32), a.cap);
-            unsigned long long cur;
-            while ((cur = a.keys[h]) != key && cur != 0) {
-              if (++h == a.cap) h = 0;
-            }
-            if (cur == 0) continue;  // no point in that cell
-            const unsigned int s0 = a.start[h], s1 = s0 + a.cnt[h];
+            const KnnCell c = knn_find(a.cells, a.cap, key, __umulhi((unsigned int)(cell_hash(key) >> 32), a.cap));
+            if (c.key == 0) continue;  // no point in that cell
+            const unsigned int s0 = c.start, s1 = s0 + c.cnt;
             for (unsigned int j = s0; j < s1; ++j) {
               const double ex = a.sx[j] - x, ey = a.sy[j] - y, ez = a.sz[j] - z;
               offer((ex * ex + ey * ey) + ez * ez, j);
@@ -668,22 +688,50 @@ __global__ void __launch_bounds__(256) k_orient_normals(const T *__restrict__ xy
   }
 }
 
+// state of the ICP loop on the device (see k_icp_finish_step)
+struct IcpState {
+  double T[16];       // accumulated transformation
+  double update[16];  // what the working copy is moved by next
+  double fitness, rmse, rel_fitness, rel_rmse;
+  double iterations, max_iteration, n_source, evaluated;
+  double pad[8];
+  int done;  // converged, or max_iteration estimation steps taken: every later kernel of the queue returns at once
+  int pad2[15];
+};
+static_assert(sizeof(IcpState) == 448, "state layout is read by the host (registration.py)");
+
 // ---- ICP correspondence search: for every query point the nearest point of the indexed cloud closer than the
 // correspondence distance (KDTreeFlann::SearchHybrid(point, max_distance, 1): squared distance strictly below
 // max_distance^2), -1 without one.  Same shell walk as k_knn_query with k = 1; the query may lie outside the indexed
 // cloud's box (its cell is clamped, which only makes the "everything unvisited is at least r cells away" bound more
 // conservative).  Equal distances go to the lower point index, so the result does not depend on the cell order.
+// Inside the device-side ICP loop two things ride along: `move` (the loop's state) applies pcd.Transform(update) to the query
+// on the way in and writes the moved point back -- the working copy advances in place, arithmetic of k_transform -- and
+// `warm` says corr still holds the previous evaluation's match, whose distance to the moved point is the first bound, so
+// that most cells around the query are rejected by their box without a probe.  The result is the same either way.
 template <typename T>
-__global__ void __launch_bounds__(128) k_nn_search(const KnnArgs a, const T *__restrict__ q_xyz, long long q_stride, long long nq,
-                                                   double radius2, int *__restrict__ corr, const int *__restrict__ skip) {
-  if (skip && *skip) return;  // device-side ICP loop: the registration has already stopped
+__global__ void __launch_bounds__(128) k_nn_search(const KnnArgs a, T *__restrict__ q_xyz, long long q_stride, long long nq,
+                                                   double radius2, int *__restrict__ corr, const IcpState *__restrict__ move,
+                                                   int warm) {
+  if (move && move->done) return;  // device-side ICP loop: the registration has already stopped
   const KnnParams *p = a.prm;
   const double cell = p->cell;
   const int gx = p->grid[0], gy = p->grid[1], gz = p->grid[2], rmax = p->rmax;
   const long long shell_budget = a.n / 2 + 4096;
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one query per thread, small CTAs
   if (q < nq) {
-    const double x = (double)q_xyz[q], y = (double)q_xyz[q_stride + q], z = (double)q_xyz[2 * q_stride + q];
+    double x = (double)q_xyz[q], y = (double)q_xyz[q_stride + q], z = (double)q_xyz[2 * q_stride + q];
+    if (move && warm) {  // (the first evaluation of a registration looks at the source as it was handed over)
+      const double *M = move->update;
+      const double qx = ((M[0] * x + M[1] * y) + M[2] * z) + M[3];
+      const double qy = ((M[4] * x + M[5] * y) + M[6] * z) + M[7];
+      const double qz = ((M[8] * x + M[9] * y) + M[10] * z) + M[11];
+      const double qw = ((M[12] * x + M[13] * y) + M[14] * z) + M[15];
+      const bool h = qw != 1.0;
+      const T mx = (T)(h ? qx / qw : qx), my = (T)(h ? qy / qw : qy), mz = (T)(h ? qz / qw : qz);
+      q_xyz[q] = mx, q_xyz[q_stride + q] = my, q_xyz[2 * q_stride + q] = mz;
+      x = (double)mx, y = (double)my, z = (double)mz;
+    }
     if (!(isfinite(x) && isfinite(y) && isfinite(z))) {
       corr[q] = -1;
       return;
@@ -692,6 +740,15 @@ __global__ void __launch_bounds__(128) k_nn_search(const KnnArgs a, const T *__r
     cell_of(p, x, y, z, cx, cy, cz);
     double best = radius2;
     unsigned int bidx = 0xffffffffu;  // original index of the best point so far
+    if (warm > 1) {
+      const int j0 = corr[q];
+      if (j0 >= 0 && j0 < a.n) {
+        const unsigned int pos = a.rank_of[j0];
+        const double ex = a.sx[pos] - x, ey = a.sy[pos] - y, ez = a.sz[pos] - z;
+        const double d2 = (ex * ex + ey * ey) + ez * ez;
+        if (d2 < best) best = d2, bidx = (unsigned int)j0;
+      }
+    }
     const double ox = p->origin[0], oy = p->origin[1], oz = p->origin[2], eps = cell * 4e-9;
     auto offer = [&](double d2, unsigned int j) {
       if (d2 < best) {
@@ -728,13 +785,9 @@ __global__ void __launch_bounds__(128) k_nn_search(const KnnArgs a, const T *__r
             if (ix < 0 || ix >= gx) continue;
             if (lbzy + axis_gap2(x, ox, ix, cell, eps) > best) continue;  // every point of that cell is farther than the best
             const unsigned long long key = cell_key(ix, iy, iz);
-            unsigned int h = __umulhi((unsigned int)(cell_hash(key) >> 32), a.cap);
-            unsigned long long cur;
-            while ((cur = a.keys[h]) != key && cur != 0) {
-              if (++h == a.cap) h = 0;
-            }
-            if (cur == 0) continue;
-            const unsigned int s0 = a.start[h], s1 = s0 + a.cnt[h];
+            const KnnCell c = knn_find(a.cells, a.cap, key, __umulhi((unsigned int)(cell_hash(key) >> 32), a.cap));
+            if (c.key == 0) continue;
+            const unsigned int s0 = c.start, s1 = s0 + c.cnt;
             for (unsigned int j = s0; j < s1; ++j) {
               const double ex = a.sx[j] - x, ey = a.sy[j] - y, ez = a.sz[j] - z;
               offer((ex * ex + ey * ey) + ez * ez, j);
@@ -827,14 +880,30 @@ __global__ void __launch_bounds__(256) k_icp_sums(const TS *__restrict__ src, lo
   }
 }
 
-// one warp per sum: lane l adds rows l, l + 32, ... in order, then a fixed shuffle tree -- the same bits every run
-__global__ void __launch_bounds__(kIcpSums * 32) k_icp_finish(const double *__restrict__ partial, int blocks, double *__restrict__ sums) {
-  const int col = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// Sums of the per-block rows, the same bits every run and the same in both entry points: lane = column (a row is one
+// coalesced 256-byte read), warp w adds rows w, w + 8, ... in order, then the eight warp sums are added in warp order.
+constexpr int kStepThreads = 256;  // few enough that the deciding thread of k_icp_finish_step keeps the 6 x 6 system in registers
+__device__ __forceinline__ void icp_reduce_rows(const double *__restrict__ partial, int blocks, double (&s_part)[kStepThreads / 32][kIcpSums],
+                                                double (&s_sum)[kIcpSums]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double v = 0.0;
-  for (int b = lane; b < blocks; b += 32) v += partial[(size_t)b * kIcpSums + col];
+#pragma unroll 16
+  for (int b = warp; b < blocks; b += kStepThreads / 32) v += partial[(size_t)b * kIcpSums + lane];
+  s_part[warp][lane] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double t = 0.0;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if (lane == 0) sums[col] = v;
+    for (int w = 0; w < kStepThreads / 32; ++w) t += s_part[w][lane];
+    s_sum[lane] = t;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kStepThreads) k_icp_finish(const double *__restrict__ partial, int blocks, double *__restrict__ sums) {
+  __shared__ double s_part[kStepThreads / 32][kIcpSums], s_sum[kIcpSums];
+  icp_reduce_rows(partial, blocks, s_part, s_sum);
+  if (threadIdx.x < kIcpSums) sums[threadIdx.x] = s_sum[threadIdx.x];
 }
 
 template <typename TS, typename TT>
@@ -850,45 +919,8 @@ static void icp_sums_launch(int plane, int blocks, cudaStream_t st, const void *
 // an evaluation -- fitness / inlier RMSE, the reference's stopping rule, the 6 x 6 solve and the pose composition -- so that
 // the host reads back once per few iterations instead of once per iteration (Open3D 0.19 RegistrationICP, restated in
 // repas_vision_b200/registration.py; mpa_icp_export.py:187-197).
-struct IcpState {
-  double T[16];       // accumulated transformation
-  double update[16];  // what the working copy is moved by next
-  double fitness, rmse, rel_fitness, rel_rmse;
-  double iterations, max_iteration, n_source, evaluated;
-  double pad[8];
-  int done;  // converged, or max_iteration estimation steps taken: every later kernel of the queue returns at once
-  int pad2[15];
-};
-static_assert(sizeof(IcpState) == 448, "state layout is read by the host (registration.py)");
-
 __global__ void k_icp_begin(IcpState *s, const __grid_constant__ IcpState init) {
   if (threadIdx.x == 0) *s = init;
-}
-
-// pcd.Transform(update) on the working copy, in place (every thread owns its point); arithmetic of k_transform
-template <typename T>
-__global__ void __launch_bounds__(256) k_icp_apply(const IcpState *__restrict__ s, T *__restrict__ xyz, long long stride, long long n) {
-  if (s->done) return;
-  double M[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) M[i] = s->update[i];
-  const long long step = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
-    const double x = (double)xyz[i], y = (double)xyz[stride + i], z = (double)xyz[2 * stride + i];
-    const double qx = ((M[0] * x + M[1] * y) + M[2] * z) + M[3];
-    const double qy = ((M[4] * x + M[5] * y) + M[6] * z) + M[7];
-    const double qz = ((M[8] * x + M[9] * y) + M[10] * z) + M[11];
-    const double qw = ((M[12] * x + M[13] * y) + M[14] * z) + M[15];
-    double px = qx, py = qy, pz = qz;
-    if (qw != 1.0) {
-      px = qx / qw;
-      py = qy / qw;
-      pz = qz / qw;
-    }
-    xyz[i] = (T)px;
-    xyz[stride + i] = (T)py;
-    xyz[2 * stride + i] = (T)pz;
-  }
 }
 
 // x = solve(A, b) for the symmetric 6 x 6 system by elimination with partial pivoting; false when a pivot vanishes
@@ -925,64 +957,141 @@ __device__ bool icp_solve6(double A[6][6], double b[6], double x[6]) {
   return true;
 }
 
-// finishes an evaluation (sums of the per-block rows in a fixed order, as k_icp_finish) and takes the loop's next decision
-__global__ void __launch_bounds__(kIcpSums * 32) k_icp_finish_step(const double *__restrict__ partial, int blocks, double *__restrict__ sums,
-                                                                   IcpState *__restrict__ s) {
-  if (s->done) return;
-  __shared__ double s_sum[kIcpSums];
-  const int col = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double v = 0.0;
-  for (int b = lane; b < blocks; b += 32) v += partial[(size_t)b * kIcpSums + col];
+// x = solve(A, b) for a symmetric positive definite 6 x 6 system, A = L D L^T without pivoting, everything in registers
+// (what J^T J is unless the correspondences are degenerate); false when a pivot is not positive -- the caller then takes
+// the pivoting elimination above
+__device__ __forceinline__ bool icp_solve6_spd(const double (&A)[6][6], const double (&b)[6], double (&x)[6]) {
+  double L[6][6], D[6], rD[6];
+  bool ok = true;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if (lane == 0) {
-    s_sum[col] = v;
-    sums[col] = v;
+  for (int j = 0; j < 6; ++j) {
+    double d = A[j][j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k] * D[k];
+    ok = ok && d > 0.0 && isfinite(d);
+    D[j] = d;
+    rD[j] = 1.0 / d;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double v = A[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k] * D[k];
+      L[i][j] = v * rD[j];
+    }
   }
-  __syncthreads();
+  double z[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double v = b[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) v -= L[i][k] * z[k];
+    z[i] = v;
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double v = z[i] * rD[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; ++k) v -= L[k][i] * x[k];
+    x[i] = v;
+    ok = ok && isfinite(v);
+  }
+  return ok;
+}
+
+// finishes an evaluation (sums of the per-block rows exactly as k_icp_finish adds them) and takes the loop's next decision.
+// One thread decides; it fetches the state while the other warps add the rows.
+__global__ void __launch_bounds__(kStepThreads) k_icp_finish_step(const double *__restrict__ partial, int blocks, double *__restrict__ sums,
+                                                                  IcpState *__restrict__ s) {
+  if (s->done) return;
+#ifdef RV_ICP_TIMING  // experiment: cycles of the phases into the state's reserved words
+  const long long t_begin = clock64();
+#endif
+  __shared__ double s_part[kStepThreads / 32][kIcpSums], s_sum[kIcpSums];
+  double T[16], prev_fitness = 0, prev_rmse = 0, rel_fitness = 0, rel_rmse = 0, iterations = 0, max_iteration = 0, n_source = 1,
+                evaluated = 0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) T[i] = s->T[i];
+    prev_fitness = s->fitness, prev_rmse = s->rmse, rel_fitness = s->rel_fitness, rel_rmse = s->rel_rmse;
+    iterations = s->iterations, max_iteration = s->max_iteration, n_source = s->n_source, evaluated = s->evaluated;
+  }
+  icp_reduce_rows(partial, blocks, s_part, s_sum);
+  if (threadIdx.x < kIcpSums) sums[threadIdx.x] = s_sum[threadIdx.x];
   if (threadIdx.x != 0) return;
+#ifdef RV_ICP_TIMING
+  const long long t_reduced = clock64();
+  long long t_solved = t_reduced, t_angles = t_reduced;
+#endif
   const double count = s_sum[0];
-  const double fitness = count > 0.0 ? count / s->n_source : 0.0;
+  const double fitness = count > 0.0 ? count / n_source : 0.0;
   const double rmse = count > 0.0 ? sqrt(s_sum[1] / count) : 0.0;
   bool stop = false;
-  if (s->evaluated != 0.0)  // the reference compares with the evaluation before this estimation step
-    stop = fabs(s->fitness - fitness) < s->rel_fitness && fabs(s->rmse - rmse) < s->rel_rmse;
+  if (evaluated != 0.0)  // the reference compares with the evaluation before this estimation step
+    stop = fabs(prev_fitness - fitness) < rel_fitness && fabs(prev_rmse - rmse) < rel_rmse;
   s->fitness = fitness;
   s->rmse = rmse;
   s->evaluated = 1.0;
-  if (stop || s->iterations >= s->max_iteration) {
+  if (stop || iterations >= max_iteration) {
     s->done = 1;
     return;
   }
   // TransformationEstimationPointToPlane::ComputeTransformation: x = solve(J^T J, -J^T r), update = [Rz Ry Rx | t]
-  double U[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  double U[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};  // rows 0..2; the last row is (0, 0, 0, 1)
   if (count > 0.0) {
     double A[6][6], b[6], x[6];
     int t = 9;
+#pragma unroll
     for (int u = 0; u < 6; ++u) {
       b[u] = -s_sum[3 + u];
+#pragma unroll
       for (int w = u; w < 6; ++w) A[u][w] = A[w][u] = s_sum[t++];
     }
-    if (icp_solve6(A, b, x)) {
-      const double ca = cos(x[0]), sa = sin(x[0]), cb = cos(x[1]), sb = sin(x[1]), cc = cos(x[2]), sc = sin(x[2]);
+    bool solved = icp_solve6_spd(A, b, x);
+    if (!solved) {
+      double A2[6][6], b2[6];
+      for (int u = 0; u < 6; ++u) {
+        b2[u] = b[u];
+        for (int w = 0; w < 6; ++w) A2[u][w] = A[u][w];
+      }
+      solved = icp_solve6(A2, b2, x);
+    }
+#ifdef RV_ICP_TIMING
+    t_solved = clock64();
+#endif
+    if (solved) {
+      double sa, ca, sb, cb, sc, cc;
+      sincos(x[0], &sa, &ca);
+      sincos(x[1], &sb, &cb);
+      sincos(x[2], &sc, &cc);
       // Rz(c) Ry(b) Rx(a)
       U[0] = cc * cb, U[1] = cc * sb * sa - sc * ca, U[2] = cc * sb * ca + sc * sa, U[3] = x[3];
       U[4] = sc * cb, U[5] = sc * sb * sa + cc * ca, U[6] = sc * sb * ca - cc * sa, U[7] = x[4];
       U[8] = -sb, U[9] = cb * sa, U[10] = cb * ca, U[11] = x[5];
     }
+#ifdef RV_ICP_TIMING
+    t_angles = clock64();
+#endif
   }
-  double N[16];
-  for (int r = 0; r < 4; ++r)
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
     for (int c = 0; c < 4; ++c) {
       double acc = 0.0;
-      for (int k = 0; k < 4; ++k) acc += U[4 * r + k] * s->T[4 * k + c];
-      N[4 * r + c] = acc;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc += U[4 * r + k] * T[4 * k + c];
+      s->T[4 * r + c] = acc;
+      s->update[4 * r + c] = U[4 * r + c];
     }
-  for (int i = 0; i < 16; ++i) {
-    s->T[i] = N[i];
-    s->update[i] = U[i];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {  // last row of the update is (0, 0, 0, 1): 0 * T[k][c] terms kept as the sum adds them
+    s->T[12 + c] = ((0.0 * T[c] + 0.0 * T[4 + c]) + 0.0 * T[8 + c]) + T[12 + c];
+    s->update[12 + c] = c == 3 ? 1.0 : 0.0;
   }
-  s->iterations += 1.0;
+  s->iterations = iterations + 1.0;
+#ifdef RV_ICP_TIMING
+  s->pad[0] = (double)(t_reduced - t_begin), s->pad[1] = (double)(t_solved - t_reduced), s->pad[2] = (double)(t_angles - t_solved);
+  s->pad[3] = (double)(clock64() - t_angles);
+#endif
 }
 
 template <bool kNormals>
@@ -1033,13 +1142,9 @@ static size_t knn_layout(void *d_ws, const void *d_xyz, int64_t plane_stride, in
   a.cap = (unsigned int)cap;
   a.prm = reinterpret_cast<KnnParams *>(w);
   w += 256;
-  a.keys = reinterpret_cast<unsigned long long *>(w);
-  w += up256(cap * 8);
-  a.cnt = reinterpret_cast<unsigned int *>(w);
-  w += up256(cap * 4);
-  const size_t clear_bytes = (size_t)(w - reinterpret_cast<char *>(d_ws));
-  a.start = reinterpret_cast<unsigned int *>(w);
-  w += up256(cap * 4);
+  a.cells = reinterpret_cast<KnnCell *>(w);
+  w += up256(cap * 8) + 2 * up256(cap * 4);  // (the span rv_knn_workspace_bytes has always reserved for the table)
+  const size_t clear_bytes = 256 + cap * sizeof(KnnCell);
   a.slot_of = reinterpret_cast<unsigned int *>(w);
   w += up256((size_t)n * 4);
   a.rank_of = reinterpret_cast<unsigned int *>(w);
@@ -1079,7 +1184,7 @@ static int knn_prepare(rv_ctx *ctx, const char *who, const void *d_xyz, int64_t 
   RV_LAUNCHED(ctx);
   for (int round = 0; round <= kRefineRounds; ++round) {
     if (round > 0) {
-      k_knn_clear<<<grid_for(ctx, (long long)cap), 256, 0, st>>>(a.prm, a.keys, a.cnt, a.cap);
+      k_knn_clear<<<grid_for(ctx, (long long)cap), 256, 0, st>>>(a.prm, a.cells, a.cap);
       RV_LAUNCHED(ctx);
     }
     if (dtype == RV_F32) k_knn_cells<float><<<g, 256, 0, st>>>(a);
@@ -1211,9 +1316,9 @@ int rv_nn_search(rv_ctx *ctx, const void *d_index_ws, size_t ws_bytes, int64_t n
   knn_layout(const_cast<void *>(d_index_ws), nullptr, 0, n_indexed, 1, a);
   const double r2 = max_distance * max_distance;
   if (dtype == RV_F32)
-    k_nn_search<float><<<(unsigned int)((n_query + 127) / 128), 128, 0, st>>>(a, reinterpret_cast<const float *>(d_query_xyz), query_stride, n_query, r2, d_nearest, nullptr);
+    k_nn_search<float><<<(unsigned int)((n_query + 127) / 128), 128, 0, st>>>(a, const_cast<float *>(reinterpret_cast<const float *>(d_query_xyz)), query_stride, n_query, r2, d_nearest, nullptr, 0);
   else
-    k_nn_search<double><<<(unsigned int)((n_query + 127) / 128), 128, 0, st>>>(a, reinterpret_cast<const double *>(d_query_xyz), query_stride, n_query, r2, d_nearest, nullptr);
+    k_nn_search<double><<<(unsigned int)((n_query + 127) / 128), 128, 0, st>>>(a, const_cast<double *>(reinterpret_cast<const double *>(d_query_xyz)), query_stride, n_query, r2, d_nearest, nullptr, 0);
   RV_LAUNCHED(ctx);
   return RV_OK;
 }
@@ -1250,7 +1355,7 @@ int rv_icp_sums(rv_ctx *ctx, int point_to_plane, const void *d_source_xyz, int64
   else
     icp_sums_launch<double, double>(pl, blocks, st, d_source_xyz, source_stride, n_source, d_target_xyz, target_stride, d_target_normals, normal_stride, d_nearest, partial);
   RV_LAUNCHED(ctx);
-  k_icp_finish<<<1, kIcpSums * 32, 0, st>>>(partial, blocks, d_sums);
+  k_icp_finish<<<1, kStepThreads, 0, st>>>(partial, blocks, d_sums);
   RV_LAUNCHED(ctx);
   return RV_OK;
 }
@@ -1301,17 +1406,12 @@ int rv_icp_iterate(rv_ctx *ctx, void *d_state, int first, int steps, void *d_wor
   int blocks = grid_for(ctx, n_source, 4);
   if (blocks > kIcpMaxBlocks) blocks = kIcpMaxBlocks;
   double *partial = d_sums + kIcpSums;
-  const int ag = grid_for(ctx, n_source);
   for (int it = first ? 0 : 1; it <= steps; ++it) {
-    if (it > 0) {  // pcd.Transform(update)
-      if (work_dtype == RV_F32) k_icp_apply<float><<<ag, 256, 0, st>>>(state, reinterpret_cast<float *>(d_work_xyz), work_stride, n_source);
-      else k_icp_apply<double><<<ag, 256, 0, st>>>(state, reinterpret_cast<double *>(d_work_xyz), work_stride, n_source);
-      RV_LAUNCHED(ctx);
-    }
+    const int warm = it > 0 ? 1 + RV_NN_WARM : 0;  // pcd.Transform(update) rides on the search; d_nearest holds the previous evaluation's matches
     if (work_dtype == RV_F32)
-      k_nn_search<float><<<(unsigned int)((n_source + 127) / 128), 128, 0, st>>>(a, reinterpret_cast<const float *>(d_work_xyz), work_stride, n_source, r2, d_nearest, skip);
+      k_nn_search<float><<<(unsigned int)((n_source + 127) / 128), 128, 0, st>>>(a, reinterpret_cast<float *>(d_work_xyz), work_stride, n_source, r2, d_nearest, state, warm);
     else
-      k_nn_search<double><<<(unsigned int)((n_source + 127) / 128), 128, 0, st>>>(a, reinterpret_cast<const double *>(d_work_xyz), work_stride, n_source, r2, d_nearest, skip);
+      k_nn_search<double><<<(unsigned int)((n_source + 127) / 128), 128, 0, st>>>(a, reinterpret_cast<double *>(d_work_xyz), work_stride, n_source, r2, d_nearest, state, warm);
     RV_LAUNCHED(ctx);
     if (work_dtype == RV_F32 && target_dtype == RV_F32)
       icp_sums_launch<float, float>(1, blocks, st, d_work_xyz, work_stride, n_source, d_target_xyz, target_stride, d_target_normals, normal_stride, d_nearest, partial, skip);
@@ -1322,7 +1422,7 @@ int rv_icp_iterate(rv_ctx *ctx, void *d_state, int first, int steps, void *d_wor
     else
       icp_sums_launch<double, double>(1, blocks, st, d_work_xyz, work_stride, n_source, d_target_xyz, target_stride, d_target_normals, normal_stride, d_nearest, partial, skip);
     RV_LAUNCHED(ctx);
-    k_icp_finish_step<<<1, kIcpSums * 32, 0, st>>>(partial, blocks, d_sums, state);
+    k_icp_finish_step<<<1, kStepThreads, 0, st>>>(partial, blocks, d_sums, state);
     RV_LAUNCHED(ctx);
   }
   return RV_OK;

@@ -41,6 +41,15 @@ VARIANTS.update({
     "k4_g1_i6_e256x6": "-DRV_VOX_GROUPS=1 -DRV_VOX_INSERT_OCC=6 -DRV_VOX_EMIT_THREADS=256 -DRV_VOX_EMIT_OCC=6",
     "k4_g1_i6_e128x12": "-DRV_VOX_GROUPS=1 -DRV_VOX_INSERT_OCC=6 -DRV_VOX_EMIT_THREADS=128 -DRV_VOX_EMIT_OCC=12",
 })
+# ICP search tunables (tools/icp_sweep.sh): cell size of the nearest-point index in surface spacings, warm-started bound
+VARIANTS.update({
+    "icp_c10": "-DRV_NN_CELL_SPACINGS=1.0", "icp_c15": "-DRV_NN_CELL_SPACINGS=1.5", "icp_c20": "-DRV_NN_CELL_SPACINGS=2.0",
+    "icp_c30": "-DRV_NN_CELL_SPACINGS=3.0", "icp_c40": "-DRV_NN_CELL_SPACINGS=4.0",
+    "icp_c20_cold": "-DRV_NN_CELL_SPACINGS=2.0 -DRV_NN_WARM=0", "icp_c30_cold": "-DRV_NN_CELL_SPACINGS=3.0 -DRV_NN_WARM=0",
+    "icp_c10_cold": "-DRV_NN_CELL_SPACINGS=1.0 -DRV_NN_WARM=0",
+    "icp_c25": "-DRV_NN_CELL_SPACINGS=2.5", "icp_c35": "-DRV_NN_CELL_SPACINGS=3.5",
+    "icp_c30_timing": "-DRV_NN_CELL_SPACINGS=3.0 -DRV_ICP_TIMING",
+})
 
 
 def main():
