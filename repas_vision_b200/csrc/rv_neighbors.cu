@@ -123,10 +123,25 @@ __global__ void __launch_bounds__(256) k_knn_bounds(const T *__restrict__ in, lo
       lo[a] = l < lo[a] ? l : lo[a];
       hi[a] = h > hi[a] ? h : hi[a];
     }
-    if ((threadIdx.x & 31) == 0) {
-      rv_atomic_min_f64(bounds + a, lo[a]);
-      rv_atomic_max_f64(bounds + 3 + a, hi[a]);
+  }
+  // one update per CTA: every request to these six words queues at one L2 slice
+  __shared__ double s_lo[8][3], s_hi[8][3];
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) s_lo[warp][a] = lo[a], s_hi[warp][a] = hi[a];
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    const int a = threadIdx.x % 3;
+    const bool is_hi = threadIdx.x >= 3;
+    double v = is_hi ? s_hi[0][a] : s_lo[0][a];
+    for (int w = 1; w < 8; ++w) {
+      const double u = is_hi ? s_hi[w][a] : s_lo[w][a];
+      v = is_hi ? (u > v ? u : v) : (u < v ? u : v);
     }
+    if (is_hi) rv_atomic_max_f64(bounds + 3 + a, v);
+    else rv_atomic_min_f64(bounds + a, v);
   }
 }
 
@@ -229,6 +244,10 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_knn_cells(const KnnArgs a) {
   if (!a.prm->redo) return;  // the table of the previous round stands
   const T *in = reinterpret_cast<const T *>(a.in);
+  __shared__ unsigned int s_created;
+  if (threadIdx.x == 0) s_created = 0;
+  __syncthreads();
+  unsigned int created = 0;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
     int ix, iy, iz;
@@ -237,31 +256,46 @@ __global__ void __launch_bounds__(256) k_knn_cells(const KnnArgs a) {
     unsigned int h = __umulhi((unsigned int)(cell_hash(key) >> 32), a.cap);
     for (;;) {
       const unsigned long long cur = atomicCAS(&a.cells[h].key, 0ull, key);
-      if (cur == 0) atomicAdd(&a.prm->occupied, 1u);
+      if (cur == 0) ++created;
       if (cur == 0 || cur == key) break;
       if (++h == a.cap) h = 0;
     }
     a.slot_of[i] = h;
     a.rank_of[i] = atomicAdd(&a.cells[h].cnt, 1u);
   }
+  // cells in use, one update per CTA (every request to that word queues at one L2 slice)
+  if (created) atomicAdd(&s_created, created);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_created) atomicAdd(&a.prm->occupied, s_created);
 }
 
+// every used cell gets a range of the cell-sorted arrays: scan inside the CTA, one cursor update per 256 table slots
 __global__ void __launch_bounds__(256) k_knn_alloc(const KnnArgs a) {
-  const int lane = threadIdx.x & 31;
-  const unsigned int stride = gridDim.x * blockDim.x;
-  for (unsigned int h = blockIdx.x * blockDim.x + threadIdx.x; h < a.cap; h += stride) {  // cap % 32 == 0: whole warps
-    const unsigned int c = a.cells[h].cnt;
+  __shared__ unsigned int s_warp[8], s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (unsigned int base = blockIdx.x * 256u; base < a.cap; base += gridDim.x * 256u) {
+    const unsigned int h = base + threadIdx.x;
+    const unsigned int c = h < a.cap ? a.cells[h].cnt : 0u;
     unsigned int incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += up;
     }
-    const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
-    unsigned int base = 0;
-    if (lane == 0 && total) base = atomicAdd(&a.prm->cursor, total);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    a.cells[h].start = base + incl - c;
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int run = 0;
+      for (int w = 0; w < 8; ++w) {
+        const unsigned int t = s_warp[w];
+        s_warp[w] = run;
+        run += t;
+      }
+      s_base = run ? atomicAdd(&a.prm->cursor, run) : 0u;
+    }
+    __syncthreads();
+    if (h < a.cap) a.cells[h].start = s_base + s_warp[warp] + incl - c;
+    __syncthreads();
   }
 }
 
