@@ -743,8 +743,11 @@ static_assert(sizeof(IcpState) == 448, "state layout is read by the host (regist
 // on the way in and writes the moved point back -- the working copy advances in place, arithmetic of k_transform -- and
 // `warm` says corr still holds the previous evaluation's match, whose distance to the moved point is the first bound, so
 // that most cells around the query are rejected by their box without a probe.  The result is the same either way.
+#ifndef RV_NN_SEARCH_OCC
+#define RV_NN_SEARCH_OCC 12  // CTAs of 128 per SM the register budget is held to: the walk hides its loads with warps
+#endif
 template <typename T>
-__global__ void __launch_bounds__(128) k_nn_search(const KnnArgs a, T *__restrict__ q_xyz, long long q_stride, long long nq,
+__global__ void __launch_bounds__(128, RV_NN_SEARCH_OCC) k_nn_search(const KnnArgs a, T *__restrict__ q_xyz, long long q_stride, long long nq,
                                                    double radius2, int *__restrict__ corr, const IcpState *__restrict__ move,
                                                    int warm) {
   if (move && move->done) return;  // device-side ICP loop: the registration has already stopped

@@ -48,6 +48,8 @@ VARIANTS.update({
     "icp_c20_cold": "-DRV_NN_CELL_SPACINGS=2.0 -DRV_NN_WARM=0", "icp_c30_cold": "-DRV_NN_CELL_SPACINGS=3.0 -DRV_NN_WARM=0",
     "icp_c10_cold": "-DRV_NN_CELL_SPACINGS=1.0 -DRV_NN_WARM=0",
     "icp_c25": "-DRV_NN_CELL_SPACINGS=2.5", "icp_c35": "-DRV_NN_CELL_SPACINGS=3.5",
+    "icp_occ9": "-DRV_NN_SEARCH_OCC=9", "icp_occ12": "-DRV_NN_SEARCH_OCC=12", "icp_occ14": "-DRV_NN_SEARCH_OCC=14",
+    "icp_occ16": "-DRV_NN_SEARCH_OCC=16",
     "icp_c30_timing": "-DRV_NN_CELL_SPACINGS=3.0 -DRV_ICP_TIMING",
 })
 
