@@ -427,7 +427,10 @@ __device__ V3 smallest_eigenvector(const double *C) {
 constexpr int kQueryThreads = 128;
 
 template <bool kNormals>
-__global__ void __launch_bounds__(kQueryThreads) k_knn_query(const KnnArgs a) {
+#ifndef RV_KNN_QUERY_OCC
+#define RV_KNN_QUERY_OCC 1
+#endif
+__global__ void __launch_bounds__(kQueryThreads, RV_KNN_QUERY_OCC) k_knn_query(const KnnArgs a) {
   // the sorted candidate lists live in shared memory, [rank][thread]: as per-thread arrays they were local memory, 150 MB of
   // it in flight, and the kernel waited on that (long-scoreboard stalls, 127 MB of DRAM writes for a 6 MB result)
   extern __shared__ __align__(16) unsigned char s_raw[];
