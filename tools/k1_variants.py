@@ -41,6 +41,16 @@ VARIANTS.update({
     "k4_g1_i6_e256x6": "-DRV_VOX_GROUPS=1 -DRV_VOX_INSERT_OCC=6 -DRV_VOX_EMIT_THREADS=256 -DRV_VOX_EMIT_OCC=6",
     "k4_g1_i6_e128x12": "-DRV_VOX_GROUPS=1 -DRV_VOX_INSERT_OCC=6 -DRV_VOX_EMIT_THREADS=128 -DRV_VOX_EMIT_OCC=12",
 })
+# more resident compute warps: 16 warps of 128 pixels on the 2048-pixel tile, or 1024-pixel tiles with more CTAs per SM
+VARIANTS.update({
+    "k1w_base": "",
+    "k1w_cw16_i4_s2_w48": "-DRV_K1_CW=16 -DRV_K1_ITERS=4 -DRV_K1_STAGES=2 -DRV_K1_WARPS_PER_SM=48",
+    "k1w_cw16_i4_s3_w48": "-DRV_K1_CW=16 -DRV_K1_ITERS=4 -DRV_K1_STAGES=3 -DRV_K1_WARPS_PER_SM=48",
+    "k1w_cw8_i4_s2_w48": "-DRV_K1_CW=8 -DRV_K1_ITERS=4 -DRV_K1_STAGES=2 -DRV_K1_WARPS_PER_SM=48",
+    "k1w_cw8_i4_s2_w56": "-DRV_K1_CW=8 -DRV_K1_ITERS=4 -DRV_K1_STAGES=2 -DRV_K1_WARPS_PER_SM=56",
+    "k1w_cw8_i4_s3_w48": "-DRV_K1_CW=8 -DRV_K1_ITERS=4 -DRV_K1_STAGES=3 -DRV_K1_WARPS_PER_SM=48",
+    "k1w_cw4_i8_s2_w40": "-DRV_K1_CW=4 -DRV_K1_ITERS=8 -DRV_K1_STAGES=2 -DRV_K1_WARPS_PER_SM=40",
+})
 # ICP search tunables (tools/icp_sweep.sh): cell size of the nearest-point index in surface spacings, warm-started bound
 VARIANTS.update({
     "icp_c10": "-DRV_NN_CELL_SPACINGS=1.0", "icp_c15": "-DRV_NN_CELL_SPACINGS=1.5", "icp_c20": "-DRV_NN_CELL_SPACINGS=2.0",
