@@ -15,6 +15,9 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > ${O}_bench_r
 timeout 600 python tools/bench_kernels.py > ${O}_bench_kernels.jsonl 2> ${O}_bench_kernels.err
 timeout 300 python tools/k4_probe.py > ${O}_k4_probe.jsonl 2>&1
 timeout 300 python tools/k4_probe.py --voxel 0.02 >> ${O}_k4_probe.jsonl 2>&1
+timeout 300 python tools/icp_probe.py > ${O}_icp_probe.jsonl 2>&1
+timeout 300 python tools/icp_probe.py --host-loop >> ${O}_icp_probe.jsonl 2>&1
+timeout 300 python tools/knn_probe.py > ${O}_knn_probe.jsonl 2>&1
 for c in "bgr unit" "bgr packed8" "nv12 unit" "nv12 packed8" "bgr unit --r-max 0"; do set -- $c; timeout 300 python tools/k1_probe.py --color $1 --colors $2 $3 $4; done > ${O}_k1_probe.jsonl 2>&1
 # ncu passes (never a bench value): launch lists (cold, serialised), warm K4 list, then one full capture per kernel family
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 400 --csv --log-file ${O}_launches_bench_k1.csv \
@@ -27,4 +30,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_de
   python tools/k1_probe.py --color nv12 --colors packed8 --reps 2 > ${O}_ncu_k1_nv12.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_vox|k_transform" -c 12 -f -o ${O}_k34 \
   python tools/k4_probe.py --reps 1 > ${O}_ncu_k34.log 2>&1
+timeout 600 ncu --cache-control none --metrics gpu__time_duration.sum --clock-control none --csv --log-file ${O}_launches_icp_warm.csv \
+  python tools/icp_probe.py --reps 1 > ${O}_ncu_launches_icp.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_nn_search|k_icp|k_knn_query" -c 12 -f -o ${O}_icp \
+  python tools/icp_probe.py --reps 1 > ${O}_ncu_icp.log 2>&1
 echo done
