@@ -34,4 +34,9 @@ timeout 600 ncu --cache-control none --metrics gpu__time_duration.sum --clock-co
   python tools/icp_probe.py --reps 1 > ${O}_ncu_launches_icp.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_nn_search|k_icp|k_knn_query" -c 12 -f -o ${O}_icp \
   python tools/icp_probe.py --reps 1 > ${O}_ncu_icp.log 2>&1
+# gpurun brings back at most 64 MiB: condense the captures here, keep only the headline kernel's report itself
+for r in k1 k1_nv12 k34 icp; do python tools/ncu_summary.py ${O}_$r.ncu-rep > ${O}_${r}_ncu_raw_subset.csv 2>> ${O}_ncu_summary.err; done
+ncu -i ${O}_k1.ncu-rep --page source --csv 2>/dev/null | gzip > ${O}_k1_source.csv.gz
+rm -f ${O}_k1_nv12.ncu-rep ${O}_k34.ncu-rep ${O}_icp.ncu-rep
+du -sh gpurun_out
 echo done
