@@ -436,9 +436,11 @@ __global__ void __launch_bounds__(kQueryThreads, RV_KNN_QUERY_OCC) k_knn_query(c
   extern __shared__ __align__(16) unsigned char s_raw[];
   double *s_best = reinterpret_cast<double *>(s_raw);              // !kNormals: ascending squared distances
   unsigned int *s_bidx = reinterpret_cast<unsigned int *>(s_raw);  // kNormals: sorted positions of the neighbours, nearest first
+  float *s_key = reinterpret_cast<float *>(s_raw) + (size_t)a.k * kQueryThreads;  // kNormals: their squared distances rounded to float32
   const int tid = threadIdx.x;
 #define BEST(t) s_best[(t) * kQueryThreads + tid]
 #define BIDX(t) s_bidx[(t) * kQueryThreads + tid]
+#define FKEY(t) s_key[(t) * kQueryThreads + tid]
   const KnnParams *p = a.prm;
   const int k = a.k;
   const double cell = p->cell;
@@ -456,21 +458,35 @@ __global__ void __launch_bounds__(kQueryThreads, RV_KNN_QUERY_OCC) k_knn_query(c
     };
     auto offer = [&](double d2, unsigned int j) {
       if (kNormals) {
-        // hybrid search = the k nearest among the points closer than the radius: the others need not enter the list.  Only
-        // the sorted positions are kept (4 bytes an entry: four times the resident warps of a distance + index list); the
-        // distance of an entry is recomputed when an insertion has to be placed, by bisection.
-        if (!(d2 < a.radius2) || (m == k && !(d2 < kth))) return;
+        // hybrid search = the k nearest among the points closer than the radius: the others need not enter the list.  An entry
+        // is the sorted position (4 bytes) and the squared distance rounded to float32 (4 bytes).  Rounding is monotonic, so
+        // two different keys order the exact distances the same way; only equal keys need the exact distance, which is
+        // then recomputed from the points.
+        if (!(d2 < a.radius2)) return;
+        const float fd = (float)d2;
+        if (m == k) {
+          const float fk = FKEY(k - 1);
+          if (fd > fk || (fd == fk && !(d2 < dist2_of(BIDX(k - 1))))) return;
+        }
         const int last = m < k ? m : k - 1;  // a full list drops its last entry
         int lo = 0, hi = last;
         while (lo < hi) {  // first entry farther than d2: equal distances stay in arrival order
           const int mid = (lo + hi) >> 1;
-          if (dist2_of(BIDX(mid)) > d2) hi = mid;
+          const float fm = FKEY(mid);
+          bool farther = fm > fd;
+          if (fm == fd) farther = dist2_of(BIDX(mid)) > d2;
+          if (farther) hi = mid;
           else lo = mid + 1;
         }
-        for (int t = last; t > lo; --t) BIDX(t) = BIDX(t - 1);
+        for (int t = last; t > lo; --t) {
+          BIDX(t) = BIDX(t - 1);
+          FKEY(t) = FKEY(t - 1);
+        }
         BIDX(lo) = j;
+        FKEY(lo) = fd;
         if (m < k) ++m;
-        if (m == k) kth = lo == k - 1 ? d2 : dist2_of(BIDX(k - 1));
+        // what prunes cells and ends the walk: an upper bound of the exact k-th distance (one float32 ulp above its key)
+        if (m == k) kth = (double)FKEY(k - 1) * (1.0 + 1.1920928955078125e-7) + 1.5e-45;  // (+ one subnormal step)
       } else if (m < k || d2 < kth) {  // sorted insertion
         int t = m < k ? m : k - 1;
         while (t > 0) {
@@ -581,6 +597,7 @@ __global__ void __launch_bounds__(kQueryThreads, RV_KNN_QUERY_OCC) k_knn_query(c
   }
 #undef BEST
 #undef BIDX
+#undef FKEY
 }
 
 // ---- statistics.  The reference sums in index order (std::accumulate / std::inner_product); a parallel sum differs from
@@ -1136,7 +1153,7 @@ __global__ void __launch_bounds__(kStepThreads) k_icp_finish_step(const double *
 
 template <bool kNormals>
 cudaError_t knn_query_launch(const KnnArgs &a, cudaStream_t st) {
-  const size_t smem = (size_t)a.k * kQueryThreads * (kNormals ? 4 : 8);  // at most 64 KB (k = 64 distances)
+  const size_t smem = (size_t)a.k * kQueryThreads * 8;  // distances, or positions + float32 keys: at most 64 KB (k = 64)
   if (smem > 48 * 1024) {  // opt in per launch: the attribute belongs to the current device's copy of the function
     const cudaError_t e = cudaFuncSetAttribute(k_knn_query<kNormals>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

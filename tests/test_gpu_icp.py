@@ -244,3 +244,36 @@ def test_device_loop_equals_host_loop(rv, O):
             if dtype == "f64":
                 assert np.array_equal(a.correspondence_set, b.correspondence_set)
         assert a.iterations < 50  # converged by the stopping rule, not by the cap
+
+
+def test_device_loop_survives_a_stale_match_buffer(rv, O):
+    """rv_icp_iterate starts every search after the first from the match the buffer holds (the previous evaluation's, by
+    contract).  A caller that breaks the contract -- a buffer of arbitrary integers, some far out of range -- still gets the
+    exact nearest points: the stale entry is only ever a candidate whose distance is measured."""
+    import torch
+    from repas_vision_b200 import _ops
+    moved, tgt, D = _scene(O, seed=41, n_t=6000, n_s=2500)
+    source = rv.PointCloud.from_arrays(moved, None)
+    target = rv.PointCloud.from_arrays(tgt, None)
+    target.estimate_normals(search_param=rv.KDTreeSearchParamHybrid(radius=0.02, max_nn=30))
+    n, nt, dev = len(source), len(target), source.device
+    index = _ops.nn_index_build(target._data, nt, 0.02)
+    scratch = _ops.icp_scratch(dev)
+    results = []
+    rng = np.random.default_rng(3)
+    for garbage in (None, rng.integers(-2**31, 2**31 - 1, n), rng.integers(0, nt, n), np.full(n, nt), np.full(n, -1)):
+        work = source._data.clone()
+        nearest = torch.empty(n, dtype=torch.int32, device=dev)
+        state = _ops.icp_state(dev)
+        _ops.icp_begin(state, np.eye(4), 3, 1e-6, 1e-6, n)
+        _ops.icp_iterate(state, True, 1, work, n, index, target._data, nt, target._normals, 0.02, nearest, scratch)
+        if garbage is not None:
+            nearest.copy_(torch.from_numpy(garbage.astype(np.int64).astype(np.int32)).to(dev))
+        _ops.icp_iterate(state, False, 2, work, n, index, target._data, nt, target._normals, 0.02, nearest, scratch)
+        results.append((state.cpu().numpy().copy(), nearest.cpu().numpy().copy(), work.cpu().numpy().copy()))
+    for st, near, work in results[1:]:
+        assert np.array_equal(st[:40], results[0][0][:40])
+        assert np.array_equal(near, results[0][1]) and np.array_equal(work, results[0][2])
+    # and they are the oracle's nearest points of the final working copy
+    ref, _, _ = O.nearest_correspondences(results[0][2][:3, :n].T.copy(), target.points, 0.02)
+    assert np.array_equal(results[0][1], ref)
