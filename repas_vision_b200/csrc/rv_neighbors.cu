@@ -45,6 +45,9 @@ struct KnnParams {  // written by k_knn_setup, read by the later kernels
 #ifndef RV_NN_CELL_SPACINGS
 #define RV_NN_CELL_SPACINGS 3.0
 #endif
+#ifndef RV_KNN_CELL_FACTOR
+#define RV_KNN_CELL_FACTOR 1.2  // cell edge of a k-nearest search in radii of the disc that holds k points of a surface
+#endif
 #ifndef RV_NN_WARM
 #define RV_NN_WARM 1
 #endif
@@ -185,7 +188,7 @@ __global__ void k_knn_setup(KnnParams *p, long long n, int k, double radius) {
   // nearest neighbours (a disc of ~sqrt(k / pi) spacings) are normally complete after the 27 cells around the query, and no
   // larger than a search radius; a line or a single point degenerate gracefully
   const double spacing = sqrt(a * b / (double)n);
-  double f = 1.2 * sqrt((double)k / 3.141592653589793);
+  double f = RV_KNN_CELL_FACTOR * sqrt((double)k / 3.141592653589793);
   if (f < 2.0) f = 2.0;
   if (k == 1 && radius > 0.0) f = RV_NN_CELL_SPACINGS;  // nearest-point index of ICP: queries sit off the surface
   double s = f * spacing;

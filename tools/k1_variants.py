@@ -60,6 +60,8 @@ VARIANTS.update({
     "icp_c25": "-DRV_NN_CELL_SPACINGS=2.5", "icp_c35": "-DRV_NN_CELL_SPACINGS=3.5",
     "icp_occ9": "-DRV_NN_SEARCH_OCC=9", "icp_occ12": "-DRV_NN_SEARCH_OCC=12", "icp_occ14": "-DRV_NN_SEARCH_OCC=14",
     "icp_occ16": "-DRV_NN_SEARCH_OCC=16",
+    "knn_f09": "-DRV_KNN_CELL_FACTOR=0.9", "knn_f12": "-DRV_KNN_CELL_FACTOR=1.2", "knn_f16": "-DRV_KNN_CELL_FACTOR=1.6",
+    "knn_f20": "-DRV_KNN_CELL_FACTOR=2.0", "knn_f07": "-DRV_KNN_CELL_FACTOR=0.7",
     "knn_q1": "-DRV_KNN_QUERY_OCC=1", "knn_q10": "-DRV_KNN_QUERY_OCC=10", "knn_q12": "-DRV_KNN_QUERY_OCC=12",
     "icp_c30_timing": "-DRV_NN_CELL_SPACINGS=3.0 -DRV_ICP_TIMING",
 })
