@@ -200,7 +200,7 @@ def evaluate_registration(source: PointCloud, target: PointCloud, max_correspond
     return res
 
 
-ICP_STEPS_PER_READBACK = 4  # iterations queued between two looks at the device-side state
+ICP_STEPS_PER_READBACK = 8  # iterations queued between two looks at the device-side state (2 / 4 / 8 / 16: 1.17 / 1.15 / 1.11 / 1.19 ms on the 349 k-point case)
 
 
 def _icp_on_device(m: _Matcher, source: PointCloud, transformation: np.ndarray, crit: ICPConvergenceCriteria) -> RegistrationResult:

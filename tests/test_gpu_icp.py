@@ -234,7 +234,8 @@ def test_device_loop_equals_host_loop(rv, O):
         source = rv.PointCloud.from_arrays(moved.astype(np.float32) if dtype == "f32" else moved, None, dtype=dtype)
         tg = rv.PointCloud.from_arrays(tgt.astype(np.float32) if dtype == "f32" else tgt, None, dtype=dtype)
         tg._normals = target._normals
-        for cap, T0 in ((0, np.eye(4)), (1, np.eye(4)), (3, init), (4, np.eye(4)), (5, init), (50, np.eye(4)), (50, init)):
+        for cap, T0 in ((0, np.eye(4)), (1, np.eye(4)), (3, init), (4, np.eye(4)), (5, init), (8, np.eye(4)), (9, init), (50, np.eye(4)),
+                        (50, init)):
             crit = rv.ICPConvergenceCriteria(max_iteration=cap, relative_fitness=1e-6, relative_rmse=1e-6)
             a = rv.registration_icp(source, tg, 0.02, T0, est, crit)
             b = rv.registration_icp(source, tg, 0.02, T0, est, crit, device_loop=False)

@@ -20,8 +20,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--host-loop", action="store_true")
+    ap.add_argument("--steps-per-readback", type=int, default=0, help="override registration.ICP_STEPS_PER_READBACK")
     ap.add_argument("--dump-state", action="store_true", help="print the reserved words of the device loop's state (timing builds)")
     a = ap.parse_args()
+    if a.steps_per_readback:
+        rv.registration.ICP_STEPS_PER_READBACK = a.steps_per_readback
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     gen = torch.Generator(device=dev).manual_seed(7)
@@ -62,7 +65,7 @@ def main():
         ts.append(e0.elapsed_time(e1))
     ms = float(np.median(ts))
     print(json.dumps({"source_points": len(src), "target_points": len(kept), "iterations": reg.iterations, "fitness": reg.fitness,
-                      "ms": ms, "ms_per_iteration": ms / (reg.iterations + 1), "device_loop": not a.host_loop}))
+                      "ms": ms, "ms_per_iteration": ms / (reg.iterations + 1), "device_loop": not a.host_loop, "steps_per_readback": rv.registration.ICP_STEPS_PER_READBACK}))
 
 
 if __name__ == "__main__":
