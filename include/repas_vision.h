@@ -267,10 +267,10 @@ int rv_transform_merge(rv_ctx *ctx, int n_views, const void *const *d_in, const 
  *  d_keys       [3, out_capacity] int32 voxel indices, or NULL
  *  d_counts_out [out_capacity] int32 points per voxel, or NULL
  *  d_m          one int64: number of voxels (true number even if > out_capacity)
- *  d_ws         rv_voxel_workspace_bytes(n) bytes, 64-B aligned: 1.5 n eight-byte hash keys + 4-byte chain heads, one
- *               8-byte list entry and one 4-byte link per point, one bit per point of run heads, a small pool for voxels
- *               with very long chains (about 34 bytes per point) and room for a fusion's transformed coordinates (24 bytes
- *               per point, untouched by this call); keys and chain heads are initialised by the call
+ *  d_ws         rv_voxel_workspace_bytes(n) bytes, 64-B aligned: 1.5 n sixteen-byte table slots (hash key + chain head),
+ *               one 8-byte list entry and one 4-byte slot index per point, one bit per point of run heads, a small pool
+ *               for voxels with very long chains (about 44 bytes per point) and room for a fusion's transformed
+ *               coordinates (24 bytes per point, untouched by this call); the table is initialised by the call
  * Each voxel index must fit 21 bits (extent/voxel < 2^21); otherwise d_m is set to -1.  n < 2^31.
  * Voxels made of at most eight runs of consecutive points (practically all of a 5 mm grid over camera clouds) are summed
  * point by point in index order in float64: their means equal the sequential Open3D loop bit for bit; voxels of more runs

@@ -155,7 +155,7 @@ __global__ void k_stats_init(double *b) {
 // --------------------------------------------------------------------- voxel grid
 // Hash grid without per-point records (round 1 wrote a 64-byte record per run of points and read it back twice: 6.1 x the
 // algorithmic DRAM traffic).  Workspace:
-//   [header 256 B][per-part counters 2048 x 8 B][keys: cap x 8 B][chain: cap x 4 B][list: n x 8 B][next: n x 4 B]
+//   [header 256 B][per-part counters 2048 x 8 B][table: cap x 16 B {key, chain head}][list: n x 8 B][joiner slots: n x 4 B]
 //   [head masks: ceil(n / 32) x 4 B][long-voxel pool: (n / 9 + 1) x 64 B][fusion only: transformed xyz, n x 24 B]
 // k_vox_insert  reads the coordinates only (RV_VOX_GROUPS 32-point groups per warp and step, their loads and first-probe
 //               compare-and-swaps issued before anything is consumed).  Points arrive in pixel order, so consecutive points
@@ -215,6 +215,12 @@ struct __align__(64) VoxLong {
 };
 static_assert(sizeof(VoxLong) == 64, "pool record layout");
 
+struct __align__(16) VoxSlot {
+  unsigned long long key;  // 0 = empty, else packed(ix,iy,iz) + 1
+  unsigned int chain;      // 0 = no joiner yet; list position + 1 of the most recent joiner; kVoxLongTag | pool index once long
+  unsigned int pad;
+};
+
 struct VoxArgs {
   VoxView view[kVoxViews];
   int n_views, identity, has_color;
@@ -222,10 +228,10 @@ struct VoxArgs {
   double voxel, rvoxel;
   const double *bounds;  // device
   VoxHeader *hdr;
-  unsigned long long *keys;  // 0 = empty, else packed(ix,iy,iz) + 1
-  unsigned int *chain;       // per slot: list position of the most recent joiner, kVoxNil = none, tag | pool index once long
-  uint2 *list;               // (point index, slot) of every head; part p owns list[p * span, ...)
-  unsigned int *next;        // per list position of a joiner: the joiner linked before it
+  VoxSlot *slots;            // the table: key and chain head of a voxel in one 16-byte record (one sector for both)
+  uint2 *list;               // part p owns list[p * span, ...): creators (point index, slot) from the front, joiners
+                             // (point index, list position of the joiner linked before it or kVoxNil) from the back
+  unsigned int *jslot;       // per list position of a joiner: its slot (read by k_vox_long only)
   unsigned int *headmask;    // per 32-point group: bit l set = point l starts a run
   VoxLong *pool;
   void *mxyz;    // fusion only: the transformed coordinates (three planes of n, the cloud's element type), written once by the
@@ -397,7 +403,7 @@ __global__ void __launch_bounds__(256, RV_VOX_INSERT_OCC) k_vox_insert(const Vox
       cur[g] = 0;
       if (lead[g]) {
         h[g] = __umulhi((unsigned int)(vox_hash(key[g]) >> 32), a.cap);  // uniform over [0, cap)
-        cur[g] = atomicCAS(a.keys + h[g], 0ull, key[g]);                   // the table is at most two thirds full: usually empty
+        cur[g] = atomicCAS(&a.slots[h[g]].key, 0ull, key[g]);             // the table is at most two thirds full: usually empty
       }
     }
 #pragma unroll
@@ -406,7 +412,7 @@ __global__ void __launch_bounds__(256, RV_VOX_INSERT_OCC) k_vox_insert(const Vox
       if (lead[g]) {
         while (cur[g] != 0ull && cur[g] != key[g]) {  // another voxel's slot: linear probing
           if (++h[g] == a.cap) h[g] = 0;
-          cur[g] = atomicCAS(a.keys + h[g], 0ull, key[g]);
+          cur[g] = atomicCAS(&a.slots[h[g]].key, 0ull, key[g]);
         }
         created = cur[g] == 0ull;
       }
@@ -425,8 +431,9 @@ __global__ void __launch_bounds__(256, RV_VOX_INSERT_OCC) k_vox_insert(const Vox
         a.list[p0 + cbase + __popc(cb & lt)] = make_uint2(i32, h[g]);
       } else if (lead[g]) {
         const unsigned int pos = (unsigned int)(p1 - 1 - (long long)(jbase + __popc(jb & lt)));
-        a.list[pos] = make_uint2(i32, h[g]);
-        a.next[pos] = atomicExch(a.chain + h[g], pos);  // link behind whoever joined this voxel before
+        const unsigned int before = atomicExch(&a.slots[h[g]].chain, pos + 1u);  // link behind whoever joined this voxel before
+        a.list[pos] = make_uint2(i32, before ? before - 1u : kVoxNil);
+        a.jslot[pos] = h[g];
       }
     }
   }
@@ -534,13 +541,16 @@ __global__ void __launch_bounds__(kVoxEmitThreads, RV_VOX_EMIT_OCC) k_vox_emit(c
     // points are added in index order (the order of Open3D's loop); whatever a longer chain holds follows in chain order
     unsigned int idx[8];
     idx[0] = me.x;
-    unsigned int link = a.chain[me.y];
+    const uint4 slot = *reinterpret_cast<const uint4 *>(a.slots + me.y);  // key and chain head in one load
+    const unsigned long long key = ((unsigned long long)slot.y << 32) | slot.x;
+    unsigned int link = slot.z ? slot.z - 1u : kVoxNil;
 #pragma unroll
     for (int q = 1; q < 8; ++q) {
       idx[q] = kVoxNil;
       if (link != kVoxNil) {
-        idx[q] = a.list[link].x;
-        link = a.next[link];
+        const uint2 e = a.list[link];  // (point, the joiner before it)
+        idx[q] = e.x;
+        link = e.y;
       }
     }
 #define RV_CX(i, j)                                     \
@@ -560,7 +570,6 @@ __global__ void __launch_bounds__(kVoxEmitThreads, RV_VOX_EMIT_OCC) k_vox_emit(c
       RV_CX(3, 4)
     }
 #undef RV_CX
-    const unsigned long long key = a.keys[me.y];
     // pool slots for the long voxels of this warp step: one atomic per warp (a coarse grid makes every voxel long, and
     // same-address atomics serialise)
     const bool is_long = link != kVoxNil;
@@ -575,7 +584,9 @@ __global__ void __launch_bounds__(kVoxEmitThreads, RV_VOX_EMIT_OCC) k_vox_emit(c
     if (is_long) {
       // more than eight runs: hand the voxel to the atomic path (its joiners add themselves in parallel in k_vox_long).
       // (Letting the thread gather runs 9..16 itself, so that a fine grid has no long voxel and k_vox_long returns at once
-      // instead of walking the joiners for 10 us, made this kernel 29 us slower: 62 -> 91 us.)
+      // instead of walking the joiners for 10 us, made this kernel 29 us slower: 62 -> 91 us.  So did gathering all points
+      // of a voxel of up to four points in one go -- every load in flight together, added in index order afterwards --:
+      // the 48-80 registers that takes cost more resident warps than the shorter chain gives back, 146-163 vs 132 us.)
       const unsigned int q = qbase + __popc(lm & rv_lanemask_lt());
       VoxLong *rec = a.pool + q;
       rec->key = key;
@@ -588,7 +599,7 @@ __global__ void __launch_bounds__(kVoxEmitThreads, RV_VOX_EMIT_OCC) k_vox_emit(c
       rec->count = own.count;
 #pragma unroll
       for (int c = 0; c < 6; ++c) rec->sum[c] = own.s[c];
-      a.chain[me.y] = kVoxLongTag | q;
+      a.slots[me.y].chain = kVoxLongTag | q;
       continue;
     }
     VoxSum acc;
@@ -611,9 +622,10 @@ __global__ void __launch_bounds__(256) k_vox_long(const VoxArgs a, int n_parts) 
     const long long p1 = p0 + a.span < a.n ? p0 + a.span : a.n;
     const unsigned int joiners = a.parts[p].y;
     for (unsigned int j = threadIdx.x; j < joiners; j += blockDim.x) {
-      const uint2 e = a.list[p1 - 1 - (long long)j];
-      const unsigned int v = a.chain[e.y];
-      if (v == kVoxNil || !(v & kVoxLongTag)) continue;
+      const long long at = p1 - 1 - (long long)j;
+      const uint2 e = a.list[at];
+      const unsigned int v = a.slots[a.jslot[at]].chain;
+      if (!(v & kVoxLongTag)) continue;
       VoxSum s;
 #pragma unroll
       for (int c = 0; c < 6; ++c) s.s[c] = 0.0;
@@ -651,19 +663,17 @@ unsigned long long vox_capacity(long long n) {  // 1.5 slots per point, a multip
 size_t vox_align(size_t b) { return (b + 255) & ~(size_t)255; }
 
 struct VoxLayout {
-  size_t keys, chain, list, next, masks, pool, mxyz, total;
+  size_t slots, list, jslot, masks, pool, mxyz, total;
 };
 VoxLayout vox_layout(long long n) {
   VoxLayout L;
   const unsigned long long cap = vox_capacity(n);
   size_t off = kVoxHead;
-  L.keys = off;
-  off += vox_align((size_t)cap * 8);
-  L.chain = off;
-  off += vox_align((size_t)cap * 4);
+  L.slots = off;
+  off += vox_align((size_t)cap * sizeof(VoxSlot));
   L.list = off;
   off += vox_align((size_t)n * 8);
-  L.next = off;
+  L.jslot = off;
   off += vox_align((size_t)n * 4);
   L.masks = off;
   off += vox_align((size_t)((n + 31) / 32) * 4);
@@ -898,17 +908,15 @@ static int vox_run_all(rv_ctx *ctx, const char *who, int n_views, const void *co
   a.rvoxel = 1.0 / voxel_size;
   a.hdr = reinterpret_cast<VoxHeader *>(w);
   a.parts = reinterpret_cast<uint2 *>(w + 256);
-  a.keys = reinterpret_cast<unsigned long long *>(w + L.keys);
-  a.chain = reinterpret_cast<unsigned int *>(w + L.chain);
+  a.slots = reinterpret_cast<VoxSlot *>(w + L.slots);
   a.list = reinterpret_cast<uint2 *>(w + L.list);
-  a.next = reinterpret_cast<unsigned int *>(w + L.next);
+  a.jslot = reinterpret_cast<unsigned int *>(w + L.jslot);
   a.headmask = reinterpret_cast<unsigned int *>(w + L.masks);
   a.pool = reinterpret_cast<VoxLong *>(w + L.pool);
   a.mxyz = a.identity ? nullptr : (void *)(w + L.mxyz);
   a.cap = (unsigned int)cap;
-  // header, part counters and keys are cleared, the chain heads set to "none"; nothing else needs initialising
-  RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, L.keys + (size_t)cap * 8, st));
-  RV_CUDA(ctx, cudaMemsetAsync(w + L.chain, 0xff, (size_t)cap * 4, st));
+  // header, part counters and the table (empty keys, no joiners) are cleared; nothing else needs initialising
+  RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, L.slots + (size_t)cap * sizeof(VoxSlot), st));
   const double *bounds = d_bounds;
   if (!bounds) {
     k_bounds_init<<<1, 32, 0, st>>>(a.hdr->bounds);
