@@ -8,7 +8,7 @@ There is no CPU fallback: compute entry points raise RuntimeError without the li
 from . import _lib
 from .calibration import (Camera, load_camera, load_color_intrinsics, load_extrinsics, load_intrinsics,
                           load_intrinsics_json, load_transform_matrix, read_depth_to_color_extrinsics, scale_intrinsics)
-from .cloud import (CloudBatch, KDTreeSearchParamHybrid, PointCloud, create_from_rgbd_image, create_masked_pointcloud, depth_to_meters,
+from .cloud import (AxisAlignedBoundingBox, CloudBatch, KDTreeSearchParamHybrid, PointCloud, create_from_rgbd_image, create_masked_pointcloud, depth_to_meters,
                     deproject_batch, deproject_pixel_to_point, fuse_views, get_depth_at_pixel, median_depth_windows,
                     merge, nv12_to_bgr, register_depth_to_color)
 from .ply import read_point_cloud, write_point_cloud

@@ -19,6 +19,8 @@ shapes, moves buffers and mirrors the reference's argument meaning and error beh
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 import torch
 
@@ -311,6 +313,40 @@ class PointCloud:
         self._normals = normals
         return self
 
+    def rotate(self, R, center=None) -> "PointCloud":
+        """Open3D PointCloud.rotate (mpa_icp.py:411, mpa_final_view_with_export.py:412 on the sampled CAD cloud):
+        p = R (p - center) + center, normals n = R n; `center` defaults to the cloud's centre.  Two K3 passes, in that
+        order, so every operation rounds as written.  In place, returns self."""
+        R = np.asarray(R, dtype=np.float64)
+        if R.shape != (3, 3):
+            raise ValueError(f"Expected 3x3 matrix, got shape {R.shape}")
+        c = self.get_center() if center is None else np.asarray(center, dtype=np.float64).reshape(3)
+        if np.any(c != 0.0):
+            self.translate(-c)
+        T = np.eye(4)
+        T[:3, :3] = R
+        T[:3, 3] = c
+        return self.transform(T)  # (rotates the normals by R as Open3D does)
+
+    @staticmethod
+    def get_rotation_matrix_from_xyz(rotation) -> np.ndarray:
+        """Open3D Geometry3D.get_rotation_matrix_from_xyz: Rx(a) Ry(b) Rz(c) for rotation = (a, b, c) in radians."""
+        a, b, c = (float(v) for v in np.asarray(rotation, dtype=np.float64).reshape(3))
+        ca, sa, cb, sb, cc, sc = math.cos(a), math.sin(a), math.cos(b), math.sin(b), math.cos(c), math.sin(c)
+        Rx = np.array([[1, 0, 0], [0, ca, -sa], [0, sa, ca]])
+        Ry = np.array([[cb, 0, sb], [0, 1, 0], [-sb, 0, cb]])
+        Rz = np.array([[cc, -sc, 0], [sc, cc, 0], [0, 0, 1]])
+        return Rx @ Ry @ Rz
+
+    def get_axis_aligned_bounding_box(self) -> "AxisAlignedBoundingBox":
+        """Open3D PointCloud.get_axis_aligned_bounding_box (one reduction kernel, one read-back)."""
+        st = _ops.cloud_stats(self._data, self._n) if self._n else np.zeros(9)
+        return AxisAlignedBoundingBox(st[0:3].copy(), st[3:6].copy())
+
+    def crop(self, bounding_box: "AxisAlignedBoundingBox") -> "PointCloud":
+        """Open3D PointCloud.crop with an axis-aligned box: the points inside it, bounds included."""
+        return self.crop_aabb(bounding_box.min_bound, bounding_box.max_bound)
+
     def get_center(self) -> np.ndarray:
         """Mean of the points (zeros for an empty cloud)."""
         return _ops.cloud_stats(self._data, self._n)[6:9] / self._n if self._n else np.zeros(3)
@@ -365,6 +401,35 @@ class PointCloud:
     def crop_aabb(self, min_bound, max_bound) -> "PointCloud":
         """keep min_bound <= p <= max_bound per axis, inclusive."""
         return self._filtered(aabb=(np.asarray(min_bound, dtype=np.float64), np.asarray(max_bound, dtype=np.float64)))
+
+
+class AxisAlignedBoundingBox:
+    """o3d.geometry.AxisAlignedBoundingBox as the scripts use it: the two corners and what follows from them."""
+
+    def __init__(self, min_bound, max_bound):
+        self.min_bound = np.asarray(min_bound, dtype=np.float64).reshape(3)
+        self.max_bound = np.asarray(max_bound, dtype=np.float64).reshape(3)
+
+    def get_min_bound(self) -> np.ndarray:
+        return self.min_bound
+
+    def get_max_bound(self) -> np.ndarray:
+        return self.max_bound
+
+    def get_center(self) -> np.ndarray:
+        return (self.min_bound + self.max_bound) * 0.5
+
+    def get_extent(self) -> np.ndarray:
+        return self.max_bound - self.min_bound
+
+    def get_max_extent(self) -> float:
+        return float(self.get_extent().max())
+
+    def volume(self) -> float:
+        return float(np.prod(self.get_extent()))
+
+    def __repr__(self):
+        return f"AxisAlignedBoundingBox: min: {tuple(self.min_bound)}, max: {tuple(self.max_bound)}"
 
 
 def merge(clouds) -> PointCloud:

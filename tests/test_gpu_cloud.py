@@ -698,3 +698,41 @@ def test_transform_matches_the_reference_point_form(rv, golden):
         got32 = rv.PointCloud.from_arrays(P.astype(np.float32), None, dtype="f32").transform(T).points
         ref32 = np.stack([T[:3, :3] @ p + T[:3, 3] for p in P.astype(np.float32).astype(np.float64)])
         assert np.abs(got32 - ref32).max() <= 4e-7  # float32 spacing at |coordinate| <= 4 m
+
+
+def test_rotate_bounding_box_and_crop_like_open3d(rv):
+    """PointCloud.rotate (R (p - c) + c, normals by R), get_axis_aligned_bounding_box, crop and get_rotation_matrix_from_xyz
+    as the CAD-placement scripts call them (mpa_icp.py:95-96,411; mpa_final_view_with_export.py:412)."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(12)
+    P = rng.uniform(-1.0, 1.0, (5000, 3)) + (0.2, -0.1, 1.5)
+    C = rng.uniform(0.0, 1.0, (5000, 3))
+    ang = (0.3, -0.7, 1.1)
+    R = rv.PointCloud.get_rotation_matrix_from_xyz(ang)
+    assert np.allclose(R, Rotation.from_euler("XYZ", ang).as_matrix(), atol=1e-15)  # Rx Ry Rz
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-15)
+    c = np.array([0.1, 0.2, 1.4])
+    pc = rv.PointCloud.from_arrays(P, C)
+    pc.estimate_normals(rv.KDTreeSearchParamHybrid(0.2, 20))
+    N = pc.normals.copy()
+    assert pc.rotate(R, center=c) is pc
+    ref = ((P - c) @ R.T) + c
+    assert np.allclose(pc.points, ref, rtol=0, atol=1e-15)
+    # the same operations in the same order: translate, then ((R0 x + R1 y) + R2 z) + c
+    d = P - c
+    exact = np.stack([((R[i, 0] * d[:, 0] + R[i, 1] * d[:, 1]) + R[i, 2] * d[:, 2]) + c[i] for i in range(3)], axis=1)
+    assert np.array_equal(pc.points, exact)
+    assert np.allclose(pc.normals, N @ R.T, atol=1e-15) and np.array_equal(pc.colors, C)
+    # default centre: the cloud's own centre stays where it is
+    pc2 = rv.PointCloud.from_arrays(P, None)
+    before = pc2.get_center()
+    pc2.rotate(R)
+    assert np.allclose(pc2.get_center(), before, atol=1e-12)
+    box = pc2.get_axis_aligned_bounding_box()
+    assert np.array_equal(box.min_bound, pc2.points.min(axis=0)) and np.array_equal(box.get_max_bound(), pc2.points.max(axis=0))
+    assert np.allclose(box.get_center(), (box.min_bound + box.max_bound) / 2) and box.volume() > 0
+    small = rv.AxisAlignedBoundingBox(box.get_center() - 0.3, box.get_center() + 0.3)
+    inside = pc2.crop(small)
+    Q = pc2.points
+    keep = np.all((Q >= small.min_bound) & (Q <= small.max_bound), axis=1)
+    assert np.array_equal(inside.points, Q[keep]) and 0 < keep.sum() < len(Q)
