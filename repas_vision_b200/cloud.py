@@ -151,11 +151,47 @@ class PointCloud:
         """(N,3) float64 like np.asarray(pcd.points): one device->host copy per plane, transposed on the host."""
         return _ops.planes_to_host(self._data, 0, 3, self._n)
 
+    @points.setter
+    def points(self, value) -> None:
+        """`pcd.points = o3d.utility.Vector3dVector(pts)` (create_masked_ply.py:103): a new coordinate vector.  Colours and
+        normals stay only when they still have one row per point (Open3D keeps them as separate vectors; has_colors() /
+        has_normals() are false there as well when the lengths differ)."""
+        dt = self._data.dtype
+        p = _ops.to_device(np.asarray(value) if not isinstance(value, torch.Tensor) else value, self.device, dt)
+        if p.dim() != 2 or p.shape[1] != 3:
+            raise ValueError("points must have shape (N, 3)")
+        n = int(p.shape[0])
+        keep_color = self._has_color and n == self._n and n > 0
+        data = torch.empty((6 if keep_color else 3, max(n, 1)), dtype=dt, device=self.device)
+        data[:3, :n] = p.t()
+        if keep_color:
+            data[3:6, :n] = self._data[3:6, :n]
+        if self._normals is not None and n != self._n:
+            self._normals = None
+        self._data, self._n, self._has_color = data, n, keep_color
+
     @property
     def colors(self) -> np.ndarray:
         if not self._has_color:
             return np.zeros((0, 3))
         return _ops.planes_to_host(self._data, 3, 3, self._n)
+
+    @colors.setter
+    def colors(self, value) -> None:
+        """`pcd.colors = o3d.utility.Vector3dVector(rgb01)` (create_masked_ply.py:104): one unit-RGB row per point; an empty
+        vector removes the colours."""
+        c = _ops.to_device(np.asarray(value) if not isinstance(value, torch.Tensor) else value, self.device, self._data.dtype)
+        if c.numel() == 0:
+            self._data, self._has_color = self._data[:3].contiguous(), False
+            return
+        if c.dim() != 2 or c.shape[1] != 3 or int(c.shape[0]) != self._n:
+            raise ValueError("colors must have shape (N, 3) with one row per point")
+        if self._data.shape[0] < 6:
+            data = torch.empty((6, self._data.shape[1]), dtype=self._data.dtype, device=self.device)
+            data[:3] = self._data[:3]
+            self._data = data
+        self._data[3:6, :self._n] = c.t()
+        self._has_color = True
 
     def has_colors(self) -> bool:
         return self._has_color and self._n > 0
@@ -241,6 +277,17 @@ class PointCloud:
     @property
     def normals(self) -> np.ndarray:
         return self._normals[:, :self._n].t().cpu().numpy() if self._normals is not None else np.zeros((0, 3))
+
+    @normals.setter
+    def normals(self, value) -> None:
+        """`pcd.normals = o3d.utility.Vector3dVector(n)`: one row per point (float64 on the device), empty = none."""
+        v = _ops.to_device(np.asarray(value) if not isinstance(value, torch.Tensor) else value, self.device, torch.float64)
+        if v.numel() == 0:
+            self._normals = None
+            return
+        if v.dim() != 2 or v.shape[1] != 3 or int(v.shape[0]) != self._n:
+            raise ValueError("normals must have shape (N, 3) with one row per point")
+        self._normals = v.t().contiguous()
 
     def estimate_normals(self, search_param=None, fast_normal_computation: bool = True) -> "PointCloud":
         """Open3D PointCloud.estimate_normals with a KDTreeSearchParamHybrid(radius, max_nn) neighbourhood (the only form

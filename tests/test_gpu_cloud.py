@@ -736,3 +736,55 @@ def test_rotate_bounding_box_and_crop_like_open3d(rv):
     Q = pc2.points
     keep = np.all((Q >= small.min_bound) & (Q <= small.max_bound), axis=1)
     assert np.array_equal(inside.points, Q[keep]) and 0 < keep.sum() < len(Q)
+
+
+def test_open3d_shaped_namespace_builds_the_same_clouds(rv, tmp_path):
+    """`from repas_vision_b200 import o3d_compat as o3d`: the reference's way of building and using a cloud
+    (create_masked_ply.py:102-104,168-177; mpa_icp_export.py:174-197) gives what the package's own entry points give."""
+    from repas_vision_b200 import o3d_compat as o3d
+    from synth import bumpy_surface
+    rng = np.random.default_rng(8)
+    P = bumpy_surface(rng, 6000)
+    C = rng.uniform(0.0, 1.0, (6000, 3))
+    pcd = o3d.geometry.PointCloud()
+    assert pcd.is_empty() and not pcd.has_colors() and np.asarray(pcd.points).shape == (0, 3)
+    pcd.points = o3d.utility.Vector3dVector(P)
+    pcd.colors = o3d.utility.Vector3dVector(C)
+    ref = rv.PointCloud.from_arrays(P, C)
+    assert len(pcd) == 6000 and pcd.has_colors()
+    assert np.array_equal(np.asarray(pcd.points), P) and np.array_equal(np.asarray(pcd.colors), C)
+    with pytest.raises(ValueError):
+        pcd.colors = o3d.utility.Vector3dVector(C[:10])
+    with pytest.raises(RuntimeError):
+        o3d.utility.Vector3dVector(np.zeros((4, 2)))
+    # the same pipeline through both spellings
+    a, b = pcd.voxel_down_sample(0.01), ref.voxel_down_sample(0.01)
+    ka, kb = np.lexsort(a.points.T), np.lexsort(b.points.T)
+    # (voxels of more than eight runs are summed with float64 atomics: equal to rounding, not to the bit)
+    assert len(a) == len(b) and np.allclose(a.points[ka], b.points[kb], rtol=0, atol=1e-13) and np.allclose(a.colors[ka], b.colors[kb], rtol=0, atol=1e-13)
+    a2, ind = a.remove_statistical_outlier(nb_neighbors=20, std_ratio=2.0)
+    a2.estimate_normals(search_param=o3d.geometry.KDTreeSearchParamHybrid(radius=0.02, max_nn=30))
+    a2.orient_normals_towards_camera_location(np.array([0.0, 0.0, 0.0]))
+    assert a2.has_normals() and np.asarray(a2.normals).shape == (len(a2), 3)
+    D = rv.registration.vector6d_to_matrix4d([0.01, -0.01, 0.02, 0.002, -0.001, 0.003])
+    src = o3d.geometry.PointCloud()
+    src.points = o3d.utility.Vector3dVector((np.asarray(a2.points)[::2] @ D[:3, :3].T) + D[:3, 3])
+    reg = o3d.pipelines.registration.registration_icp(
+        src, a2, 0.02, np.eye(4), o3d.pipelines.registration.TransformationEstimationPointToPlane(),
+        o3d.pipelines.registration.ICPConvergenceCriteria(max_iteration=50, relative_fitness=1e-6, relative_rmse=1e-6))
+    assert reg.fitness > 0.99 and np.allclose(reg.transformation @ D, np.eye(4), atol=1e-6)
+    # points assigned again with the same length keep colours and normals; another length drops them
+    n0 = np.asarray(a2.normals).copy()
+    a2.points = o3d.utility.Vector3dVector(np.asarray(a2.points) + 1.0)
+    assert a2.has_colors() and np.array_equal(np.asarray(a2.normals), n0)
+    a2.normals = o3d.utility.Vector3dVector(-n0)
+    assert np.array_equal(np.asarray(a2.normals), -n0)
+    a2.points = o3d.utility.Vector3dVector(P[:100])
+    assert len(a2) == 100 and not a2.has_colors() and not a2.has_normals()
+    # PLY through the namespace
+    path = tmp_path / "cloud.ply"
+    assert o3d.io.write_point_cloud(str(path), pcd, write_ascii=False, compressed=True)
+    back = o3d.io.read_point_cloud(str(path))
+    assert np.array_equal(np.asarray(back.points), P) and np.array_equal(np.asarray(back.colors), np.round(C * 255.0) / 255.0)
+    with pytest.raises(AttributeError, match="outside the point-cloud path"):
+        o3d.geometry.TriangleMesh
