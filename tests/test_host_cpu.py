@@ -310,3 +310,23 @@ def test_depth_dtype_policy():
     assert _depth_kind(torch.from_numpy(f64))[0] == "f32"
     with pytest.raises(RuntimeError):
         _depth_kind(torch.from_numpy(u.astype(np.int32)))
+
+
+def test_open3d_shaped_namespace_lists_the_path_and_names_what_it_leaves_out():
+    """o3d_compat imports without a GPU; the vector constructors validate shapes like Open3D's; everything outside the
+    point-cloud path raises an AttributeError that says so."""
+    from repas_vision_b200 import o3d_compat as o3d
+    import repas_vision_b200 as rv
+    assert o3d.geometry.PointCloud is rv.PointCloud and o3d.io.read_point_cloud is rv.read_point_cloud
+    assert o3d.pipelines.registration.registration_icp is rv.registration_icp
+    v = o3d.utility.Vector3dVector([[1, 2, 3], [4, 5, 6]])
+    assert v.dtype == np.float64 and v.shape == (2, 3) and o3d.utility.Vector3dVector().shape == (0, 3)
+    assert o3d.utility.IntVector([1, 2]).dtype == np.int32 and o3d.utility.DoubleVector([0.5]).tolist() == [0.5]
+    with pytest.raises(RuntimeError):
+        o3d.utility.Vector3dVector(np.zeros((3, 4)))
+    for expr in ("o3d.visualization", "o3d.geometry.TriangleMesh", "o3d.pipelines.registration.compute_fpfh_feature",
+                 "o3d.io.read_triangle_mesh"):
+        with pytest.raises(AttributeError, match="outside the point-cloud path"):
+            eval(expr)
+    R = o3d.geometry.get_rotation_matrix_from_xyz((0.0, 0.0, np.pi / 2))
+    assert np.allclose(R, [[0, -1, 0], [1, 0, 0], [0, 0, 1]], atol=1e-15)
