@@ -267,7 +267,8 @@ int rv_transform_merge(rv_ctx *ctx, int n_views, const void *const *d_in, const 
  *  d_keys       [3, out_capacity] int32 voxel indices, or NULL
  *  d_counts_out [out_capacity] int32 points per voxel, or NULL
  *  d_m          one int64: number of voxels (true number even if > out_capacity)
- *  d_ws         rv_voxel_workspace_bytes(n) bytes, 64-B aligned: 1.5 n sixteen-byte table slots (hash key + chain head),
+ *  d_ws         rv_voxel_workspace_bytes(n) bytes, 64-B aligned: 1.5 n sixteen-byte table slots (hash key + chain head)
+ *               and one bit per slot,
  *               one 8-byte list entry and one 4-byte slot index per point, one bit per point of run heads, a small pool
  *               for voxels with very long chains (about 44 bytes per point) and room for a fusion's transformed
  *               coordinates (24 bytes per point, untouched by this call); the table is initialised by the call

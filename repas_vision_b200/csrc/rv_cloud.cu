@@ -155,7 +155,7 @@ __global__ void k_stats_init(double *b) {
 // --------------------------------------------------------------------- voxel grid
 // Hash grid without per-point records (round 1 wrote a 64-byte record per run of points and read it back twice: 6.1 x the
 // algorithmic DRAM traffic).  Workspace:
-//   [header 256 B][per-part counters 2048 x 8 B][table: cap x 16 B {key, chain head}][list: n x 8 B][joiner slots: n x 4 B]
+//   [header 256 B][per-part counters 2048 x 8 B][long-voxel bits: cap / 8 B][table: cap x 16 B {key, chain head}][list: n x 8 B][joiner slots: n x 4 B]
 //   [head masks: ceil(n / 32) x 4 B][long-voxel pool: (n / 9 + 1) x 64 B][fusion only: transformed xyz, n x 24 B]
 // k_vox_insert  reads the coordinates only (RV_VOX_GROUPS 32-point groups per warp and step, their loads and first-probe
 //               compare-and-swaps issued before anything is consumed).  Points arrive in pixel order, so consecutive points
@@ -232,6 +232,8 @@ struct VoxArgs {
   uint2 *list;               // part p owns list[p * span, ...): creators (point index, slot) from the front, joiners
                              // (point index, list position of the joiner linked before it or kVoxNil) from the back
   unsigned int *jslot;       // per list position of a joiner: its slot (read by k_vox_long only)
+  unsigned int *longmap;     // one bit per slot: the voxel went to the pool (k_vox_long's joiners look here first: 0.3 MB
+                             // that stays in the L2, where the table is 41 MB of random reads)
   unsigned int *headmask;    // per 32-point group: bit l set = point l starts a run
   VoxLong *pool;
   void *mxyz;    // fusion only: the transformed coordinates (three planes of n, the cloud's element type), written once by the
@@ -600,6 +602,7 @@ __global__ void __launch_bounds__(kVoxEmitThreads, RV_VOX_EMIT_OCC) k_vox_emit(c
 #pragma unroll
       for (int c = 0; c < 6; ++c) rec->sum[c] = own.s[c];
       a.slots[me.y].chain = kVoxLongTag | q;
+      atomicOr(a.longmap + (me.y >> 5), 1u << (me.y & 31u));
       continue;
     }
     VoxSum acc;
@@ -623,9 +626,10 @@ __global__ void __launch_bounds__(256) k_vox_long(const VoxArgs a, int n_parts) 
     const unsigned int joiners = a.parts[p].y;
     for (unsigned int j = threadIdx.x; j < joiners; j += blockDim.x) {
       const long long at = p1 - 1 - (long long)j;
+      const unsigned int slot = a.jslot[at];
+      if (!((a.longmap[slot >> 5] >> (slot & 31u)) & 1u)) continue;
       const uint2 e = a.list[at];
-      const unsigned int v = a.slots[a.jslot[at]].chain;
-      if (!(v & kVoxLongTag)) continue;
+      const unsigned int v = a.slots[slot].chain;
       VoxSum s;
 #pragma unroll
       for (int c = 0; c < 6; ++c) s.s[c] = 0.0;
@@ -663,12 +667,14 @@ unsigned long long vox_capacity(long long n) {  // 1.5 slots per point, a multip
 size_t vox_align(size_t b) { return (b + 255) & ~(size_t)255; }
 
 struct VoxLayout {
-  size_t slots, list, jslot, masks, pool, mxyz, total;
+  size_t longmap, slots, list, jslot, masks, pool, mxyz, total;
 };
 VoxLayout vox_layout(long long n) {
   VoxLayout L;
   const unsigned long long cap = vox_capacity(n);
   size_t off = kVoxHead;
+  L.longmap = off;
+  off += vox_align((size_t)(cap / 32) * 4);  // cap is a multiple of 32
   L.slots = off;
   off += vox_align((size_t)cap * sizeof(VoxSlot));
   L.list = off;
@@ -908,6 +914,7 @@ static int vox_run_all(rv_ctx *ctx, const char *who, int n_views, const void *co
   a.rvoxel = 1.0 / voxel_size;
   a.hdr = reinterpret_cast<VoxHeader *>(w);
   a.parts = reinterpret_cast<uint2 *>(w + 256);
+  a.longmap = reinterpret_cast<unsigned int *>(w + L.longmap);
   a.slots = reinterpret_cast<VoxSlot *>(w + L.slots);
   a.list = reinterpret_cast<uint2 *>(w + L.list);
   a.jslot = reinterpret_cast<unsigned int *>(w + L.jslot);
@@ -915,7 +922,7 @@ static int vox_run_all(rv_ctx *ctx, const char *who, int n_views, const void *co
   a.pool = reinterpret_cast<VoxLong *>(w + L.pool);
   a.mxyz = a.identity ? nullptr : (void *)(w + L.mxyz);
   a.cap = (unsigned int)cap;
-  // header, part counters and the table (empty keys, no joiners) are cleared; nothing else needs initialising
+  // header, part counters, long-voxel bits and the table (empty keys, no joiners) are cleared; nothing else needs initialising
   RV_CUDA(ctx, cudaMemsetAsync(d_ws, 0, L.slots + (size_t)cap * sizeof(VoxSlot), st));
   const double *bounds = d_bounds;
   if (!bounds) {

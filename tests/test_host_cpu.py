@@ -51,7 +51,7 @@ def test_library_exports_every_declared_symbol(built):
     assert lib.rv_register_workspace_bytes(64, 480, 640, 720, 1280) == tables + 16 * per_frame
     # header + part counters, keys, chain heads, list, links, run-head bits, long-voxel pool, a fusion's transformed xyz (each
     # rounded up to 256 B)
-    assert lib.rv_voxel_workspace_bytes(1000) == (256 + 2048 * 8) + 24064 + 8192 + 4096 + 256 + 112 * 64 + 24064
+    assert lib.rv_voxel_workspace_bytes(1000) == (256 + 2048 * 8) + 256 + 24064 + 8192 + 4096 + 256 + 112 * 64 + 24064
 
 
 def test_shared_object_holds_only_sm100a_code(built):
