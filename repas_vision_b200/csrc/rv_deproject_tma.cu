@@ -102,9 +102,13 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
       : "memory");
   return ok != 0;
 }
+#ifndef RV_K1_POLL_NS
+#define RV_K1_POLL_NS 0  // experiment: an explicit sleep between polls (0 = none: try_wait's own suspension only)
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+    if (RV_K1_POLL_NS) __nanosleep(RV_K1_POLL_NS);
   }
 }
 // 1-D bulk copy global -> shared, completion reported to an mbarrier in bytes (TMA engine, no tensor map)

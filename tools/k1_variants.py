@@ -51,6 +51,7 @@ VARIANTS.update({
     "k1w_cw8_i4_s3_w48": "-DRV_K1_CW=8 -DRV_K1_ITERS=4 -DRV_K1_STAGES=3 -DRV_K1_WARPS_PER_SM=48",
     "k1w_cw4_i8_s2_w40": "-DRV_K1_CW=4 -DRV_K1_ITERS=8 -DRV_K1_STAGES=2 -DRV_K1_WARPS_PER_SM=40",
 })
+VARIANTS.update({"k1p_ns0": "", "k1p_ns32": "-DRV_K1_POLL_NS=32", "k1p_ns100": "-DRV_K1_POLL_NS=100", "k1p_ns300": "-DRV_K1_POLL_NS=300"})
 # ICP search tunables (tools/icp_sweep.sh): cell size of the nearest-point index in surface spacings, warm-started bound
 VARIANTS.update({
     "icp_c10": "-DRV_NN_CELL_SPACINGS=1.0", "icp_c15": "-DRV_NN_CELL_SPACINGS=1.5", "icp_c20": "-DRV_NN_CELL_SPACINGS=2.0",
