@@ -250,8 +250,8 @@ def transform_merge(views, Ts, has_color: bool, out_dtype=None, want_bounds=Fals
     ptrs = (C.c_void_p * nv)(*[v[0].data_ptr() for v in views])
     strides = (C.c_int64 * nv)(*[pstride(v[0]) for v in views])
     ns = (C.c_int64 * nv)(*[int(v[1]) for v in views])
-    Tflat = np.ascontiguousarray(np.stack([np.asarray(T, dtype=np.float64).reshape(4, 4) for T in Ts])).reshape(-1)
-    Tc = (C.c_double * (16 * nv))(*Tflat.tolist())
+    Tflat = np.ascontiguousarray(np.stack([np.asarray(T, dtype=np.float64).reshape(4, 4) for T in Ts]))  # alive during the call
+    Tc = Tflat.ctypes.data_as(C.POINTER(C.c_double))
     bounds = None
     if want_bounds:
         bounds = torch.empty(6, dtype=torch.float64, device=dev)
@@ -285,7 +285,7 @@ def voxel_downsample(data: torch.Tensor, n: int, has_color: bool, voxel_size: fl
     out = torch.empty((planes, max(cap, 1)), dtype=out_dt, device=dev)
     keys = torch.empty((3, max(cap, 1)), dtype=torch.int32, device=dev) if want_keys else None
     cnts = torch.empty(max(cap, 1), dtype=torch.int32, device=dev) if want_counts else None
-    m = torch.zeros(1, dtype=torch.int64, device=dev)
+    m = torch.empty(1, dtype=torch.int64, device=dev)  # always written by the call (0 for an empty cloud, -1 on overflow)
     ws = workspace(ctx.lib.rv_voxel_workspace_bytes(n), dev)
     if not (float(voxel_size) > 0.0):
         raise ValueError("voxel_size <= 0")
@@ -311,13 +311,13 @@ def fuse_voxel(views, Ts, has_color: bool, voxel_size: float, *, out_dtype=None,
     out = torch.empty((planes, max(total, 1)), dtype=out_dt, device=dev)
     keys = torch.empty((3, max(total, 1)), dtype=torch.int32, device=dev) if want_keys else None
     cnts = torch.empty(max(total, 1), dtype=torch.int32, device=dev) if want_counts else None
-    m = torch.zeros(1, dtype=torch.int64, device=dev)
+    m = torch.empty(1, dtype=torch.int64, device=dev)  # always written by the call (0 for an empty cloud, -1 on overflow)
     ws = workspace(ctx.lib.rv_voxel_workspace_bytes(total), dev)
     ptrs = (C.c_void_p * nv)(*[v[0].data_ptr() for v in views])
     strides = (C.c_int64 * nv)(*[pstride(v[0]) for v in views])
     ns = (C.c_int64 * nv)(*[int(v[1]) for v in views])
-    Tflat = np.ascontiguousarray(np.stack([np.asarray(T, dtype=np.float64).reshape(4, 4) for T in Ts])).reshape(-1)
-    Tc = (C.c_double * (16 * nv))(*Tflat.tolist())
+    Tflat = np.ascontiguousarray(np.stack([np.asarray(T, dtype=np.float64).reshape(4, 4) for T in Ts]))  # alive during the call
+    Tc = Tflat.ctypes.data_as(C.POINTER(C.c_double))
     ctx.check(ctx.lib.rv_fuse_voxel(ctx.handle, nv, ptrs, strides, ns, Tc, _RV_DT[in_dt], int(has_color), float(voxel_size),
                                     ptr(out), out.shape[1], _RV_DT[out_dt], total, ptr(keys), ptr(cnts), ptr(m), ptr(ws),
                                     ws.numel(), stream_ptr(dev)))
