@@ -12,10 +12,10 @@
 //   k_knn_setup    cell size from the bounding box, the point count and k: large enough that the 27 cells around a point
 //                  normally hold its k nearest neighbours, no larger than a search radius
 //   k_knn_refine   four times the expected points per used cell (a far outlier inflated the box): shrink the cells and rebuild, up to 3x
-//   k_knn_cells    cell key of every point -> open-addressing table of 8-byte keys; the rank inside the cell comes back
-//                  from the per-cell counter
-//   k_knn_alloc    every used cell gets a range of the cell-sorted arrays (one cursor update per warp of table slots)
-//   k_knn_scatter  points into cell order
+//   k_knn_cells    cell key of every point -> open-addressing table of 16-byte entries {key, count, start}: one load answers a
+//                  probe; the rank inside the cell comes back from the entry's counter
+//   k_knn_alloc    every used cell gets a range of the cell-sorted arrays (scan inside the CTA, one cursor update per 256 slots)
+//   k_knn_scatter  points into cell order (and where every point went, for the warm start of the ICP search)
 //   k_knn_query    one thread per point: shells of cells at Chebyshev distance 0, 1, 2, ... around the point's cell, a sorted
 //                  list of the k smallest squared distances; the search stops once the k-th distance is within the cube
 //                  already visited (any unvisited point is at least r * cell away), so the result is exact
@@ -24,6 +24,10 @@
 //                  redone in INDEX ORDER like std::accumulate only when a point lies within rounding distance of the
 //                  threshold, so the kept set always equals the sequential reference's
 //   k_sor_mask     the keep mask; rv_select_by_mask (rv_deproject.cu) then compacts the cloud in order.
+// The same grid serves normal estimation (k_knn_query<true>: hybrid search, covariance, smallest eigenvector) and ICP
+// (k_nn_search: nearest point within the correspondence distance; k_icp_sums / k_icp_finish_step: the estimation step and the
+// loop's decisions on the device), described where they are defined.  Words every thread updates -- bounds, cell counter,
+// range cursor -- are updated once per CTA: requests to one word queue at one L2 slice.
 #include "rv_common.cuh"
 
 namespace {
